@@ -1,0 +1,113 @@
+"""ctypes binding of libagx.so (include/agx.h).  This is the only place Python touches the C ABI.
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no CPU fallback:
+if the shared object is missing or a struct mirror disagrees with the library, importing fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libagx.so")
+
+AGX_MAX_ACTIONS = 5
+AGX_CTRL_STATE_MAX = 12
+AGX_RESET_DRAWS_MAX = 16
+AGX_NOISE_DRAWS = 18
+
+TASK_IDS = {"hovering": 0, "tracking": 1, "balloon": 2, "avoid": 3, "planning": 4}
+CTL_IDS = {"pos": 0, "vel": 1, "atti": 2, "rate": 3, "prop": 4}
+FLAG_MUTATE_ACTIONS, FLAG_CTRL_RESET, FLAG_NO_NOISE = 1, 2, 4
+INT_RK4, INT_EULER = 0, 1
+
+_f3 = C.c_float * 3
+_f5 = C.c_float * AGX_MAX_ACTIONS
+
+
+class AgxParams(C.Structure):
+    _fields_ = [
+        ("task", C.c_int32), ("ctl_mode", C.c_int32), ("num_actions", C.c_int32), ("num_obs", C.c_int32),
+        ("integrator", C.c_int32), ("flags", C.c_int32), ("max_episode_length", C.c_int32),
+        ("ctrl_state_dim", C.c_int32), ("reset_draws", C.c_int32), ("_pad0", C.c_int32),
+        ("dt", C.c_float), ("gravity", C.c_float), ("mass", C.c_float), ("inertia", _f3), ("arm", C.c_float),
+        ("k_thrust", C.c_float), ("k_torque", C.c_float), ("max_lin_vel", C.c_float), ("max_ang_vel", C.c_float),
+        ("act_lo", _f5), ("act_hi", _f5),
+        ("rate_p", _f3), ("rate_i", _f3), ("rate_d", _f3), ("rate_int_lim", C.c_float), ("rate_i_fade", C.c_float),
+        ("att_p", _f3), ("att_yaw_w", C.c_float), ("att_rate_lim", _f3),
+        ("vel_p", _f3), ("vel_i", _f3), ("vel_d", _f3), ("vel_int_lim", _f3), ("pos_p", _f3), ("vel_sp_lim", _f3),
+        ("hover_thrust", C.c_float), ("tilt_max_tan", C.c_float), ("thr_min", C.c_float), ("thr_max", C.c_float),
+        ("target", C.c_float * 18), ("target_yaw", C.c_float), ("noise_sigma", C.c_float * 4),
+    ]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+
+class AgxStepIO(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p), ("action", C.c_void_p), ("actions_out", C.c_void_p), ("prev_action", C.c_void_p),
+        ("ctrl_state", C.c_void_p), ("progress", C.c_void_p), ("reset", C.c_void_p), ("timeout", C.c_void_p),
+        ("obs", C.c_void_p), ("reward", C.c_void_p), ("cmd", C.c_void_p), ("reward_terms", C.c_void_p),
+        ("aux", C.c_void_p), ("rand_reset", C.c_void_p), ("rand_noise", C.c_void_p),
+        ("seed", C.c_uint64), ("step", C.c_uint64), ("step_dev", C.c_void_p), ("env_offset", C.c_int64),
+    ]
+
+
+class AgxError(RuntimeError):
+    pass
+
+
+def bind(lib):
+    """Attach prototypes of every symbol include/agx.h declares."""
+    lib.agx_version.restype = C.c_int
+    lib.agx_error_string.restype = C.c_char_p
+    lib.agx_sizeof_params.restype = C.c_int
+    lib.agx_sizeof_step_io.restype = C.c_int
+    lib.agx_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.agx_params_default.argtypes = [C.POINTER(AgxParams), C.c_int, C.c_int]
+    lib.agx_step.argtypes = [C.POINTER(AgxParams), C.c_int64, C.POINTER(AgxStepIO), C.c_void_p]
+    lib.agx_reset_idx.argtypes = [
+        C.POINTER(AgxParams), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
+    ]
+    lib.agx_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
+    return lib
+
+
+EXPORTS = (
+    "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_set_option",
+    "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill",
+)
+
+_lib = None
+
+
+def load():
+    """Load libagx.so once; raise (never fall back) if it is absent or ABI-incompatible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). airgym_b200 has no CPU fallback."
+        )
+    lib = bind(C.CDLL(LIB_PATH))
+    if lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO):
+        raise ImportError("libagx.so struct layout differs from airgym_b200/_capi.py (rebuild the library)")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = "agx call"):
+    if code != 0:
+        raise AgxError(f"{what} failed with code {code}: {load().agx_error_string().decode()}")
+
+
+def default_params(task: str, ctl_mode: str) -> AgxParams:
+    p = AgxParams()
+    check(load().agx_params_default(C.byref(p), TASK_IDS[task], CTL_IDS[ctl_mode]), "agx_params_default")
+    return p

@@ -1,0 +1,676 @@
+// agx_math.cuh — per-env arithmetic of the fused quadrotor step, written once as
+// __host__ __device__ inline functions: the sm_100a kernels in agx_step.cu instantiate it one env
+// per thread, and tests/hostsim compiles the very same text with g++ to debug it against the oracle
+// on a box without a GPU (test infrastructure only; the product never runs the host build).
+//
+// Numerics: IEEE fp32, no fast-math; clamps are comparison based so that NaN propagates exactly as
+// torch.clamp / torch.max(torch.min()) do in the reference (quirk Q5, hovering.py:393-397).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "agx.h"
+
+#if defined(__CUDACC__)
+#define AGX_HD __host__ __device__ __forceinline__
+#else
+#define AGX_HD inline
+#endif
+
+namespace agx {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+
+struct V3 { float x, y, z; };
+struct Q4 { float x, y, z, w; };  // xyzw, like the reference state row (hovering.py:75)
+
+AGX_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+AGX_HD float sq(float x) { return x * x; }
+AGX_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+AGX_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+AGX_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+AGX_HD V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+AGX_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+AGX_HD V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+AGX_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
+
+// ---- rotation conventions of pytorch3d.transforms [EXT] restated ------------------
+
+// quaternion_to_matrix on (w,x,y,z) = (q.w,q.x,q.y,q.z); row-major 3x3; 2/|q|^2 scaling.
+AGX_HD void quat_to_matrix(Q4 q, float* m) {
+    const float two_s = 2.0f / (q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    m[0] = 1.0f - two_s * (q.y * q.y + q.z * q.z);
+    m[1] = two_s * (q.x * q.y - q.z * q.w);
+    m[2] = two_s * (q.x * q.z + q.y * q.w);
+    m[3] = two_s * (q.x * q.y + q.z * q.w);
+    m[4] = 1.0f - two_s * (q.x * q.x + q.z * q.z);
+    m[5] = two_s * (q.y * q.z - q.x * q.w);
+    m[6] = two_s * (q.x * q.z - q.y * q.w);
+    m[7] = two_s * (q.y * q.z + q.x * q.w);
+    m[8] = 1.0f - two_s * (q.x * q.x + q.y * q.y);
+}
+
+// euler_angles_to_matrix(a,'XYZ') = Rx(a0) Ry(a1) Rz(a2)
+AGX_HD void euler_xyz_to_matrix(float a0, float a1, float a2, float* m) {
+    const float c0 = cosf(a0), s0 = sinf(a0), c1 = cosf(a1), s1 = sinf(a1), c2 = cosf(a2), s2 = sinf(a2);
+    // A = Rx Ry
+    const float a00 = c1, a01 = 0.0f, a02 = s1;
+    const float a10 = s0 * s1, a11 = c0, a12 = -s0 * c1;
+    const float a20 = -c0 * s1, a21 = s0, a22 = c0 * c1;
+    m[0] = a00 * c2 + a01 * s2;  m[1] = a01 * c2 - a00 * s2;  m[2] = a02;
+    m[3] = a10 * c2 + a11 * s2;  m[4] = a11 * c2 - a10 * s2;  m[5] = a12;
+    m[6] = a20 * c2 + a21 * s2;  m[7] = a21 * c2 - a20 * s2;  m[8] = a22;
+}
+
+AGX_HD float sqrt_pos(float x) { return x > 0.0f ? sqrtf(x) : 0.0f; }
+
+// matrix_to_quaternion: max-of-four-candidates, returns xyzw with w >= 0 (standardised).
+AGX_HD Q4 matrix_to_quat(const float* m) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6],
+                m21 = m[7], m22 = m[8];
+    const float qa0 = sqrt_pos(1.0f + m00 + m11 + m22);
+    const float qa1 = sqrt_pos(1.0f + m00 - m11 - m22);
+    const float qa2 = sqrt_pos(1.0f - m00 + m11 - m22);
+    const float qa3 = sqrt_pos(1.0f - m00 - m11 + m22);
+    float w, x, y, z, d;
+    if (qa0 >= qa1 && qa0 >= qa2 && qa0 >= qa3) {
+        d = 2.0f * (qa0 > 0.1f ? qa0 : 0.1f);
+        w = qa0 * qa0 / d; x = (m21 - m12) / d; y = (m02 - m20) / d; z = (m10 - m01) / d;
+    } else if (qa1 >= qa2 && qa1 >= qa3) {
+        d = 2.0f * (qa1 > 0.1f ? qa1 : 0.1f);
+        w = (m21 - m12) / d; x = qa1 * qa1 / d; y = (m10 + m01) / d; z = (m02 + m20) / d;
+    } else if (qa2 >= qa3) {
+        d = 2.0f * (qa2 > 0.1f ? qa2 : 0.1f);
+        w = (m02 - m20) / d; x = (m10 + m01) / d; y = qa2 * qa2 / d; z = (m12 + m21) / d;
+    } else {
+        d = 2.0f * (qa3 > 0.1f ? qa3 : 0.1f);
+        w = (m10 - m01) / d; x = (m20 + m02) / d; y = (m21 + m12) / d; z = qa3 * qa3 / d;
+    }
+    Q4 q;
+    if (w < 0.0f) { q.x = -x; q.y = -y; q.z = -z; q.w = -w; }
+    else { q.x = x; q.y = y; q.z = z; q.w = w; }
+    return q;
+}
+
+// Hamilton product, xyzw
+AGX_HD Q4 qmul(Q4 a, Q4 b) {
+    Q4 r;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    return r;
+}
+AGX_HD Q4 qconj(Q4 a) { Q4 r; r.x = -a.x; r.y = -a.y; r.z = -a.z; r.w = a.w; return r; }
+AGX_HD Q4 qnormalize(Q4 a) {
+    const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+    Q4 r; r.x = a.x / n; r.y = a.y / n; r.z = a.z / n; r.w = a.w / n; return r;
+}
+// third column of the rotation matrix of a unit quaternion (body z in world)
+AGX_HD V3 quat_body_z(Q4 q) {
+    return v3(2.0f * (q.x * q.z + q.y * q.w), 2.0f * (q.y * q.z - q.x * q.w),
+              1.0f - 2.0f * (q.x * q.x + q.y * q.y));
+}
+AGX_HD V3 mat_mul_v(const float* m, V3 v) {
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z,
+              m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+AGX_HD V3 mat_tmul_v(const float* m, V3 v) {
+    return v3(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z,
+              m[2] * v.x + m[5] * v.y + m[8] * v.z);
+}
+
+// compute_yaw_diff(a, b) (hovering.py:33-38)
+AGX_HD float yaw_diff(float a, float b) {
+    float d = b - a;
+    if (d < -kPi) d = d + kTwoPi;
+    if (d > kPi) d = d - kTwoPi;
+    return d;
+}
+
+// ---- Philox4x32-10 counter RNG (perf mode; explicit-randomness mode bypasses it) ----------------------
+struct U4 { uint32_t x, y, z, w; };
+
+AGX_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+AGX_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// counter = (global env id lo, step lo, stream_id | step_hi<<8 ... , block)
+struct PhiloxCtx { uint32_t k0, k1, env_lo, env_hi, step_lo, step_hi; };
+
+AGX_HD U4 philox_block(const PhiloxCtx& c, uint32_t stream_id, uint32_t blk) {
+    U4 ctr;
+    ctr.x = c.env_lo;
+    ctr.y = c.step_lo;
+    ctr.z = (c.env_hi << 16) ^ (c.step_hi << 4) ^ stream_id;  // env_hi/step_hi are 0 in practice
+    ctr.w = blk;
+    return philox4x32_10(ctr, c.k0, c.k1);
+}
+AGX_HD float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
+
+AGX_HD void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
+    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;  // (0,1]
+    const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;         // [0,1)
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * u2, &s, &c);
+#else
+    s = sinf(kTwoPi * u2); c = cosf(kTwoPi * u2);
+#endif
+    *z0 = r * c; *z1 = r * s;
+}
+
+// `count` uniforms of stream `sid` (0: pre-step reset, 1: post-step reset)
+AGX_HD void philox_uniforms(const PhiloxCtx& c, uint32_t sid, int count, float* u) {
+    for (int b = 0; b * 4 < count; ++b) {
+        const U4 r = philox_block(c, sid, (uint32_t)b);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < 4; ++j)
+            if (b * 4 + j < count) u[b * 4 + j] = u32_to_unit(w[j]);
+    }
+}
+// `count` (<= 20) standard normals of stream 2
+AGX_HD void philox_normals(const PhiloxCtx& c, int count, float* z) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        if (b * 4 >= count) break;
+        const U4 r = philox_block(c, 2u, (uint32_t)b);
+        float n0, n1, n2, n3;
+        box_muller(r.x, r.y, &n0, &n1);
+        box_muller(r.z, r.w, &n2, &n3);
+        const float n[4] = {n0, n1, n2, n3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (b * 4 + j < count) z[b * 4 + j] = n[j];
+    }
+}
+
+// ---- reset samplers ---------------------------------------------------------------------------------
+// U(lo,hi) exactly as torch_rand_float: (hi - lo) * u + lo (airgym/utils/torch_utils.py:192-193)
+AGX_HD float urange(float u, float lo, float hi) { return (hi - lo) * u + lo; }
+
+// Hovering.reset_idx (hovering.py:310-335) / Tracking.reset_idx (tracking.py:159-192): 12 uniforms in
+// call order xy(2) z(1) roll,pitch(2) yaw(1) linvel(3) angvel(3); writes the 13-float root state.
+template <int TASK>
+AGX_HD void reset_sample(const float* u, float* s) {
+    float a0, a1, a2;
+    if (TASK == AGX_TASK_TRACKING) {
+        s[0] = 0.1f * urange(u[0], -1.0f, 1.0f);
+        s[1] = 0.1f * urange(u[1], -1.0f, 1.0f);
+        s[2] = 0.1f * urange(u[2], -1.0f, 1.0f) + 1.0f;
+        a0 = 0.1f * urange(u[3], -kPi, kPi);
+        a1 = 0.1f * urange(u[4], -kPi, kPi);
+        a2 = 0.2f * urange(u[5], -kPi, kPi);
+    } else {
+        s[0] = urange(u[0], -1.0f, 1.0f);
+        s[1] = urange(u[1], -1.0f, 1.0f);
+        s[2] = urange(u[2], -1.0f, 1.0f);
+        a0 = 0.01f * urange(u[3], -kPi, kPi);
+        a1 = 0.01f * urange(u[4], -kPi, kPi);
+        a2 = 0.05f * urange(u[5], -kPi, kPi);
+    }
+    float m[9];
+    euler_xyz_to_matrix(a0, a1, a2, m);
+    const Q4 q = matrix_to_quat(m);
+    s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+    s[7] = 0.5f * urange(u[6], -1.0f, 1.0f);
+    s[8] = 0.5f * urange(u[7], -1.0f, 1.0f);
+    s[9] = 0.5f * urange(u[8], -1.0f, 1.0f);
+    s[10] = 0.2f * urange(u[9], -1.0f, 1.0f);
+    s[11] = 0.2f * urange(u[10], -1.0f, 1.0f);
+    s[12] = 0.2f * urange(u[11], -1.0f, 1.0f);
+}
+
+// ---- PX4-aligned controller cascade (builder-defined; replaces the rlPx4Controller FFI, -------------
+// hovering.py:217-250).  Everything is expressed in the sim's FLU body / ENU world frames; with
+// PX4's diagonal gains this is identical to converting to FRD/NED, running PX4 and converting back.
+// Controller state cs[]: [0:3] rate integrator, [3:6] previous body rate, [6:9] velocity integrator,
+// [9:12] previous world velocity.
+
+// quad-X mixer for the URDF rotor order prop_1(+x,-y) prop_2(-x,+y) prop_3(+x,+y) prop_4(-x,-y) with
+// reaction torques (-,-,+,+) (hovering.py:272-275): c_i = T + s_r tau_x + s_p tau_y + s_y tau_z.
+AGX_HD void mixer(float T, V3 tau, float* cmd) {
+    cmd[0] = clampf(T - tau.x - tau.y - tau.z, 0.0f, 1.0f);
+    cmd[1] = clampf(T + tau.x + tau.y - tau.z, 0.0f, 1.0f);
+    cmd[2] = clampf(T + tau.x - tau.y + tau.z, 0.0f, 1.0f);
+    cmd[3] = clampf(T - tau.x + tau.y + tau.z, 0.0f, 1.0f);
+}
+
+// PX4 RateControl: tau = P e + int - D d(w)/dt; integrator faded out for large errors, clamped.
+AGX_HD V3 rate_loop(const AgxParams& P, V3 w_sp, V3 w_b, float* cs) {
+    const float wsp[3] = {w_sp.x, w_sp.y, w_sp.z};
+    const float wb[3] = {w_b.x, w_b.y, w_b.z};
+    float tau[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float e = wsp[i] - wb[i];
+        const float wdot = (wb[i] - cs[3 + i]) / P.dt;
+        tau[i] = P.rate_p[i] * e + cs[i] - P.rate_d[i] * wdot;
+        const float ef = e / P.rate_i_fade;
+        float fade = 1.0f - ef * ef;
+        fade = fade < 0.0f ? 0.0f : fade;
+        cs[i] = clampf(cs[i] + fade * P.rate_i[i] * e * P.dt, -P.rate_int_lim, P.rate_int_lim);
+        cs[3 + i] = wb[i];
+    }
+    return v3(tau[0], tau[1], tau[2]);
+}
+
+// PX4 AttitudeControl::update: reduced-attitude (tilt first) law with yaw weight → body-rate set-point.
+AGX_HD V3 attitude_loop(const AgxParams& P, Q4 q, Q4 qd) {
+    const V3 ez = quat_body_z(q);
+    const V3 ezd = quat_body_z(qd);
+    const float d = dot(ez, ezd);
+    Q4 qd_red;
+    if (d < -1.0f + 1e-5f) {
+        qd_red = qd;  // opposite thrust directions: no unique tilt rotation, use the full attitude
+    } else {
+        const V3 c = cross(ez, ezd);
+        Q4 t; t.x = c.x; t.y = c.y; t.z = c.z; t.w = d + 1.0f;  // shortest rotation ez → ezd
+        qd_red = qmul(qnormalize(t), q);
+    }
+    Q4 qmix = qmul(qconj(qd_red), qd);
+    if (qmix.w < 0.0f) { qmix.x = -qmix.x; qmix.y = -qmix.y; qmix.z = -qmix.z; qmix.w = -qmix.w; }
+    const float mw = clampf(qmix.w, -1.0f, 1.0f);
+    const float mz = clampf(qmix.z, -1.0f, 1.0f);
+    Q4 yawq; yawq.x = 0.0f; yawq.y = 0.0f;
+    yawq.w = cosf(P.att_yaw_w * acosf(mw));
+    yawq.z = sinf(P.att_yaw_w * asinf(mz));
+    const Q4 qdd = qmul(qd_red, yawq);
+    Q4 qe = qmul(qconj(q), qdd);
+    const float sgn = qe.w < 0.0f ? -2.0f : 2.0f;
+    V3 r;
+    r.x = clampf(sgn * qe.x * P.att_p[0], -P.att_rate_lim[0], P.att_rate_lim[0]);
+    r.y = clampf(sgn * qe.y * P.att_p[1], -P.att_rate_lim[1], P.att_rate_lim[1]);
+    r.z = clampf(sgn * qe.z * P.att_p[2], -P.att_rate_lim[2], P.att_rate_lim[2]);
+    return r;
+}
+
+// PX4 PositionControl::_velocityControl + _accelerationControl + bodyzToAttitude (ENU form):
+// PID on velocity → specific-force vector → tilt limit → collective thrust + attitude set-point.
+AGX_HD void velocity_loop(const AgxParams& P, V3 v_sp, float yaw_sp, V3 v, float* cs, Q4* q_sp,
+                          float* thrust) {
+    const float vsp[3] = {v_sp.x, v_sp.y, v_sp.z};
+    const float vv[3] = {v.x, v.y, v.z};
+    float acc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float e = vsp[i] - vv[i];
+        const float vdot = (vv[i] - cs[9 + i]) / P.dt;
+        acc[i] = P.vel_p[i] * e + cs[6 + i] - P.vel_d[i] * vdot;
+        cs[6 + i] = clampf(cs[6 + i] + P.vel_i[i] * e * P.dt, -P.vel_int_lim[i], P.vel_int_lim[i]);
+        cs[9 + i] = vv[i];
+    }
+    float fx = acc[0], fy = acc[1], fz = acc[2] + P.gravity;
+    const float fz_min = 0.1f * P.gravity;
+    fz = fz < fz_min ? fz_min : fz;
+    const float h = sqrtf(fx * fx + fy * fy);
+    const float hmax = fz * P.tilt_max_tan;
+    if (h > hmax) { const float k = hmax / h; fx = fx * k; fy = fy * k; }
+    const float fn = sqrtf(fx * fx + fy * fy + fz * fz);
+    const V3 bz = v3(fx / fn, fy / fn, fz / fn);
+    *thrust = clampf(P.hover_thrust * fn / P.gravity, P.thr_min, P.thr_max);
+    // bodyzToAttitude: x axis from the yaw heading, orthogonalised against body z
+    const V3 yc = v3(-sinf(yaw_sp), cosf(yaw_sp), 0.0f);
+    V3 bx = cross(yc, bz);
+    const float bxn = norm(bx);
+    bx = v3(bx.x / bxn, bx.y / bxn, bx.z / bxn);
+    const V3 by = cross(bz, bx);
+    const float m[9] = {bx.x, by.x, bz.x, bx.y, by.y, bz.y, bx.z, by.z, bz.z};
+    *q_sp = matrix_to_quat(m);
+}
+
+// Full cascade dispatch.  a[] = shaped+clamped action, s[] = root state row (canonical quaternion).
+template <int MODE>
+AGX_HD void controller(const AgxParams& P, const float* s, const float* a, float* cs, float* cmd) {
+    if (MODE == AGX_CTL_PROP) {  // hovering.py:251-252
+        cmd[0] = a[0]; cmd[1] = a[1]; cmd[2] = a[2]; cmd[3] = a[3];
+        return;
+    }
+    Q4 q; q.x = s[3]; q.y = s[4]; q.z = s[5]; q.w = s[6];
+    float R[9];
+    quat_to_matrix(q, R);
+    const V3 w_b = mat_tmul_v(R, v3(s[10], s[11], s[12]));  // world → body rates (set_q_world, :249)
+    V3 w_sp;
+    float thrust;
+    if (MODE == AGX_CTL_RATE) {
+        w_sp = v3(a[0], a[1], a[2]);
+        thrust = a[3];
+    } else {
+        Q4 q_sp;
+        if (MODE == AGX_CTL_ATTI) {  // action = (w,x,y,z,thrust)
+            Q4 t; t.w = a[0]; t.x = a[1]; t.y = a[2]; t.z = a[3];
+            const float n2 = t.w * t.w + t.x * t.x + t.y * t.y + t.z * t.z;
+            if (n2 < 1e-12f) { t.w = 1.0f; t.x = 0.0f; t.y = 0.0f; t.z = 0.0f; }
+            q_sp = qnormalize(t);
+            thrust = a[4];
+        } else {
+            V3 v_sp;
+            if (MODE == AGX_CTL_POS) {
+                v_sp.x = clampf(P.pos_p[0] * (a[0] - s[0]), -P.vel_sp_lim[0], P.vel_sp_lim[0]);
+                v_sp.y = clampf(P.pos_p[1] * (a[1] - s[1]), -P.vel_sp_lim[1], P.vel_sp_lim[1]);
+                v_sp.z = clampf(P.pos_p[2] * (a[2] - s[2]), -P.vel_sp_lim[2], P.vel_sp_lim[2]);
+            } else {
+                v_sp = v3(a[0], a[1], a[2]);
+            }
+            velocity_loop(P, v_sp, a[3], v3(s[7], s[8], s[9]), cs, &q_sp, &thrust);
+        }
+        w_sp = attitude_loop(P, qnormalize(q), q_sp);
+    }
+    const V3 tau = rate_loop(P, w_sp, w_b, cs);
+    mixer(thrust, tau, cmd);
+}
+
+// ---- rigid body (builder-defined; replaces gym.simulate, hovering.py:290) -----------
+struct Deriv { V3 dp, dv, dw; Q4 dq; };
+
+AGX_HD Deriv body_deriv(const AgxParams& P, V3 v, Q4 q, V3 w, float fz_over_m, V3 tau) {
+    Deriv d;
+    d.dp = v;
+    const V3 bz = quat_body_z(q);
+    d.dv = v3(bz.x * fz_over_m, bz.y * fz_over_m, bz.z * fz_over_m - P.gravity);
+    d.dq.x = 0.5f * (q.w * w.x + q.y * w.z - q.z * w.y);
+    d.dq.y = 0.5f * (q.w * w.y + q.z * w.x - q.x * w.z);
+    d.dq.z = 0.5f * (q.w * w.z + q.x * w.y - q.y * w.x);
+    d.dq.w = 0.5f * (-q.x * w.x - q.y * w.y - q.z * w.z);
+    const V3 Iw = v3(P.inertia[0] * w.x, P.inertia[1] * w.y, P.inertia[2] * w.z);
+    const V3 g = cross(w, Iw);
+    d.dw = v3((tau.x - g.x) / P.inertia[0], (tau.y - g.y) / P.inertia[1], (tau.z - g.z) / P.inertia[2]);
+    return d;
+}
+
+AGX_HD Q4 qaxpy(Q4 q, float h, Q4 d) {
+    Q4 r; r.x = q.x + h * d.x; r.y = q.y + h * d.y; r.z = q.z + h * d.z; r.w = q.w + h * d.w; return r;
+}
+
+// One dt of the composite rigid body under a zero-order-hold body-frame wrench.
+// s: in/out root state row; thrust[4]: rotor forces [N] (already zeroed for envs reset this step,
+// hovering.py:268); tau_z: rotor reaction torque (hovering.py:270-275, NOT zeroed).
+AGX_HD void integrate(const AgxParams& P, float* s, const float* thrust, float tau_z, float* Rnew) {
+    V3 p = v3(s[0], s[1], s[2]);
+    Q4 q; q.x = s[3]; q.y = s[4]; q.z = s[5]; q.w = s[6];
+    V3 v = v3(s[7], s[8], s[9]);
+    float R[9];
+    quat_to_matrix(q, R);
+    V3 w = mat_tmul_v(R, v3(s[10], s[11], s[12]));  // body rates
+    const float fz_over_m = (thrust[0] + thrust[1] + thrust[2] + thrust[3]) / P.mass;
+    const V3 tau = v3(P.arm * (-thrust[0] + thrust[1] + thrust[2] - thrust[3]),
+                      P.arm * (-thrust[0] + thrust[1] - thrust[2] + thrust[3]), tau_z);
+    const float h = P.dt;
+    if (P.integrator == AGX_INT_EULER) {  // semi-implicit Euler (PhysX-like A/B switch)
+        const Deriv k = body_deriv(P, v, q, w, fz_over_m, tau);
+        v = v + h * k.dv;
+        p = p + h * v;
+        w = w + h * k.dw;
+        const Deriv k2 = body_deriv(P, v, q, w, fz_over_m, tau);
+        q = qaxpy(q, h, k2.dq);
+    } else {  // classic RK4
+        const Deriv k1 = body_deriv(P, v, q, w, fz_over_m, tau);
+        const Deriv k2 = body_deriv(P, v + (0.5f * h) * k1.dv, qaxpy(q, 0.5f * h, k1.dq),
+                                    w + (0.5f * h) * k1.dw, fz_over_m, tau);
+        const Deriv k3 = body_deriv(P, v + (0.5f * h) * k2.dv, qaxpy(q, 0.5f * h, k2.dq),
+                                    w + (0.5f * h) * k2.dw, fz_over_m, tau);
+        const Deriv k4 = body_deriv(P, v + h * k3.dv, qaxpy(q, h, k3.dq), w + h * k3.dw, fz_over_m, tau);
+        const float h6 = h / 6.0f;
+        p = p + h6 * (k1.dp + 2.0f * k2.dp + 2.0f * k3.dp + k4.dp);
+        v = v + h6 * (k1.dv + 2.0f * k2.dv + 2.0f * k3.dv + k4.dv);
+        w = w + h6 * (k1.dw + 2.0f * k2.dw + 2.0f * k3.dw + k4.dw);
+        q.x = q.x + h6 * (k1.dq.x + 2.0f * k2.dq.x + 2.0f * k3.dq.x + k4.dq.x);
+        q.y = q.y + h6 * (k1.dq.y + 2.0f * k2.dq.y + 2.0f * k3.dq.y + k4.dq.y);
+        q.z = q.z + h6 * (k1.dq.z + 2.0f * k2.dq.z + 2.0f * k3.dq.z + k4.dq.z);
+        q.w = q.w + h6 * (k1.dq.w + 2.0f * k2.dq.w + 2.0f * k3.dq.w + k4.dq.w);
+    }
+    q = qnormalize(q);
+    quat_to_matrix(q, Rnew);
+    V3 ww = mat_mul_v(Rnew, w);  // back to world-frame angular velocity (IsaacGym root-state convention)
+    const float vn = norm(v);
+    if (vn > P.max_lin_vel) v = (P.max_lin_vel / vn) * v;
+    const float wn = norm(ww);
+    if (wn > P.max_ang_vel) ww = (P.max_ang_vel / wn) * ww;
+    s[0] = p.x; s[1] = p.y; s[2] = p.z;
+    s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+    s[7] = v.x; s[8] = v.y; s[9] = v.z;
+    s[10] = ww.x; s[11] = ww.y; s[12] = ww.z;
+}
+
+// ---- random source: explicit rows (parity mode) or Philox (perf mode) ---------------------------------
+struct RandSrc {
+    const float* reset_row;  // [2,D] or nullptr
+    const float* noise_row;  // [18] or nullptr
+    PhiloxCtx ph;
+};
+
+AGX_HD void draw_reset(const RandSrc& r, int which, int D, float* u) {
+    if (r.reset_row) {
+        for (int i = 0; i < D; ++i) u[i] = r.reset_row[which * D + i];
+    } else {
+        philox_uniforms(r.ph, (uint32_t)which, D, u);
+    }
+}
+AGX_HD void draw_noise(const RandSrc& r, float* z) {
+    if (r.noise_row) {
+#pragma unroll
+        for (int i = 0; i < AGX_NOISE_DRAWS; ++i) z[i] = r.noise_row[i];
+    } else {
+        philox_normals(r.ph, AGX_NOISE_DRAWS, z);
+    }
+}
+
+// ---- the fused per-env step ----------------------------------------------------------------------------
+// Per-env working set held in registers by the kernel (and in a plain struct by the host build).
+struct EnvRegs {
+    float s[13];
+    float a[AGX_MAX_ACTIONS];    // in: raw action; out: shaped + clamped (reference self.actions)
+    float pa[AGX_MAX_ACTIONS];   // reference self.pre_actions
+    float cs[AGX_CTRL_STATE_MAX];
+    int64_t progress;
+    int pending;                 // in: reference reset_buf != 0
+    int reset;                   // out: new reset_buf
+    int timeout;                 // out: time_out_buf
+    float a_last_remap;          // out: 0.5+0.5a of the last action column (Q4 write-back)
+    float rew;
+    float cmd[4];
+    float terms[9];
+};
+
+template <int TASK>
+AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e) {
+    float u[AGX_RESET_DRAWS_MAX];
+    draw_reset(rnd, which, P.reset_draws, u);
+    reset_sample<TASK>(u, e.s);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+    e.progress = 0;
+#pragma unroll
+    for (int i = 0; i < AGX_MAX_ACTIONS; ++i) e.pa[i] = 0.0f;
+    if (P.flags & AGX_FLAG_CTRL_RESET) {
+#pragma unroll
+        for (int i = 0; i < AGX_CTRL_STATE_MAX; ++i) e.cs[i] = 0.0f;
+    }
+}
+
+// Tracking.compute_traj_lemniscate (tracking.py:194-200), point k of 10
+AGX_HD V3 lemniscate(int64_t progress, int k, float dt) {
+    const float t = (float)(progress + 5 * k) * dt * 0.25f;
+    const float st = sinf(t), ct = cosf(t);
+    const float den = 1.0f + ct * ct;
+    return v3(3.0f * st / den, 3.0f * st * ct / den, 1.0f);
+}
+
+template <int TASK, int MODE>
+AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, EnvRegs& e, float* obs) {
+    constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
+    constexpr bool kThrustMode = (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI);
+
+    // -- pre_physics_step: resets pending from the previous step (hovering.py:209-211, quirk Q1)
+    if (e.pending) do_reset<TASK>(P, rnd, 0, e);
+
+    // -- action shaping (hovering.py:212-216)
+    if (kThrustMode) {
+        e.a[A - 1] = 0.5f + 0.5f * e.a[A - 1];
+        e.a_last_remap = e.a[A - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < A; ++i) {  // tensor_clamp = max(min(t, hi), lo)
+        float t = e.a[i];
+        t = (t > P.act_hi[i]) ? P.act_hi[i] : t;
+        t = (t < P.act_lo[i]) ? P.act_lo[i] : t;
+        e.a[i] = t;
+    }
+
+    // -- quaternion sign canonicalisation, written back into the state (hovering.py:224-226)
+    if (e.s[6] < 0.0f) { e.s[3] = -e.s[3]; e.s[4] = -e.s[4]; e.s[5] = -e.s[5]; e.s[6] = -e.s[6]; }
+
+    // -- controller cascade → normalised rotor commands (hovering.py:235-252)
+    controller<MODE>(P, e.s, e.a, e.cs, e.cmd);
+
+    // -- wrench (hovering.py:256-281): thrust zeroed for envs reset this step, torque not
+    float thrust[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) thrust[i] = e.pending ? 0.0f : e.cmd[i] * P.k_thrust;
+    const float tau_z = P.k_torque * (-e.cmd[0] - e.cmd[1] + e.cmd[2] + e.cmd[3]);
+
+    // -- gym.simulate (hovering.py:290)
+    float R[9];
+    integrate(P, e.s, thrust, tau_z, R);
+
+    e.progress += 1;  // hovering.py:297
+
+    // -- compute_observations + add_noise (hovering.py:337-358; tracking.py:202-214)
+    float z[AGX_NOISE_DRAWS];
+    if (P.flags & AGX_FLAG_NO_NOISE) {
+#pragma unroll
+        for (int i = 0; i < AGX_NOISE_DRAWS; ++i) z[i] = 0.0f;
+    } else {
+        draw_noise(rnd, z);
+    }
+    const V3 p = v3(e.s[0], e.s[1], e.s[2]);
+    const V3 v = v3(e.s[7], e.s[8], e.s[9]);
+    const V3 w = v3(e.s[10], e.s[11], e.s[12]);
+    float o[18];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = R[i] + P.noise_sigma[0] * z[i];
+    o[9] = p.x + P.noise_sigma[1] * z[9];
+    o[10] = p.y + P.noise_sigma[1] * z[10];
+    o[11] = p.z + P.noise_sigma[1] * z[11];
+    o[12] = v.x + P.noise_sigma[2] * z[12];
+    o[13] = v.y + P.noise_sigma[2] * z[13];
+    o[14] = v.z + P.noise_sigma[2] * z[14];
+    o[15] = w.x + P.noise_sigma[3] * z[15];
+    o[16] = w.y + P.noise_sigma[3] * z[16];
+    o[17] = w.z + P.noise_sigma[3] * z[17];
+    V3 ref0 = v3(0.0f, 0.0f, 0.0f);
+    if (TASK == AGX_TASK_TRACKING) {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) obs[i] = o[i];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const V3 r = lemniscate(e.progress, k, P.dt);
+            if (k == 0) ref0 = r;
+            obs[18 + 3 * k + 0] = r.x - p.x;
+            obs[18 + 3 * k + 1] = r.y - p.y;
+            obs[18 + 3 * k + 2] = r.z - p.z;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) obs[i] = o[i] - P.target[i];  // hovering.py:356
+    }
+
+    // -- compute_quadcopter_reward (hovering.py:371-459; tracking.py:223-296)
+    const float c0 = clampf(e.cmd[0], 0.0f, 1.0f), c1 = clampf(e.cmd[1], 0.0f, 1.0f),
+                c2 = clampf(e.cmd[2], 0.0f, 1.0f), c3 = clampf(e.cmd[3], 0.0f, 1.0f);
+    const float effort = 0.1f * ((1.0f - c0) + (1.0f - c1) + (1.0f - c2) + (1.0f - c3)) / 4.0f;
+    float d[AGX_MAX_ACTIONS];
+#pragma unroll
+    for (int i = 0; i < A; ++i) d[i] = e.a[i] - e.pa[i];
+    float cont, thrust_r = 0.0f;
+    if (!kThrustMode) {
+        float ss = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) ss += d[i] * d[i];
+        cont = 0.2f * expf(-sqrtf(ss));
+    } else {
+        float ss = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A - 1; ++i) ss += d[i] * d[i];
+        if (TASK == AGX_TASK_TRACKING)
+            cont = 0.1f * expf(-sqrtf(ss)) + 0.5f / (1.0f + sq(2.0f * d[A - 1]));
+        else
+            cont = 0.2f * expf(-sqrtf(ss)) + 0.5f / (1.0f + sq(3.0f * d[A - 1]));
+        thrust_r = 0.1f * (1.0f - fabsf(0.1533f - e.a[A - 1]));
+    }
+    const float yaw = atan2f(-R[1], R[0]);  // pytorch3d matrix_to_euler_angles(.,'XYZ')[2] (quirk Q6)
+    const float yd = yaw_diff(P.target_yaw, yaw) / kPi;
+    const float wz2 = w.z * w.z;
+    Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
+    const float up_z = (2.0f * q.w * q.w - 1.0f) + q.z * q.z * 2.0f;  // quat_axis(q,2)[2] (hovering.py:464-481)
+    const float ups_r = sq((up_z + 1.0f) / 2.0f);
+    int reset;
+    float reward;
+    if (TASK == AGX_TASK_TRACKING) {
+        const V3 dd = ref0 - p;
+        const float dist = norm(dd);
+        const float dist_r = 1.0f / (1.0f + sq(1.8f * dist));
+        const float yaw_r = 1.0f / (1.0f + sq(4.0f * yd));
+        const float spin_r = 1.0f / (1.0f + sq(2.0f * wz2));
+        reward = cont + effort;
+        if (kThrustMode) reward = reward + thrust_r;
+        reward = reward + dist_r + dist_r * (spin_r + yaw_r + ups_r);
+        reset = (e.progress >= (int64_t)(P.max_episode_length - 1)) ? 1 : 0;
+        if (dist > 1.0f) reset = 1;
+        e.terms[0] = dist; e.terms[1] = dist_r; e.terms[2] = yaw_r; e.terms[3] = spin_r;
+        e.terms[4] = cont; e.terms[5] = thrust_r; e.terms[6] = effort; e.terms[7] = ups_r;
+    } else {
+        const V3 rel = v3(P.target[9] - p.x, P.target[10] - p.y, P.target[11] - p.z);
+        const float pd = norm(rel);
+        const float pos_r = 0.7f / (1.0f + sq(1.6f * pd));
+        const float vn = norm(v);
+        const float dp = (rel.x / pd) * (v.x / vn) + (rel.y / pd) * (v.y / vn) + (rel.z / pd) * (v.z / vn);
+        const float ang = fabsf(acosf(clampf(dp, -1.0f, 1.0f)));
+        const float veld = 0.1f * expf(-ang / kPi);
+        const float yaw_r = 1.0f / (1.0f + sq(3.0f * yd));
+        const float spin_r = 1.0f / (1.0f + sq(3.0f * wz2));
+        reward = cont + effort;
+        if (kThrustMode) reward = reward + thrust_r;
+        reward = reward + pos_r + pos_r * (veld + ups_r + spin_r + yaw_r);
+        reset = (e.progress >= (int64_t)(P.max_episode_length - 1)) ? 1 : 0;
+        if (pd > 4.0f) reset = 1;
+        if (rel.z < -2.0f) reset = 1;
+        if (rel.z > 2.0f) reset = 1;
+        if (up_z < 0.0f) reset = 1;
+        e.terms[0] = cont; e.terms[1] = effort; e.terms[2] = thrust_r; e.terms[3] = pos_r;
+        e.terms[4] = veld; e.terms[5] = ups_r; e.terms[6] = spin_r; e.terms[7] = yaw_r;
+    }
+    if (MODE == AGX_CTL_ATTI && e.a[0] < 0.0f) reset = 1;  // hovering.py:442-444
+    e.terms[8] = reward;
+    e.rew = reward;
+    e.reset = reset;
+
+    // -- pre_actions = actions.clone() (hovering.py:369)
+#pragma unroll
+    for (int i = 0; i < A; ++i) e.pa[i] = e.a[i];
+
+    // -- end-of-step reset_idx (hovering.py:300-302): fresh draw, reset_buf stays 1, progress 0
+    if (reset) do_reset<TASK>(P, rnd, 1, e);
+
+    e.timeout = (e.progress > (int64_t)P.max_episode_length) ? 1 : 0;  // hovering.py:304
+}
+
+}  // namespace agx

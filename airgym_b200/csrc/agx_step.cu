@@ -1,0 +1,457 @@
+// agx_step.cu — fused env-step kernels for sm_100a + the C ABI declared in include/agx.h.
+//
+// One thread = one env.  A CTA owns a tile of BLOCK consecutive envs:
+//   * the [BLOCK,13] root-state rows (52-B rows, not 16-B aligned individually) are one contiguous,
+//     16-B aligned span, fetched with a single TMA bulk copy (cp.async.bulk → SASS UBLKCP) into shared
+//     memory behind an mbarrier; each thread then reads its row at stride 13 words (bank-conflict free),
+//   * everything else a thread needs is already coalesced (float4 action rows, SoA controller planes,
+//     int64 progress/reset),
+//   * results go back the same way: the state tile and the [BLOCK,18] observation tile are written to
+//     shared memory and leave with one bulk store each; 48/16-wide observation rows use a padded
+//     shared layout and a coalesced float4 copy-out instead (dense rows would be 16-way bank conflicted).
+// A partial last tile (or a caller buffer that breaks the 16-B rule) takes the cooperative-copy path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "agx.h"
+#include "agx_math.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+// ---- PTX wrappers: mbarrier + TMA bulk copies ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int NOBS>
+struct ObsLayout {
+    // dense rows only when the row stride in words is conflict-light (18 → 2-way); else pad to odd
+    static constexpr bool kDense = (NOBS == 18);
+    static constexpr int kStride = kDense ? NOBS : (NOBS | 1);
+};
+
+template <int TASK>
+struct TaskTraits;
+template <>
+struct TaskTraits<AGX_TASK_HOVERING> { static constexpr int kObs = 18; };
+template <>
+struct TaskTraits<AGX_TASK_TRACKING> { static constexpr int kObs = 48; };
+
+// ---- the fused step kernel ----------------------------------------------------------------------------
+template <int TASK, int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ AgxStepIO io, const int64_t n,
+                const int use_bulk) {
+    using namespace agx;
+    constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
+    constexpr int NOBS = TaskTraits<TASK>::kObs;
+    constexpr int K = (MODE == AGX_CTL_PROP) ? 0 : ((MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI) ? 6 : 12);
+    using OL = ObsLayout<NOBS>;
+
+    __shared__ __align__(128) float s_state[BLOCK * 13];
+    __shared__ __align__(128) float s_obs[BLOCK * OL::kStride];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
+    const int tile_n = (int)((n - tile0) < (int64_t)BLOCK ? (n - tile0) : (int64_t)BLOCK);
+    const bool bulk = use_bulk && (tile_n == BLOCK);  // CTA-uniform
+    const int64_t env = tile0 + tid;
+    const bool active = tid < tile_n;
+    const uint64_t step = io.step_dev ? io.step_dev[0] : io.step;
+
+    // ---- stage the state tile into shared memory
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, BLOCK * 13 * 4);
+            bulk_g2s(s_state, io.state + tile0 * 13, BLOCK * 13 * 4, &s_bar);
+        }
+    } else {
+        const float* src = io.state + tile0 * 13;
+        for (int i = tid; i < tile_n * 13; i += BLOCK) s_state[i] = src[i];
+    }
+
+    // ---- coalesced per-env loads (overlap with the bulk copy in flight)
+    EnvRegs e;
+    if (active) {
+        if (A == 4) {
+            const float4 a4 = reinterpret_cast<const float4*>(io.action)[env];
+            const float4 p4 = reinterpret_cast<const float4*>(io.prev_action)[env];
+            e.a[0] = a4.x; e.a[1] = a4.y; e.a[2] = a4.z; e.a[3] = a4.w; e.a[4] = 0.0f;
+            e.pa[0] = p4.x; e.pa[1] = p4.y; e.pa[2] = p4.z; e.pa[3] = p4.w; e.pa[4] = 0.0f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { e.a[i] = io.action[env * 5 + i]; e.pa[i] = io.prev_action[env * 5 + i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
+        e.progress = io.progress[env];
+        e.pending = io.reset[env] != 0;
+    }
+
+    if (bulk) {
+        __syncthreads();  // barrier init visible to all waiters
+        mbar_wait(&s_bar, 0);
+    } else {
+        __syncthreads();
+    }
+
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) e.s[i] = s_state[tid * 13 + i];
+
+        RandSrc rnd;
+        rnd.reset_row = io.rand_reset ? io.rand_reset + env * (int64_t)(2 * P.reset_draws) : nullptr;
+        rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
+        const uint64_t genv = (uint64_t)(io.env_offset + env);
+        rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
+        rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
+        rnd.ph.step_lo = (uint32_t)step; rnd.ph.step_hi = (uint32_t)(step >> 32);
+
+        env_step<TASK, MODE>(P, rnd, e, &s_obs[tid * OL::kStride]);
+
+#pragma unroll
+        for (int i = 0; i < 13; ++i) s_state[tid * 13 + i] = e.s[i];
+
+        // ---- coalesced per-env stores
+        if (A == 4) {
+            reinterpret_cast<float4*>(io.actions_out)[env] = make_float4(e.a[0], e.a[1], e.a[2], e.a[3]);
+            reinterpret_cast<float4*>(io.prev_action)[env] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { io.actions_out[env * 5 + i] = e.a[i]; io.prev_action[env * 5 + i] = e.pa[i]; }
+        }
+        if ((P.flags & AGX_FLAG_MUTATE_ACTIONS) && (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI))
+            io.action[env * A + (A - 1)] = e.a_last_remap;
+#pragma unroll
+        for (int k = 0; k < K; ++k) io.ctrl_state[(int64_t)k * n + env] = e.cs[k];
+        io.progress[env] = e.progress;
+        io.reset[env] = (int64_t)e.reset;
+        io.timeout[env] = (uint8_t)e.timeout;
+        io.reward[env] = e.rew;
+        if (io.cmd) reinterpret_cast<float4*>(io.cmd)[env] = make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]);
+        if (io.reward_terms) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) io.reward_terms[(int64_t)k * n + env] = e.terms[k];
+        }
+    }
+
+    // ---- tiles leave shared memory
+    if (bulk) {
+        fence_async_smem();  // generic-proxy smem writes → visible to the async (TMA) proxy
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(io.state + tile0 * 13, s_state, BLOCK * 13 * 4);
+            if (OL::kDense) bulk_s2g(io.obs + tile0 * NOBS, s_obs, BLOCK * NOBS * 4);
+            bulk_commit();
+        }
+    } else {
+        __syncthreads();
+        float* dst = io.state + tile0 * 13;
+        for (int i = tid; i < tile_n * 13; i += BLOCK) dst[i] = s_state[i];
+    }
+    if (!(bulk && OL::kDense)) {
+        float* dst = io.obs + tile0 * NOBS;
+        if (OL::kDense) {
+            for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i];
+        } else if (tile_n == BLOCK) {  // padded rows → dense float4 stores (BLOCK*NOBS % 4 == 0)
+            for (int i4 = tid; i4 < BLOCK * NOBS / 4; i4 += BLOCK) {
+                float4 v;
+                const int i = i4 * 4;
+                v.x = s_obs[i + i / NOBS];
+                v.y = s_obs[(i + 1) + (i + 1) / NOBS];
+                v.z = s_obs[(i + 2) + (i + 2) / NOBS];
+                v.w = s_obs[(i + 3) + (i + 3) / NOBS];
+                reinterpret_cast<float4*>(dst)[i4] = v;
+            }
+        } else {
+            for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i + i / NOBS];
+        }
+    }
+    if (bulk && tid == 0) bulk_wait_read0();  // smem must stay alive until the bulk stores have read it
+    if (io.step_dev && tid == 0) {  // every CTA read step_dev[0] above; the last one to retire bumps it
+        const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL);
+        if (t == (unsigned long long)gridDim.x - 1ULL) {
+            io.step_dev[1] = 0;
+            io.step_dev[0] = step + 1;
+        }
+    }
+}
+
+// ---- standalone reset_idx kernel -------------------------------------------------------------------------
+template <int TASK>
+__global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_t n, int64_t m,
+                                     const int64_t* __restrict__ env_ids, float* state, float* prev_action,
+                                     float* ctrl_state, int64_t* progress, int64_t* reset,
+                                     const float* __restrict__ rand, uint64_t seed, uint64_t step,
+                                     int64_t env_offset) {
+    using namespace agx;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int64_t env = env_ids[j];
+    if (env < 0 || env >= n) return;
+    float u[AGX_RESET_DRAWS_MAX];
+    if (rand) {
+        for (int i = 0; i < P.reset_draws; ++i) u[i] = rand[j * P.reset_draws + i];
+    } else {
+        PhiloxCtx ph;
+        const uint64_t genv = (uint64_t)(env_offset + env);
+        ph.k0 = (uint32_t)seed; ph.k1 = (uint32_t)(seed >> 32);
+        ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
+        ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
+        philox_uniforms(ph, 3u, P.reset_draws, u);  // stream 3: standalone reset_idx
+    }
+    float s[13];
+    reset_sample<TASK>(u, s);
+    for (int i = 0; i < 13; ++i) state[env * 13 + i] = s[i];
+    for (int i = 0; i < P.num_actions; ++i) prev_action[env * P.num_actions + i] = 0.0f;
+    if ((P.flags & AGX_FLAG_CTRL_RESET) && ctrl_state)
+        for (int k = 0; k < P.ctrl_state_dim; ++k) ctrl_state[(int64_t)k * n + env] = 0.0f;
+    progress[env] = 0;
+    reset[env] = 1;
+}
+
+__global__ void agx_philox_fill_kernel(float* out, int64_t n, int width, int stream_id, uint64_t seed,
+                                       uint64_t step, int64_t env_offset) {
+    using namespace agx;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    PhiloxCtx ph;
+    const uint64_t genv = (uint64_t)(env_offset + env);
+    ph.k0 = (uint32_t)seed; ph.k1 = (uint32_t)(seed >> 32);
+    ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
+    ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
+    float v[20];
+    if (stream_id == 2) philox_normals(ph, width, v);
+    else philox_uniforms(ph, (uint32_t)stream_id, width, v);
+    for (int i = 0; i < width; ++i) out[env * width + i] = v[i];
+}
+
+int g_block = 128;
+int g_use_bulk = 1;
+
+template <int TASK, int MODE>
+int launch_step(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st) {
+    if (n == 0) return AGX_OK;
+    if (g_block == 64) {
+        const unsigned grid = (unsigned)((n + 63) / 64);
+        agx_step_kernel<TASK, MODE, 64><<<grid, 64, 0, st>>>(P, io, n, g_use_bulk);
+    } else {
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        agx_step_kernel<TASK, MODE, 128><<<grid, 128, 0, st>>>(P, io, n, g_use_bulk);
+    }
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_step launch: %s", cudaGetErrorString(err));
+    return AGX_OK;
+}
+
+template <int TASK>
+int dispatch_mode(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st) {
+    switch (P.ctl_mode) {
+        case AGX_CTL_POS: return launch_step<TASK, AGX_CTL_POS>(P, n, io, st);
+        case AGX_CTL_VEL: return launch_step<TASK, AGX_CTL_VEL>(P, n, io, st);
+        case AGX_CTL_ATTI: return launch_step<TASK, AGX_CTL_ATTI>(P, n, io, st);
+        case AGX_CTL_RATE: return launch_step<TASK, AGX_CTL_RATE>(P, n, io, st);
+        case AGX_CTL_PROP: return launch_step<TASK, AGX_CTL_PROP>(P, n, io, st);
+        default: return fail(AGX_ERR_ARG, "agx_step: unknown ctl_mode%s");
+    }
+}
+
+bool misaligned(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int agx_version(void) { return AGX_VERSION; }
+const char* agx_error_string(void) { return g_err; }
+int agx_sizeof_params(void) { return (int)sizeof(AgxParams); }
+int agx_sizeof_step_io(void) { return (int)sizeof(AgxStepIO); }
+
+int agx_set_option(const char* key, int value) {
+    if (!key) return fail(AGX_ERR_ARG, "agx_set_option: null key%s");
+    if (!strcmp(key, "block")) {
+        if (value != 64 && value != 128) return fail(AGX_ERR_ARG, "agx_set_option: block must be 64|128%s");
+        g_block = value;
+        return AGX_OK;
+    }
+    if (!strcmp(key, "use_bulk")) { g_use_bulk = value ? 1 : 0; return AGX_OK; }
+    return fail(AGX_ERR_ARG, "agx_set_option: unknown key '%s'", key);
+}
+
+int agx_params_default(AgxParams* p, int task, int ctl_mode) {
+    if (!p) return fail(AGX_ERR_ARG, "agx_params_default: null params%s");
+    if (task != AGX_TASK_HOVERING && task != AGX_TASK_TRACKING)
+        return fail(AGX_ERR_UNSUPPORTED, "agx_params_default: task not built yet%s");
+    if (ctl_mode < AGX_CTL_POS || ctl_mode > AGX_CTL_PROP) return fail(AGX_ERR_ARG, "agx_params_default: bad ctl_mode%s");
+    memset(p, 0, sizeof(*p));
+    const double pi = 3.14159265358979323846;
+    p->task = task;
+    p->ctl_mode = ctl_mode;
+    p->num_actions = (ctl_mode == AGX_CTL_ATTI) ? 5 : 4;
+    p->num_obs = (task == AGX_TASK_TRACKING) ? 48 : 18;
+    p->integrator = AGX_INT_RK4;
+    p->flags = AGX_FLAG_MUTATE_ACTIONS;
+    p->dt = 0.01f;
+    const double episode_s = (task == AGX_TASK_TRACKING) ? 36.0 : 24.0;  // *_config.py episode_length_s
+    p->max_episode_length = (int)(episode_s / 0.01);
+    p->ctrl_state_dim = (ctl_mode == AGX_CTL_PROP) ? 0 : ((ctl_mode == AGX_CTL_RATE || ctl_mode == AGX_CTL_ATTI) ? 6 : 12);
+    p->reset_draws = 12;
+    p->gravity = 9.81f;
+    const double m_base = 0.585, m_prop = 0.004, arm = 0.05374, hz = 0.024;
+    p->mass = (float)(m_base + 4.0 * m_prop);
+    p->inertia[0] = (float)(0.04 + 4.0 * (1e-6 + m_prop * (arm * arm + hz * hz)));
+    p->inertia[1] = p->inertia[0];
+    p->inertia[2] = (float)(0.04 + 4.0 * (1e-6 + m_prop * (2.0 * arm * arm)));
+    p->arm = (float)arm;
+    p->k_thrust = 9.59f;
+    p->k_torque = 0.2f;
+    p->max_lin_vel = 100.0f;
+    p->max_ang_vel = 100.0f;
+    const float lim_pos = (task == AGX_TASK_TRACKING) ? 6.0f : 3.0f;
+    float lo[5] = {0, 0, 0, 0, 0}, hi[5] = {0, 0, 0, 0, 0};
+    switch (ctl_mode) {
+        case AGX_CTL_POS: for (int i = 0; i < 3; ++i) { lo[i] = -lim_pos; hi[i] = lim_pos; } lo[3] = -6; hi[3] = 6; break;
+        case AGX_CTL_VEL: for (int i = 0; i < 4; ++i) { lo[i] = -6; hi[i] = 6; } break;
+        case AGX_CTL_ATTI: for (int i = 0; i < 4; ++i) { lo[i] = -1; hi[i] = 1; } lo[4] = 0; hi[4] = 1; break;
+        case AGX_CTL_RATE: for (int i = 0; i < 3; ++i) { lo[i] = -6; hi[i] = 6; } lo[3] = 0; hi[3] = 1; break;
+        case AGX_CTL_PROP: for (int i = 0; i < 4; ++i) { lo[i] = 0; hi[i] = 1; } break;
+    }
+    for (int i = 0; i < 5; ++i) { p->act_lo[i] = lo[i]; p->act_hi[i] = hi[i]; }
+    const float rp[3] = {0.15f, 0.15f, 0.2f}, ri[3] = {0.2f, 0.2f, 0.1f}, rd[3] = {0.003f, 0.003f, 0.0f};
+    const float ap[3] = {6.5f, 6.5f, 2.8f};
+    const double arl[3] = {220.0, 220.0, 200.0};
+    const float vp[3] = {1.8f, 1.8f, 4.0f}, vi[3] = {0.4f, 0.4f, 2.0f}, vd[3] = {0.2f, 0.2f, 0.0f};
+    const float vil[3] = {1.0f, 1.0f, 2.0f}, pp[3] = {0.95f, 0.95f, 1.0f}, vsl[3] = {6.0f, 6.0f, 6.0f};
+    for (int i = 0; i < 3; ++i) {
+        p->rate_p[i] = rp[i]; p->rate_i[i] = ri[i]; p->rate_d[i] = rd[i];
+        p->att_p[i] = ap[i]; p->att_rate_lim[i] = (float)(arl[i] * pi / 180.0);
+        p->vel_p[i] = vp[i]; p->vel_i[i] = vi[i]; p->vel_d[i] = vd[i]; p->vel_int_lim[i] = vil[i];
+        p->pos_p[i] = pp[i]; p->vel_sp_lim[i] = vsl[i];
+    }
+    p->rate_int_lim = 0.3f;
+    p->rate_i_fade = (float)(400.0 * pi / 180.0);
+    p->att_yaw_w = 0.4f;
+    p->hover_thrust = (float)((m_base + 4.0 * m_prop) * 9.81 / (4.0 * 9.59));
+    p->tilt_max_tan = 1.0f;
+    p->thr_min = 0.0f;
+    p->thr_max = 1.0f;
+    const float tgt[18] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 18; ++i) p->target[i] = tgt[i];
+    p->target_yaw = 0.0f;  // atan2(-0, 1)
+    p->noise_sigma[0] = 1e-3f; p->noise_sigma[1] = 5e-3f; p->noise_sigma[2] = 2e-2f; p->noise_sigma[3] = 4e-1f;
+    return AGX_OK;
+}
+
+int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream) {
+    if (!p || !io) return fail(AGX_ERR_ARG, "agx_step: null params/io%s");
+    if (n < 0) return fail(AGX_ERR_ARG, "agx_step: n < 0%s");
+    if (!io->state || !io->action || !io->actions_out || !io->prev_action || !io->progress || !io->reset ||
+        !io->timeout || !io->obs || !io->reward)
+        return fail(AGX_ERR_ARG, "agx_step: a required buffer is null%s");
+    if (p->ctrl_state_dim > 0 && !io->ctrl_state) return fail(AGX_ERR_ARG, "agx_step: ctrl_state is null%s");
+    const void* ptrs[] = {io->state, io->action, io->actions_out, io->prev_action, io->ctrl_state, io->progress,
+                          io->reset, io->obs, io->reward, io->cmd, io->reward_terms, io->rand_reset, io->rand_noise};
+    for (const void* q : ptrs)
+        if (misaligned(q)) return fail(AGX_ERR_ALIGN, "agx_step: buffer not 16-byte aligned%s");
+    const int want_actions = (p->ctl_mode == AGX_CTL_ATTI) ? 5 : 4;
+    if (p->num_actions != want_actions) return fail(AGX_ERR_ARG, "agx_step: num_actions does not match ctl_mode%s");
+    if (p->reset_draws < 12 || p->reset_draws > AGX_RESET_DRAWS_MAX) return fail(AGX_ERR_ARG, "agx_step: bad reset_draws%s");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (p->task) {
+        case AGX_TASK_HOVERING:
+            if (p->num_obs != 18) return fail(AGX_ERR_ARG, "agx_step: hovering needs num_obs=18%s");
+            return dispatch_mode<AGX_TASK_HOVERING>(*p, n, *io, st);
+        case AGX_TASK_TRACKING:
+            if (p->num_obs != 48) return fail(AGX_ERR_ARG, "agx_step: tracking needs num_obs=48%s");
+            return dispatch_mode<AGX_TASK_TRACKING>(*p, n, *io, st);
+        default: return fail(AGX_ERR_UNSUPPORTED, "agx_step: task not built yet%s");
+    }
+}
+
+int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_ids, float* state,
+                  float* prev_action, float* ctrl_state, int64_t* progress, int64_t* reset, float* aux,
+                  const float* rand, uint64_t seed, uint64_t step, int64_t env_offset, void* stream) {
+    (void)aux;
+    if (!p || !env_ids || !state || !prev_action || !progress || !reset) return fail(AGX_ERR_ARG, "agx_reset_idx: null argument%s");
+    if (n < 0 || m < 0) return fail(AGX_ERR_ARG, "agx_reset_idx: negative size%s");
+    if (m == 0) return AGX_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    if (p->task == AGX_TASK_HOVERING)
+        agx_reset_idx_kernel<AGX_TASK_HOVERING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
+                                                                      progress, reset, rand, seed, step, env_offset);
+    else if (p->task == AGX_TASK_TRACKING)
+        agx_reset_idx_kernel<AGX_TASK_TRACKING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
+                                                                      progress, reset, rand, seed, step, env_offset);
+    else
+        return fail(AGX_ERR_UNSUPPORTED, "agx_reset_idx: task not built yet%s");
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_reset_idx launch: %s", cudaGetErrorString(err));
+    return AGX_OK;
+}
+
+int agx_philox_fill(float* out, int64_t n, int width, int stream_id, uint64_t seed, uint64_t step,
+                    int64_t env_offset, void* stream) {
+    if (!out || n < 0 || width < 1 || width > 20 || stream_id < 0 || stream_id > 3)
+        return fail(AGX_ERR_ARG, "agx_philox_fill: bad argument%s");
+    if (n == 0) return AGX_OK;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    agx_philox_fill_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, n, width, stream_id, seed,
+                                                                                   step, env_offset);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_philox_fill launch: %s", cudaGetErrorString(err));
+    return AGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+/*
+ * agx.h — C ABI of libagx.so, the B200 (sm_100a) batched quadrotor env-step library.
+ *
+ * This is the drop-in boundary for the hot path of emNavi/AirGym: every entry
+ * point replaces a stretch of the reference's Python/torch/IsaacGym/rlPx4Controller step and is
+ * what a ctypes binding on the reference side would call.
+ *
+ * Conventions
+ *   - plain C: POD structs, raw device pointers, sizes; no C++/torch types.
+ *   - all pointers in AgxStepIO are DEVICE pointers owned by the caller (torch tensors);
+ *     `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing syncs.
+ *   - return value: 0 = AGX_OK, negative = error (agx_error_string() explains); no exceptions.
+ *   - state rows are the reference's root-state rows: [px py pz | qx qy qz qw | vx vy vz | wx wy wz]
+ *     f32, world frame, xyzw quaternion (reference airgym/envs/base/hovering.py:70-77).
+ */
+#ifndef AGX_H
+#define AGX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGX_VERSION 100
+
+enum AgxError {
+    AGX_OK = 0,
+    AGX_ERR_ARG = -1,      /* bad argument (null pointer, n < 0, unknown task/mode ...) */
+    AGX_ERR_ALIGN = -2,    /* a buffer violates the documented alignment */
+    AGX_ERR_CUDA = -3,     /* CUDA launch/runtime error; agx_error_string() holds the text */
+    AGX_ERR_UNSUPPORTED = -4
+};
+
+/* task ids: reference airgym/envs/__init__.py:5-62 (names of the registered tasks) */
+enum AgxTask {
+    AGX_TASK_HOVERING = 0, /* airgym/envs/base/hovering.py */
+    AGX_TASK_TRACKING = 1, /* airgym/envs/task/tracking.py */
+    AGX_TASK_BALLOON = 2,  /* airgym/envs/task/balloon.py */
+    AGX_TASK_AVOID = 3,    /* airgym/envs/task/avoid.py */
+    AGX_TASK_PLANNING = 4  /* airgym/envs/task/planning.py */
+};
+
+/* control modes: reference --ctl_mode {pos,vel,atti,rate,prop} = PY/LV/CTA/CTBR/SRT
+ * (airgym/utils/helpers.py:103, hovering.py:93-123) */
+enum AgxCtlMode {
+    AGX_CTL_POS = 0,  /* PY:   position + yaw        (A=4) */
+    AGX_CTL_VEL = 1,  /* LV:   linear velocity + yaw (A=4) */
+    AGX_CTL_ATTI = 2, /* CTA:  quaternion wxyz + collective thrust (A=5) */
+    AGX_CTL_RATE = 3, /* CTBR: body rates + collective thrust (A=4) */
+    AGX_CTL_PROP = 4  /* SRT:  single-rotor thrusts (A=4) */
+};
+
+enum AgxIntegrator { AGX_INT_RK4 = 0, AGX_INT_EULER = 1 };
+
+enum AgxFlags {
+    AGX_FLAG_MUTATE_ACTIONS = 1,   /* write the 0.5+0.5a remap of the last action column back into
+                                      `action` (reference quirk Q4, hovering.py:212-215) */
+    AGX_FLAG_CTRL_RESET = 2,       /* zero controller integrators on episode reset (reference never
+                                      does: the rlPx4Controller objects are not told about resets) */
+    AGX_FLAG_NO_NOISE = 4          /* skip observation noise (debug/KATs) */
+};
+
+#define AGX_MAX_ACTIONS 5
+#define AGX_CTRL_STATE_MAX 12
+#define AGX_RESET_DRAWS_MAX 16
+#define AGX_NOISE_DRAWS 18
+
+/* Everything the fused step needs that is not per-env data.  Mirrors the reference's nested cfg
+ * classes (hovering_config.py:8-69), URDF constants (assets/robots/X152b/model.urdf) and the
+ * literals in hovering.py; controller gains are builder-defined. */
+typedef struct AgxParams {
+    int32_t task;              /* AgxTask */
+    int32_t ctl_mode;          /* AgxCtlMode */
+    int32_t num_actions;       /* 5 for atti else 4 (hovering.py:46) */
+    int32_t num_obs;           /* 18 hovering/balloon, 48 tracking, 16 avoid/planning */
+    int32_t integrator;        /* AgxIntegrator */
+    int32_t flags;             /* AgxFlags bit set */
+    int32_t max_episode_length;/* int(episode_length_s / dt) (hovering.py:48) */
+    int32_t ctrl_state_dim;    /* floats of controller state per env: 0 prop, 6 rate/atti, 12 vel/pos */
+    int32_t reset_draws;       /* uniforms consumed by one reset_idx of this task (12 hovering/tracking) */
+    int32_t _pad0;
+
+    float dt;                  /* 0.01 (hovering_config.py:29) */
+    float gravity;             /* 9.81, along -z (hovering_config.py:31) */
+    float mass;                /* 0.585 + 4*0.004 (model.urdf:19,36) */
+    float inertia[3];          /* composite diag inertia about base_link */
+    float arm;                 /* 0.05374: |x|=|y| of the rotor joints (model.urdf:86-105) */
+    float k_thrust;            /* 9.59 N per unit cmd per rotor (hovering.py:256) */
+    float k_torque;            /* 0.2 N m per unit cmd (hovering.py:270) */
+    float max_lin_vel;         /* 100 (assets/__init__.py:34-35) */
+    float max_ang_vel;         /* 100 */
+
+    float act_lo[AGX_MAX_ACTIONS]; /* action limits (hovering.py:93-123, tracking.py:95-123) */
+    float act_hi[AGX_MAX_ACTIONS];
+
+    /* PX4-aligned cascade gains (builder-defined, PX4 defaults) */
+    float rate_p[3], rate_i[3], rate_d[3];
+    float rate_int_lim;        /* 0.3 */
+    float rate_i_fade;         /* rad(400 deg/s): integrator fade-out scale */
+    float att_p[3];
+    float att_yaw_w;           /* 0.4 */
+    float att_rate_lim[3];     /* rad(220,220,200 deg/s) */
+    float vel_p[3], vel_i[3], vel_d[3];
+    float vel_int_lim[3];
+    float pos_p[3];
+    float vel_sp_lim[3];       /* clamp of the velocity set-point out of the position loop */
+    float hover_thrust;        /* m g / (4 k_thrust) */
+    float tilt_max_tan;        /* tan(45 deg) */
+    float thr_min, thr_max;
+
+    float target[18];          /* cfg.env.target_state (hovering_config.py:12) */
+    float target_yaw;          /* third intrinsic-XYZ euler angle of target[0:9] = atan2(-t01, t00) */
+    float noise_sigma[4];      /* 1e-3, 5e-3, 2e-2, 4e-1 (hovering.py:350-353) */
+} AgxParams;
+
+/* Per-call buffer table.  N = number of envs, A = num_actions, K = ctrl_state_dim, D = reset_draws.
+ * Alignment: every non-null pointer must be 16-byte aligned (torch allocations are 512-B aligned). */
+typedef struct AgxStepIO {
+    float*   state;        /* [N,13] in/out: root states (hovering.py:73)                      */
+    float*   action;       /* [N,A]  in (out for the last column when AGX_FLAG_MUTATE_ACTIONS) */
+    float*   actions_out;  /* [N,A]  out: shaped+clamped actions = reference self.actions      */
+    float*   prev_action;  /* [N,A]  in/out: reference self.pre_actions                        */
+    float*   ctrl_state;   /* [K,N]  in/out: controller integrators (SoA planes); NULL if K=0  */
+    int64_t* progress;     /* [N]    in/out: reference progress_buf (int64, hovering.py:164)   */
+    int64_t* reset;        /* [N]    in: pending resets, out: new resets (reference reset_buf) */
+    uint8_t* timeout;      /* [N]    out: reference time_out_buf (bool)                        */
+    float*   obs;          /* [N,num_obs] out: reference obs_buf                               */
+    float*   reward;       /* [N]    out: reference rew_buf                                    */
+    float*   cmd;          /* [N,4]  out: reference cmd_thrusts, or NULL                       */
+    float*   reward_terms; /* [9,N]  out: reference item_reward_info planes, or NULL           */
+    float*   aux;          /* task-specific in/out state (tracking: NULL; balloon: [N,?]) or NULL */
+    const float* rand_reset; /* [N,2,D] U[0,1) draws for the pre-/post-step reset, or NULL → Philox */
+    const float* rand_noise; /* [N,18]  N(0,1) draws for the observation noise, or NULL → Philox  */
+    uint64_t seed;         /* Philox key   (used when a rand_* pointer is NULL) */
+    uint64_t step;         /* Philox counter word: the caller's global step index */
+    uint64_t* step_dev;    /* optional DEVICE counter [2] = {step, ticket}: when non-NULL the kernel uses
+                              step_dev[0] instead of `step` and the last CTA to retire increments it, so a
+                              captured CUDA graph can be replayed without re-baking the step index */
+    int64_t  env_offset;   /* global id of env 0 of this shard (partition-invariant RNG, §8e) */
+} AgxStepIO;
+
+/* library info */
+int         agx_version(void);
+const char* agx_error_string(void);   /* thread-local text of the last error */
+int         agx_sizeof_params(void);  /* sizeof(AgxParams): lets a binding check its struct mirror */
+int         agx_sizeof_step_io(void);
+
+/* Tuning knobs (process-wide): "block" = 64|128 threads per CTA, "use_bulk" = 0|1 (TMA bulk-copy
+ * staging vs cooperative copies). */
+int agx_set_option(const char* key, int value);
+
+/* Fill `p` with the defaults of (task, ctl_mode): replaces the reference's cfg classes + the
+ * limits set in Hovering.__init__ (hovering.py:93-123) / Tracking.__init__ (tracking.py:95-123). */
+int agx_params_default(AgxParams* p, int task, int ctl_mode);
+
+/* One fused env step over n envs: replaces Hovering.step (hovering.py:286-308) =
+ * pre_physics_step (:203-281, incl. the rlPx4Controller FFI :217-250) + gym.simulate (:290) +
+ * compute_observations (:337-358) + compute_reward (:360-459) + reset_idx (:310-335) + time-outs (:304);
+ * for AGX_TASK_TRACKING additionally tracking.py:159-296. */
+int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream);
+
+/* reset_idx(env_ids) as a standalone call (hovering.py:310-335, tracking.py:159-192):
+ * env_ids [m] int64 device pointer; rand [m,D] U[0,1) draws in env_ids order or NULL → Philox. */
+int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_ids,
+                  float* state, float* prev_action, float* ctrl_state, int64_t* progress,
+                  int64_t* reset, float* aux, const float* rand, uint64_t seed, uint64_t step,
+                  int64_t env_offset, void* stream);
+
+/* Fill out[n, width] with the library's Philox4x32-10 stream `stream_id` (0 pre-reset uniforms,
+ * 1 post-reset uniforms, 2 noise normals) exactly as agx_step would draw it — lets tests and
+ * the oracle consume identical numbers. */
+int agx_philox_fill(float* out, int64_t n, int width, int stream_id, uint64_t seed, uint64_t step,
+                    int64_t env_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGX_H */

@@ -1,0 +1,290 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own task code (needs /root/reference; run in the build
+container only — nothing at test/bench time reads /root/reference).
+
+The reference hot path imports three dependencies that are absent here.  They are stubbed with the
+oracle's restatements, so that every in-tree line of the reference — Hovering/Tracking `pre_physics_step`, `step`,
+`reset_idx`, `compute_observations`, `add_noise`, `compute_reward`, `compute_quadcopter_reward`, the jit helpers
+`quat_rotate/quat_axis/torch_normal_float`, `torch_rand_float`, `tensor_clamp`, `compute_yaw_diff` — runs unmodified:
+
+    isaacgym.{gymapi,gymtorch,gymutil}   → a fake `gym` whose `simulate()` applies the force/torque tensors the
+                                            reference assembled (hovering.py:256-281) with oracle/rigid_body.py
+    isaacgym.torch_utils                 → the reference's vendored copy airgym/utils/torch_utils.py
+    rlPx4Controller.pyParallelControl    → oracle/px4_controller.py behind the call-site API (numpy f64 in/out)
+    pytorch3d.transforms                 → oracle/rotations.py
+    rospy, std_msgs                      → empty shells (dead code path, hovering.py:362-363)
+
+For each case the oracle is run seed-for-seed next to the reference and must agree to 1e-6 (this is what pins the
+oracle); the reference's outputs plus the random draws the step consumed are stored so the CUDA kernel can later
+be fed identical numbers on a box without /root/reference.
+
+Usage:  python tests/golden/make_golden.py            (writes tests/golden/<task>_<mode>[_short].npz)
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import QuadSpec, make_oracle  # noqa: E402
+from oracle import rotations as ORot  # noqa: E402
+from oracle.px4_controller import ParallelControl  # noqa: E402
+from oracle.rigid_body import simulate  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    # isaacgym: torch_utils is the reference's own vendored copy
+    spec = importlib.util.spec_from_file_location("isaacgym.torch_utils", os.path.join(REF, "airgym/utils/torch_utils.py"))
+    tu = importlib.util.module_from_spec(spec)
+    if not hasattr(np, "float"):  # the reference targets numpy<1.24 (airgym/utils/torch_utils.py:135 uses np.float)
+        np.float = float
+    spec.loader.exec_module(tu)
+    sys.modules["isaacgym.torch_utils"] = tu
+
+    class _GymApi(types.ModuleType):
+        LOCAL_SPACE = 1
+        SIM_PHYSX = 1
+        SIM_FLEX = 0
+
+        def __getattr__(self, k):  # Vec3, Transform, ... are only touched by code paths we do not run
+            return lambda *a, **kw: None
+
+    gymapi = _GymApi("isaacgym.gymapi")
+    gymtorch = mod("isaacgym.gymtorch", wrap_tensor=lambda t: t, unwrap_tensor=lambda t: t)
+    gymutil = mod("isaacgym.gymutil", parse_device_str=lambda s: ("cpu", 0))
+    sys.modules["isaacgym.gymapi"] = gymapi
+    mod("isaacgym", gymapi=gymapi, gymtorch=gymtorch, gymutil=gymutil, torch_utils=tu)
+
+    mod("pytorch3d")
+    mod("pytorch3d.transforms", euler_angles_to_matrix=ORot.euler_angles_to_matrix,
+        matrix_to_quaternion=ORot.matrix_to_quaternion, quaternion_to_matrix=ORot.quaternion_to_matrix,
+        matrix_to_euler_angles=lambda m, convention="XYZ": ORot.matrix_to_euler_xyz(m))
+    sys.modules["pytorch3d"].transforms = sys.modules["pytorch3d.transforms"]
+
+    mod("rospy")
+    mod("matplotlib")  # airgym/utils/__init__.py imports a plotting Logger; not on the path
+    mod("matplotlib.pyplot")
+
+    class Float64MultiArray:
+        data = None
+
+    mod("std_msgs")
+    mod("std_msgs.msg", Float64MultiArray=Float64MultiArray)
+
+    # rlPx4Controller: the call-site API (hovering.py:98-116,235-250) in front of the oracle's cascade
+    state = {"spec": None}
+
+    def make(mode):
+        class _Ctl:
+            def __init__(self, num_envs):
+                s = state["spec"]
+                assert s.ctl_mode == mode
+                self.impl = ParallelControl(num_envs, s, torch.float32)
+
+            def set_status(self, pos, q, lin, ang, dt):
+                t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32)
+                self.impl.set_status(t(pos), t(q), t(lin), t(ang), dt)
+
+            def set_q_world(self, q):
+                self.impl.set_q_world(torch.as_tensor(np.asarray(q), dtype=torch.float32))
+
+            def update(self, actions, angvel=None, dt=None):
+                a = torch.as_tensor(np.asarray(actions), dtype=torch.float32)
+                w = None if angvel is None else torch.as_tensor(np.asarray(angvel), dtype=torch.float32)
+                return self.impl.update(a, w, dt).numpy().astype(np.float64)
+
+        return _Ctl
+
+    mod("rlPx4Controller")
+    mod("rlPx4Controller.pyParallelControl", ParallelRateControl=make("rate"), ParallelVelControl=make("vel"),
+        ParallelAttiControl=make("atti"), ParallelPosControl=make("pos"))
+    return state
+
+
+class FakeGym:
+    """Receives the wrench exactly as the reference hands it to IsaacGym and integrates with the oracle's body."""
+
+    def __init__(self, env, spec):
+        self.env, self.spec = env, spec
+        self.forces = self.torques = None
+
+    def apply_rigid_body_force_tensors(self, sim, forces, torques, space):
+        self.forces, self.torques = forces.clone(), torques.clone()
+
+    def simulate(self, sim):
+        f, t = self.forces, self.torques
+        assert float(f[:, 0].abs().max()) == 0 and float(f[:, :, 0:2].abs().max()) == 0  # only rotor links, only local z
+        assert float(t[:, :, 0:2].abs().max()) == 0
+        rotor = f[:, 1:5, 2].to(torch.float32)
+        tau_z = t[:, 1:5, 2].sum(-1).to(torch.float32)
+        simulate(self.spec, self.env.root_states, rotor, tau_z)
+
+    def refresh_actor_root_state_tensor(self, sim): pass
+    def set_actor_root_state_tensor(self, sim, tensor): pass
+    def fetch_results(self, sim, flag): pass
+    def step_graphics(self, sim): pass
+
+
+def make_reference_env(task, mode, N, ctl_state, episode_length_s=None):
+    import airgym.envs.base.hovering as ref_hov  # noqa: the reference module, unmodified
+    import airgym.envs.task.tracking as ref_trk
+    from airgym.envs.base.hovering_config import HoveringCfg
+    from airgym.envs.task.tracking_config import TrackingCfg
+
+    spec = QuadSpec(task=task, ctl_mode=mode)
+    if episode_length_s is not None:
+        spec.episode_length_s = episode_length_s
+    ctl_state["spec"] = spec
+    cls, cfg = (ref_hov.Hovering, HoveringCfg()) if task == "hovering" else (ref_trk.Tracking, TrackingCfg())
+    if episode_length_s is not None:
+        cfg.env.episode_length_s = episode_length_s
+    cfg.env.num_envs, cfg.env.ctl_mode = N, mode
+    env = cls.__new__(cls)  # __init__ needs a live IsaacGym; reproduce its attribute set-up (hovering.py:42-147)
+    env.cfg, env.ctl_mode, env.device = cfg, mode, "cpu"
+    env.num_envs, env.num_obs = N, cfg.env.num_observations
+    env.num_actions = 5 if mode == "atti" else 4
+    env.max_episode_length = int(cfg.env.episode_length_s / cfg.sim.dt)
+    env.dt = cfg.sim.dt
+    env.sim, env.viewer, env.counter = None, None, 1  # counter=1 skips the progress print
+    env.obs_buf = torch.zeros(N, env.num_obs)
+    env.rew_buf = torch.zeros(N)
+    env.reset_buf = torch.ones(N, dtype=torch.long)
+    env.time_out_buf = torch.zeros(N, dtype=torch.bool)
+    env.progress_buf = torch.zeros(N, dtype=torch.long)
+    env.extras = {}
+    env.vec_root_tensor = torch.zeros(N, 1, 13)
+    env.vec_root_tensor[:, 0, 6] = 1.0
+    env.root_tensor = env.vec_root_tensor
+    env.root_states = env.vec_root_tensor[:, 0, :]
+    env.root_positions = env.root_states[..., 0:3]
+    env.root_quats = env.root_states[..., 3:7]
+    env.root_linvels = env.root_states[..., 7:10]
+    env.root_angvels = env.root_states[..., 10:13]
+    env.privileged_obs_buf = None
+    env.initial_root_states = env.root_states.clone()
+    env.cmd_thrusts = torch.zeros(N, 4)
+    env.action_lower_limits = torch.tensor(spec.act_lo)
+    env.action_upper_limits = torch.tensor(spec.act_hi)
+    from rlPx4Controller.pyParallelControl import (ParallelAttiControl, ParallelPosControl, ParallelRateControl,
+                                                   ParallelVelControl)
+    if mode == "pos": env.parallel_pos_control = ParallelPosControl(N)
+    if mode == "vel": env.parallel_vel_control = ParallelVelControl(N)
+    if mode == "atti": env.parallel_atti_control = ParallelAttiControl(N)
+    if mode == "rate": env.parallel_rate_control = ParallelRateControl(N)
+    env.forces = torch.zeros(N, 5, 3)
+    env.torques = torch.zeros(N, 5, 3)
+    env.thrusts = torch.zeros(N, 4, 3)
+    env.target_states = torch.tensor(cfg.env.target_state, dtype=torch.float32).repeat(N, 1)
+    env.actions = torch.zeros(N, env.num_actions)
+    env.pre_actions = torch.zeros(N, env.num_actions)
+    if task == "tracking":
+        env.thrust_cmds_damp = torch.zeros(N, 4); env.thrust_rot_damp = torch.zeros(N, 4)
+        env.int_pos_error = torch.zeros(N, 10); env.int_yaw_error = torch.zeros(N, 10)
+        env.pre_root_positions = torch.zeros(N, 3)
+    env.gym = FakeGym(env, spec)
+    return env, spec
+
+
+def action_sequence(mode, N, A, T, gen):
+    a = torch.rand(T, N, A, generator=gen) * 2 - 1
+    if mode == "pos":
+        a[..., :3] *= 2.0
+    if mode in ("rate", "atti"):
+        a[..., -1] = a[..., -1] * 0.3 - 0.55  # thrust near hover after the 0.5+0.5a remap
+    a[T // 2] *= 10.0  # exercise the clamp
+    return a
+
+
+def run_case(task, mode, N, T, seed, ctl_state, episode_length_s=None, tag=""):
+    ref, spec = make_reference_env(task, mode, N, ctl_state, episode_length_s)
+    orc = make_oracle(spec, N, rng="torch")
+    A = spec.num_actions
+    gen = torch.Generator().manual_seed(1000 + seed)
+    acts = action_sequence(mode, N, A, T, gen)
+    keys = type(orc).REWARD_KEYS
+    rec = {k: [] for k in ("state", "obs", "rew", "reset", "progress", "timeout", "actions", "pre_actions", "cmd",
+                           "terms", "draw_reset", "draw_noise", "action_in_after")}
+    # reference run
+    torch.manual_seed(seed)
+    ref_out = []
+    for t in range(T):
+        a = acts[t].clone()
+        obs, _, rew, reset, extras = ref.step(a)
+        info = extras["item_reward_info"]
+        terms = torch.stack([info[k].to(torch.float32) if torch.is_tensor(info[k]) else torch.full((N,), float(info[k]))
+                             for k in keys], 0)
+        ref_out.append(dict(state=ref.root_states.clone(), obs=obs.clone(), rew=rew.clone(), reset=reset.clone(),
+                            progress=ref.progress_buf.clone(), timeout=extras["time_outs"].clone(),
+                            actions=ref.actions.clone().to(torch.float32), pre_actions=ref.pre_actions.clone().to(torch.float32),
+                            cmd=ref.cmd_thrusts.clone().to(torch.float32), terms=terms, action_in_after=a.clone()))
+    # oracle run, same seed → must agree; its recorded draws go into the fixture
+    torch.manual_seed(seed)
+    worst = 0.0
+    n_resets = 0
+    for t in range(T):
+        a = acts[t].clone()
+        orc.step(a)
+        o = dict(state=orc.root_states, obs=orc.obs_buf, rew=orc.rew_buf, actions=orc.actions, pre_actions=orc.pre_actions,
+                 cmd=orc.cmd_thrusts, terms=orc.reward_terms_matrix(), action_in_after=a)
+        r = ref_out[t]
+        for k, v in o.items():
+            rv = r[k]
+            same_nan = torch.isnan(v) == torch.isnan(rv)
+            assert same_nan.all(), (task, mode, t, k, "NaN pattern differs")
+            err = float(torch.nan_to_num((v.to(torch.float64) - rv.to(torch.float64)).abs()).max())
+            worst = max(worst, err)
+            assert err < 2e-6, (task, mode, t, k, err)
+        assert torch.equal(orc.reset_buf, r["reset"]), (task, mode, t, "reset")
+        assert torch.equal(orc.progress_buf, r["progress"]), (task, mode, t, "progress")
+        assert torch.equal(orc.time_out_buf, r["timeout"]), (task, mode, t, "timeout")
+        n_resets += int(r["reset"].sum())
+        for k in ("state", "obs", "rew", "reset", "progress", "timeout", "actions", "pre_actions", "cmd", "terms",
+                  "action_in_after"):
+            rec[k].append(r[k].numpy())
+        rec["draw_reset"].append(orc.last_draws["reset"].numpy().copy())
+        rec["draw_noise"].append(orc.last_draws["noise"].numpy().copy())
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out["action_in"] = acts.numpy()
+    out["meta"] = np.array([N, T, seed, A, spec.max_episode_length], dtype=np.int64)
+    name = f"{task}_{mode}{tag}.npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(f"{name}: oracle==reference to {worst:.1e} over {T} steps, {n_resets} env-resets")
+
+
+def main():
+    assert os.path.isdir(REF), "needs the reference checkout"
+    ctl_state = install_stubs()
+    sys.path.insert(0, REF)
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **kw):  # hovering.py:373 hard-codes .to('cuda')
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **kw)
+
+    torch.Tensor.to = to_cpu
+    try:
+        for mode in ("rate", "prop", "atti", "vel", "pos"):
+            run_case("hovering", mode, 16, 24, 7, ctl_state)
+        run_case("hovering", "rate", 16, 30, 11, ctl_state, episode_length_s=0.12, tag="_short")  # time-out resets (Q1)
+        for mode in ("vel", "rate", "atti"):
+            run_case("tracking", mode, 16, 24, 5, ctl_state)
+        run_case("tracking", "vel", 16, 30, 3, ctl_state, episode_length_s=0.12, tag="_short")
+    finally:
+        torch.Tensor.to = orig_to
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+// hostsim.cpp — TEST INFRASTRUCTURE.  Compiles airgym_b200/csrc/agx_math.cuh (the exact text the sm_100a kernel
+// instantiates per thread) with g++ and loops it over envs on the CPU, so the kernel's arithmetic can be
+// debugged against oracle/ in a container without a GPU.  Never loaded by the product.
+#include <stdint.h>
+#include "agx.h"
+#include "agx_math.cuh"
+
+using namespace agx;
+
+template <int TASK, int MODE>
+static void run(const AgxParams& P, int64_t n, const AgxStepIO& io) {
+    constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
+    const int K = P.ctrl_state_dim;
+    for (int64_t env = 0; env < n; ++env) {
+        EnvRegs e;
+        for (int i = 0; i < 13; ++i) e.s[i] = io.state[env * 13 + i];
+        for (int i = 0; i < 5; ++i) { e.a[i] = 0; e.pa[i] = 0; }
+        for (int i = 0; i < A; ++i) { e.a[i] = io.action[env * A + i]; e.pa[i] = io.prev_action[env * A + i]; }
+        for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
+        e.progress = io.progress[env];
+        e.pending = io.reset[env] != 0;
+        RandSrc rnd;
+        rnd.reset_row = io.rand_reset ? io.rand_reset + env * (int64_t)(2 * P.reset_draws) : nullptr;
+        rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
+        const uint64_t genv = (uint64_t)(io.env_offset + env);
+        rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
+        rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
+        rnd.ph.step_lo = (uint32_t)io.step; rnd.ph.step_hi = (uint32_t)(io.step >> 32);
+        env_step<TASK, MODE>(P, rnd, e, io.obs + env * P.num_obs);
+        for (int i = 0; i < 13; ++i) io.state[env * 13 + i] = e.s[i];
+        for (int i = 0; i < A; ++i) { io.actions_out[env * A + i] = e.a[i]; io.prev_action[env * A + i] = e.pa[i]; }
+        if ((P.flags & AGX_FLAG_MUTATE_ACTIONS) && (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI))
+            io.action[env * A + (A - 1)] = e.a_last_remap;
+        for (int k = 0; k < K; ++k) io.ctrl_state[(int64_t)k * n + env] = e.cs[k];
+        io.progress[env] = e.progress;
+        io.reset[env] = e.reset;
+        io.timeout[env] = (uint8_t)e.timeout;
+        io.reward[env] = e.rew;
+        if (io.cmd) for (int i = 0; i < 4; ++i) io.cmd[env * 4 + i] = e.cmd[i];
+        if (io.reward_terms) for (int k = 0; k < 9; ++k) io.reward_terms[(int64_t)k * n + env] = e.terms[k];
+    }
+}
+
+template <int TASK>
+static int by_mode(const AgxParams& P, int64_t n, const AgxStepIO& io) {
+    switch (P.ctl_mode) {
+        case AGX_CTL_POS: run<TASK, AGX_CTL_POS>(P, n, io); return 0;
+        case AGX_CTL_VEL: run<TASK, AGX_CTL_VEL>(P, n, io); return 0;
+        case AGX_CTL_ATTI: run<TASK, AGX_CTL_ATTI>(P, n, io); return 0;
+        case AGX_CTL_RATE: run<TASK, AGX_CTL_RATE>(P, n, io); return 0;
+        case AGX_CTL_PROP: run<TASK, AGX_CTL_PROP>(P, n, io); return 0;
+    }
+    return -1;
+}
+
+extern "C" int hostsim_step(const AgxParams* p, int64_t n, const AgxStepIO* io) {
+    if (p->task == AGX_TASK_HOVERING) return by_mode<AGX_TASK_HOVERING>(*p, n, *io);
+    if (p->task == AGX_TASK_TRACKING) return by_mode<AGX_TASK_TRACKING>(*p, n, *io);
+    return -4;
+}
+
+extern "C" int hostsim_philox_fill(float* out, int64_t n, int width, int stream_id, uint64_t seed, uint64_t step,
+                                   int64_t env_offset) {
+    for (int64_t env = 0; env < n; ++env) {
+        PhiloxCtx ph;
+        const uint64_t genv = (uint64_t)(env_offset + env);
+        ph.k0 = (uint32_t)seed; ph.k1 = (uint32_t)(seed >> 32);
+        ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
+        ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
+        float v[20];
+        if (stream_id == 2) philox_normals(ph, width, v);
+        else philox_uniforms(ph, (uint32_t)stream_id, width, v);
+        for (int i = 0; i < width; ++i) out[env * width + i] = v[i];
+    }
+    return 0;
+}

@@ -1,0 +1,116 @@
+"""Host logic: the kernel body (airgym_b200/csrc/agx_math.cuh compiled by g++ — tests/hostsim) against the oracle and
+the golden fixtures.  Runs without a GPU; the same comparisons run against the real kernel in test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from airgym_b200 import _capi
+from oracle import QuadSpec, make_oracle
+from tests.hostsim.driver import HostEnv, build
+from tests.util import assert_close, golden_cases, load_golden
+
+MODES = ["pos", "vel", "atti", "rate", "prop"]
+
+
+def _sync_from_oracle(he, orc, K):
+    he.state[:] = orc.root_states.numpy()
+    he.prev_action[:] = orc.pre_actions.numpy()
+    he.progress[:] = orc.progress_buf.numpy()
+    he.reset[:] = orc.reset_buf.numpy()
+    if K:
+        he.ctrl_state[:K] = orc.controller.state.numpy().T[:K]
+
+
+@pytest.mark.parametrize("task", ["hovering", "tracking"])
+@pytest.mark.parametrize("mode", MODES)
+def test_per_step_parity_vs_oracle(built, task, mode):
+    torch.manual_seed(3)
+    N, T = 96, 40
+    spec = QuadSpec(task=task, ctl_mode=mode)
+    orc = make_oracle(spec, N, rng="torch")
+    he = HostEnv(_capi.default_params(task, mode), N)
+    K = spec.ctrl_state_dim
+    for t in range(T):
+        a = torch.rand(N, spec.num_actions) * 2 - 1
+        if t == 7:
+            orc.progress_buf[:10] = spec.max_episode_length - 2  # force time-out resets
+        _sync_from_oracle(he, orc, K)
+        a_np = a.numpy().copy()
+        orc.step(a)
+        d = orc.last_draws
+        he.step(a_np, d["reset"].numpy().copy(), d["noise"].numpy().copy())
+        tag = f"{task}/{mode} t={t}"
+        assert_close(he.state, orc.root_states, tag + " state")
+        assert_close(he.obs, orc.obs_buf, tag + " obs")
+        assert_close(he.reward, orc.rew_buf, tag + " rew")
+        assert_close(he.cmd, orc.cmd_thrusts, tag + " cmd")
+        assert_close(he.terms, orc.reward_terms_matrix(), tag + " terms")
+        assert_close(he.actions_out, orc.actions, tag + " actions", rtol=0, atol=0)
+        assert_close(he.prev_action, orc.pre_actions, tag + " pre_actions", rtol=0, atol=0)
+        assert_close(a_np, a, tag + " in-place remap", rtol=0, atol=0)
+        if K:
+            assert_close(he.ctrl_state[:K].T, orc.controller.state[:, :K], tag + " ctrl")
+        assert np.array_equal(he.reset, orc.reset_buf.numpy()), tag
+        assert np.array_equal(he.progress, orc.progress_buf.numpy()), tag
+        assert np.array_equal(he.timeout.astype(bool), orc.time_out_buf.numpy()), tag
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_trajectory_vs_reference_golden(built, name):
+    g, task, mode, N, T, A, max_len = load_golden(name)
+    P = _capi.default_params(task, mode)
+    P.max_episode_length = max_len
+    he = HostEnv(P, N)
+    for t in range(T):
+        a = g["action_in"][t].copy()
+        he.step(a, g["draw_reset"][t].copy(), g["draw_noise"][t].copy())
+        tag = f"{name} t={t}"
+        assert_close(he.state, g["state"][t], tag + " state", rtol=3e-4, atol=1e-4)  # free-running trajectory
+        assert_close(he.obs, g["obs"][t], tag + " obs", rtol=3e-4, atol=1e-4)
+        assert_close(he.reward, g["rew"][t], tag + " rew", rtol=3e-4, atol=1e-4)
+        assert np.array_equal(he.reset, g["reset"][t]), tag
+        assert np.array_equal(he.progress, g["progress"][t]), tag
+        assert_close(a, g["action_in_after"][t], tag + " Q4", rtol=0, atol=0)
+
+
+def test_nan_semantics_at_exact_target(built):
+    """Quirk Q5 (hovering.py:393-397): zero velocity → 0/0 → NaN reward, not a clamped number."""
+    P = _capi.default_params("hovering", "prop")
+    P.flags |= _capi.FLAG_NO_NOISE
+    he = HostEnv(P, 4)
+    he.reset[:] = 0
+    he.state[:, 2] = 0.5
+    P.gravity = 0.0  # keeps v exactly 0 with zero thrust
+    he.step(np.zeros((4, 4), np.float32))
+    assert np.isnan(he.reward).all()
+    assert np.isnan(he.terms[4]).all() and not np.isnan(he.terms[3]).any()
+
+
+def _philox_ref(ctr, key):
+    """Independent numpy Philox4x32-10 (Salmon et al. 2011)."""
+    c = [np.uint64(x) for x in ctr]
+    k = [np.uint64(x) for x in key]
+    M0, M1, W0, W1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k[0], p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ k[1], p0 & mask]
+        k = [(k[0] + W0) & mask, (k[1] + W1) & mask]
+    return [int(x) for x in c]
+
+
+def test_philox_known_answers_and_stream_layout(built):
+    # Random123 known-answer vectors for philox4x32-10
+    assert _philox_ref([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert _philox_ref([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    lib = build()
+    n, seed, step, off = 5, 0x1234567811223344, 77, 1000
+    out = np.zeros((n, 12), np.float32)
+    lib.hostsim_philox_fill(out.ctypes.data, n, 12, 1, seed, step, off)
+    for e in range(n):
+        for b in range(3):
+            w = _philox_ref([off + e, step, 1, b], [seed & 0xFFFFFFFF, seed >> 32])
+            assert np.array_equal(out[e, 4 * b:4 * b + 4], np.array([(x >> 8) * 2.0**-24 for x in w], np.float32))
+    z = np.zeros((200000, 18), np.float32)
+    lib.hostsim_philox_fill(z.ctypes.data, z.shape[0], 18, 2, seed, step, 0)
+    assert abs(z.mean()) < 2e-3 and abs(z.std() - 1) < 2e-3 and abs((z**3).mean()) < 1e-2
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 1e-2

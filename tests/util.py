@@ -1,0 +1,35 @@
+"""Shared helpers for the parity tests."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4   # BASELINE.json north_star: "within 1e-4 rel fp32 on states/rewards"
+ATOL = 2e-5   # floor for entries near zero (quaternion components, noise-dominated obs, cancelled reward terms)
+
+
+def golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    task, mode = name.split("_")[0], name.split("_")[1]
+    N, T, seed, A, max_len = [int(x) for x in g["meta"]]
+    return g, task, mode, N, T, A, max_len
+
+
+def assert_close(got, ref, what, rtol=RTOL, atol=ATOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    nan_g, nan_r = np.isnan(got), np.isnan(ref)
+    assert (nan_g == nan_r).all(), f"{what}: NaN pattern differs at {np.argwhere(nan_g != nan_r)[:5]}"
+    err = np.abs(np.nan_to_num(got) - np.nan_to_num(ref))
+    bound = atol + rtol * np.abs(np.nan_to_num(ref))
+    bad = err > bound
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - bound), err.shape)
+        raise AssertionError(f"{what}: {bad.sum()} entries off; worst at {i}: got {got[i]!r} ref {ref[i]!r} err {err[i]:.3e}")
+    return float(err.max()) if err.size else 0.0
