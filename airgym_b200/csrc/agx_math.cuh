@@ -170,11 +170,13 @@ AGX_HD float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.96046447753906
 AGX_HD void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
     const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;  // (0,1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;         // [0,1)
-    const float r = sqrtf(-2.0f * logf(u1));
     float s, c;
 #if defined(__CUDA_ARCH__)
-    sincospif(2.0f * u2, &s, &c);
+    // SFU path (MUFU.LG2 / MUFU.SIN / MUFU.COS): abs error ~2^-21 on N(0,1) draws, far below the noise itself
+    const float r = sqrtf(-2.0f * __logf(u1));
+    __sincosf(kTwoPi * u2, &s, &c);
 #else
+    const float r = sqrtf(-2.0f * logf(u1));
     s = sinf(kTwoPi * u2); c = cosf(kTwoPi * u2);
 #endif
     *z0 = r * c; *z1 = r * s;
@@ -341,16 +343,13 @@ AGX_HD void velocity_loop(const AgxParams& P, V3 v_sp, float yaw_sp, V3 v, float
 
 // Full cascade dispatch.  a[] = shaped+clamped action, s[] = root state row (canonical quaternion).
 template <int MODE>
-AGX_HD void controller(const AgxParams& P, const float* s, const float* a, float* cs, float* cmd) {
+AGX_HD void controller(const AgxParams& P, const float* s, V3 w_b, const float* a, float* cs, float* cmd) {
     if (MODE == AGX_CTL_PROP) {  // hovering.py:251-252
         cmd[0] = a[0]; cmd[1] = a[1]; cmd[2] = a[2]; cmd[3] = a[3];
         return;
     }
     Q4 q; q.x = s[3]; q.y = s[4]; q.z = s[5]; q.w = s[6];
-    float R[9];
-    quat_to_matrix(q, R);
-    const V3 w_b = mat_tmul_v(R, v3(s[10], s[11], s[12]));  // world → body rates (set_q_world, :249)
-    V3 w_sp;
+    V3 w_sp;  // w_b = R(q)^T w_world: world → body rates (what set_q_world is for, hovering.py:249)
     float thrust;
     if (MODE == AGX_CTL_RATE) {
         w_sp = v3(a[0], a[1], a[2]);
@@ -405,13 +404,10 @@ AGX_HD Q4 qaxpy(Q4 q, float h, Q4 d) {
 // One dt of the composite rigid body under a zero-order-hold body-frame wrench.
 // s: in/out root state row; thrust[4]: rotor forces [N] (already zeroed for envs reset this step,
 // hovering.py:268); tau_z: rotor reaction torque (hovering.py:270-275, NOT zeroed).
-AGX_HD void integrate(const AgxParams& P, float* s, const float* thrust, float tau_z, float* Rnew) {
+AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, float tau_z, float* Rnew) {
     V3 p = v3(s[0], s[1], s[2]);
     Q4 q; q.x = s[3]; q.y = s[4]; q.z = s[5]; q.w = s[6];
-    V3 v = v3(s[7], s[8], s[9]);
-    float R[9];
-    quat_to_matrix(q, R);
-    V3 w = mat_tmul_v(R, v3(s[10], s[11], s[12]));  // body rates
+    V3 v = v3(s[7], s[8], s[9]);  // w: body rates R(q)^T w_world, computed once by the caller
     const float fz_over_m = (thrust[0] + thrust[1] + thrust[2] + thrust[3]) / P.mass;
     const V3 tau = v3(P.arm * (-thrust[0] + thrust[1] + thrust[2] - thrust[3]),
                       P.arm * (-thrust[0] + thrust[1] - thrust[2] + thrust[3]), tau_z);
@@ -514,8 +510,27 @@ AGX_HD V3 lemniscate(int64_t progress, int k, float dt) {
     return v3(3.0f * st / den, 3.0f * st * ct / den, 1.0f);
 }
 
+// Observation noise draws, already scaled by sigma (hovering.py:350-353).  Independent of the env state, so the
+// kernel evaluates it while the state/action loads are still in flight.
+AGX_HD void scaled_noise(const AgxParams& P, const RandSrc& rnd, float* z) {
+    if (P.flags & AGX_FLAG_NO_NOISE) {
+#pragma unroll
+        for (int i = 0; i < AGX_NOISE_DRAWS; ++i) z[i] = 0.0f;
+        return;
+    }
+    draw_noise(rnd, z);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) z[i] = P.noise_sigma[0] * z[i];
+#pragma unroll
+    for (int i = 9; i < 12; ++i) z[i] = P.noise_sigma[1] * z[i];
+#pragma unroll
+    for (int i = 12; i < 15; ++i) z[i] = P.noise_sigma[2] * z[i];
+#pragma unroll
+    for (int i = 15; i < 18; ++i) z[i] = P.noise_sigma[3] * z[i];
+}
+
 template <int TASK, int MODE>
-AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, EnvRegs& e, float* obs) {
+AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, EnvRegs& e, float* obs) {
     constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
     constexpr bool kThrustMode = (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI);
 
@@ -538,8 +553,16 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, EnvRegs& e, float* 
     // -- quaternion sign canonicalisation, written back into the state (hovering.py:224-226)
     if (e.s[6] < 0.0f) { e.s[3] = -e.s[3]; e.s[4] = -e.s[4]; e.s[5] = -e.s[5]; e.s[6] = -e.s[6]; }
 
+    // -- body rates, shared by the controller and the integrator
+    float R[9];
+    {
+        Q4 q0; q0.x = e.s[3]; q0.y = e.s[4]; q0.z = e.s[5]; q0.w = e.s[6];
+        quat_to_matrix(q0, R);
+    }
+    const V3 w_b = mat_tmul_v(R, v3(e.s[10], e.s[11], e.s[12]));
+
     // -- controller cascade → normalised rotor commands (hovering.py:235-252)
-    controller<MODE>(P, e.s, e.a, e.cs, e.cmd);
+    controller<MODE>(P, e.s, w_b, e.a, e.cs, e.cmd);
 
     // -- wrench (hovering.py:256-281): thrust zeroed for envs reset this step, torque not
     float thrust[4];
@@ -547,35 +570,27 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, EnvRegs& e, float* 
     for (int i = 0; i < 4; ++i) thrust[i] = e.pending ? 0.0f : e.cmd[i] * P.k_thrust;
     const float tau_z = P.k_torque * (-e.cmd[0] - e.cmd[1] + e.cmd[2] + e.cmd[3]);
 
-    // -- gym.simulate (hovering.py:290)
-    float R[9];
-    integrate(P, e.s, thrust, tau_z, R);
+    // -- gym.simulate (hovering.py:290); R becomes R(q_new)
+    integrate(P, e.s, w_b, thrust, tau_z, R);
 
     e.progress += 1;  // hovering.py:297
 
-    // -- compute_observations + add_noise (hovering.py:337-358; tracking.py:202-214)
-    float z[AGX_NOISE_DRAWS];
-    if (P.flags & AGX_FLAG_NO_NOISE) {
-#pragma unroll
-        for (int i = 0; i < AGX_NOISE_DRAWS; ++i) z[i] = 0.0f;
-    } else {
-        draw_noise(rnd, z);
-    }
+    // -- compute_observations + add_noise (hovering.py:337-358; tracking.py:202-214); z = sigma * N(0,1)
     const V3 p = v3(e.s[0], e.s[1], e.s[2]);
     const V3 v = v3(e.s[7], e.s[8], e.s[9]);
     const V3 w = v3(e.s[10], e.s[11], e.s[12]);
     float o[18];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[i] = R[i] + P.noise_sigma[0] * z[i];
-    o[9] = p.x + P.noise_sigma[1] * z[9];
-    o[10] = p.y + P.noise_sigma[1] * z[10];
-    o[11] = p.z + P.noise_sigma[1] * z[11];
-    o[12] = v.x + P.noise_sigma[2] * z[12];
-    o[13] = v.y + P.noise_sigma[2] * z[13];
-    o[14] = v.z + P.noise_sigma[2] * z[14];
-    o[15] = w.x + P.noise_sigma[3] * z[15];
-    o[16] = w.y + P.noise_sigma[3] * z[16];
-    o[17] = w.z + P.noise_sigma[3] * z[17];
+    for (int i = 0; i < 9; ++i) o[i] = R[i] + z[i];
+    o[9] = p.x + z[9];
+    o[10] = p.y + z[10];
+    o[11] = p.z + z[11];
+    o[12] = v.x + z[12];
+    o[13] = v.y + z[13];
+    o[14] = v.z + z[14];
+    o[15] = w.x + z[15];
+    o[16] = w.y + z[16];
+    o[17] = w.z + z[17];
     V3 ref0 = v3(0.0f, 0.0f, 0.0f);
     if (TASK == AGX_TASK_TRACKING) {
 #pragma unroll

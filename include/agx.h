@@ -147,7 +147,8 @@ int         agx_sizeof_params(void);  /* sizeof(AgxParams): lets a binding check
 int         agx_sizeof_step_io(void);
 
 /* Tuning knobs (process-wide): "block" = 64|128 threads per CTA, "use_bulk" = 0|1 (TMA bulk-copy
- * staging vs cooperative copies). */
+ * staging vs cooperative copies), "pdl" = 0|1 (programmatic dependent launch: the next step's prologue overlaps
+ * this step's tail; stream order of all memory effects is unchanged). */
 int agx_set_option(const char* key, int value);
 
 /* Fill `p` with the defaults of (task, ctl_mode): replaces the reference's cfg classes + the

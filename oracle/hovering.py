@@ -122,6 +122,7 @@ class HoveringOracle:
         # quaternion sign canonicalisation written into the state (hovering.py:224-226)
         self.root_states[..., 3:7] = torch.where(self.root_states[..., 6:7] < 0, -self.root_states[..., 3:7],
                                                  self.root_states[..., 3:7])
+        self.pre_step_quat = self.root_states[:, 3:7].clone()  # (test hook: attitude seen by the controller)
         pos, quat = self.root_states[:, 0:3].clone(), self.root_states[:, 3:7].clone()
         linvel, angvel = self.root_states[:, 7:10].clone(), self.root_states[:, 10:13].clone()
         q_wxyz = quat[:, [3, 0, 1, 2]]

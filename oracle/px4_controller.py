@@ -84,6 +84,7 @@ class ParallelControl:
         qmix = torch.where(qmix[:, 3:4] < 0, -qmix, qmix)
         mw = _clamp(qmix[:, 3], -1.0, 1.0)
         mz = _clamp(qmix[:, 2], -1.0, 1.0)
+        self.last_conditioning = (d.clone(), mw.clone())  # test hook: 1+d and asin(mz) near |mz|=1 amplify rounding
         zero = torch.zeros_like(mw)
         yawq = torch.stack((zero, zero, torch.sin(s.att_yaw_w * torch.asin(mz)), torch.cos(s.att_yaw_w * torch.acos(mw))), -1)
         qdd = R.qmul(qd_red, yawq)

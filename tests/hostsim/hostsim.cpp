@@ -26,7 +26,9 @@ static void run(const AgxParams& P, int64_t n, const AgxStepIO& io) {
         rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
         rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
         rnd.ph.step_lo = (uint32_t)io.step; rnd.ph.step_hi = (uint32_t)(io.step >> 32);
-        env_step<TASK, MODE>(P, rnd, e, io.obs + env * P.num_obs);
+        float z[AGX_NOISE_DRAWS];
+        scaled_noise(P, rnd, z);
+        env_step<TASK, MODE>(P, rnd, z, e, io.obs + env * P.num_obs);
         for (int i = 0; i < 13; ++i) io.state[env * 13 + i] = e.s[i];
         for (int i = 0; i < A; ++i) { io.actions_out[env * A + i] = e.a[i]; io.prev_action[env * A + i] = e.pa[i]; }
         if ((P.flags & AGX_FLAG_MUTATE_ACTIONS) && (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI))
