@@ -144,10 +144,12 @@ AGX_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 AGX_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        // one 32x32->64 multiply per lane pair (IMAD.WIDE.U32) yields both halves
+        const uint64_t p0 = (uint64_t)0xD2511F53u * (uint64_t)c.x;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * (uint64_t)c.z;
         U4 n;
-        n.x = hi1 ^ c.y ^ k0; n.y = lo1; n.z = hi0 ^ c.w ^ k1; n.w = lo0;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0; n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1; n.w = (uint32_t)p0;
         c = n;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }

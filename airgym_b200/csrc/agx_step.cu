@@ -166,6 +166,10 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
         rnd.ph.step_lo = (uint32_t)step; rnd.ph.step_hi = (uint32_t)(step >> 32);
         scaled_noise(P, rnd, z);
+        // keep the consumers of the loads below this point: the compiler would otherwise hoist the first use of the
+        // action registers above the noise code and park every warp on the load latency before doing useful work
+#pragma unroll
+        for (int i = 0; i < AGX_MAX_ACTIONS; ++i) asm volatile("" : "+f"(e.a[i]), "+f"(e.pa[i]));
     }
 
     if (bulk) {

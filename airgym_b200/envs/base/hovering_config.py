@@ -63,3 +63,4 @@ class HoveringCfg(BaseConfig):
         ctrl_reset_on_reset = False  # reference behaviour: controller integrators survive episode resets
         mutate_input_actions = True  # reference quirk Q4 (hovering.py:212-215)
         reward_terms = True          # fill extras["item_reward_info"]
+        export_cmd_thrusts = True    # keep the env attribute `cmd_thrusts` up to date (hovering.py:90,238-252)

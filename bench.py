@@ -6,7 +6,7 @@
     torchrun --nproc-per-node N bench.py --gpus N ...              N ranks, envs sharded (weak scaling, no collective)
 
 A "step" is one fused env step (agx_step) over one batch of 65 536 envs.  To keep the inputs larger than the 126 MB
-L2 the bench rotates through R=16 independent env replicas (R x ~20 MB of state/obs/action buffers), one launch per
+L2 the bench rotates through R=8 independent env replicas (R x ~21 MB of state/obs/action buffers = 170 MB), one launch per
 step, replayed from a CUDA graph; the e2e leg goes through the public env.step() with HOST action/result buffers.
 """
 import argparse
@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NUM_ENVS = 65536
-REPLICAS = 16
+REPLICAS = 8
 ALGO_BYTES_PER_ENV_STEP = 288  # reads 113 B + writes 174 B (Hovering/CTBR fp32)
 WORKLOAD = "Hovering, 65536 envs/GPU, CTBR (ctl_mode=rate), fused step kernel"
 
@@ -183,6 +183,7 @@ def make_envs(num_envs, replicas, rank, world, device):
         cfg = HoveringCfg()
         cfg.env.num_envs, cfg.env.ctl_mode, cfg.seed = num_envs, "rate", 1234 + r
         cfg.backend.reward_terms = False  # extras["item_reward_info"] is optional logging
+        cfg.backend.export_cmd_thrusts = False  # internal attribute of the reference env, not part of step()'s return
         cfg.backend.mutate_input_actions = False  # the bench re-feeds one action tensor; Q4's write-back would drift it
         env = Hovering(cfg, None, None, device, True)
         env.set_seed(1234 + r, env_offset=rank * num_envs)
@@ -279,9 +280,9 @@ def run_ours(args):
 
     import __graft_entry__ as graft
 
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from airgym_b200.dist_utils import rank_world
+
+    rank, local, world = rank_world()
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
