@@ -56,6 +56,17 @@ class AgxStepIO(C.Structure):
     ]
 
 
+class AgxPpoHyper(C.Structure):
+    _fields_ = [
+        ("e_clip", C.c_float), ("critic_coef", C.c_float), ("entropy_coef", C.c_float), ("bounds_loss_coef", C.c_float),
+        ("kl_threshold", C.c_float), ("grad_norm", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("weight_decay", C.c_float), ("adaptive_lr", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+AGX_PPO_STATS = 8
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -74,12 +85,17 @@ def bind(lib):
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
     ]
     lib.agx_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
+    lib.agx_gae.argtypes = [C.c_int64, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 8
+    lib.agx_ppo_workspace_floats.restype = C.c_int64
+    lib.agx_ppo_loss.argtypes = [C.POINTER(AgxPpoHyper), C.c_int64, C.c_int] + [C.c_void_p] * 15
+    lib.agx_adam_step.argtypes = [C.POINTER(AgxPpoHyper), C.c_int64] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
     return lib
 
 
 EXPORTS = (
     "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_set_option",
-    "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill",
+    "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
+    "agx_ppo_loss", "agx_adam_step",
 )
 
 _lib = None

@@ -1,0 +1,222 @@
+// agx_ppo.cu — PPO update kernels for sm_100a behind the C ABI (include/agx.h, row a13).
+// All three are bandwidth-/latency-trivial next to the env step; the point of fusing them is to remove the hundreds
+// of tiny torch launches and every host sync (.item()) from the update loop so that it can live in one CUDA graph.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "agx.h"
+#include "agx_ppo_math.cuh"
+
+int agx_internal_fail(int code, const char* msg);  // agx_step.cu: sets the thread-local text behind agx_error_string()
+
+namespace {
+
+int fail_ppo(int code, const char* msg) { return agx_internal_fail(code, msg); }
+
+constexpr int kGaeBlock = 128;
+constexpr int kLossBlock = 256;
+constexpr int kLossGridMax = 296;   // 2 CTAs per SM on 148 SMs
+constexpr int kPartial = 16;        // floats per CTA partial: 5 stats + 5 logstd grads (+pad)
+
+// ---- GAE: one thread per env, rows staged through shared memory so global traffic stays coalesced -----------
+__global__ void __launch_bounds__(kGaeBlock)
+agx_gae_kernel(int64_t n, int h, float gamma, float tau, const float* __restrict__ rewards,
+               const float* __restrict__ values, const uint8_t* __restrict__ dones,
+               const float* __restrict__ last_values, const uint8_t* __restrict__ last_dones,
+               float* __restrict__ adv, float* __restrict__ ret) {
+    extern __shared__ float smem[];
+    float* s_r = smem;                          // [kGaeBlock, h+1] padded rows (odd stride when h is even)
+    const int stride = h | 1;
+    float* s_v = s_r + kGaeBlock * stride;
+    float* s_a = s_v + kGaeBlock * stride;
+    float* s_t = s_a + kGaeBlock * stride;
+    uint8_t* s_d = reinterpret_cast<uint8_t*>(s_t + kGaeBlock * stride);  // [kGaeBlock, h]
+    const int64_t tile0 = (int64_t)blockIdx.x * kGaeBlock;
+    const int tile_n = (int)((n - tile0) < kGaeBlock ? (n - tile0) : kGaeBlock);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < tile_n * h; i += kGaeBlock) {
+        const int r = i / h, c = i - r * h;
+        s_r[r * stride + c] = rewards[tile0 * h + i];
+        s_v[r * stride + c] = values[tile0 * h + i];
+        s_d[r * h + c] = dones[tile0 * h + i];
+    }
+    __syncthreads();
+    if (tid < tile_n) {
+        agx::gae_row(h, gamma, tau, s_r + tid * stride, s_v + tid * stride, s_d + tid * h, last_values[tile0 + tid],
+                     (float)last_dones[tile0 + tid], s_a + tid * stride, s_t + tid * stride);
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_n * h; i += kGaeBlock) {
+        const int r = i / h, c = i - r * h;
+        adv[tile0 * h + i] = s_a[r * stride + c];
+        ret[tile0 * h + i] = s_t[r * stride + c];
+    }
+}
+
+// ---- fused PPO loss forward + backward ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int A>
+__global__ void __launch_bounds__(kLossBlock)
+agx_ppo_loss_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t b, const float* __restrict__ mu,
+                    const float* __restrict__ logstd, const float* __restrict__ value,
+                    const float* __restrict__ actions, const float* __restrict__ old_neglogp,
+                    const float* __restrict__ adv, const float* __restrict__ returns, float* old_mu,
+                    float* old_sigma, float* __restrict__ grad_mu, float* __restrict__ grad_value,
+                    float* __restrict__ grad_logstd, float* __restrict__ stats, float* workspace) {
+    __shared__ float s_part[kLossBlock / 32][kPartial];
+    __shared__ bool s_last;
+    float ls[agx::kMaxAct], sig[agx::kMaxAct];
+#pragma unroll
+    for (int i = 0; i < agx::kMaxAct; ++i) { ls[i] = i < A ? logstd[i] : 0.0f; sig[i] = i < A ? expf(ls[i]) : 0.0f; }
+    float acc[kPartial];
+#pragma unroll
+    for (int i = 0; i < kPartial; ++i) acc[i] = 0.0f;
+    const float inv_b = 1.0f / (float)b;
+    for (int64_t s = (int64_t)blockIdx.x * kLossBlock + threadIdx.x; s < b; s += (int64_t)gridDim.x * kLossBlock) {
+        float m[agx::kMaxAct], ac[agx::kMaxAct], om[agx::kMaxAct], os[agx::kMaxAct];
+#pragma unroll
+        for (int i = 0; i < agx::kMaxAct; ++i) {
+            if (i < A) { m[i] = mu[s * A + i]; ac[i] = actions[s * A + i]; om[i] = old_mu[s * A + i]; os[i] = old_sigma[s * A + i]; }
+            else { m[i] = 0; ac[i] = 0; om[i] = 0; os[i] = 1; }
+        }
+        agx::PpoSampleOut o;
+        agx::ppo_sample(hp, A, m, ls, value[s], ac, old_neglogp[s], adv[s], returns[s], om, os, o);
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            grad_mu[s * A + i] = o.g_mu[i] * inv_b;
+            old_mu[s * A + i] = m[i];          // PPODataset.update_mu_sigma
+            old_sigma[s * A + i] = sig[i];
+            acc[5 + i] += o.g_logstd[i];
+        }
+        grad_value[s] = o.g_value * inv_b;
+        acc[0] += o.a_loss; acc[1] += o.c_loss; acc[2] += o.entropy; acc[3] += o.b_loss; acc[4] += o.kl;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 5 + A; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) s_part[warp][i] = v;
+    }
+    __syncthreads();
+    float* partials = workspace;                                   // [gridDim.x, kPartial]
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(workspace + (int64_t)kLossGridMax * kPartial);
+    if (threadIdx.x < 5 + A) {
+        float v = 0.0f;
+        for (int w = 0; w < kLossBlock / 32; ++w) v += s_part[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * kPartial + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {  // fixed-order final reduction → bitwise reproducible
+        __threadfence();
+        if (threadIdx.x < 5 + A) {
+            float v = 0.0f;
+            for (unsigned int c = 0; c < gridDim.x; ++c) v += partials[(int64_t)c * kPartial + threadIdx.x];
+            if (threadIdx.x < 5) stats[threadIdx.x] = v * inv_b;
+            else grad_logstd[threadIdx.x - 5] = v * inv_b - hp.entropy_coef;  // d(-coef * mean entropy)/d logstd_i = -coef
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// ---- fused grad-scale + clip_grad_norm_ + Adam + adaptive LR (single CTA) ------------------------------------------
+constexpr int kAdamBlock = 1024;
+__global__ void __launch_bounds__(kAdamBlock)
+agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __restrict__ p, const float* __restrict__ g,
+                float* __restrict__ m, float* __restrict__ v, float* lr_dev, long long* step_dev, const float* kl_dev,
+                float grad_scale, float* norm_out) {
+    __shared__ float s_red[kAdamBlock / 32];
+    __shared__ float s_norm;
+    float ss = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += kAdamBlock) { const float x = g[i] * grad_scale; ss += x * x; }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < kAdamBlock / 32 ? s_red[threadIdx.x] : 0.0f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) s_norm = sqrtf(t);
+    }
+    __syncthreads();
+    const float norm = s_norm;
+    float clip = 1.0f;
+    if (hp.grad_norm > 0.0f) { clip = hp.grad_norm / (norm + 1e-6f); clip = clip > 1.0f ? 1.0f : clip; }  // clip_grad_norm_
+    const long long t = step_dev[0] + 1;
+    const float lr = lr_dev[0];
+    const float bc1 = 1.0f - powf(hp.beta1, (float)t), bc2 = 1.0f - powf(hp.beta2, (float)t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int64_t i = threadIdx.x; i < n; i += kAdamBlock) {
+        float gi = g[i] * grad_scale * clip;
+        const float pi = p[i];
+        if (hp.weight_decay != 0.0f) gi += hp.weight_decay * pi;
+        const float mi = hp.beta1 * m[i] + (1.0f - hp.beta1) * gi;
+        const float vi = hp.beta2 * v[i] + (1.0f - hp.beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + hp.eps);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        step_dev[0] = t;
+        if (norm_out) *norm_out = norm;
+        if (hp.adaptive_lr && kl_dev) lr_dev[0] = agx::adaptive_lr(lr, kl_dev[0] * grad_scale, hp.kl_threshold);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int agx_gae(int64_t n, int h, float gamma, float tau, const float* rewards, const float* values, const uint8_t* dones,
+            const float* last_values, const uint8_t* last_dones, float* adv, float* returns, void* stream) {
+    if (n < 0 || h <= 0 || !rewards || !values || !dones || !last_values || !last_dones || !adv || !returns)
+        return fail_ppo(AGX_ERR_ARG, "agx_gae: bad argument");
+    if (n == 0) return AGX_OK;
+    const size_t smem = (size_t)kGaeBlock * (4 * (h | 1) * sizeof(float) + h);
+    if (smem > 200 * 1024) return fail_ppo(AGX_ERR_UNSUPPORTED, "agx_gae: horizon too long for the shared-memory tile");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(agx_gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned grid = (unsigned)((n + kGaeBlock - 1) / kGaeBlock);
+    agx_gae_kernel<<<grid, kGaeBlock, smem, reinterpret_cast<cudaStream_t>(stream)>>>(n, h, gamma, tau, rewards, values, dones,
+                                                                                     last_values, last_dones, adv, returns);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_gae: launch failed");
+}
+
+int64_t agx_ppo_workspace_floats(void) { return (int64_t)kLossGridMax * kPartial + 4; }
+
+int agx_ppo_loss(const AgxPpoHyper* hp, int64_t b, int a, const float* mu, const float* logstd, const float* value,
+                 const float* actions, const float* old_neglogp, const float* adv, const float* returns, float* old_mu,
+                 float* old_sigma, float* grad_mu, float* grad_value, float* grad_logstd, float* stats, float* workspace,
+                 void* stream) {
+    if (!hp || b <= 0 || !mu || !logstd || !value || !actions || !old_neglogp || !adv || !returns || !old_mu || !old_sigma ||
+        !grad_mu || !grad_value || !grad_logstd || !stats || !workspace)
+        return fail_ppo(AGX_ERR_ARG, "agx_ppo_loss: bad argument");
+    if (a != 4 && a != 5) return fail_ppo(AGX_ERR_UNSUPPORTED, "agx_ppo_loss: actions_num must be 4 or 5");
+    int64_t grid = (b + kLossBlock - 1) / kLossBlock;
+    if (grid > kLossGridMax) grid = kLossGridMax;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a == 4)
+        agx_ppo_loss_kernel<4><<<(unsigned)grid, kLossBlock, 0, st>>>(*hp, b, mu, logstd, value, actions, old_neglogp, adv, returns,
+                                                                       old_mu, old_sigma, grad_mu, grad_value, grad_logstd, stats, workspace);
+    else
+        agx_ppo_loss_kernel<5><<<(unsigned)grid, kLossBlock, 0, st>>>(*hp, b, mu, logstd, value, actions, old_neglogp, adv, returns,
+                                                                       old_mu, old_sigma, grad_mu, grad_value, grad_logstd, stats, workspace);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_ppo_loss: launch failed");
+}
+
+int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale, float* grad_norm_out, void* stream) {
+    if (!hp || n_params <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev)
+        return fail_ppo(AGX_ERR_ARG, "agx_adam_step: bad argument");
+    agx_adam_kernel<<<1, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *hp, n_params, params, grads, exp_avg, exp_avg_sq, lr_dev, reinterpret_cast<long long*>(step_dev), kl_dev, grad_scale,
+        grad_norm_out);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_adam_step: launch failed");
+}
+
+}  // extern "C"

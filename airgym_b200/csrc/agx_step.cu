@@ -26,6 +26,12 @@ int fail(int code, const char* fmt, const char* detail = "") {
     return code;
 }
 
+}  // namespace
+
+int agx_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+
+namespace {
+
 // ---- PTX wrappers: mbarrier + TMA bulk copies ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

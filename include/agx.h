@@ -174,6 +174,54 @@ int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_i
 int agx_philox_fill(float* out, int64_t n, int width, int stream_id, uint64_t seed, uint64_t step,
                     int64_t env_offset, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * PPO update kernels.  Reference: lib/agent/a2c_base.py:463-478 (GAE), a2c_continuous.py:299-369
+ * (calc_gradients), lib/core/common_losses.py:10-48, lib/core/torch_ext.py:27-36 (policy_kl), lib/core/schedulers.py:19-32,
+ * a2c_base.py:293-316 (grad clip + optimizer step; torch.optim.Adam, a2c_continuous.py:401).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct AgxPpoHyper {
+    float e_clip;            /* 0.2  (ppo_hovering.yaml:52) */
+    float critic_coef;       /* 2    (:58) — loss uses 0.5 * c_loss * critic_coef */
+    float entropy_coef;      /* 0    (:50) */
+    float bounds_loss_coef;  /* 1e-4 (:61) */
+    float kl_threshold;      /* 0.008 (:45) adaptive LR */
+    float grad_norm;         /* 1.5  (:48) clip_grad_norm_ max norm; <= 0 disables clipping */
+    float beta1, beta2, eps; /* Adam 0.9 / 0.999 / 1e-8 (a2c_continuous.py:401) */
+    float weight_decay;      /* 0 */
+    int32_t adaptive_lr;     /* 1: lr_schedule adaptive ("legacy": after every minibatch, a2c_continuous.py:112-118) */
+    int32_t _pad;
+} AgxPpoHyper;
+
+#define AGX_PPO_STATS 8  /* a_loss, c_loss, entropy, b_loss, kl, (3 spare) — means over the minibatch */
+
+/* GAE + returns over env-major rollout rows.  rewards/values/adv/returns [n,h] f32, dones [n,h] u8 = the done flag
+ * stored BEFORE each step (a2c_base.py:663), last_values [n], last_dones [n] u8 (flags after the last step). */
+int agx_gae(int64_t n, int h, float gamma, float tau, const float* rewards, const float* values,
+            const uint8_t* dones, const float* last_values, const uint8_t* last_dones, float* adv, float* returns,
+            void* stream);
+
+/* floats of scratch agx_ppo_loss needs (per-CTA partial sums + a ticket); the caller zero-fills it ONCE at allocation */
+int64_t agx_ppo_workspace_floats(void);
+
+/* One minibatch of calc_gradients, forward AND backward of everything after the network heads:
+ * in:  mu [b,a], logstd [a], value [b] (normalised), actions [b,a], old_neglogp [b], adv [b], returns [b] (normalised),
+ * i/o: old_mu/old_sigma [b,a] — read for the KL, then overwritten with the current mu/sigma
+ *      (PPODataset.update_mu_sigma, lib/core/datasets.py:20-24),
+ * out: grad_mu [b,a], grad_value [b] = d(mean loss)/d(.), grad_logstd [a], stats [AGX_PPO_STATS] (means).
+ * Deterministic: per-CTA partials are combined in a fixed order by the last CTA. */
+int agx_ppo_loss(const AgxPpoHyper* hp, int64_t b, int a, const float* mu, const float* logstd, const float* value,
+                 const float* actions, const float* old_neglogp, const float* adv, const float* returns,
+                 float* old_mu, float* old_sigma, float* grad_mu, float* grad_value, float* grad_logstd,
+                 float* stats, float* workspace, void* stream);
+
+/* Fused trancate_gradients_and_step (a2c_base.py:293-316) + adaptive LR (schedulers.py:19-32) on flat buffers:
+ * grads are scaled by grad_scale (1/world after an all-reduce SUM), clipped to hp->grad_norm (torch clip_grad_norm_),
+ * Adam-stepped with the learning rate held in lr_dev[0]; then lr_dev[0] is updated from kl_dev[0]*grad_scale for the
+ * NEXT minibatch.  step_dev[0] is Adam's step count.  One CTA; no host sync anywhere. */
+int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const float* grads, float* exp_avg,
+                  float* exp_avg_sq, float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale,
+                  float* grad_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,3 +76,38 @@ extern "C" int hostsim_philox_fill(float* out, int64_t n, int width, int stream_
     }
     return 0;
 }
+
+// ---- PPO math (agx_ppo_math.cuh) on the host ----------------------------------------------------------------------
+#include "agx_ppo_math.cuh"
+
+extern "C" int hostsim_gae(int64_t n, int h, float gamma, float tau, const float* rewards, const float* values,
+                           const uint8_t* dones, const float* last_values, const uint8_t* last_dones, float* adv, float* ret) {
+    for (int64_t e = 0; e < n; ++e)
+        gae_row(h, gamma, tau, rewards + e * h, values + e * h, dones + e * h, last_values[e], (float)last_dones[e],
+                adv + e * h, ret + e * h);
+    return 0;
+}
+
+extern "C" int hostsim_ppo_loss(const AgxPpoHyper* hp, int64_t b, int a, const float* mu, const float* logstd,
+                                const float* value, const float* actions, const float* old_neglogp, const float* adv,
+                                const float* returns, float* old_mu, float* old_sigma, float* grad_mu, float* grad_value,
+                                float* grad_logstd, float* stats) {
+    double acc[16] = {0};
+    for (int64_t s = 0; s < b; ++s) {
+        float m[kMaxAct] = {0}, ac[kMaxAct] = {0}, om[kMaxAct] = {0}, os[kMaxAct] = {1, 1, 1, 1, 1};
+        for (int i = 0; i < a; ++i) { m[i] = mu[s * a + i]; ac[i] = actions[s * a + i]; om[i] = old_mu[s * a + i]; os[i] = old_sigma[s * a + i]; }
+        PpoSampleOut o;
+        ppo_sample(*hp, a, m, logstd, value[s], ac, old_neglogp[s], adv[s], returns[s], om, os, o);
+        for (int i = 0; i < a; ++i) {
+            grad_mu[s * a + i] = o.g_mu[i] / (float)b;
+            old_mu[s * a + i] = m[i];
+            old_sigma[s * a + i] = expf(logstd[i]);
+            acc[5 + i] += o.g_logstd[i];
+        }
+        grad_value[s] = o.g_value / (float)b;
+        acc[0] += o.a_loss; acc[1] += o.c_loss; acc[2] += o.entropy; acc[3] += o.b_loss; acc[4] += o.kl;
+    }
+    for (int i = 0; i < 5; ++i) stats[i] = (float)(acc[i] / (double)b);
+    for (int i = 0; i < a; ++i) grad_logstd[i] = (float)(acc[5 + i] / (double)b) - hp->entropy_coef;
+    return 0;
+}

@@ -20,9 +20,15 @@ def load_golden(name):
     return g, task, mode, N, T, A, max_len
 
 
+def _np(x):
+    if hasattr(x, "detach"):
+        x = x.detach().cpu()
+    return np.asarray(x, dtype=np.float64)
+
+
 def assert_close(got, ref, what, rtol=RTOL, atol=ATOL):
-    got = np.asarray(got, dtype=np.float64)
-    ref = np.asarray(ref, dtype=np.float64)
+    got = _np(got)
+    ref = _np(ref)
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
     nan_g, nan_r = np.isnan(got), np.isnan(ref)
     assert (nan_g == nan_r).all(), f"{what}: NaN pattern differs at {np.argwhere(nan_g != nan_r)[:5]}"
