@@ -1,0 +1,448 @@
+"""A2CAgent — PPO (continuous actions) with the reference's algorithm and entry points
+(lib/agent/a2c_continuous.py:37-476 on top of lib/agent/a2c_base.py:78-711), rebuilt around device-resident state:
+
+* rollout buffers are env-major [N, H, ...], so `swap_and_flatten01` (a2c_base.py:26-33) is a free view and minibatches are
+  the same contiguous env-major slices the reference's PPODataset cuts (lib/core/datasets.py:29-46);
+* GAE, the whole loss forward+backward after the network heads, and grad-scale + clip_grad_norm_ + Adam + the adaptive-KL
+  learning-rate rule are single kernels in libagx.so (agx_gae / agx_ppo_loss / agx_adam_step); the learning rate and
+  Adam's step counter live on the device, so there is no `.item()` between minibatches and both the rollout (H env steps +
+  policy inference) and the update pass replay from CUDA graphs;
+* multi-GPU: envs sharded by rank, one NCCL all-reduce per minibatch over [flat grads ‖ loss stats incl. KL], global advantage
+  moments and input/value normalisation moments all-reduced so replicas stay identical.
+"""
+import ctypes as C
+import os
+import time
+from datetime import datetime
+
+import torch
+import torch.distributed as dist
+
+from ... import _capi
+from ..model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+from ..utils import vecenv
+
+
+def rescale_actions(low, high, action):
+    d = (high - low) / 2.0
+    m = (high + low) / 2.0
+    return action * d + m
+
+
+class A2CAgent:
+    def __init__(self, base_name, params):
+        self.name = base_name
+        self.network_config = params["network"]
+        self.config = config = params["config"]
+        self.experiment_name = config.get("full_experiment_name") or config["name"] + datetime.now().strftime("_%d-%H-%M-%S")
+        self.multi_gpu = config.get("multi_gpu", False)
+        self.local_rank = self.global_rank = 0
+        self.world_size = 1
+        if self.multi_gpu:
+            self.local_rank = int(os.getenv("LOCAL_RANK", "0"))
+            self.global_rank = int(os.getenv("RANK", "0"))
+            self.world_size = int(os.getenv("WORLD_SIZE", "1"))
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", rank=self.global_rank, world_size=self.world_size,
+                                        device_id=torch.device(f"cuda:{self.local_rank}"))
+            config["device"] = f"cuda:{self.local_rank}"
+            if self.global_rank != 0:
+                config["print_stats"] = False
+        self.ppo_device = config.get("device", "cuda:0")
+        torch.cuda.set_device(self.ppo_device)
+        self.env_config = dict(config.get("env_config", {}))
+        self.env_config.setdefault("sim_device", self.ppo_device)
+        self.num_actors = config["num_actors"]
+        self.env_name = config["env_name"]
+        self.vec_env = vecenv.create_vec_env(self.env_name, self.num_actors, **self.env_config)
+        self.env = self.vec_env.env
+        if self.multi_gpu:  # shard the global env axis: partition-invariant Philox streams
+            self.env.set_seed(self.env.rng_seed, env_offset=self.global_rank * self.num_actors)
+        self.env_info = self.vec_env.get_env_info()
+        self.value_size = 1
+        self.obs_shape = self.env_info["observation_space"].shape
+        self.actions_num = self.env_info["action_space"].shape[0]
+        dev = self.ppo_device
+        self.actions_low = torch.from_numpy(self.env_info["action_space"].low.copy()).float().to(dev)
+        self.actions_high = torch.from_numpy(self.env_info["action_space"].high.copy()).float().to(dev)
+        self.clip_actions = config.get("clip_actions", True)
+
+        self.save_freq = config.get("save_frequency", 0)
+        self.save_best_after = config.get("save_best_after", 100)
+        self.print_stats = config.get("print_stats", True)
+        self.max_epochs = config.get("max_epochs", -1)
+        self.max_frames = config.get("max_frames", -1)
+        self.is_adaptive_lr = config.get("lr_schedule") == "adaptive"
+        self.kl_threshold = config.get("kl_threshold", 0.008)
+        self.e_clip = config["e_clip"]
+        if config.get("clip_value", False):
+            raise NotImplementedError("clip_value: True is not used by the shipped yamls")
+        self.rewards_shaper = config["reward_shaper"]
+        self.horizon_length = config["horizon_length"]
+        self.normalize_advantage = config["normalize_advantage"]
+        self.normalize_input = config["normalize_input"]
+        self.normalize_value = config.get("normalize_value", False)
+        self.truncate_grads = config.get("truncate_grads", False)
+        self.critic_coef = config["critic_coef"]
+        self.grad_norm = config["grad_norm"]
+        self.gamma, self.tau = config["gamma"], config["tau"]
+        self.entropy_coef = config["entropy_coef"]
+        self.bounds_loss_coef = config.get("bounds_loss_coef", None)
+        self.value_bootstrap = config.get("value_bootstrap")
+        self.batch_size = self.horizon_length * self.num_actors
+        self.batch_size_envs = self.batch_size
+        self.minibatch_size = config.get("minibatch_size", self.num_actors * config.get("minibatch_size_per_env", 0))
+        assert self.minibatch_size > 0 and self.batch_size % self.minibatch_size == 0, "batch_size % minibatch_size != 0"
+        self.num_minibatches = self.batch_size // self.minibatch_size
+        self.mini_epochs_num = config["mini_epochs"]
+        self.last_lr = float(config["learning_rate"])
+        self.frame = 0
+        self.epoch_num = 0
+        self.curr_frames = 0
+        self.mean_rewards = self.last_mean_rewards = -1000000000
+        self.train_dir = config.get("train_dir", "runs")
+        self.experiment_dir = os.path.join(self.train_dir, self.experiment_name)
+        self.nn_dir = os.path.join(self.experiment_dir, "nn")
+        if self.global_rank == 0:
+            os.makedirs(self.nn_dir, exist_ok=True)
+        self.use_cuda_graph = config.get("use_cuda_graph", True)
+        self.algo_observer = config.get("features", {}).get("observer", None)
+
+        keys = {"actions_num": self.actions_num, "input_shape": self.obs_shape, "num_seqs": self.num_actors,
+                "value_size": 1, "normalize_value": self.normalize_value, "normalize_input": self.normalize_input}
+        self.model = ModelA2CContinuousLogStd(params, keys).to(dev)
+        self.flat_params, self.flat_grads = self.model.flatten_parameters(extra_grad_slots=_capi.AGX_PPO_STATS)
+        self.n_params = self.model.num_flat
+        self.stats = self.flat_grads[self.n_params:]  # loss statistics ride behind the grads through the all-reduce
+        self.exp_avg = torch.zeros(self.n_params, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_params, device=dev)
+        self.lr_dev = torch.full((1,), self.last_lr, device=dev, dtype=torch.float32)
+        self.opt_step = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.grad_norm_dev = torch.zeros(1, device=dev)
+        self._lib = _capi.load()
+        self.workspace = torch.zeros(int(self._lib.agx_ppo_workspace_floats()), device=dev)
+        hp = _capi.AgxPpoHyper()
+        hp.e_clip, hp.critic_coef, hp.entropy_coef = self.e_clip, self.critic_coef, self.entropy_coef
+        hp.bounds_loss_coef = self.bounds_loss_coef if self.bounds_loss_coef is not None else 0.0
+        hp.kl_threshold = self.kl_threshold
+        hp.grad_norm = self.grad_norm if self.truncate_grads else 0.0
+        hp.beta1, hp.beta2, hp.eps, hp.weight_decay = 0.9, 0.999, 1e-8, config.get("weight_decay", 0.0)
+        hp.adaptive_lr = 1 if self.is_adaptive_lr else 0
+        self.hyper = hp
+        if self.normalize_value:
+            self.value_mean_std = self.model.value_mean_std
+        self._graphs = {}
+        self.init_tensors()
+
+    # ---- buffers --------------------------------------------------------------------------------------------------------
+    def init_tensors(self):
+        N, H, A, dev = self.num_actors, self.horizon_length, self.actions_num, self.ppo_device
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        self.buf = {"obses": f(N, H, *self.obs_shape), "actions": f(N, H, A), "mus": f(N, H, A), "sigmas": f(N, H, A),
+                    "neglogpacs": f(N, H), "values": f(N, H), "rewards": f(N, H),
+                    "dones": torch.zeros(N, H, device=dev, dtype=torch.uint8)}
+        self.advs, self.returns = f(N, H), f(N, H)
+        self.dones = torch.ones(N, device=dev, dtype=torch.uint8)  # a2c_base.py:406
+        self.last_values = f(N)
+        self.obs = torch.zeros(N, *self.obs_shape, device=dev)
+        self.env_actions = f(N, A)
+        self.current_rewards, self.current_shaped_rewards, self.current_lengths = f(N), f(N), f(N)
+        self.ep_stats = torch.zeros(4, device=dev, dtype=torch.float64)  # Σreward, Σshaped, Σlength, #episodes (per epoch)
+        self.grad_mu, self.grad_value, self.grad_logstd = f(self.minibatch_size, A), f(self.minibatch_size), f(A)
+        self.norm_values, self.norm_returns, self.advantages = f(N * H, 1), f(N * H, 1), f(N * H)
+        self.epoch_loss_sums = torch.zeros(_capi.AGX_PPO_STATS, device=dev)
+
+    # ---- env interaction ----------------------------------------------------------------------------------------------
+    def preprocess_actions(self, actions):
+        if self.clip_actions:
+            return rescale_actions(self.actions_low, self.actions_high, torch.clamp(actions, -1.0, 1.0))
+        return actions
+
+    def env_reset(self):
+        self.obs.copy_(self.vec_env.reset())
+        return self.obs
+
+    def _rollout_step(self, n):
+        b = self.buf
+        self.model.eval()
+        res = self.model({"is_train": False, "prev_actions": None, "obs": self.obs})
+        b["obses"][:, n] = self.obs
+        b["dones"][:, n] = self.dones
+        b["actions"][:, n] = res["actions"]
+        b["neglogpacs"][:, n] = res["neglogpacs"]
+        b["values"][:, n] = res["values"].squeeze(-1)
+        b["mus"][:, n] = res["mus"]
+        b["sigmas"][:, n] = res["sigmas"]
+        self.env_actions.copy_(self.preprocess_actions(res["actions"]))
+        obs, rewards, dones, infos = self.vec_env.step(self.env_actions)
+        shaped = self.rewards_shaper(rewards)
+        if self.value_bootstrap and "time_outs" in infos:
+            shaped = shaped + self.gamma * res["values"].squeeze(-1) * infos["time_outs"].float()
+        b["rewards"][:, n] = shaped
+        self.obs.copy_(obs)
+        self.dones.copy_(dones)
+        # episode statistics, on device (the reference keeps a 100-game window on the host, a2c_base.py:680-695)
+        self.current_rewards += rewards
+        self.current_shaped_rewards += shaped
+        self.current_lengths += 1
+        d = self.dones.float()
+        self.ep_stats[0] += (self.current_rewards * d).sum()
+        self.ep_stats[1] += (self.current_shaped_rewards * d).sum()
+        self.ep_stats[2] += (self.current_lengths * d).sum()
+        self.ep_stats[3] += d.sum()
+        nd = 1.0 - d
+        self.current_rewards *= nd
+        self.current_shaped_rewards *= nd
+        self.current_lengths *= nd
+
+    def _rollout(self):
+        for n in range(self.horizon_length):
+            self._rollout_step(n)
+        self.model.eval()
+        _, value = self.model.heads(self.obs)
+        self.last_values.copy_(self.model.denorm_value(value).squeeze(-1))
+        b = self.buf
+        st = torch.cuda.current_stream().cuda_stream
+        _capi.check(self._lib.agx_gae(self.num_actors, self.horizon_length, self.gamma, self.tau, b["rewards"].data_ptr(),
+                                      b["values"].data_ptr(), b["dones"].data_ptr(), self.last_values.data_ptr(),
+                                      self.dones.data_ptr(), self.advs.data_ptr(), self.returns.data_ptr(), C.c_void_p(st)), "agx_gae")
+
+    def play_steps(self):
+        """a2c_base.py:651-711: H policy+env steps, bootstrap value, GAE — one CUDA-graph replay."""
+        with torch.no_grad():
+            self._run_graphed("rollout", self._rollout)
+
+    # ---- dataset ----------------------------------------------------------------------------------------------------------
+    def _allreduce(self, t):
+        if self.multi_gpu and self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def _rms_update(self, rms, x):
+        """RunningMeanStd train-mode update; with >1 rank the batch moments are merged across ranks first so that
+        replicas keep identical statistics (the reference keeps per-rank statistics)."""
+        x64 = x.double()
+        n = x.shape[0]
+        if self.multi_gpu and self.world_size > 1:
+            s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
+            self._allreduce(s)
+            k = x.shape[1]
+            n = n * self.world_size
+            mean = s[:k] / n
+            var = (s[k:] - n * mean * mean) / (n - 1)
+        else:
+            var, mean = torch.var_mean(x64, dim=0)
+        rms.update_from_moments(mean, var, n)
+
+    def _prepare_dataset(self):
+        """a2c_continuous.py:140-177"""
+        values, returns = self.buf["values"].view(-1, 1), self.returns.view(-1, 1)
+        adv = (returns - values).sum(dim=1)
+        if self.normalize_value:
+            vms = self.value_mean_std
+            vms.eval()
+            self._rms_update(vms, values)
+            self.norm_values.copy_(vms(values))
+            self._rms_update(vms, returns)
+            self.norm_returns.copy_(vms(returns))
+        else:
+            self.norm_values.copy_(values)
+            self.norm_returns.copy_(returns)
+        if self.normalize_advantage:
+            if self.multi_gpu and self.world_size > 1:  # global moments (north_star: all-reduce of Σadv, Σadv², n)
+                a64 = adv.double()
+                s = torch.stack((a64.sum(), (a64 * a64).sum()))
+                self._allreduce(s)
+                n = adv.numel() * self.world_size
+                mean = s[0] / n
+                std = torch.sqrt((s[1] - n * mean * mean) / (n - 1))
+                adv = ((adv - mean.float()) / (std.float() + 1e-8))
+            else:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        self.advantages.copy_(adv)
+
+    def prepare_dataset(self):
+        with torch.no_grad():
+            self._run_graphed("dataset", self._prepare_dataset)
+
+    # ---- update ---------------------------------------------------------------------------------------------------------
+    def _minibatch(self, i, update_rms):
+        """calc_gradients (a2c_continuous.py:299-369) + trancate_gradients_and_step (a2c_base.py:293-316) + LR rule."""
+        mb, A = self.minibatch_size, self.actions_num
+        sl = slice(i * mb, (i + 1) * mb)
+        b = self.buf
+        obs = b["obses"].view(-1, *self.obs_shape)[sl]
+        if self.normalize_input and update_rms:
+            with torch.no_grad():
+                self._rms_update(self.model.running_mean_std, obs)
+        self.model.eval()  # statistics are updated explicitly above; forward only normalises
+        mu, value = self.model.heads(obs)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: t.data_ptr()
+        _capi.check(self._lib.agx_ppo_loss(
+            C.byref(self.hyper), mb, A, p(mu), p(self.model.logstd), p(value), p(b["actions"].view(-1, A)[sl]),
+            p(b["neglogpacs"].view(-1)[sl]), p(self.advantages[sl]), p(self.norm_returns[sl]), p(b["mus"].view(-1, A)[sl]),
+            p(b["sigmas"].view(-1, A)[sl]), p(self.grad_mu), p(self.grad_value), p(self.grad_logstd), p(self.stats),
+            p(self.workspace), st), "agx_ppo_loss")
+        self.flat_grads[: self.n_params].zero_()
+        torch.autograd.backward((mu, value), (self.grad_mu, self.grad_value.view(-1, 1)))
+        self.model.logstd.grad += self.grad_logstd
+        scale = 1.0
+        if self.multi_gpu and self.world_size > 1:
+            self._allreduce(self.flat_grads)  # grads ‖ stats (KL) in one message
+            scale = 1.0 / self.world_size
+        self.epoch_loss_sums += self.stats * scale
+        _capi.check(self._lib.agx_adam_step(
+            C.byref(self.hyper), self.n_params, p(self.flat_params), p(self.flat_grads), p(self.exp_avg), p(self.exp_avg_sq),
+            p(self.lr_dev), p(self.opt_step), p(self.stats[4:5]), scale, p(self.grad_norm_dev), st), "agx_adam_step")
+
+    def _update_pass(self, update_rms):
+        for i in range(self.num_minibatches):
+            self._minibatch(i, update_rms)
+
+    def _run_graphed(self, key, fn, *args):
+        """Replay `fn` from a CUDA graph (captured on first use after one eager warm-up run)."""
+        if not self.use_cuda_graph:
+            return fn(*args)
+        g = self._graphs.get(key)
+        if g is None:  # first call: eager on a side stream (the warm-up cuBLAS / autograd need before capture)
+            self._graphs[key] = "warm"
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                out = fn(*args)
+            torch.cuda.current_stream().wait_stream(side)
+            return out
+        if g == "warm":
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                fn(*args)
+            self._graphs[key] = graph
+            graph.replay()
+            return None
+        g.replay()
+        return None
+
+    def train_epoch(self):
+        """a2c_continuous.py:78-138"""
+        t0 = time.time()
+        self.ep_stats.zero_()
+        self.play_steps()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        self.prepare_dataset()
+        self.epoch_loss_sums.zero_()
+        graph_update = self.use_cuda_graph and not (self.multi_gpu and self.world_size > 1)
+        for mini_ep in range(self.mini_epochs_num):
+            first = mini_ep == 0  # input statistics are only updated during the first mini-epoch (:130-131)
+            if graph_update:
+                self._run_graphed("update_rms" if first else "update", self._update_pass, first)
+            else:
+                self._update_pass(first)
+        torch.cuda.synchronize()
+        t2 = time.time()
+        self.last_lr = float(self.lr_dev.item())
+        return t1 - t0, t2 - t1, t2 - t0
+
+    # ---- driver -----------------------------------------------------------------------------------------------------------
+    def train(self):
+        """a2c_continuous.py:179-294"""
+        self.env_reset()
+        if self.multi_gpu and self.world_size > 1:
+            dist.broadcast(self.flat_params, 0)  # flat-tensor broadcast instead of a pickled state_dict (:188-192)
+            for rms in (getattr(self.model, "running_mean_std", None), getattr(self.model, "value_mean_std", None)):
+                if rms is not None:
+                    for t in (rms.running_mean, rms.running_var, rms.count):
+                        dist.broadcast(t, 0)
+        total_time = 0.0
+        self.history = []
+        while True:
+            self.epoch_num += 1
+            play_time, update_time, sum_time = self.train_epoch()
+            total_time += sum_time
+            curr_frames = self.batch_size * self.world_size
+            self.frame += curr_frames
+            ep = self.ep_stats.clone()
+            if self.multi_gpu and self.world_size > 1:
+                self._allreduce(ep)
+            ep = ep.tolist()
+            n_mb = self.num_minibatches * self.mini_epochs_num
+            losses = (self.epoch_loss_sums / n_mb).tolist()
+            if ep[3] > 0:
+                self.mean_rewards = ep[0] / ep[3]
+            rec = {"epoch": self.epoch_num, "frame": self.frame, "fps_step_inference": curr_frames / play_time,
+                   "fps_total": curr_frames / sum_time, "play_time": play_time, "update_time": update_time,
+                   "mean_reward": self.mean_rewards if ep[3] > 0 else None, "mean_length": ep[2] / ep[3] if ep[3] > 0 else None,
+                   "episodes": ep[3], "a_loss": losses[0], "c_loss": losses[1], "entropy": losses[2], "b_loss": losses[3],
+                   "kl": losses[4], "lr": self.last_lr}
+            self.history.append(rec)
+            should_exit = False
+            if self.global_rank == 0:
+                if self.print_stats:
+                    print(f"fps step and policy inference: {rec['fps_step_inference']:.0f} fps total: {rec['fps_total']:.0f} "
+                          f"epoch: {self.epoch_num}/{self.max_epochs} frames: {self.frame} reward: {rec['mean_reward']} "
+                          f"kl: {rec['kl']:.5f} lr: {self.last_lr:.2e}", flush=True)
+                if ep[3] > 0:
+                    name = self.config["name"] + "_ep_" + str(self.epoch_num) + "_rew_" + str(self.mean_rewards)
+                    if self.save_freq > 0 and self.epoch_num % self.save_freq == 0:
+                        self.save(os.path.join(self.nn_dir, "last_" + name))
+                    if self.mean_rewards > self.last_mean_rewards and self.epoch_num >= self.save_best_after:
+                        self.last_mean_rewards = self.mean_rewards
+                        self.save(os.path.join(self.nn_dir, self.config["name"]))
+                        if self.last_mean_rewards > self.config.get("score_to_win", float("inf")):
+                            should_exit = True
+                if self.max_epochs != -1 and self.epoch_num >= self.max_epochs:
+                    self.save(os.path.join(self.nn_dir, "last_" + self.config["name"] + "_ep_" + str(self.epoch_num)))
+                    should_exit = True
+                if self.max_frames != -1 and self.frame >= self.max_frames:
+                    should_exit = True
+            if self.multi_gpu and self.world_size > 1:
+                flag = torch.tensor([float(should_exit)], device=self.ppo_device)
+                dist.broadcast(flag, 0)
+                should_exit = bool(flag.item())
+            if should_exit:
+                return self.last_mean_rewards, self.epoch_num
+
+    # ---- checkpoints: reference key layout (a2c_base.py:528-577, torch_ext.py:74-84) ------------------------------------------
+    def get_full_state_weights(self):
+        names = [n for n, _ in self.model.named_parameters()]
+        state, off = {}, 0
+        for idx, (n, prm) in enumerate(self.model.named_parameters()):
+            k = prm.numel()
+            state[idx] = {"step": self.opt_step.clone().float().squeeze(), "exp_avg": self.exp_avg[off:off + k].view_as(prm).clone(),
+                          "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(prm).clone()}
+            off += k
+        groups = [{"lr": self.last_lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": self.hyper.weight_decay,
+                   "amsgrad": False, "params": list(range(len(names)))}]
+        return {"model": {k: v.clone() for k, v in self.model.state_dict().items()}, "epoch": self.epoch_num, "frame": self.frame,
+                "optimizer": {"state": state, "param_groups": groups}, "last_mean_rewards": self.last_mean_rewards, "env_state": None}
+
+    def set_full_state_weights(self, weights, set_epoch=True):
+        sd = weights["model"]
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(sd[k])  # in place: parameters stay views of the flat buffer
+        if set_epoch:
+            self.epoch_num, self.frame = weights["epoch"], weights["frame"]
+        opt = weights.get("optimizer")
+        if opt and opt.get("state"):
+            off = 0
+            for idx, (_, prm) in enumerate(self.model.named_parameters()):
+                k = prm.numel()
+                s = opt["state"].get(idx)
+                if s is not None:
+                    self.exp_avg[off:off + k].copy_(s["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + k].copy_(s["exp_avg_sq"].reshape(-1))
+                    self.opt_step.fill_(int(s["step"]))
+                off += k
+            self.last_lr = float(opt["param_groups"][0]["lr"])
+            self.lr_dev.fill_(self.last_lr)
+        self.last_mean_rewards = weights.get("last_mean_rewards", -1000000000)
+
+    def save(self, fn):
+        torch.save(self.get_full_state_weights(), fn + ".pth")
+        return fn + ".pth"
+
+    def restore(self, fn, set_epoch=True):
+        self.set_full_state_weights(torch.load(fn, map_location=self.ppo_device, weights_only=False), set_epoch)

@@ -69,6 +69,9 @@ def build_parser():
     p.add_argument("--horovod", action="store_true", default=False)
     p.add_argument("--rl_device", type=str, default="cuda:0")
     p.add_argument("--ctl_mode", required=True, type=str, help="pos, vel, atti, rate, prop")
+    # additions of this backend (not in the reference)
+    p.add_argument("--config", type=str, default=None, help="PPO yaml, e.g. the reference's scripts/config/ppo_hovering.yaml")
+    p.add_argument("--max_epochs", type=int, default=None)
     return p
 
 

@@ -1,0 +1,197 @@
+"""GPU tests of the PPO row (a13): the three update kernels through the C ABI against the oracle (which is pinned to the
+reference's lib/ code by tests/golden/ppo_hovering.npz), and the trainer end to end."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from airgym_b200 import _capi
+from oracle import ppo as O
+from tests.util import GOLDEN_DIR, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _hyper(entropy_coef=0.0):
+    hp = _capi.AgxPpoHyper()
+    hp.e_clip, hp.critic_coef, hp.entropy_coef, hp.bounds_loss_coef = 0.2, 2.0, entropy_coef, 1e-4
+    hp.kl_threshold, hp.grad_norm, hp.beta1, hp.beta2, hp.eps, hp.weight_decay, hp.adaptive_lr = 0.008, 1.5, 0.9, 0.999, 1e-8, 0.0, 1
+    return hp
+
+
+@pytest.mark.parametrize("N,H", [(1000, 24), (65536, 24), (300, 64)])
+def test_gae_kernel_vs_oracle(built, N, H):
+    lib = _capi.load()
+    torch.manual_seed(0)
+    rewards, values = torch.rand(N, H), torch.randn(N, H)
+    dones = (torch.rand(N, H) < 0.1).to(torch.uint8)
+    last_v, last_d = torch.randn(N), (torch.rand(N) < 0.3).to(torch.uint8)
+    d = lambda t: t.cuda()
+    r, v, dn, lv, ld = d(rewards), d(values), d(dones), d(last_v), d(last_d)
+    adv, ret = torch.zeros(N, H, device="cuda"), torch.zeros(N, H, device="cuda")
+    _capi.check(lib.agx_gae(N, H, 0.99, 0.95, r.data_ptr(), v.data_ptr(), dn.data_ptr(), lv.data_ptr(), ld.data_ptr(),
+                            adv.data_ptr(), ret.data_ptr(), None))
+    tm = lambda x: x.t().unsqueeze(-1)
+    ref = O.discount_values(last_d.float(), last_v.unsqueeze(1), dones.t().float(), tm(values), tm(rewards), 0.99, 0.95)
+    assert_close(adv.cpu(), ref.squeeze(-1).t(), "gae", rtol=1e-5, atol=1e-6)
+    assert_close(ret.cpu(), (ref + tm(values)).squeeze(-1).t(), "returns", rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("A,B", [(4, 300), (5, 4096), (4, 200000)])
+def test_ppo_loss_kernel_vs_autograd(built, A, B):
+    lib = _capi.load()
+    torch.manual_seed(1)
+    mu = (torch.randn(B, A) * 0.8).requires_grad_(True)
+    mu.data[:20] *= 2.0
+    logstd = (torch.randn(A) * 0.3).requires_grad_(True)
+    value = torch.randn(B, 1, requires_grad=True)
+    actions = mu.detach() + torch.randn(B, A) * 0.7
+    old_mu, old_sigma = mu.detach() + 0.05 * torch.randn(B, A), torch.exp(logstd.detach() + 0.05 * torch.randn(B, A))
+    old_nlp = O.neglogp(actions, old_mu, old_sigma, torch.log(old_sigma)) + 0.3 * torch.randn(B)
+    adv, ret = torch.randn(B), torch.randn(B, 1)
+    hp = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.01, bounds_loss_coef=1e-4)
+    ls_b = mu * 0.0 + logstd
+    loss, terms = O.total_loss(mu, ls_b, torch.exp(ls_b), value, {"actions": actions, "old_logp_actions": old_nlp, "advantages": adv,
+                                                                  "returns": ret, "mu": old_mu, "sigma": old_sigma}, hp)
+    loss.backward()
+    d = lambda t: t.detach().cuda().contiguous()
+    g_mu, g_val, g_ls = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda"), torch.zeros(A, device="cuda")
+    stats = torch.zeros(8, device="cuda")
+    ws = torch.zeros(int(lib.agx_ppo_workspace_floats()), device="cuda")
+    om, os_ = d(old_mu), d(old_sigma)
+    ins = [d(mu), d(logstd), d(value.reshape(-1)), d(actions), d(old_nlp), d(adv), d(ret.reshape(-1))]
+    H = _hyper(0.01)
+    for rep in range(2):  # second call: the ticket in the workspace must have been re-armed; write-back makes KL ~ 0
+        _capi.check(lib.agx_ppo_loss(C.byref(H), B, A, *[t.data_ptr() for t in ins], om.data_ptr(), os_.data_ptr(), g_mu.data_ptr(),
+                                     g_val.data_ptr(), g_ls.data_ptr(), stats.data_ptr(), ws.data_ptr(), None))
+        torch.cuda.synchronize()
+        if rep == 0:
+            for j, k in enumerate(("a_loss", "c_loss", "entropy", "b_loss", "kl")):
+                assert_close(stats[j].cpu(), terms[k].detach(), k, rtol=2e-5, atol=1e-7)
+            assert_close(g_mu.cpu(), mu.grad, "grad mu", rtol=1e-4, atol=1e-9)
+            assert_close(g_val.cpu(), value.grad.reshape(-1), "grad value", rtol=1e-5, atol=1e-10)
+            assert_close(g_ls.cpu(), logstd.grad, "grad logstd", rtol=2e-4, atol=1e-7)
+            assert_close(om.cpu(), mu.detach(), "mu write-back", rtol=0, atol=0)
+        else:
+            assert abs(float(stats[4])) < 1e-4
+
+
+def test_adam_kernel_matches_torch_adam_and_lr_rule(built):
+    lib = _capi.load()
+    torch.manual_seed(2)
+    n = 18121
+    p0 = torch.randn(n)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], 3e-4, eps=1e-8)
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr_dev = torch.tensor([3e-4], device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    norm = torch.zeros(1, device="cuda")
+    H = _hyper()
+    lr = 3e-4
+    for it, kl in enumerate((0.001, 0.03, 0.006, 0.0001)):
+        g = torch.randn(n) * (3.0 if it % 2 == 0 else 0.001)  # alternate clipped / unclipped
+        ref_p.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref_p], 1.5)
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        opt.step()
+        kl_dev = torch.tensor([kl * 2.0], device="cuda")  # grad_scale 0.5 halves both grads and KL (2-rank all-reduce SUM)
+        _capi.check(lib.agx_adam_step(C.byref(H), n, p.data_ptr(), (g * 2.0).cuda().data_ptr(), m.data_ptr(), v.data_ptr(), lr_dev.data_ptr(),
+                                      step.data_ptr(), kl_dev.data_ptr(), 0.5, norm.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert_close(norm.cpu()[0], total, "grad norm", rtol=1e-5, atol=0)
+        assert_close(p.cpu(), ref_p.detach(), f"params after step {it}", rtol=2e-5, atol=2e-7)
+        lr = O.adaptive_lr(lr, kl)
+        assert float(lr_dev) == pytest.approx(lr, rel=1e-6)
+        assert int(step) == it + 1
+
+
+def test_minibatch_update_matches_reference_golden(built):
+    """The recorded reference minibatch (reference model + losses + clip + Adam + scheduler) through the product model
+    and the kernels: parameters after the step and the next learning rate must match."""
+    from airgym_b200.lib.config import default_ppo_config
+    from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "ppo_hovering.npz")))
+    lib = _capi.load()
+    N, Hn, A, OBS = int(g["N"]), int(g["H"]), int(g["A"]), int(g["OBS"])
+    cfg = default_ppo_config("hovering")["params"]
+    model = ModelA2CContinuousLogStd(cfg, {"actions_num": A, "input_shape": (OBS,)}).cuda()
+    sd = {k[len("step0/sd_before/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("step0/sd_before/")}
+    assert set(sd) == set(model.state_dict()), "state_dict key layout must equal the reference's"
+    model.load_state_dict(sd)
+    flat, grads = model.flatten_parameters(extra_grad_slots=8)
+    names = [n for n, _ in model.named_parameters()]
+    assert names == [str(x) for x in g["param_names"]]
+    fl = O.swap_and_flatten01
+    t = lambda k: torch.from_numpy(g[k])
+    B = N * Hn
+    mb = B // 2
+    sl = slice(0, mb)
+    obs = fl(t("obs"))[sl].cuda()
+    model.running_mean_std.train()
+    model.running_mean_std(obs)  # train-mode statistics update, then eval forward
+    model.eval()
+    mu, value = model.heads(obs)
+    assert_close(mu.detach().cpu(), g["step0/mu"], "mu", rtol=1e-4, atol=1e-5)
+    assert_close(value.detach().cpu(), g["step0/value"], "value", rtol=1e-4, atol=1e-5)
+    d = lambda x: x.cuda().contiguous()
+    om, os_ = d(fl(t("mus"))[sl]), d(fl(t("sigmas"))[sl])
+    g_mu, g_val, g_ls = torch.zeros(mb, A, device="cuda"), torch.zeros(mb, device="cuda"), torch.zeros(A, device="cuda")
+    stats = grads[model.num_flat:]
+    ws = torch.zeros(int(lib.agx_ppo_workspace_floats()), device="cuda")
+    Hh = _hyper()
+    ins = [mu, model.logstd, value, d(fl(t("actions"))[sl]), d(fl(t("neglogpacs"))[sl]), d(t("advantages")[sl]), d(t("n_ret")[sl].reshape(-1))]
+    _capi.check(lib.agx_ppo_loss(C.byref(Hh), mb, A, *[x.data_ptr() for x in ins], om.data_ptr(), os_.data_ptr(), g_mu.data_ptr(),
+                                 g_val.data_ptr(), g_ls.data_ptr(), stats.data_ptr(), ws.data_ptr(), None))
+    for j, k in enumerate(("a_loss", "c_loss", "entropy", "b_loss", "kl")):
+        assert_close(stats[j].cpu(), g[f"step0/{k}"], k, rtol=1e-4, atol=1e-7)
+    grads[: model.num_flat].zero_()
+    torch.autograd.backward((mu, value), (g_mu, g_val.view(-1, 1)))
+    model.logstd.grad += g_ls
+    for n, p in model.named_parameters():
+        assert_close(p.grad.cpu(), g[f"step0/grads/{n}"], f"grad {n}", rtol=1e-3, atol=1e-7)
+    m, v = torch.zeros(model.num_flat, device="cuda"), torch.zeros(model.num_flat, device="cuda")
+    lr_dev, step, norm = torch.tensor([float(g["step0/lr_in"])], device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, device="cuda")
+    _capi.check(lib.agx_adam_step(C.byref(Hh), model.num_flat, flat.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), lr_dev.data_ptr(),
+                                  step.data_ptr(), stats[4:5].data_ptr(), 1.0, norm.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert_close(norm.cpu()[0], g["step0/total_norm"], "grad norm", rtol=1e-4, atol=0)
+    for n, p in model.named_parameters():
+        assert_close(p.detach().cpu(), g[f"step0/sd_after/{n}"], f"param {n} after the step", rtol=1e-4, atol=1e-6)
+    assert float(lr_dev) == pytest.approx(float(g["step0/lr_out"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph):
+    """A few PPO epochs on Hovering/CTBR through Runner: losses finite, KL-driven LR moves, reward improves, checkpoint
+    round-trips with the reference's key layout; CUDA-graph mode equals eager mode in distribution (same code path)."""
+    from airgym_b200.lib.config import default_ppo_config, scale_minibatch
+    from airgym_b200.lib.torch_runner import Runner
+
+    cfg = scale_minibatch(default_ppo_config("hovering"), 2048)
+    c = cfg["params"]["config"]
+    c.update(max_epochs=12, train_dir=str(tmp_path), use_cuda_graph=graph, print_stats=False, save_best_after=1)
+    c["env_config"].update(ctl_mode="rate", num_envs=2048, seed=3)
+    cfg["params"]["seed"] = 3
+    r = Runner()
+    r.load(cfg)
+    r.run({"train": True})
+    hist = r.agent.history
+    assert len(hist) == 12 and all(np.isfinite([h["a_loss"], h["c_loss"], h["kl"]]).all() for h in hist)
+    assert hist[-1]["frame"] == 12 * 2048 * 24
+    rewards = [h["mean_reward"] for h in hist if h["mean_reward"] is not None]
+    assert len(rewards) >= 2
+    assert hist[-1]["c_loss"] < hist[0]["c_loss"]  # the critic fits the normalised returns
+    ck = r.agent.save(os.path.join(str(tmp_path), "ck"))
+    w = torch.load(ck, map_location="cpu", weights_only=False)
+    assert set(w) == {"model", "epoch", "frame", "optimizer", "last_mean_rewards", "env_state"}
+    assert {"logstd", "actor_mlp.layers.0.weight", "mu.weight", "value_head.bias", "value_mean_std.running_mean",
+            "running_mean_std.count"} <= set(w["model"])
+    before = r.agent.flat_params.clone()
+    r.agent.flat_params.add_(1.0)
+    r.agent.restore(ck)
+    assert torch.equal(r.agent.flat_params, before)

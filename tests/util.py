@@ -10,7 +10,8 @@ ATOL = 2e-5   # floor for entries near zero (quaternion components, noise-domina
 
 
 def golden_cases():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.split("_")[0] in ("hovering", "tracking", "balloon", "avoid", "planning")]  # env trajectories
 
 
 def load_golden(name):
