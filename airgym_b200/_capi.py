@@ -16,7 +16,8 @@ AGX_NOISE_DRAWS = 18
 
 TASK_IDS = {"hovering": 0, "tracking": 1, "balloon": 2, "avoid": 3, "planning": 4}
 CTL_IDS = {"pos": 0, "vel": 1, "atti": 2, "rate": 3, "prop": 4}
-FLAG_MUTATE_ACTIONS, FLAG_CTRL_RESET, FLAG_NO_NOISE = 1, 2, 4
+FLAG_MUTATE_ACTIONS, FLAG_CTRL_RESET, FLAG_NO_NOISE, FLAG_RESET_ON_COLLISION = 1, 2, 4, 8
+AGX_AUX_MAX = 8
 INT_RK4, INT_EULER = 0, 1
 
 _f3 = C.c_float * 3
@@ -36,6 +37,7 @@ class AgxParams(C.Structure):
         ("vel_p", _f3), ("vel_i", _f3), ("vel_d", _f3), ("vel_int_lim", _f3), ("pos_p", _f3), ("vel_sp_lim", _f3),
         ("hover_thrust", C.c_float), ("tilt_max_tan", C.c_float), ("thr_min", C.c_float), ("thr_max", C.c_float),
         ("target", C.c_float * 18), ("target_yaw", C.c_float), ("noise_sigma", C.c_float * 4),
+        ("collision_radius", C.c_float), ("_pad1", C.c_float),
     ]
 
     def as_dict(self):

@@ -215,6 +215,31 @@ AGX_HD float urange(float u, float lo, float hi) { return (hi - lo) * u + lo; }
 
 // Hovering.reset_idx (hovering.py:310-335) / Tracking.reset_idx (tracking.py:159-192): 12 uniforms in
 // call order xy(2) z(1) roll,pitch(2) yaw(1) linvel(3) angvel(3); writes the 13-float root state.
+// Balloon.reset_idx (balloon.py:57-93): 15 uniforms — ball x,y,z (3) then drone xy(2) z(1) roll(1) pitch(1) yaw(1)
+// linvel(3) angvel(3).  aux = [ball xyz | previous drone xyz | collision flag | pad].
+AGX_HD void reset_sample_balloon(const float* u, float* s, float* aux) {
+    aux[0] = 0.5f * urange(u[0], -1.0f, 1.0f) + 2.5f;
+    aux[1] = 2.0f * urange(u[1], -1.0f, 1.0f) + 0.0f;
+    aux[2] = 0.3f * urange(u[2], -1.0f, 1.0f) + 1.0f;
+    s[0] = 0.1f * urange(u[3], -1.0f, 1.0f) + 0.0f;
+    s[1] = 0.1f * urange(u[4], -1.0f, 1.0f) + 0.0f;
+    s[2] = 0.2f * urange(u[5], -1.0f, 1.0f) + 1.0f;
+    const float a0 = 0.1f * urange(u[6], -kPi, kPi);
+    const float a1 = 0.1f * urange(u[7], 0.0f, kPi);
+    const float a2 = 0.2f * urange(u[8], -kPi, kPi);
+    float m[9];
+    euler_xyz_to_matrix(a0, a1, a2, m);
+    const Q4 q = matrix_to_quat(m);
+    s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+    s[7] = 0.5f * urange(u[9], -1.0f, 1.0f);
+    s[8] = 0.5f * urange(u[10], -1.0f, 1.0f);
+    s[9] = 0.5f * urange(u[11], -1.0f, 1.0f);
+    s[10] = 0.2f * urange(u[12], -1.0f, 1.0f);
+    s[11] = 0.2f * urange(u[13], -1.0f, 1.0f);
+    s[12] = 0.2f * urange(u[14], -1.0f, 1.0f);
+    aux[3] = 0.0f; aux[4] = 0.0f; aux[5] = 0.0f;  // pre_root_positions[env_ids] = 0 (balloon.py:90)
+}
+
 template <int TASK>
 AGX_HD void reset_sample(const float* u, float* s) {
     float a0, a1, a2;
@@ -488,13 +513,15 @@ struct EnvRegs {
     float rew;
     float cmd[4];
     float terms[9];
+    float aux[AGX_AUX_MAX];      // task state beyond the drone (balloon: ball xyz, previous drone xyz, collision flag)
 };
 
 template <int TASK>
 AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e) {
     float u[AGX_RESET_DRAWS_MAX];
     draw_reset(rnd, which, P.reset_draws, u);
-    reset_sample<TASK>(u, e.s);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+    if (TASK == AGX_TASK_BALLOON) reset_sample_balloon(u, e.s, e.aux);
+    else reset_sample<TASK>(u, e.s);  // root_states[ids] = initial (zeros + identity quat) then overwritten
     e.progress = 0;
 #pragma unroll
     for (int i = 0; i < AGX_MAX_ACTIONS; ++i) e.pa[i] = 0.0f;
@@ -539,11 +566,17 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, Env
     // -- pre_physics_step: resets pending from the previous step (hovering.py:209-211, quirk Q1)
     if (e.pending) do_reset<TASK>(P, rnd, 0, e);
 
-    // -- action shaping (hovering.py:212-216)
+    // -- action shaping (hovering.py:212-216).  Customized family (customized.py:226-232): the remap mutates
+    //    self.actions in place but the clamp result only feeds the controller, so reward / pre_actions / the
+    //    `actions` attribute see the remapped-but-UNCLAMPED values `ar`.
+    constexpr bool kCustom = (TASK == AGX_TASK_BALLOON || TASK == AGX_TASK_AVOID || TASK == AGX_TASK_PLANNING);
     if (kThrustMode) {
         e.a[A - 1] = 0.5f + 0.5f * e.a[A - 1];
         e.a_last_remap = e.a[A - 1];
     }
+    float ar[AGX_MAX_ACTIONS];
+#pragma unroll
+    for (int i = 0; i < AGX_MAX_ACTIONS; ++i) ar[i] = e.a[i];
 #pragma unroll
     for (int i = 0; i < A; ++i) {  // tensor_clamp = max(min(t, hi), lo)
         float t = e.a[i];
@@ -605,11 +638,61 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, Env
             obs[18 + 3 * k + 1] = r.y - p.y;
             obs[18 + 3 * k + 2] = r.z - p.z;
         }
+    } else if (TASK == AGX_TASK_BALLOON) {  // balloon.py:132-145: minus R(q_ball) (the ball keeps its identity quat), minus p_ball
+        const float ident[9] = {1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) obs[i] = o[i] - ident[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) obs[9 + i] = o[9 + i] - e.aux[i];
+#pragma unroll
+        for (int i = 12; i < 18; ++i) obs[i] = o[i];
     } else {
 #pragma unroll
         for (int i = 0; i < 18; ++i) obs[i] = o[i] - P.target[i];  // hovering.py:356
     }
 
+    int reset;
+    float reward;
+    Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
+    const float up_z = (2.0f * q.w * q.w - 1.0f) + q.z * q.z * 2.0f;  // quat_axis(q,2)[2] (hovering.py:464-481)
+    const float yaw = atan2f(-R[1], R[0]);  // pytorch3d matrix_to_euler_angles(.,'XYZ')[2] (quirk Q6)
+    if (TASK == AGX_TASK_BALLOON) {
+        // -- Balloon.compute_quadcopter_reward (balloon.py:159-225) on the remapped, unclamped actions
+        const V3 ball = v3(e.aux[0], e.aux[1], e.aux[2]);
+        const V3 rel = ball - p;
+        const float check = norm(rel);
+        const float nrm = check > 1e-12f ? check : 1e-12f;  // F.normalize eps
+        const float dir_yaw = atan2f(rel.y / nrm, rel.x / nrm);
+        const float yd_b = fabsf(yaw_diff(yaw, dir_yaw));
+        const float yaw_r = 1.0f / (1.0f + sq(1.6f * yd_b));
+        const V3 prev = v3(e.aux[3], e.aux[4], e.aux[5]);
+        const float guidance = 30.0f * (norm(ball - prev) - check);
+        const float ups_r = 0.5f * sq((up_z + 1.0f) / 2.0f);
+        const float hit_r = check < 0.1f ? 800.0f : 0.0f;
+        float sa = 0.0f, sd = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) { sa += ar[i] * ar[i]; sd += sq(ar[i] - e.pa[i]); }
+        const float effort_b = 0.1f * expf(-sa);
+        const float smooth = 0.1f * expf(-sqrtf(sd));
+        reward = guidance + yaw_r + hit_r + smooth + ups_r + effort_b;
+        reset = (e.progress >= (int64_t)(P.max_episode_length - 1)) ? 1 : 0;
+        if (ar[A - 1] < -1.0f) reset = 1;
+        if (ar[A - 1] > 1.0f) reset = 1;
+        if (rel.x < -0.2f) reset = 1;
+        if (v.x < 0.0f) reset = 1;
+        if (check > 4.0f) reset = 1;
+        if (p.z < 0.5f) reset = 1;
+        if (p.z > 1.5f) reset = 1;
+        if (check < 0.1f) reset = 1;
+        // check_collisions (customized.py:393-397) — builder-defined contact model: the drone's r = 0.2 collision sphere
+        // (model.urdf:13-18) against the ground plane; the ball shares the drone's collision mask and never collides.
+        const float collided = p.z < P.collision_radius ? 1.0f : 0.0f;
+        e.aux[6] = collided;
+        if ((P.flags & AGX_FLAG_RESET_ON_COLLISION) && collided > 0.0f) reset = 1;  // customized.py:328-330
+        e.aux[3] = p.x; e.aux[4] = p.y; e.aux[5] = p.z;  // pre_root_positions = root_positions.clone()
+        e.terms[0] = guidance; e.terms[1] = hit_r; e.terms[2] = smooth; e.terms[3] = effort_b; e.terms[4] = ups_r;
+        e.terms[5] = yaw_r; e.terms[6] = 0.0f; e.terms[7] = 0.0f;
+    } else {
     // -- compute_quadcopter_reward (hovering.py:371-459; tracking.py:223-296)
     const float c0 = clampf(e.cmd[0], 0.0f, 1.0f), c1 = clampf(e.cmd[1], 0.0f, 1.0f),
                 c2 = clampf(e.cmd[2], 0.0f, 1.0f), c3 = clampf(e.cmd[3], 0.0f, 1.0f);
@@ -633,14 +716,9 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, Env
             cont = 0.2f * expf(-sqrtf(ss)) + 0.5f / (1.0f + sq(3.0f * d[A - 1]));
         thrust_r = 0.1f * (1.0f - fabsf(0.1533f - e.a[A - 1]));
     }
-    const float yaw = atan2f(-R[1], R[0]);  // pytorch3d matrix_to_euler_angles(.,'XYZ')[2] (quirk Q6)
     const float yd = yaw_diff(P.target_yaw, yaw) / kPi;
     const float wz2 = w.z * w.z;
-    Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
-    const float up_z = (2.0f * q.w * q.w - 1.0f) + q.z * q.z * 2.0f;  // quat_axis(q,2)[2] (hovering.py:464-481)
     const float ups_r = sq((up_z + 1.0f) / 2.0f);
-    int reset;
-    float reward;
     if (TASK == AGX_TASK_TRACKING) {
         const V3 dd = ref0 - p;
         const float dist = norm(dd);
@@ -676,11 +754,16 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, Env
         e.terms[4] = veld; e.terms[5] = ups_r; e.terms[6] = spin_r; e.terms[7] = yaw_r;
     }
     if (MODE == AGX_CTL_ATTI && e.a[0] < 0.0f) reset = 1;  // hovering.py:442-444
+    }  // !balloon
     e.terms[8] = reward;
     e.rew = reward;
     e.reset = reset;
 
-    // -- pre_actions = actions.clone() (hovering.py:369)
+    // -- pre_actions = actions.clone() (hovering.py:369); `e.a` leaves as the env's `actions` attribute
+    if (kCustom) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) e.a[i] = ar[i];
+    }
 #pragma unroll
     for (int i = 0; i < A; ++i) e.pa[i] = e.a[i];
 

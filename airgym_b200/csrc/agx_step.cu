@@ -90,6 +90,8 @@ template <>
 struct TaskTraits<AGX_TASK_HOVERING> { static constexpr int kObs = 18; };
 template <>
 struct TaskTraits<AGX_TASK_TRACKING> { static constexpr int kObs = 48; };
+template <>
+struct TaskTraits<AGX_TASK_BALLOON> { static constexpr int kObs = 18; };
 
 // ---- the fused step kernel ----------------------------------------------------------------------------
 template <int TASK, int MODE, int BLOCK>
@@ -147,6 +149,11 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
         e.progress = io.progress[env];
         e.pending = io.reset[env] != 0;
+        if (TASK == AGX_TASK_BALLOON) {
+            const float4 x0 = reinterpret_cast<const float4*>(io.aux)[env * 2], x1 = reinterpret_cast<const float4*>(io.aux)[env * 2 + 1];
+            e.aux[0] = x0.x; e.aux[1] = x0.y; e.aux[2] = x0.z; e.aux[3] = x0.w;
+            e.aux[4] = x1.x; e.aux[5] = x1.y; e.aux[6] = x1.z; e.aux[7] = x1.w;
+        }
     }
     // Philox step index: device counter (graph replay) or launch argument.  Every CTA takes a ticket AFTER its read
     // (data dependency through `zero`); the CTA holding the last ticket bumps the counter at the end.
@@ -207,6 +214,10 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
             io.action[env * A + (A - 1)] = e.a_last_remap;
 #pragma unroll
         for (int k = 0; k < K; ++k) io.ctrl_state[(int64_t)k * n + env] = e.cs[k];
+        if (TASK == AGX_TASK_BALLOON) {
+            reinterpret_cast<float4*>(io.aux)[env * 2] = make_float4(e.aux[0], e.aux[1], e.aux[2], e.aux[3]);
+            reinterpret_cast<float4*>(io.aux)[env * 2 + 1] = make_float4(e.aux[4], e.aux[5], e.aux[6], e.aux[7]);
+        }
         io.progress[env] = e.progress;
         io.reset[env] = (int64_t)e.reset;
         io.timeout[env] = (uint8_t)e.timeout;
@@ -261,7 +272,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
 template <int TASK>
 __global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_t n, int64_t m,
                                      const int64_t* __restrict__ env_ids, float* state, float* prev_action,
-                                     float* ctrl_state, int64_t* progress, int64_t* reset,
+                                     float* ctrl_state, int64_t* progress, int64_t* reset, float* aux,
                                      const float* __restrict__ rand, uint64_t seed, uint64_t step,
                                      int64_t env_offset) {
     using namespace agx;
@@ -281,7 +292,14 @@ __global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_
         philox_uniforms(ph, 3u, P.reset_draws, u);  // stream 3: standalone reset_idx
     }
     float s[13];
-    reset_sample<TASK>(u, s);
+    if (TASK == AGX_TASK_BALLOON) {
+        float ax[AGX_AUX_MAX];
+        for (int i = 0; i < AGX_AUX_MAX; ++i) ax[i] = aux[env * AGX_AUX_MAX + i];
+        reset_sample_balloon(u, s, ax);
+        for (int i = 0; i < AGX_AUX_MAX; ++i) aux[env * AGX_AUX_MAX + i] = ax[i];
+    } else {
+        reset_sample<TASK>(u, s);
+    }
     for (int i = 0; i < 13; ++i) state[env * 13 + i] = s[i];
     for (int i = 0; i < P.num_actions; ++i) prev_action[env * P.num_actions + i] = 0.0f;
     if ((P.flags & AGX_FLAG_CTRL_RESET) && ctrl_state)
@@ -383,7 +401,7 @@ int agx_set_option(const char* key, int value) {
 
 int agx_params_default(AgxParams* p, int task, int ctl_mode) {
     if (!p) return fail(AGX_ERR_ARG, "agx_params_default: null params%s");
-    if (task != AGX_TASK_HOVERING && task != AGX_TASK_TRACKING)
+    if (task != AGX_TASK_HOVERING && task != AGX_TASK_TRACKING && task != AGX_TASK_BALLOON)
         return fail(AGX_ERR_UNSUPPORTED, "agx_params_default: task not built yet%s");
     if (ctl_mode < AGX_CTL_POS || ctl_mode > AGX_CTL_PROP) return fail(AGX_ERR_ARG, "agx_params_default: bad ctl_mode%s");
     memset(p, 0, sizeof(*p));
@@ -393,12 +411,14 @@ int agx_params_default(AgxParams* p, int task, int ctl_mode) {
     p->num_actions = (ctl_mode == AGX_CTL_ATTI) ? 5 : 4;
     p->num_obs = (task == AGX_TASK_TRACKING) ? 48 : 18;
     p->integrator = AGX_INT_RK4;
-    p->flags = AGX_FLAG_MUTATE_ACTIONS;
+    p->flags = AGX_FLAG_MUTATE_ACTIONS;  // (collision flag for the Customized family is added below)
     p->dt = 0.01f;
-    const double episode_s = (task == AGX_TASK_TRACKING) ? 36.0 : 24.0;  // *_config.py episode_length_s
+    const double episode_s = (task == AGX_TASK_TRACKING) ? 36.0 : (task == AGX_TASK_BALLOON ? 8.0 : 24.0);  // *_config.py episode_length_s
     p->max_episode_length = (int)(episode_s / 0.01);
     p->ctrl_state_dim = (ctl_mode == AGX_CTL_PROP) ? 0 : ((ctl_mode == AGX_CTL_RATE || ctl_mode == AGX_CTL_ATTI) ? 6 : 12);
-    p->reset_draws = 12;
+    p->reset_draws = (task == AGX_TASK_BALLOON) ? 15 : 12;
+    p->collision_radius = 0.2f;
+    if (task == AGX_TASK_BALLOON) p->flags |= AGX_FLAG_RESET_ON_COLLISION;  // balloon_config.py:19
     p->gravity = 9.81f;
     const double m_base = 0.585, m_prop = 0.004, arm = 0.05374, hz = 0.024;
     p->mass = (float)(m_base + 4.0 * m_prop);
@@ -416,7 +436,12 @@ int agx_params_default(AgxParams* p, int task, int ctl_mode) {
         case AGX_CTL_POS: for (int i = 0; i < 3; ++i) { lo[i] = -lim_pos; hi[i] = lim_pos; } lo[3] = -6; hi[3] = 6; break;
         case AGX_CTL_VEL: for (int i = 0; i < 4; ++i) { lo[i] = -6; hi[i] = 6; } break;
         case AGX_CTL_ATTI: for (int i = 0; i < 4; ++i) { lo[i] = -1; hi[i] = 1; } lo[4] = 0; hi[4] = 1; break;
-        case AGX_CTL_RATE: for (int i = 0; i < 3; ++i) { lo[i] = -6; hi[i] = 6; } lo[3] = 0; hi[3] = 1; break;
+        case AGX_CTL_RATE: {  // Customized family: +-1 rad/s (customized.py:109-113), Hovering/Tracking +-6
+            const float r = (task == AGX_TASK_BALLOON || task == AGX_TASK_AVOID || task == AGX_TASK_PLANNING) ? 1.0f : 6.0f;
+            for (int i = 0; i < 3; ++i) { lo[i] = -r; hi[i] = r; }
+            lo[3] = 0; hi[3] = 1;
+            break;
+        }
         case AGX_CTL_PROP: for (int i = 0; i < 4; ++i) { lo[i] = 0; hi[i] = 1; } break;
     }
     for (int i = 0; i < 5; ++i) { p->act_lo[i] = lo[i]; p->act_hi[i] = hi[i]; }
@@ -467,6 +492,10 @@ int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream) {
         case AGX_TASK_TRACKING:
             if (p->num_obs != 48) return fail(AGX_ERR_ARG, "agx_step: tracking needs num_obs=48%s");
             return dispatch_mode<AGX_TASK_TRACKING>(*p, n, *io, st);
+        case AGX_TASK_BALLOON:
+            if (p->num_obs != 18) return fail(AGX_ERR_ARG, "agx_step: balloon needs num_obs=18%s");
+            if (!io->aux || misaligned(io->aux)) return fail(AGX_ERR_ARG, "agx_step: balloon needs a 16-byte aligned aux buffer%s");
+            return dispatch_mode<AGX_TASK_BALLOON>(*p, n, *io, st);
         default: return fail(AGX_ERR_UNSUPPORTED, "agx_step: task not built yet%s");
     }
 }
@@ -474,7 +503,6 @@ int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream) {
 int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_ids, float* state,
                   float* prev_action, float* ctrl_state, int64_t* progress, int64_t* reset, float* aux,
                   const float* rand, uint64_t seed, uint64_t step, int64_t env_offset, void* stream) {
-    (void)aux;
     if (!p || !env_ids || !state || !prev_action || !progress || !reset) return fail(AGX_ERR_ARG, "agx_reset_idx: null argument%s");
     if (n < 0 || m < 0) return fail(AGX_ERR_ARG, "agx_reset_idx: negative size%s");
     if (m == 0) return AGX_OK;
@@ -482,11 +510,15 @@ int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_i
     const unsigned grid = (unsigned)((m + 127) / 128);
     if (p->task == AGX_TASK_HOVERING)
         agx_reset_idx_kernel<AGX_TASK_HOVERING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
-                                                                      progress, reset, rand, seed, step, env_offset);
+                                                                      progress, reset, aux, rand, seed, step, env_offset);
     else if (p->task == AGX_TASK_TRACKING)
         agx_reset_idx_kernel<AGX_TASK_TRACKING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
-                                                                      progress, reset, rand, seed, step, env_offset);
-    else
+                                                                      progress, reset, aux, rand, seed, step, env_offset);
+    else if (p->task == AGX_TASK_BALLOON) {
+        if (!aux) return fail(AGX_ERR_ARG, "agx_reset_idx: balloon needs aux%s");
+        agx_reset_idx_kernel<AGX_TASK_BALLOON><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
+                                                                     progress, reset, aux, rand, seed, step, env_offset);
+    } else
         return fail(AGX_ERR_UNSUPPORTED, "agx_reset_idx: task not built yet%s");
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_reset_idx launch: %s", cudaGetErrorString(err));

@@ -58,13 +58,15 @@ enum AgxFlags {
                                       `action` (reference quirk Q4, hovering.py:212-215) */
     AGX_FLAG_CTRL_RESET = 2,       /* zero controller integrators on episode reset (reference never
                                       does: the rlPx4Controller objects are not told about resets) */
-    AGX_FLAG_NO_NOISE = 4          /* skip observation noise (debug/KATs) */
+    AGX_FLAG_NO_NOISE = 4,         /* skip observation noise (debug/KATs) */
+    AGX_FLAG_RESET_ON_COLLISION = 8 /* cfg.env.reset_on_collision (customized.py:328-330) */
 };
 
 #define AGX_MAX_ACTIONS 5
 #define AGX_CTRL_STATE_MAX 12
 #define AGX_RESET_DRAWS_MAX 16
 #define AGX_NOISE_DRAWS 18
+#define AGX_AUX_MAX 8           /* floats of per-env task state in AgxStepIO.aux */
 
 /* Everything the fused step needs that is not per-env data.  Mirrors the reference's nested cfg
  * classes (hovering_config.py:8-69), URDF constants (assets/robots/X152b/model.urdf) and the
@@ -112,6 +114,8 @@ typedef struct AgxParams {
     float target[18];          /* cfg.env.target_state (hovering_config.py:12) */
     float target_yaw;          /* third intrinsic-XYZ euler angle of target[0:9] = atan2(-t01, t00) */
     float noise_sigma[4];      /* 1e-3, 5e-3, 2e-2, 4e-1 (hovering.py:350-353) */
+    float collision_radius;    /* 0.2: the drone's collision sphere (robots/X152b/model.urdf:13-18) */
+    float _pad1;
 } AgxParams;
 
 /* Per-call buffer table.  N = number of envs, A = num_actions, K = ctrl_state_dim, D = reset_draws.
@@ -129,7 +133,8 @@ typedef struct AgxStepIO {
     float*   reward;       /* [N]    out: reference rew_buf                                    */
     float*   cmd;          /* [N,4]  out: reference cmd_thrusts, or NULL                       */
     float*   reward_terms; /* [9,N]  out: reference item_reward_info planes, or NULL           */
-    float*   aux;          /* task-specific in/out state (tracking: NULL; balloon: [N,?]) or NULL */
+    float*   aux;          /* [N,AGX_AUX_MAX] task state in/out, or NULL for hovering/tracking.  Balloon: ball xyz (balloon_states
+                              positions), previous drone xyz (pre_root_positions), collision flag (collisions), pad */
     const float* rand_reset; /* [N,2,D] U[0,1) draws for the pre-/post-step reset, or NULL → Philox */
     const float* rand_noise; /* [N,18]  N(0,1) draws for the observation noise, or NULL → Philox  */
     uint64_t seed;         /* Philox key   (used when a rand_* pointer is NULL) */

@@ -350,4 +350,6 @@ class TrackingOracle(HoveringOracle):
 
 
 def make_oracle(spec: QuadSpec, num_envs: int, dtype=torch.float32, rng="torch"):
-    return {"hovering": HoveringOracle, "tracking": TrackingOracle}[spec.task](spec, num_envs, dtype, rng)
+    from .customized import BalloonOracle
+
+    return {"hovering": HoveringOracle, "tracking": TrackingOracle, "balloon": BalloonOracle}[spec.task](spec, num_envs, dtype, rng)

@@ -23,8 +23,9 @@ def _limits(task: str, ctl_mode: str):
         return [-6.0] * 4, [6.0] * 4
     if ctl_mode == "atti":
         return [-1.0, -1.0, -1.0, -1.0, 0.0], [1.0] * 5
-    if ctl_mode == "rate":
-        return [-6.0, -6.0, -6.0, 0.0], [6.0, 6.0, 6.0, 1.0]
+    if ctl_mode == "rate":  # Customized family: +-1 rad/s (customized.py:109-113)
+        r = 1.0 if task in ("balloon", "avoid", "planning") else 6.0
+        return [-r, -r, -r, 0.0], [r, r, r, 1.0]
     if ctl_mode == "prop":
         return [0.0] * 4, [1.0] * 4
     raise ValueError(f"unknown ctl_mode {ctl_mode!r}")
@@ -75,8 +76,8 @@ class QuadSpec:
     noise_sigma: List[float] = field(default_factory=lambda: [1e-3, 5e-3, 2e-2, 4e-1])  # hovering.py:350-353
 
     def __post_init__(self):
-        if self.task == "tracking" and self.episode_length_s == 24.0:
-            self.episode_length_s = 36.0
+        if self.episode_length_s == 24.0:  # *_config.py episode_length_s
+            self.episode_length_s = {"tracking": 36.0, "balloon": 8.0, "avoid": 6.0, "planning": 16.0}.get(self.task, 24.0)
         self.act_lo, self.act_hi = _limits(self.task, self.ctl_mode)
 
     @property
@@ -111,4 +112,4 @@ class QuadSpec:
 
     @property
     def reset_draws(self) -> int:
-        return 12
+        return {"balloon": 15}.get(self.task, 12)

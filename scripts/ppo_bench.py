@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""PPO throughput / learning-curve probe:  python scripts/ppo_bench.py --task hovering --ctl_mode rate --num_envs 65536 --epochs 20
+Prints one JSON line (rank 0) with samples/s for rollout ("step+inference"), update, and total, plus the reward curve.
+Under torchrun the envs are sharded and gradients all-reduced (multi_gpu)."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from airgym_b200.lib.config import default_ppo_config, scale_minibatch  # noqa: E402
+from airgym_b200.lib.torch_runner import Runner  # noqa: E402
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--task", default="hovering")
+    ap.add_argument("--ctl_mode", default="rate")
+    ap.add_argument("--num_envs", type=int, default=65536)
+    ap.add_argument("--epochs", type=int, default=20)
+    ap.add_argument("--no_graph", action="store_true")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--skip", type=int, default=3, help="epochs excluded from the timing (graph capture / warm-up)")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = scale_minibatch(default_ppo_config(a.task), a.num_envs)
+    c = cfg["params"]["config"]
+    c.update(max_epochs=a.epochs, use_cuda_graph=not a.no_graph, print_stats=False, save_frequency=0, save_best_after=10**9,
+             train_dir="/tmp/agx_runs", multi_gpu=world > 1)
+    c["env_config"].update(ctl_mode=a.ctl_mode, num_envs=a.num_envs, seed=a.seed)
+    cfg["params"]["seed"] = a.seed
+    r = Runner()
+    r.load(cfg)
+    r.run({"train": True})
+    if int(os.environ.get("RANK", "0")) == 0:
+        h = r.agent.history[a.skip:]
+        frames = sum(x["frame"] - (r.agent.history[i + a.skip - 1]["frame"] if i + a.skip > 0 else 0) for i, x in enumerate(h))
+        play, upd = sum(x["play_time"] for x in h), sum(x["update_time"] for x in h)
+        print(json.dumps({
+            "task": a.task, "ctl_mode": a.ctl_mode, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "epochs_timed": len(h),
+            "minibatch": c["minibatch_size"], "cuda_graph": not a.no_graph,
+            "samples_per_s_rollout": frames / play, "samples_per_s_update": frames / upd, "samples_per_s_total": frames / (play + upd),
+            "ms_per_epoch_rollout": 1e3 * play / len(h), "ms_per_epoch_update": 1e3 * upd / len(h),
+            "reward_curve": [None if x["mean_reward"] is None else round(x["mean_reward"], 2) for x in r.agent.history][:: max(1, a.epochs // 25)],
+            "kl_last": h[-1]["kl"], "lr_last": h[-1]["lr"]}), flush=True)

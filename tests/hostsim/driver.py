@@ -43,6 +43,7 @@ class HostEnv:
         self.reward = np.zeros(n, np.float32)
         self.cmd = np.zeros((n, 4), np.float32)
         self.terms = np.zeros((9, n), np.float32)
+        self.aux = np.zeros((n, _capi.AGX_AUX_MAX), np.float32)
 
     def step(self, action, rand_reset=None, rand_noise=None, seed=0, step=0, env_offset=0):
         io = _capi.AgxStepIO()
@@ -52,6 +53,7 @@ class HostEnv:
         io.ctrl_state, io.progress, io.reset, io.timeout = ptr(self.ctrl_state), ptr(self.progress), ptr(self.reset), ptr(self.timeout)
         io.obs, io.reward, io.cmd, io.reward_terms = ptr(self.obs), ptr(self.reward), ptr(self.cmd), ptr(self.terms)
         io.rand_reset, io.rand_noise = ptr(rand_reset), ptr(rand_noise)
+        io.aux = ptr(self.aux)
         io.seed, io.step, io.env_offset = seed, step, env_offset
         rc = self.lib.hostsim_step(C.byref(self.P), self.n, C.byref(io))
         assert rc == 0, rc

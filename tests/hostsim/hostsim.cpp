@@ -19,6 +19,7 @@ static void run(const AgxParams& P, int64_t n, const AgxStepIO& io) {
         for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
         e.progress = io.progress[env];
         e.pending = io.reset[env] != 0;
+        for (int k = 0; k < AGX_AUX_MAX; ++k) e.aux[k] = io.aux ? io.aux[env * AGX_AUX_MAX + k] : 0.0f;
         RandSrc rnd;
         rnd.reset_row = io.rand_reset ? io.rand_reset + env * (int64_t)(2 * P.reset_draws) : nullptr;
         rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
@@ -34,6 +35,7 @@ static void run(const AgxParams& P, int64_t n, const AgxStepIO& io) {
         if ((P.flags & AGX_FLAG_MUTATE_ACTIONS) && (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI))
             io.action[env * A + (A - 1)] = e.a_last_remap;
         for (int k = 0; k < K; ++k) io.ctrl_state[(int64_t)k * n + env] = e.cs[k];
+        if (io.aux) for (int k = 0; k < AGX_AUX_MAX; ++k) io.aux[env * AGX_AUX_MAX + k] = e.aux[k];
         io.progress[env] = e.progress;
         io.reset[env] = e.reset;
         io.timeout[env] = (uint8_t)e.timeout;
@@ -58,6 +60,7 @@ static int by_mode(const AgxParams& P, int64_t n, const AgxStepIO& io) {
 extern "C" int hostsim_step(const AgxParams* p, int64_t n, const AgxStepIO* io) {
     if (p->task == AGX_TASK_HOVERING) return by_mode<AGX_TASK_HOVERING>(*p, n, *io);
     if (p->task == AGX_TASK_TRACKING) return by_mode<AGX_TASK_TRACKING>(*p, n, *io);
+    if (p->task == AGX_TASK_BALLOON) return by_mode<AGX_TASK_BALLOON>(*p, n, *io);
     return -4;
 }
 

@@ -48,7 +48,7 @@ def test_error_paths_return_codes_not_exceptions(built):
         _capi.check(-1, "x")
 
 
-@pytest.mark.parametrize("task", ["hovering", "tracking"])
+@pytest.mark.parametrize("task", ["hovering", "tracking", "balloon"])
 @pytest.mark.parametrize("mode", ["pos", "vel", "atti", "rate", "prop"])
 def test_params_default_equals_oracle_spec(built, task, mode):
     """The constants are written down twice (agx_params_default in C, oracle/spec.py); they must agree."""

@@ -20,8 +20,9 @@ def test_oracle_matches_reference_trajectory(name):
         orc.step(a, torch.from_numpy(g["draw_reset"][t]), torch.from_numpy(g["draw_noise"][t]))
         assert_close(orc.root_states, g["state"][t], f"{name} t={t} state", rtol=1e-5, atol=2e-6)
         assert_close(orc.obs_buf, g["obs"][t], f"{name} t={t} obs", rtol=1e-5, atol=2e-6)
-        assert_close(orc.rew_buf, g["rew"][t], f"{name} t={t} rew", rtol=1e-5, atol=2e-6)
-        assert_close(orc.reward_terms_matrix(), g["terms"][t], f"{name} t={t} terms", rtol=1e-5, atol=2e-6)
+        ra = 6e-5 if task == "balloon" else 2e-6  # balloon: 30x guidance amplification (tests/util.py task_tols)
+        assert_close(orc.rew_buf, g["rew"][t], f"{name} t={t} rew", rtol=1e-5, atol=ra)
+        assert_close(orc.reward_terms_matrix(), g["terms"][t], f"{name} t={t} terms", rtol=1e-5, atol=ra)
         assert_close(orc.cmd_thrusts, g["cmd"][t], f"{name} t={t} cmd", rtol=1e-5, atol=2e-6)
         assert_close(orc.actions, g["actions"][t], f"{name} t={t} actions", rtol=0, atol=0)
         assert_close(a, g["action_in_after"][t], f"{name} t={t} in-place action remap (Q4)", rtol=0, atol=0)

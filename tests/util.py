@@ -40,3 +40,9 @@ def assert_close(got, ref, what, rtol=RTOL, atol=ATOL):
         i = np.unravel_index(np.argmax(err - bound), err.shape)
         raise AssertionError(f"{what}: {bad.sum()} entries off; worst at {i}: got {got[i]!r} ref {ref[i]!r} err {err[i]:.3e}")
     return float(err.max()) if err.size else 0.0
+
+
+def task_tols(task):
+    """(rtol, atol) for reward-like outputs: Balloon's guidance term is 30 x (difference of two norms), i.e. it amplifies
+    the last-ulp differences of positions ~30x / |value|; everything else uses the north_star bar."""
+    return (1e-4, 3e-3) if task == "balloon" else (RTOL, ATOL)
