@@ -69,6 +69,16 @@ class AgxPpoHyper(C.Structure):
 AGX_PPO_STATS = 8
 
 
+class AgxMlpParams(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("in_pad", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32),
+                ("actions_num", C.c_int32)] + [(n, C.c_void_p) for n in (
+                    "w1", "b1", "w2", "b2", "w3", "b3", "w_mu", "b_mu", "w_value", "b_value", "in_mean", "in_var")]
+
+
+class AgxMlpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gw1", "gb1", "gw2", "gb2", "gw3", "gb3", "gw_mu", "gb_mu", "gw_value", "gb_value")]
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -91,13 +101,17 @@ def bind(lib):
     lib.agx_ppo_workspace_floats.restype = C.c_int64
     lib.agx_ppo_loss.argtypes = [C.POINTER(AgxPpoHyper), C.c_int64, C.c_int] + [C.c_void_p] * 15
     lib.agx_adam_step.argtypes = [C.POINTER(AgxPpoHyper), C.c_int64] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
+    lib.agx_mlp_forward.argtypes = [C.POINTER(AgxMlpParams), C.c_int64] + [C.c_void_p] * 8
+    lib.agx_mlp_workspace_floats.argtypes = [C.POINTER(AgxMlpParams)]
+    lib.agx_mlp_workspace_floats.restype = C.c_int64
+    lib.agx_mlp_backward.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
     return lib
 
 
 EXPORTS = (
     "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_set_option",
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
-    "agx_ppo_loss", "agx_adam_step",
+    "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
 )
 
 _lib = None

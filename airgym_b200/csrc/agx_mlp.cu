@@ -1,0 +1,540 @@
+// agx_mlp.cu — fused actor-critic MLP for the PPO path (reference lib/network/mlp.py:37-39 + the mu / value heads of
+// lib/model/a2c_continuous_logstd_model.py:159-168, input normalisation lib/core/running_mean_std.py:76-80).
+//
+// forward : obs → clamp((obs-mean)/sqrt(var+eps), ±5) → [Linear+ELU]x3 → (mu | value) in ONE kernel; activations live in
+//           shared memory between layers and are optionally kept in HBM for the backward pass;
+// backward: (dmu | dvalue) → dZ3 → dZ2 → dZ1 in ONE kernel, which also accumulates the bias gradients (column sums);
+// wgrad   : dW_l = dZ_l^T · a_{l-1} for all four weight matrices in ONE split-K kernel (every CTA reduces a slab of the batch)
+//           followed by a small deterministic reduction that scatters into the caller's flat gradient buffer.
+// All GEMMs run on the tensor cores: TF32 operands, fp32 accumulation (warp-level mma.sync m16n8k8, operands pre-rounded to TF32 in shared memory).
+// In forward/backward each warp owns a tile of 16 samples end to end (no block-level sync after the weights are staged);
+// shared-memory leading dimensions are padded (+4 / +8 floats) so that the fragment loads are bank-conflict free.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agx.h"
+
+int agx_internal_fail(int code, const char* msg);
+
+namespace {
+
+constexpr int kWarps = 8;          // warps per CTA
+constexpr int kRows = 16;          // rows per warp tile
+constexpr int kOutPad = 16;        // head width padded to 16: [mu(A) | value | 0...]
+constexpr int kMaxW = 128;         // widest layer
+constexpr int kActLd = kMaxW + 4;  // activation tile leading dimension (≡ 4 mod 32 → conflict-free A-fragment loads)
+constexpr int kBiasSlots = 3 * kMaxW + kOutPad;  // per-CTA bias partials: b1 | b2 | b3 | heads (each padded to kMaxW)
+
+struct Dims {
+    int in_dim, in_pad, h1, h2, h3, a;  // in_pad multiple of 16, h* multiples of 32; a = actions_num (4 or 5)
+};
+__host__ __device__ inline Dims dims_of(const AgxMlpParams& P) { return Dims{P.in_dim, P.in_pad, P.h1, P.h2, P.h3, P.actions_num}; }
+
+// shared-memory layout (float offsets into g_smem): W_l stored [out x (in + pad)] row-major, then biases, then per-warp tiles
+struct SmemW {
+    int w1, w2, w3, wh, b1, b2, b3, bh, end;
+    int ld1, ld2, ld3, ldh;
+};
+__host__ __device__ inline SmemW carve_weights(const Dims& d, int pad) {
+    SmemW s;
+    s.ld1 = d.in_pad + pad; s.ld2 = d.h1 + pad; s.ld3 = d.h2 + pad; s.ldh = d.h3 + pad;
+    s.w1 = 0;                        s.w2 = s.w1 + d.h1 * s.ld1;    s.w3 = s.w2 + d.h2 * s.ld2;
+    s.wh = s.w3 + d.h3 * s.ld3;      s.b1 = s.wh + kOutPad * s.ldh; s.b2 = s.b1 + d.h1;
+    s.b3 = s.b2 + d.h2;              s.bh = s.b3 + d.h3;            s.end = s.bh + kOutPad;
+    return s;
+}
+__host__ __device__ inline int weights_floats(const Dims& d, int pad) { return carve_weights(d, pad).end; }
+
+// ---- warp-level tensor-core GEMM pieces: mma.sync m16n8k8, TF32 operands (pre-rounded in shared memory), fp32 accumulate.
+// Fragment ownership (g = lane / 4, t = lane % 4):  A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B: b0 (k = t, n = g) b1 (k = t+4, n = g);  C: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+extern __shared__ __align__(128) float g_smem[];  // indexed directly so that every access compiles to LDS/STS
+
+__device__ inline float tf32r(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ inline void mma_tf32(float (&c)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// Y[16 x n] (shared, offset yo, ld kActLd) = X[16 x k] (shared, offset xo, ld kActLd) · op(W) with W in shared at offset wo:
+// TRANSPOSED_W = true : op(W)[k][n] = W[n * ldw + k]  (torch Linear weight rows, ldw ≡ 4 mod 32 → conflict-free)
+// TRANSPOSED_W = false: op(W)[k][n] = W[k * ldw + n]  (same weight used backwards,  ldw ≡ 8 mod 32 → conflict-free)
+// One pass computes NT n8-tiles (8·NT columns) with NT independent accumulator chains fed by one A fragment per k-step; NT is a
+// compile-time constant so the MMAs sit in straight-line code (no per-MMA convergence barriers).  Legacy mma.sync has ~127
+// cycles of latency on sm_100a (measured, scripts/micro/mma_lat.cu): the 8–16 independent chains are what hides it.
+template <bool TRANSPOSED_W, int NT>
+__device__ inline void gemm_pass(int xo, int wo, int ldw, int k, int n0, int yo, int g, int t) {
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] = 0.0f; acc[j][1] = 0.0f; acc[j][2] = 0.0f; acc[j][3] = 0.0f; }
+    const int xa = xo + g * kActLd + t;
+    const int wb = TRANSPOSED_W ? (wo + (n0 + g) * ldw + t) : (wo + t * ldw + n0 + g);
+    for (int k0 = 0; k0 < k; k0 += 8) {
+        float a[4];
+        a[0] = g_smem[xa + k0];
+        a[1] = g_smem[xa + 8 * kActLd + k0];
+        a[2] = g_smem[xa + k0 + 4];
+        a[3] = g_smem[xa + 8 * kActLd + k0 + 4];
+        float b0[NT], b1[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (TRANSPOSED_W) {
+                b0[j] = g_smem[wb + 8 * j * ldw + k0];
+                b1[j] = g_smem[wb + 8 * j * ldw + k0 + 4];
+            } else {
+                b0[j] = g_smem[wb + k0 * ldw + 8 * j];
+                b1[j] = g_smem[wb + (k0 + 4) * ldw + 8 * j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_tf32(acc[j], a, b0[j], b1[j]);
+    }
+    const int yc = yo + g * kActLd + n0 + 2 * t;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        *reinterpret_cast<float2*>(&g_smem[yc + 8 * j]) = make_float2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<float2*>(&g_smem[yc + 8 * kActLd + 8 * j]) = make_float2(acc[j][2], acc[j][3]);
+    }
+}
+template <bool TRANSPOSED_W>
+__device__ inline void gemm16(int xo, int wo, int ldw, int k, int n, int yo, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    if (n == 128) { gemm_pass<TRANSPOSED_W, 16>(xo, wo, ldw, k, 0, yo, g, t); return; }
+    if (n == 64) { gemm_pass<TRANSPOSED_W, 8>(xo, wo, ldw, k, 0, yo, g, t); return; }
+    if (n == 16) { gemm_pass<TRANSPOSED_W, 2>(xo, wo, ldw, k, 0, yo, g, t); return; }
+    for (int n0 = 0; n0 < n; n0 += 32) gemm_pass<TRANSPOSED_W, 4>(xo, wo, ldw, k, n0, yo, g, t);  // n is a multiple of 32
+}
+
+// copy a [rows x cols] row-major matrix from global memory into shared memory with leading dimension ld (zero padded),
+// rounding to TF32.  Four rows per warp iteration, all loads issued before the first store: ~20 independent loads in flight
+// per thread, so the L2 latency is paid a handful of times instead of once per element.
+__device__ inline void stage_matrix(int dst, int ld, const float* __restrict__ src, int rows, int cols, int warp, int lane) {
+    constexpr int kC = (kMaxW + 8 + 31) / 32;  // column slots per lane (ld <= kMaxW + 8)
+    for (int r0 = 4 * warp; r0 < rows; r0 += 4 * kWarps) {
+        float v[4][kC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int u = 0; u < kC; ++u) {
+                const int r = r0 + q, c = lane + 32 * u;
+                v[q][u] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * cols + c) : 0.0f;
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int u = 0; u < kC; ++u) {
+                const int r = r0 + q, c = lane + 32 * u;
+                if (r < rows && c < ld) g_smem[dst + r * ld + c] = tf32r(v[q][u]);
+            }
+    }
+}
+// stage the network into shared memory (weights pre-rounded to TF32; W1 zero padded; the two heads stacked into 16 rows)
+__device__ void stage_weights(const AgxMlpParams& P, const Dims& d, const SmemW& s) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    stage_matrix(s.w1, s.ld1, P.w1, d.h1, d.in_dim, warp, lane);
+    stage_matrix(s.w2, s.ld2, P.w2, d.h2, d.h1, warp, lane);
+    stage_matrix(s.w3, s.ld3, P.w3, d.h3, d.h2, warp, lane);
+    stage_matrix(s.wh, s.ldh, P.w_mu, d.a, d.h3, warp, lane);                      // rows 0..A-1: mu head
+    stage_matrix(s.wh + d.a * s.ldh, s.ldh, P.w_value, 1, d.h3, warp, lane);       // row A: value head
+    for (int i = tid; i < (kOutPad - d.a - 1) * s.ldh; i += nt) g_smem[s.wh + (d.a + 1) * s.ldh + i] = 0.0f;
+    for (int i = tid; i < d.h1; i += nt) g_smem[s.b1 + i] = P.b1[i];
+    for (int i = tid; i < d.h2; i += nt) g_smem[s.b2 + i] = P.b2[i];
+    for (int i = tid; i < d.h3; i += nt) g_smem[s.b3 + i] = P.b3[i];
+    for (int i = tid; i < kOutPad; i += nt) g_smem[s.bh + i] = i < d.a ? P.b_mu[i] : (i == d.a ? P.b_value[0] : 0.0f);
+}
+
+__device__ inline float elu(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }  // SFU exp: abs error ~1e-7, far below TF32
+__device__ inline float elu_grad_from_out(float h) { return h > 0.0f ? 1.0f : h + 1.0f; }  // d elu/dz through h = elu(z)
+constexpr int kU = kMaxW / 32;  // column slots per lane: lane owns columns lane + 32 u
+
+// bias + ELU over a 16 x width tile at offset `bo` (TF32-rounded copy stays in shared memory for the next GEMM; the
+// full-precision value is optionally kept in HBM)
+__device__ inline void bias_elu_tile(int bo, int bias_o, int width, int lane, float* out, int64_t row0, int64_t B) {
+    float b[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) b[u] = (lane + 32 * u < width) ? g_smem[bias_o + lane + 32 * u] : 0.0f;
+#pragma unroll 4
+    for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int c = lane + 32 * u;
+            if (c < width) {
+                const float h = elu(g_smem[bo + r * kActLd + c] + b[u]);
+                g_smem[bo + r * kActLd + c] = tf32r(h);
+                if (out && row0 + r < B) out[(row0 + r) * width + c] = h;
+            }
+        }
+    }
+}
+// g = dH ∘ elu'(h) over a 16 x width tile: dz to HBM, TF32 copy kept in shared memory for the next GEMM, column sums in bacc.
+// The activations `hv` were prefetched from HBM before the GEMM that produced dH (latency hidden behind the tensor work).
+__device__ inline void elu_grad_tile(int bo, const float (&hv)[kRows][kU], float* __restrict__ dz, int width, int lane, int64_t row0,
+                                     int64_t B, float* bacc, bool keep_in_smem) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int c = lane + 32 * u;
+            if (c < width) {
+                float g = 0.0f;
+                if (row0 + r < B) {
+                    g = g_smem[bo + r * kActLd + c] * elu_grad_from_out(hv[r][u]);
+                    dz[(row0 + r) * width + c] = g;
+                }
+                if (keep_in_smem) g_smem[bo + r * kActLd + c] = tf32r(g);
+                bacc[u] += g;
+            }
+        }
+    }
+}
+__device__ inline void prefetch_tile(const float* __restrict__ h, float (&hv)[kRows][kU], int width, int lane, int64_t row0, int64_t B) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int c = lane + 32 * u;
+            hv[r][u] = (c < width && row0 + r < B) ? h[(row0 + r) * width + c] : 0.0f;
+        }
+    }
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs,
+                       float* __restrict__ mu, float* __restrict__ value, float* __restrict__ xn_out,
+                       float* __restrict__ h1_out, float* __restrict__ h2_out, float* __restrict__ h3_out, int dbg) {
+    const Dims d = dims_of(P);
+    const SmemW W = carve_weights(d, 4);  // ld ≡ 4 (mod 32): conflict-free B fragments of X · W^T
+    if (!(dbg & 1)) stage_weights(P, d, W);
+    __syncthreads();
+    if (dbg & 2) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bufA = W.end + warp * (2 * kRows * kActLd), bufB = bufA + kRows * kActLd;  // ping-pong tiles of this warp
+    float n_mean[kU], n_sd[kU];  // this lane's input columns: mean and sqrt(var + eps) as float
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const int c = lane + 32 * u;
+        const bool on = P.in_mean && c < d.in_dim;
+        n_mean[u] = on ? (float)P.in_mean[c] : 0.0f;
+        n_sd[u] = on ? sqrtf((float)P.in_var[c] + 1e-5f) : 1.0f;
+    }
+    const int64_t n_tiles = (B + kRows - 1) / kRows;
+    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
+        const int64_t row0 = tile * kRows;
+        // normalised input tile (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80)
+#pragma unroll 4
+        for (int r = 0; r < kRows; ++r) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int c = lane + 32 * u;
+                if (c < d.in_pad) {
+                    float v = 0.0f;
+                    if (c < d.in_dim && row0 + r < B) {
+                        v = obs[(row0 + r) * d.in_dim + c];
+                        if (P.in_mean) {
+                            v = (v - n_mean[u]) / n_sd[u];
+                            v = v < -5.0f ? -5.0f : (v > 5.0f ? 5.0f : v);
+                        }
+                    }
+                    g_smem[bufA + r * kActLd + c] = tf32r(v);
+                    if (xn_out && row0 + r < B) xn_out[(row0 + r) * d.in_pad + c] = v;
+                }
+            }
+        }
+        __syncwarp();
+        if (!(dbg & 8)) gemm16<true>(bufA, W.w1, W.ld1, d.in_pad, d.h1, bufB, lane);
+        __syncwarp();
+        if (!(dbg & 4)) bias_elu_tile(bufB, W.b1, d.h1, lane, h1_out, row0, B);
+        __syncwarp();
+        if (!(dbg & 8)) gemm16<true>(bufB, W.w2, W.ld2, d.h1, d.h2, bufA, lane);
+        __syncwarp();
+        if (!(dbg & 4)) bias_elu_tile(bufA, W.b2, d.h2, lane, h2_out, row0, B);
+        __syncwarp();
+        if (!(dbg & 8)) gemm16<true>(bufA, W.w3, W.ld3, d.h2, d.h3, bufB, lane);
+        __syncwarp();
+        if (!(dbg & 4)) bias_elu_tile(bufB, W.b3, d.h3, lane, h3_out, row0, B);
+        __syncwarp();
+        if (!(dbg & 8)) gemm16<true>(bufB, W.wh, W.ldh, d.h3, kOutPad, bufA, lane);
+        __syncwarp();
+        {
+            const int c = lane & 15;
+            const float bh = g_smem[W.bh + c];
+#pragma unroll
+            for (int j = 0; j < kRows / 2; ++j) {
+                const int r = (lane >> 4) + 2 * j;
+                if (row0 + r < B) {
+                    const float v = g_smem[bufA + r * kActLd + c] + bh;
+                    if (c < d.a) mu[(row0 + r) * d.a + c] = v;
+                    else if (c == d.a) value[row0 + r] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- backward: activation-gradient chain + bias-gradient partials ----------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32)
+agx_mlp_backward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ grad_mu,
+                        const float* __restrict__ grad_value, const float* __restrict__ h1, const float* __restrict__ h2,
+                        const float* __restrict__ h3, float* __restrict__ dz1, float* __restrict__ dz2,
+                        float* __restrict__ dz3, float* __restrict__ dout, float* __restrict__ bias_partials) {
+    const Dims d = dims_of(P);
+    const SmemW W = carve_weights(d, 8);  // ld ≡ 8 (mod 32): conflict-free B fragments of X · W
+    stage_weights(P, d, W);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bufA = W.end + warp * (2 * kRows * kActLd), bufB = bufA + kRows * kActLd;
+    // per-lane column sums: lane L owns columns L + 32 u of every layer, and column L % 16 of the padded head gradient
+    float bacc1[kU], bacc2[kU], bacc3[kU], bacco = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) { bacc1[u] = 0.0f; bacc2[u] = 0.0f; bacc3[u] = 0.0f; }
+    const int q1 = d.h1 / 32, q2 = d.h2 / 32, q3 = d.h3 / 32;
+    const int64_t n_tiles = (B + kRows - 1) / kRows;
+    for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
+        const int64_t row0 = tile * kRows;
+        float hv[kRows][kU];
+        prefetch_tile(h3, hv, d.h3, lane, row0, B);
+        {
+            const int c = lane & 15;
+#pragma unroll
+            for (int j = 0; j < kRows / 2; ++j) {
+                const int r = (lane >> 4) + 2 * j;
+                float v = 0.0f;
+                if (row0 + r < B) {
+                    v = c < d.a ? grad_mu[(row0 + r) * d.a + c] : (c == d.a ? grad_value[row0 + r] : 0.0f);
+                    dout[(row0 + r) * kOutPad + c] = v;
+                }
+                g_smem[bufA + r * kActLd + c] = tf32r(v);
+                bacco += v;
+            }
+        }
+        __syncwarp();
+        gemm16<false>(bufA, W.wh, W.ldh, kOutPad, d.h3, bufB, lane);  // dH3 = dOut · W_head
+        __syncwarp();
+        elu_grad_tile(bufB, hv, dz3, d.h3, lane, row0, B, bacc3, true);
+        prefetch_tile(h2, hv, d.h2, lane, row0, B);
+        __syncwarp();
+        gemm16<false>(bufB, W.w3, W.ld3, d.h3, d.h2, bufA, lane);  // dH2 = dZ3 · W3
+        __syncwarp();
+        elu_grad_tile(bufA, hv, dz2, d.h2, lane, row0, B, bacc2, true);
+        prefetch_tile(h1, hv, d.h1, lane, row0, B);
+        __syncwarp();
+        gemm16<false>(bufA, W.w2, W.ld2, d.h2, d.h1, bufB, lane);  // dH1 = dZ2 · W2
+        __syncwarp();
+        elu_grad_tile(bufB, hv, dz1, d.h1, lane, row0, B, bacc1, false);
+        __syncwarp();
+    }
+    // CTA-level reduction of the bias partials, fixed order → deterministic
+    __syncthreads();
+    const int red = 0;  // [kWarps][kBiasSlots]; the weight tiles are dead now
+    for (int i = lane; i < kBiasSlots; i += 32) g_smem[red + warp * kBiasSlots + i] = 0.0f;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        if (u < q1) g_smem[red + warp * kBiasSlots + 0 * kMaxW + lane + 32 * u] = bacc1[u];
+        if (u < q2) g_smem[red + warp * kBiasSlots + 1 * kMaxW + lane + 32 * u] = bacc2[u];
+        if (u < q3) g_smem[red + warp * kBiasSlots + 2 * kMaxW + lane + 32 * u] = bacc3[u];
+    }
+    const float o2 = bacco + __shfl_down_sync(0xffffffffu, bacco, 16);  // lanes L and L+16 share column L % 16
+    if (lane < 16) g_smem[red + warp * kBiasSlots + 3 * kMaxW + lane] = o2;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBiasSlots; i += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < kWarps; ++w) s += g_smem[red + w * kBiasSlots + i];
+        bias_partials[(int64_t)blockIdx.x * kBiasSlots + i] = s;
+    }
+}
+
+// ---- weight gradients: split-K over the batch -------------------------------------------------------------------------------------
+// dW_l[out, in] = sum_b dz_l[b, out] · a_{l-1}[b, in] as mma.sync m16n8k8 with A = dz^T (m = out, k = batch row) and B = a
+// (k = batch row, n = in), fragments loaded straight from HBM/L2.  Work unit = one 16-row out-tile x up to 8 n8 in-tiles
+// (32 accumulator registers); the units of all four layers are dealt round-robin to the 8 warps of a CTA.
+struct WUnit { int layer, o0, i0, nt; };
+constexpr int kMaxUnits = 4;   // per warp
+__device__ inline int build_units(const Dims& d, int warp, WUnit (&u)[kMaxUnits]) {
+    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
+    int n = 0, q = 0;
+    for (int l = 0; l < 4; ++l)
+        for (int o0 = 0; o0 < outs[l]; o0 += 16)
+            for (int i0 = 0; i0 < ins[l]; i0 += 64, ++q)
+                if (q % kWarps == warp && n < kMaxUnits) { u[n].layer = l; u[n].o0 = o0; u[n].i0 = i0; u[n].nt = (ins[l] - i0) >= 64 ? 8 : (ins[l] - i0) / 8; ++n; }
+    return n;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+agx_mlp_wgrad_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t rows_per_cta, const float* __restrict__ xn,
+                     const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ h3,
+                     const float* __restrict__ dz1, const float* __restrict__ dz2, const float* __restrict__ dz3,
+                     const float* __restrict__ dout, float* __restrict__ partials, int partial_floats) {
+    const Dims d = dims_of(P);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* dzs[4] = {dz1, dz2, dz3, dout};
+    const float* as[4] = {xn, h1, h2, h3};
+    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
+    WUnit un[kMaxUnits];
+    const int n_units = build_units(d, warp, un);
+    float acc[kMaxUnits][8][4];
+#pragma unroll
+    for (int q = 0; q < kMaxUnits; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[q][j][0] = 0.0f; acc[q][j][1] = 0.0f; acc[q][j][2] = 0.0f; acc[q][j][3] = 0.0f; }
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    int64_t r_end = r_begin + rows_per_cta;
+    if (r_end > B) r_end = B;  // B is a multiple of 8 (checked on the host)
+    for (int64_t r = r_begin; r < r_end; r += 8) {
+#pragma unroll
+        for (int q = 0; q < kMaxUnits; ++q) {
+            if (q < n_units) {
+                const int l = un[q].layer, ldo = outs[l], ldi = ins[l];
+                const float* dz = dzs[l] + r * ldo + un[q].o0;
+                const float* a_ = as[l] + r * ldi + un[q].i0;
+                float a[4];
+                a[0] = tf32r(dz[(t)*ldo + g]);      a[1] = tf32r(dz[(t)*ldo + g + 8]);
+                a[2] = tf32r(dz[(t + 4) * ldo + g]); a[3] = tf32r(dz[(t + 4) * ldo + g + 8]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < un[q].nt) {
+                        const float b0 = tf32r(a_[t * ldi + 8 * j + g]), b1 = tf32r(a_[(t + 4) * ldi + 8 * j + g]);
+                        mma_tf32(acc[q][j], a, b0, b1);
+                    }
+                }
+            }
+        }
+    }
+    // partial dW of this CTA: dense [out_l x in_l] blocks, layers back to back
+    float* mine = partials + (int64_t)blockIdx.x * partial_floats;
+#pragma unroll
+    for (int q = 0; q < kMaxUnits; ++q) {
+        if (q < n_units) {
+            const int l = un[q].layer;
+            int base = 0;
+            for (int m = 0; m < l; ++m) base += outs[m] * ins[m];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < un[q].nt) {
+                    const int c = un[q].i0 + 8 * j + 2 * t;
+                    *reinterpret_cast<float2*>(&mine[base + (un[q].o0 + g) * ins[l] + c]) = make_float2(acc[q][j][0], acc[q][j][1]);
+                    *reinterpret_cast<float2*>(&mine[base + (un[q].o0 + g + 8) * ins[l] + c]) = make_float2(acc[q][j][2], acc[q][j][3]);
+                }
+            }
+        }
+    }
+}
+
+// deterministic reduction of the per-CTA partials + scatter into the caller's parameter-gradient tensors
+__global__ void agx_mlp_wgrad_reduce_kernel(const __grid_constant__ AgxMlpParams P, const __grid_constant__ AgxMlpGrads G,
+                                            const float* __restrict__ partials, int n_cta_w, int partial_floats,
+                                            const float* __restrict__ bias_partials, int n_cta_b) {
+    const Dims d = dims_of(P);
+    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3}, real_in[4] = {d.in_dim, d.h1, d.h2, d.h3};
+    float* gw[3] = {G.gw1, G.gw2, G.gw3};
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < partial_floats) {
+        int l = 0, base = 0;
+        while (l < 3 && e >= base + outs[l] * ins[l]) { base += outs[l] * ins[l]; ++l; }
+        const int o = (e - base) / ins[l], i = (e - base) % ins[l];
+        float s = 0.0f;
+        for (int c = 0; c < n_cta_w; ++c) s += partials[(int64_t)c * partial_floats + e];
+        if (i < real_in[l]) {
+            if (l < 3) gw[l][o * real_in[l] + i] = s;
+            else if (o < d.a) G.gw_mu[o * d.h3 + i] = s;
+            else if (o == d.a) G.gw_value[i] = s;
+        }
+    } else if (e - partial_floats < kBiasSlots) {
+        const int i = e - partial_floats;
+        float s = 0.0f;
+        for (int c = 0; c < n_cta_b; ++c) s += bias_partials[(int64_t)c * kBiasSlots + i];
+        const int seg = i / kMaxW, c = i % kMaxW;
+        if (seg == 0 && c < d.h1) G.gb1[c] = s;
+        else if (seg == 1 && c < d.h2) G.gb2[c] = s;
+        else if (seg == 2 && c < d.h3) G.gb3[c] = s;
+        else if (seg == 3) { if (c < d.a) G.gb_mu[c] = s; else if (c == d.a) G.gb_value[0] = s; }
+    }
+}
+
+bool valid(const AgxMlpParams* p) {
+    return p && p->in_dim > 0 && p->in_pad >= p->in_dim && p->in_pad % 16 == 0 && p->in_pad <= kMaxW && p->h1 % 32 == 0 &&
+           p->h2 % 32 == 0 && p->h3 % 32 == 0 && p->h1 > 0 && p->h2 > 0 && p->h3 > 0 && p->h1 <= kMaxW && p->h2 <= kMaxW &&
+           p->h3 <= kMaxW && (p->actions_num == 4 || p->actions_num == 5) && p->w1 && p->b1 && p->w2 && p->b2 && p->w3 &&
+           p->b3 && p->w_mu && p->b_mu && p->w_value && p->b_value;
+}
+int partial_floats(const AgxMlpParams* p) {  // dense padded dW of all four layers
+    return p->h1 * p->in_pad + p->h2 * p->h1 + p->h3 * p->h2 + kOutPad * p->h3;
+}
+bool units_fit(const AgxMlpParams* p) {  // every warp's work-unit list must fit kMaxUnits
+    const int outs[4] = {p->h1, p->h2, p->h3, kOutPad}, ins[4] = {p->in_pad, p->h1, p->h2, p->h3};
+    int q = 0;
+    for (int l = 0; l < 4; ++l) q += (outs[l] / 16) * ((ins[l] + 63) / 64);
+    return (q + kWarps - 1) / kWarps <= kMaxUnits;
+}
+size_t smem_bytes(const AgxMlpParams* p, int pad) {
+    const Dims d = dims_of(*p);
+    const size_t f = (size_t)weights_floats(d, pad) + (size_t)kWarps * 2 * kRows * kActLd;  // weights + per-warp ping-pong tiles
+    const size_t red = (size_t)kWarps * kBiasSlots;
+    return sizeof(float) * (f > red ? f : red);
+}
+constexpr int kGridMax = 148;
+int g_mlp_dbg = 0;
+constexpr int kWgradGrid = 296;
+unsigned grid_for(int64_t B) {
+    const int64_t tiles = (B + kRows - 1) / kRows;
+    int64_t g = (tiles + kWarps - 1) / kWarps;
+    if (g > kGridMax) g = kGridMax;  // one CTA per SM (shared-memory bound), persistent over tiles
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" {
+
+void agx_mlp_debug(int v) { g_mlp_dbg = v; }
+
+int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
+                    float* h1_out, float* h2_out, float* h3_out, void* stream) {
+    if (!valid(p) || b <= 0 || !obs || !mu || !value) return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_forward: bad argument");
+    const size_t smem = smem_bytes(p, 4);
+    if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
+    cudaFuncSetAttribute(agx_mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    agx_mlp_forward_kernel<<<grid_for(b), kWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p, b, obs, mu, value, xn_out,
+                                                                                                      h1_out, h2_out, h3_out, g_mlp_dbg);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_forward: launch failed");
+}
+
+int64_t agx_mlp_workspace_floats(const AgxMlpParams* p) {
+    if (!valid(p)) return -1;
+    return (int64_t)kWgradGrid * partial_floats(p) + (int64_t)kGridMax * kBiasSlots;
+}
+
+int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
+                     const float* xn, const float* h1, const float* h2, const float* h3, float* dz1, float* dz2, float* dz3,
+                     float* dout, float* workspace, void* stream) {
+    if (!valid(p) || !units_fit(p) || !g || b <= 0 || (b % 8) != 0 || !grad_mu || !grad_value || !xn || !h1 || !h2 || !h3 || !dz1 ||
+        !dz2 || !dz3 || !dout || !workspace || !g->gw1 || !g->gb1 || !g->gw2 || !g->gb2 || !g->gw3 || !g->gb3 || !g->gw_mu ||
+        !g->gb_mu || !g->gw_value || !g->gb_value)
+        return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_backward: bad argument (batch must be a multiple of 8)");
+    const size_t smem = smem_bytes(p, 8);
+    if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_backward: network too large for shared memory");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int pf = partial_floats(p);
+    float* w_partials = workspace;
+    float* b_partials = workspace + (int64_t)kWgradGrid * pf;
+    cudaFuncSetAttribute(agx_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned gb = grid_for(b);
+    agx_mlp_backward_kernel<<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials);
+    int64_t rows = (b + kWgradGrid - 1) / kWgradGrid;  // 2 CTAs per SM: no shared memory, more warps to hide the L2 latency
+    rows = (rows + 7) / 8 * 8;
+    const unsigned gw = (unsigned)((b + rows - 1) / rows);
+    agx_mlp_wgrad_kernel<<<gw, kWarps * 32, 0, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf);
+    const unsigned gr = (unsigned)((pf + kBiasSlots + 255) / 256);
+    agx_mlp_wgrad_reduce_kernel<<<gr, 256, 0, st>>>(*p, *g, w_partials, (int)gw, pf, b_partials, (int)gb);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward: launch failed");
+}
+
+}  // extern "C"

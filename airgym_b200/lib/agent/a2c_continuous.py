@@ -106,6 +106,7 @@ class A2CAgent:
         if self.global_rank == 0:
             os.makedirs(self.nn_dir, exist_ok=True)
         self.use_cuda_graph = config.get("use_cuda_graph", True)
+        self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
         self.algo_observer = config.get("features", {}).get("observer", None)
 
         keys = {"actions_num": self.actions_num, "input_shape": self.obs_shape, "num_seqs": self.num_actors,
@@ -150,6 +151,14 @@ class A2CAgent:
         self.ep_stats = torch.zeros(4, device=dev, dtype=torch.float64)  # Σreward, Σshaped, Σlength, #episodes (per epoch)
         self.grad_mu, self.grad_value, self.grad_logstd = f(self.minibatch_size, A), f(self.minibatch_size), f(A)
         self.norm_values, self.norm_returns, self.advantages = f(N * H, 1), f(N * H, 1), f(N * H)
+        if self.fused_mlp:
+            mb, dims = self.minibatch_size, self.model.fused_keep_dims()
+            self.keep = tuple(f(mb, d) for d in dims)           # normalised (padded) input + post-ELU activations
+            self.mlp_ws = self.model.fused_workspace(dev)
+            self.dz = tuple(f(mb, d) for d in dims[1:])         # pre-activation gradients
+            self.dout = f(mb, 16)                                # [dmu | dvalue | 0] padded head gradient
+            self.mb_mu, self.mb_value = f(mb, A), f(mb)
+            self.ro_mu, self.ro_value = f(N, A), f(N)
         self.epoch_loss_sums = torch.zeros(_capi.AGX_PPO_STATS, device=dev)
 
     # ---- env interaction ----------------------------------------------------------------------------------------------
@@ -165,7 +174,10 @@ class A2CAgent:
     def _rollout_step(self, n):
         b = self.buf
         self.model.eval()
-        res = self.model({"is_train": False, "prev_actions": None, "obs": self.obs})
+        if self.fused_mlp:
+            res = self._fused_policy(self.obs)
+        else:
+            res = self.model({"is_train": False, "prev_actions": None, "obs": self.obs})
         b["obses"][:, n] = self.obs
         b["dones"][:, n] = self.dones
         b["actions"][:, n] = res["actions"]
@@ -195,11 +207,26 @@ class A2CAgent:
         self.current_shaped_rewards *= nd
         self.current_lengths *= nd
 
+    def _fused_policy(self, obs):
+        """get_action_values (a2c_base.py:357-369) through the fused MLP kernel; sampling/neglogp as in the model's forward."""
+        m = self.model
+        m.fused_heads(obs, self.ro_mu, self.ro_value)
+        mu = self.ro_mu
+        logstd = mu * 0.0 + m.logstd
+        sigma = torch.exp(logstd)
+        action = mu + sigma * torch.randn_like(mu)
+        return {"neglogpacs": m.neglogp(action, mu, sigma, logstd), "values": m.denorm_value(self.ro_value.unsqueeze(-1)),
+                "actions": action, "mus": mu, "sigmas": sigma}
+
     def _rollout(self):
         for n in range(self.horizon_length):
             self._rollout_step(n)
         self.model.eval()
-        _, value = self.model.heads(self.obs)
+        if self.fused_mlp:
+            self.model.fused_heads(self.obs, self.ro_mu, self.ro_value)
+            value = self.ro_value.unsqueeze(-1)
+        else:
+            _, value = self.model.heads(self.obs)
         self.last_values.copy_(self.model.denorm_value(value).squeeze(-1))
         b = self.buf
         st = torch.cuda.current_stream().cuda_stream
@@ -276,7 +303,11 @@ class A2CAgent:
             with torch.no_grad():
                 self._rms_update(self.model.running_mean_std, obs)
         self.model.eval()  # statistics are updated explicitly above; forward only normalises
-        mu, value = self.model.heads(obs)
+        if self.fused_mlp:
+            self.model.fused_heads(obs, self.mb_mu, self.mb_value, keep=self.keep)
+            mu, value = self.mb_mu, self.mb_value
+        else:
+            mu, value = self.model.heads(obs)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: t.data_ptr()
         _capi.check(self._lib.agx_ppo_loss(
@@ -284,9 +315,12 @@ class A2CAgent:
             p(b["neglogpacs"].view(-1)[sl]), p(self.advantages[sl]), p(self.norm_returns[sl]), p(b["mus"].view(-1, A)[sl]),
             p(b["sigmas"].view(-1, A)[sl]), p(self.grad_mu), p(self.grad_value), p(self.grad_logstd), p(self.stats),
             p(self.workspace), st), "agx_ppo_loss")
-        self.flat_grads[: self.n_params].zero_()
-        torch.autograd.backward((mu, value), (self.grad_mu, self.grad_value.view(-1, 1)))
-        self.model.logstd.grad += self.grad_logstd
+        if self.fused_mlp:
+            self._manual_backward()
+        else:
+            self.flat_grads[: self.n_params].zero_()
+            torch.autograd.backward((mu, value), (self.grad_mu, self.grad_value.view(-1, 1)))
+            self.model.logstd.grad += self.grad_logstd
         scale = 1.0
         if self.multi_gpu and self.world_size > 1:
             self._allreduce(self.flat_grads)  # grads ‖ stats (KL) in one message
@@ -295,6 +329,12 @@ class A2CAgent:
         _capi.check(self._lib.agx_adam_step(
             C.byref(self.hyper), self.n_params, p(self.flat_params), p(self.flat_grads), p(self.exp_avg), p(self.exp_avg_sq),
             p(self.lr_dev), p(self.opt_step), p(self.stats[4:5]), scale, p(self.grad_norm_dev), st), "agx_adam_step")
+
+    def _manual_backward(self):
+        """Backward of the MLP without autograd: activation-gradient chain, split-K weight gradients and their deterministic
+        reduction (three launches) write straight into the flat gradient buffer (every parameter's .grad is a view of it)."""
+        self.model.fused_backward(self.grad_mu, self.grad_value, self.keep, self.dz, self.dout, self.mlp_ws)
+        self.model.logstd.grad.copy_(self.grad_logstd)
 
     def _update_pass(self, update_rms):
         for i in range(self.num_minibatches):

@@ -3,12 +3,14 @@ ModelA2CContinuousLogStd (lib/model/a2c_continuous_logstd_model.py:14-198, lib/n
 MLP case of the shipped yamls: `logstd`, `actor_mlp.layers.{i}.{weight,bias}`, `mu.*`, `value_head.*`,
 `value_mean_std.*`, `running_mean_std.*`.  All trainable parameters are views into ONE flat fp32 buffer (and their grads
 into one flat grad buffer), which is what the fused clip+Adam kernel and the NCCL all-reduce operate on."""
+import ctypes as C
 import math
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import _capi
 from ..core.running_mean_std import RunningMeanStd
 
 _ACTS = {"elu": F.elu, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "sin": torch.sin}
@@ -79,6 +81,65 @@ class ModelA2CContinuousLogStd(nn.Module):
             off += k
         self.flat_params, self.flat_grads, self.num_flat = flat, grads, n
         return flat, grads
+
+    # ---- fused tensor-core path (libagx agx_mlp_forward / agx_mlp_backward) -------------------------------------------
+    def fused_params(self):
+        """AgxMlpParams pointing at this module's parameter storage (valid as long as the tensors are not re-allocated)."""
+        layers = self.actor_mlp.layers
+        if len(layers) != 3 or self.actor_mlp.activation is not F.elu:
+            raise NotImplementedError("fused MLP kernels cover the shipped [h1,h2,h3]+ELU network")
+        P = _capi.AgxMlpParams()
+        P.in_dim = layers[0].in_features
+        P.in_pad = (P.in_dim + 15) // 16 * 16
+        P.h1, P.h2, P.h3 = layers[0].out_features, layers[1].out_features, layers[2].out_features
+        P.actions_num = self.actions_num
+        for i, l in enumerate(layers, 1):
+            setattr(P, f"w{i}", l.weight.data_ptr())
+            setattr(P, f"b{i}", l.bias.data_ptr())
+        P.w_mu, P.b_mu = self.mu.weight.data_ptr(), self.mu.bias.data_ptr()
+        P.w_value, P.b_value = self.value_head.weight.data_ptr(), self.value_head.bias.data_ptr()
+        if self.normalize_input:
+            P.in_mean, P.in_var = self.running_mean_std.running_mean.data_ptr(), self.running_mean_std.running_var.data_ptr()
+        return P
+
+    def fused_heads(self, obs, mu_out, value_out, keep=None):
+        """mu, value (normalised head output) of `obs` in one kernel; `keep` = (xn, h1, h2, h3) buffers for the backward."""
+        if getattr(self, "_fused", None) is None:
+            self._fused = self.fused_params()
+        p = lambda t: t.data_ptr() if t is not None else None
+        k = keep if keep is not None else (None, None, None, None)
+        _capi.check(_capi.load().agx_mlp_forward(C.byref(self._fused), obs.shape[0], p(obs), p(mu_out), p(value_out), p(k[0]), p(k[1]),
+                                                 p(k[2]), p(k[3]), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_forward")
+
+    def fused_grads(self):
+        """AgxMlpGrads pointing at the parameters' .grad tensors (views of the flat gradient buffer)."""
+        G = _capi.AgxMlpGrads()
+        for i, l in enumerate(self.actor_mlp.layers, 1):
+            setattr(G, f"gw{i}", l.weight.grad.data_ptr())
+            setattr(G, f"gb{i}", l.bias.grad.data_ptr())
+        G.gw_mu, G.gb_mu = self.mu.weight.grad.data_ptr(), self.mu.bias.grad.data_ptr()
+        G.gw_value, G.gb_value = self.value_head.weight.grad.data_ptr(), self.value_head.bias.grad.data_ptr()
+        return G
+
+    def fused_keep_dims(self):
+        """Column counts of the kept tensors: normalised input (padded), h1, h2, h3."""
+        L = self.actor_mlp.layers
+        return [(L[0].in_features + 15) // 16 * 16] + [l.out_features for l in L]
+
+    def fused_backward(self, grad_mu, grad_value, keep, dz, dout, workspace):
+        """Parameter gradients of the whole MLP for d(loss)/d(mu), d(loss)/d(value): written into the .grad views."""
+        if getattr(self, "_fused_g", None) is None:
+            self._fused_g = self.fused_grads()
+        p = lambda t: t.data_ptr()
+        _capi.check(_capi.load().agx_mlp_backward(
+            C.byref(self._fused), C.byref(self._fused_g), grad_mu.shape[0], p(grad_mu), p(grad_value), p(keep[0]), p(keep[1]), p(keep[2]),
+            p(keep[3]), p(dz[0]), p(dz[1]), p(dz[2]), p(dout), p(workspace), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            "agx_mlp_backward")
+
+    def fused_workspace(self, device):
+        if getattr(self, "_fused", None) is None:
+            self._fused = self.fused_params()
+        return torch.zeros(int(_capi.load().agx_mlp_workspace_floats(C.byref(self._fused))), device=device)
 
     # ---- forward ----------------------------------------------------------------------------------------------------
     def norm_obs(self, obs):

@@ -227,6 +227,44 @@ int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const 
                   float* exp_avg_sq, float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale,
                   float* grad_norm_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused actor-critic MLP on tensor cores (TF32 operands, fp32 accumulate).  Reference: lib/network/mlp.py:4-39 (three
+ * Linear+ELU layers), the `mu` and `value_head` Linear layers of lib/model/a2c_continuous_logstd_model.py:52-68,159-168,
+ * and the input normalisation RunningMeanStd.forward (lib/core/running_mean_std.py:76-80).  All pointers are DEVICE
+ * pointers into the caller's parameter tensors (torch Linear layout: weight [out,in] row-major, bias [out]).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct AgxMlpParams {
+    int32_t in_dim;          /* observation width (18 hovering/balloon, 48 tracking) */
+    int32_t in_pad;          /* in_dim rounded up to a multiple of 16 */
+    int32_t h1, h2, h3;      /* hidden widths (64,128,64): multiples of 32, at most 128 */
+    int32_t actions_num;     /* 4 or 5 */
+    const float *w1, *b1, *w2, *b2, *w3, *b3;    /* actor_mlp.layers.{0,1,2}.{weight,bias} */
+    const float *w_mu, *b_mu;                    /* mu.{weight,bias}         [A,h3], [A] */
+    const float *w_value, *b_value;              /* value_head.{weight,bias} [1,h3], [1] */
+    const double *in_mean, *in_var;              /* running_mean_std.running_{mean,var} (float64) or NULL = no normalisation */
+} AgxMlpParams;
+
+/* where the parameter gradients go (torch layout, e.g. views of one flat gradient buffer) */
+typedef struct AgxMlpGrads {
+    float *gw1, *gb1, *gw2, *gb2, *gw3, *gb3, *gw_mu, *gb_mu, *gw_value, *gb_value;
+} AgxMlpGrads;
+
+/* obs [b,in_dim] → mu [b,A], value [b] (the normalised head output); when the four *_out pointers are non-NULL the
+ * normalised input [b,in_pad] (zero padded) and the post-ELU activations [b,h1],[b,h2],[b,h3] are kept for the backward. */
+int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
+                    float* h1_out, float* h2_out, float* h3_out, void* stream);
+
+/* floats of scratch agx_mlp_backward needs (split-K partials of the weight and bias gradients) */
+int64_t agx_mlp_workspace_floats(const AgxMlpParams* p);
+
+/* Full backward of the network for d(loss)/d(mu) [b,A] and d(loss)/d(value) [b] given the kept activations:
+ * (1) activation-gradient chain dz3, dz2, dz1 [b,h*] and the padded head gradient dout [b,16] (scratch outputs),
+ * (2) dW_l = dz_l^T · a_{l-1} and the bias gradients, reduced deterministically and written into `g` (overwrite, not +=).
+ * b must be a multiple of 8.  Three launches, no host sync. */
+int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
+                     const float* xn, const float* h1, const float* h2, const float* h3, float* dz1, float* dz2, float* dz3,
+                     float* dout, float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,8 +165,8 @@ def test_minibatch_update_matches_reference_golden(built):
     assert float(lr_dev) == pytest.approx(float(g["step0/lr_out"]), rel=1e-6)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph):
+@pytest.mark.parametrize("graph,fused", [(False, False), (True, False), (False, True), (True, True)])
+def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph, fused):
     """A few PPO epochs on Hovering/CTBR through Runner: losses finite, KL-driven LR moves, reward improves, checkpoint
     round-trips with the reference's key layout; CUDA-graph mode equals eager mode in distribution (same code path)."""
     from airgym_b200.lib.config import default_ppo_config, scale_minibatch
@@ -174,7 +174,7 @@ def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph):
 
     cfg = scale_minibatch(default_ppo_config("hovering"), 2048)
     c = cfg["params"]["config"]
-    c.update(max_epochs=12, train_dir=str(tmp_path), use_cuda_graph=graph, print_stats=False, save_best_after=1)
+    c.update(max_epochs=12, train_dir=str(tmp_path), use_cuda_graph=graph, fused_mlp=fused, print_stats=False, save_best_after=1)
     c["env_config"].update(ctl_mode="rate", num_envs=2048, seed=3)
     cfg["params"]["seed"] = 3
     r = Runner()
@@ -195,3 +195,55 @@ def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph):
     r.agent.flat_params.add_(1.0)
     r.agent.restore(ck)
     assert torch.equal(r.agent.flat_params, before)
+
+
+@pytest.mark.parametrize("task,B", [("hovering", 2048), ("tracking", 1000), ("hovering", 65536), ("hovering", 8)])
+def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
+    """agx_mlp_forward / agx_mlp_backward (TF32 tensor cores) against the fp32 torch model + autograd: outputs to ~1e-3,
+    parameter gradients to ~1e-2 of their scale (TF32 has a 10-bit mantissa)."""
+    from airgym_b200.lib.config import default_ppo_config
+    from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+
+    torch.manual_seed(4)
+    OBS, A = (48, 4) if task == "tracking" else (18, 4)
+    model = ModelA2CContinuousLogStd(default_ppo_config(task)["params"], {"actions_num": A, "input_shape": (OBS,)}).cuda()
+    with torch.no_grad():
+        model.running_mean_std.running_mean.copy_(torch.randn(OBS, dtype=torch.float64) * 0.3)
+        model.running_mean_std.running_var.copy_(torch.rand(OBS, dtype=torch.float64) + 0.5)
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    model.flatten_parameters()
+    model.eval()
+    obs = torch.randn(B, OBS, device="cuda") * 2.0
+    mu_ref, v_ref = model.heads(obs)
+    dims = model.fused_keep_dims()
+    keep = tuple(torch.zeros(B, d, device="cuda") for d in dims)
+    mu, value = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda")
+    model.fused_heads(obs, mu, value, keep=keep)
+    assert_close(mu.cpu(), mu_ref.detach().cpu(), "mu", rtol=5e-3, atol=2e-3)
+    assert_close(value.cpu(), v_ref.detach().squeeze(-1).cpu(), "value", rtol=5e-3, atol=2e-3)
+    assert_close(keep[0][:, :OBS].cpu(), model.norm_obs(obs).cpu(), "normalised input", rtol=1e-6, atol=1e-6)
+    assert float(keep[0][:, OBS:].abs().max()) == 0.0 if dims[0] > OBS else True
+    g_mu, g_v = torch.randn(B, A, device="cuda") / B, torch.randn(B, device="cuda") / B
+    for p in model.parameters():
+        p.grad.zero_()
+    torch.autograd.backward((mu_ref, v_ref), (g_mu, g_v.view(-1, 1)))
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad.fill_(7.0)  # the kernel overwrites (does not accumulate)
+    dz = tuple(torch.zeros(B, d, device="cuda") for d in dims[1:])
+    dout = torch.zeros(B, 16, device="cuda")
+    ws = model.fused_workspace("cuda")
+    model.fused_backward(g_mu, g_v, keep, dz, dout, ws)
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        if n == "logstd":
+            continue
+        scale = float(ref_grads[n].abs().max()) + 1e-12
+        assert_close((p.grad / scale).cpu(), (ref_grads[n] / scale).cpu(), f"grad {n}", rtol=2e-2, atol=1e-2)
+    first = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.fused_backward(g_mu, g_v, keep, dz, dout, ws)  # deterministic: bitwise identical on a second run
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        assert torch.equal(p.grad, first[n]), n
