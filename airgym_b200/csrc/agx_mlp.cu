@@ -25,17 +25,27 @@ constexpr int kMaxW = 128;         // widest layer
 constexpr int kActLd = kMaxW + 4;  // activation tile leading dimension (≡ 4 mod 32 → conflict-free A-fragment loads)
 constexpr int kBiasSlots = 3 * kMaxW + kOutPad;  // per-CTA bias partials: b1 | b2 | b3 | heads (each padded to kMaxW)
 
+// layer widths either at run time (Dims, any supported network) or baked in at compile time (SDims: the shipped 64-128-64
+// network; every width test, loop bound and GEMM dispatch then folds away — the run-time version executes ~4x more instructions)
 struct Dims {
     int in_dim, in_pad, h1, h2, h3, a;  // in_pad multiple of 16, h* multiples of 32; a = actions_num (4 or 5)
 };
-__host__ __device__ inline Dims dims_of(const AgxMlpParams& P) { return Dims{P.in_dim, P.in_pad, P.h1, P.h2, P.h3, P.actions_num}; }
+template <int IN_PAD, int H1, int H2, int H3>
+struct SDims {
+    int in_dim, a;
+    static constexpr int in_pad = IN_PAD, h1 = H1, h2 = H2, h3 = H3;
+};
+template <class D> __host__ __device__ inline D dims_of(const AgxMlpParams& P);
+template <> __host__ __device__ inline Dims dims_of<Dims>(const AgxMlpParams& P) { return Dims{P.in_dim, P.in_pad, P.h1, P.h2, P.h3, P.actions_num}; }
+template <class D> __host__ __device__ inline D dims_of(const AgxMlpParams& P) { D d; d.in_dim = P.in_dim; d.a = P.actions_num; return d; }
 
 // shared-memory layout (float offsets into g_smem): W_l stored [out x (in + pad)] row-major, then biases, then per-warp tiles
 struct SmemW {
     int w1, w2, w3, wh, b1, b2, b3, bh, end;
     int ld1, ld2, ld3, ldh;
 };
-__host__ __device__ inline SmemW carve_weights(const Dims& d, int pad) {
+template <class D>
+__host__ __device__ inline SmemW carve_weights(const D& d, int pad) {
     SmemW s;
     s.ld1 = d.in_pad + pad; s.ld2 = d.h1 + pad; s.ld3 = d.h2 + pad; s.ldh = d.h3 + pad;
     s.w1 = 0;                        s.w2 = s.w1 + d.h1 * s.ld1;    s.w3 = s.w2 + d.h2 * s.ld2;
@@ -43,7 +53,8 @@ __host__ __device__ inline SmemW carve_weights(const Dims& d, int pad) {
     s.b3 = s.b2 + d.h2;              s.bh = s.b3 + d.h3;            s.end = s.bh + kOutPad;
     return s;
 }
-__host__ __device__ inline int weights_floats(const Dims& d, int pad) { return carve_weights(d, pad).end; }
+template <class D>
+__host__ __device__ inline int weights_floats(const D& d, int pad) { return carve_weights(d, pad).end; }
 
 // ---- warp-level tensor-core GEMM pieces: mma.sync m16n8k8, TF32 operands (pre-rounded in shared memory), fp32 accumulate.
 // Fragment ownership (g = lane / 4, t = lane % 4):  A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
@@ -135,7 +146,8 @@ __device__ inline void stage_matrix(int dst, int ld, const float* __restrict__ s
     }
 }
 // stage the network into shared memory (weights pre-rounded to TF32; W1 zero padded; the two heads stacked into 16 rows)
-__device__ void stage_weights(const AgxMlpParams& P, const Dims& d, const SmemW& s) {
+template <class D>
+__device__ void stage_weights(const AgxMlpParams& P, const D& d, const SmemW& s) {
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
     stage_matrix(s.w1, s.ld1, P.w1, d.h1, d.in_dim, warp, lane);
     stage_matrix(s.w2, s.ld2, P.w2, d.h2, d.h1, warp, lane);
@@ -155,7 +167,8 @@ constexpr int kU = kMaxW / 32;  // column slots per lane: lane owns columns lane
 
 // bias + ELU over a 16 x width tile at offset `bo` (TF32-rounded copy stays in shared memory for the next GEMM; the
 // full-precision value is optionally kept in HBM)
-__device__ inline void bias_elu_tile(int bo, int bias_o, int width, int lane, float* out, int64_t row0, int64_t B) {
+__device__ inline void bias_elu_tile(int bo, int bias_o, int width, int lane, float* out, int64_t row0, int rows_valid) {
+    if (out) out += row0 * width;
     float b[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) b[u] = (lane + 32 * u < width) ? g_smem[bias_o + lane + 32 * u] : 0.0f;
@@ -167,7 +180,7 @@ __device__ inline void bias_elu_tile(int bo, int bias_o, int width, int lane, fl
             if (c < width) {
                 const float h = elu(g_smem[bo + r * kActLd + c] + b[u]);
                 g_smem[bo + r * kActLd + c] = tf32r(h);
-                if (out && row0 + r < B) out[(row0 + r) * width + c] = h;
+                if (out && r < rows_valid) out[r * width + c] = h;
             }
         }
     }
@@ -175,7 +188,8 @@ __device__ inline void bias_elu_tile(int bo, int bias_o, int width, int lane, fl
 // g = dH ∘ elu'(h) over a 16 x width tile: dz to HBM, TF32 copy kept in shared memory for the next GEMM, column sums in bacc.
 // The activations `hv` were prefetched from HBM before the GEMM that produced dH (latency hidden behind the tensor work).
 __device__ inline void elu_grad_tile(int bo, const float (&hv)[kRows][kU], float* __restrict__ dz, int width, int lane, int64_t row0,
-                                     int64_t B, float* bacc, bool keep_in_smem) {
+                                     int rows_valid, float* bacc, bool keep_in_smem) {
+    dz += row0 * width;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
 #pragma unroll
@@ -183,9 +197,9 @@ __device__ inline void elu_grad_tile(int bo, const float (&hv)[kRows][kU], float
             const int c = lane + 32 * u;
             if (c < width) {
                 float g = 0.0f;
-                if (row0 + r < B) {
+                if (r < rows_valid) {
                     g = g_smem[bo + r * kActLd + c] * elu_grad_from_out(hv[r][u]);
-                    dz[(row0 + r) * width + c] = g;
+                    dz[r * width + c] = g;
                 }
                 if (keep_in_smem) g_smem[bo + r * kActLd + c] = tf32r(g);
                 bacc[u] += g;
@@ -193,23 +207,25 @@ __device__ inline void elu_grad_tile(int bo, const float (&hv)[kRows][kU], float
         }
     }
 }
-__device__ inline void prefetch_tile(const float* __restrict__ h, float (&hv)[kRows][kU], int width, int lane, int64_t row0, int64_t B) {
+__device__ inline void prefetch_tile(const float* __restrict__ h, float (&hv)[kRows][kU], int width, int lane, int64_t row0, int rows_valid) {
+    h += row0 * width;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const int c = lane + 32 * u;
-            hv[r][u] = (c < width && row0 + r < B) ? h[(row0 + r) * width + c] : 0.0f;
+            hv[r][u] = (c < width && r < rows_valid) ? h[r * width + c] : 0.0f;
         }
     }
 }
 
 // ---- forward ---------------------------------------------------------------------------------------------------------------
+template <class D>
 __global__ void __launch_bounds__(kWarps * 32)
 agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs,
                        float* __restrict__ mu, float* __restrict__ value, float* __restrict__ xn_out,
                        float* __restrict__ h1_out, float* __restrict__ h2_out, float* __restrict__ h3_out, int dbg) {
-    const Dims d = dims_of(P);
+    const D d = dims_of<D>(P);
     const SmemW W = carve_weights(d, 4);  // ld ≡ 4 (mod 32): conflict-free B fragments of X · W^T
     if (!(dbg & 1)) stage_weights(P, d, W);
     __syncthreads();
@@ -227,6 +243,7 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
     const int64_t n_tiles = (B + kRows - 1) / kRows;
     for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
         const int64_t row0 = tile * kRows;
+        const int rows_valid = (B - row0) < kRows ? (int)(B - row0) : kRows;
         // normalised input tile (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80)
 #pragma unroll 4
         for (int r = 0; r < kRows; ++r) {
@@ -235,7 +252,7 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
                 const int c = lane + 32 * u;
                 if (c < d.in_pad) {
                     float v = 0.0f;
-                    if (c < d.in_dim && row0 + r < B) {
+                    if (c < d.in_dim && r < rows_valid) {
                         v = obs[(row0 + r) * d.in_dim + c];
                         if (P.in_mean) {
                             v = (v - n_mean[u]) / n_sd[u];
@@ -243,22 +260,22 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
                         }
                     }
                     g_smem[bufA + r * kActLd + c] = tf32r(v);
-                    if (xn_out && row0 + r < B) xn_out[(row0 + r) * d.in_pad + c] = v;
+                    if (xn_out && r < rows_valid) xn_out[(row0 + r) * d.in_pad + c] = v;
                 }
             }
         }
         __syncwarp();
         if (!(dbg & 8)) gemm16<true>(bufA, W.w1, W.ld1, d.in_pad, d.h1, bufB, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufB, W.b1, d.h1, lane, h1_out, row0, B);
+        if (!(dbg & 4)) bias_elu_tile(bufB, W.b1, d.h1, lane, h1_out, row0, rows_valid);
         __syncwarp();
         if (!(dbg & 8)) gemm16<true>(bufB, W.w2, W.ld2, d.h1, d.h2, bufA, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufA, W.b2, d.h2, lane, h2_out, row0, B);
+        if (!(dbg & 4)) bias_elu_tile(bufA, W.b2, d.h2, lane, h2_out, row0, rows_valid);
         __syncwarp();
         if (!(dbg & 8)) gemm16<true>(bufA, W.w3, W.ld3, d.h2, d.h3, bufB, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufB, W.b3, d.h3, lane, h3_out, row0, B);
+        if (!(dbg & 4)) bias_elu_tile(bufB, W.b3, d.h3, lane, h3_out, row0, rows_valid);
         __syncwarp();
         if (!(dbg & 8)) gemm16<true>(bufB, W.wh, W.ldh, d.h3, kOutPad, bufA, lane);
         __syncwarp();
@@ -268,7 +285,7 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
 #pragma unroll
             for (int j = 0; j < kRows / 2; ++j) {
                 const int r = (lane >> 4) + 2 * j;
-                if (row0 + r < B) {
+                if (r < rows_valid) {
                     const float v = g_smem[bufA + r * kActLd + c] + bh;
                     if (c < d.a) mu[(row0 + r) * d.a + c] = v;
                     else if (c == d.a) value[row0 + r] = v;
@@ -280,12 +297,13 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
 }
 
 // ---- backward: activation-gradient chain + bias-gradient partials ----------------------------------------------------------------
+template <class D>
 __global__ void __launch_bounds__(kWarps * 32)
 agx_mlp_backward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ grad_mu,
                         const float* __restrict__ grad_value, const float* __restrict__ h1, const float* __restrict__ h2,
                         const float* __restrict__ h3, float* __restrict__ dz1, float* __restrict__ dz2,
                         float* __restrict__ dz3, float* __restrict__ dout, float* __restrict__ bias_partials) {
-    const Dims d = dims_of(P);
+    const D d = dims_of<D>(P);
     const SmemW W = carve_weights(d, 8);  // ld ≡ 8 (mod 32): conflict-free B fragments of X · W
     stage_weights(P, d, W);
     __syncthreads();
@@ -299,15 +317,16 @@ agx_mlp_backward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
     const int64_t n_tiles = (B + kRows - 1) / kRows;
     for (int64_t tile = (int64_t)blockIdx.x * kWarps + warp; tile < n_tiles; tile += (int64_t)gridDim.x * kWarps) {
         const int64_t row0 = tile * kRows;
+        const int rows_valid = (B - row0) < kRows ? (int)(B - row0) : kRows;
         float hv[kRows][kU];
-        prefetch_tile(h3, hv, d.h3, lane, row0, B);
+        prefetch_tile(h3, hv, d.h3, lane, row0, rows_valid);
         {
             const int c = lane & 15;
 #pragma unroll
             for (int j = 0; j < kRows / 2; ++j) {
                 const int r = (lane >> 4) + 2 * j;
                 float v = 0.0f;
-                if (row0 + r < B) {
+                if (r < rows_valid) {
                     v = c < d.a ? grad_mu[(row0 + r) * d.a + c] : (c == d.a ? grad_value[row0 + r] : 0.0f);
                     dout[(row0 + r) * kOutPad + c] = v;
                 }
@@ -318,17 +337,17 @@ agx_mlp_backward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
         __syncwarp();
         gemm16<false>(bufA, W.wh, W.ldh, kOutPad, d.h3, bufB, lane);  // dH3 = dOut · W_head
         __syncwarp();
-        elu_grad_tile(bufB, hv, dz3, d.h3, lane, row0, B, bacc3, true);
-        prefetch_tile(h2, hv, d.h2, lane, row0, B);
+        elu_grad_tile(bufB, hv, dz3, d.h3, lane, row0, rows_valid, bacc3, true);
+        prefetch_tile(h2, hv, d.h2, lane, row0, rows_valid);
         __syncwarp();
         gemm16<false>(bufB, W.w3, W.ld3, d.h3, d.h2, bufA, lane);  // dH2 = dZ3 · W3
         __syncwarp();
-        elu_grad_tile(bufA, hv, dz2, d.h2, lane, row0, B, bacc2, true);
-        prefetch_tile(h1, hv, d.h1, lane, row0, B);
+        elu_grad_tile(bufA, hv, dz2, d.h2, lane, row0, rows_valid, bacc2, true);
+        prefetch_tile(h1, hv, d.h1, lane, row0, rows_valid);
         __syncwarp();
         gemm16<false>(bufA, W.w2, W.ld2, d.h2, d.h1, bufB, lane);  // dH1 = dZ2 · W2
         __syncwarp();
-        elu_grad_tile(bufB, hv, dz1, d.h1, lane, row0, B, bacc1, false);
+        elu_grad_tile(bufB, hv, dz1, d.h1, lane, row0, rows_valid, bacc1, false);
         __syncwarp();
     }
     // CTA-level reduction of the bias partials, fixed order → deterministic
@@ -356,36 +375,45 @@ agx_mlp_backward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
 // dW_l[out, in] = sum_b dz_l[b, out] · a_{l-1}[b, in] as mma.sync m16n8k8 with A = dz^T (m = out, k = batch row) and B = a
 // (k = batch row, n = in), fragments loaded straight from HBM/L2.  Work unit = one 16-row out-tile x up to 8 n8 in-tiles
 // (32 accumulator registers); the units of all four layers are dealt round-robin to the 8 warps of a CTA.
+// The units are split between kWgradSplit CTAs that walk the same slab of the batch: each CTA then holds half of the dW
+// accumulators (<= 2 units = 64 registers per thread), which lets two CTAs (16 warps) share an SM and hide the L2 latency
+// of the fragment loads.
 struct WUnit { int layer, o0, i0, nt; };
-constexpr int kMaxUnits = 4;   // per warp
-__device__ inline int build_units(const Dims& d, int warp, WUnit (&u)[kMaxUnits]) {
+constexpr int kMaxUnits = 2;   // per warp
+constexpr int kWgradSplit = 2;
+template <class D>
+__device__ inline int build_units(const D& d, int warp, int half, WUnit (&u)[kMaxUnits]) {
     const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
     int n = 0, q = 0;
     for (int l = 0; l < 4; ++l)
         for (int o0 = 0; o0 < outs[l]; o0 += 16)
             for (int i0 = 0; i0 < ins[l]; i0 += 64, ++q)
-                if (q % kWarps == warp && n < kMaxUnits) { u[n].layer = l; u[n].o0 = o0; u[n].i0 = i0; u[n].nt = (ins[l] - i0) >= 64 ? 8 : (ins[l] - i0) / 8; ++n; }
+                if (q % kWgradSplit == half && (q / kWgradSplit) % kWarps == warp && n < kMaxUnits) {
+                    u[n].layer = l; u[n].o0 = o0; u[n].i0 = i0; u[n].nt = (ins[l] - i0) >= 64 ? 8 : (ins[l] - i0) / 8; ++n;
+                }
     return n;
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+template <class D>
+__global__ void __launch_bounds__(kWarps * 32, 2)
 agx_mlp_wgrad_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t rows_per_cta, const float* __restrict__ xn,
                      const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ h3,
                      const float* __restrict__ dz1, const float* __restrict__ dz2, const float* __restrict__ dz3,
                      const float* __restrict__ dout, float* __restrict__ partials, int partial_floats) {
-    const Dims d = dims_of(P);
+    const D d = dims_of<D>(P);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const float* dzs[4] = {dz1, dz2, dz3, dout};
     const float* as[4] = {xn, h1, h2, h3};
     const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
     WUnit un[kMaxUnits];
-    const int n_units = build_units(d, warp, un);
+    const int slab = blockIdx.x / kWgradSplit, half = blockIdx.x % kWgradSplit;
+    const int n_units = build_units(d, warp, half, un);
     float acc[kMaxUnits][8][4];
 #pragma unroll
     for (int q = 0; q < kMaxUnits; ++q)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[q][j][0] = 0.0f; acc[q][j][1] = 0.0f; acc[q][j][2] = 0.0f; acc[q][j][3] = 0.0f; }
-    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_begin = (int64_t)slab * rows_per_cta;
     int64_t r_end = r_begin + rows_per_cta;
     if (r_end > B) r_end = B;  // B is a multiple of 8 (checked on the host)
     for (int64_t r = r_begin; r < r_end; r += 8) {
@@ -409,7 +437,7 @@ agx_mlp_wgrad_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t 
         }
     }
     // partial dW of this CTA: dense [out_l x in_l] blocks, layers back to back
-    float* mine = partials + (int64_t)blockIdx.x * partial_floats;
+    float* mine = partials + (int64_t)slab * partial_floats;
 #pragma unroll
     for (int q = 0; q < kMaxUnits; ++q) {
         if (q < n_units) {
@@ -432,7 +460,7 @@ agx_mlp_wgrad_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t 
 __global__ void agx_mlp_wgrad_reduce_kernel(const __grid_constant__ AgxMlpParams P, const __grid_constant__ AgxMlpGrads G,
                                             const float* __restrict__ partials, int n_cta_w, int partial_floats,
                                             const float* __restrict__ bias_partials, int n_cta_b) {
-    const Dims d = dims_of(P);
+    const Dims d = dims_of<Dims>(P);
     const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3}, real_in[4] = {d.in_dim, d.h1, d.h2, d.h3};
     float* gw[3] = {G.gw1, G.gw2, G.gw3};
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -472,17 +500,20 @@ bool units_fit(const AgxMlpParams* p) {  // every warp's work-unit list must fit
     const int outs[4] = {p->h1, p->h2, p->h3, kOutPad}, ins[4] = {p->in_pad, p->h1, p->h2, p->h3};
     int q = 0;
     for (int l = 0; l < 4; ++l) q += (outs[l] / 16) * ((ins[l] + 63) / 64);
-    return (q + kWarps - 1) / kWarps <= kMaxUnits;
+    return (q + kWgradSplit * kWarps - 1) / (kWgradSplit * kWarps) <= kMaxUnits;
 }
 size_t smem_bytes(const AgxMlpParams* p, int pad) {
-    const Dims d = dims_of(*p);
+    const Dims d = dims_of<Dims>(*p);
     const size_t f = (size_t)weights_floats(d, pad) + (size_t)kWarps * 2 * kRows * kActLd;  // weights + per-warp ping-pong tiles
     const size_t red = (size_t)kWarps * kBiasSlots;
     return sizeof(float) * (f > red ? f : red);
 }
+using S32 = SDims<32, 64, 128, 64>;  // hovering / balloon (18 obs) with the shipped [64,128,64] MLP
+using S48 = SDims<48, 64, 128, 64>;  // tracking (48 obs)
+bool is_shipped(const AgxMlpParams* p, int in_pad) { return p->in_pad == in_pad && p->h1 == 64 && p->h2 == 128 && p->h3 == 64; }
 constexpr int kGridMax = 148;
 int g_mlp_dbg = 0;
-constexpr int kWgradGrid = 296;
+constexpr int kWgradGrid = 148;  // batch slabs; each slab is walked by kWgradSplit CTAs
 unsigned grid_for(int64_t B) {
     const int64_t tiles = (B + kRows - 1) / kRows;
     int64_t g = (tiles + kWarps - 1) / kWarps;
@@ -501,9 +532,16 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
     if (!valid(p) || b <= 0 || !obs || !mu || !value) return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_forward: bad argument");
     const size_t smem = smem_bytes(p, 4);
     if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
-    cudaFuncSetAttribute(agx_mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    agx_mlp_forward_kernel<<<grid_for(b), kWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p, b, obs, mu, value, xn_out,
-                                                                                                      h1_out, h2_out, h3_out, g_mlp_dbg);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define AGX_FWD(D)                                                                                                      \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(agx_mlp_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        agx_mlp_forward_kernel<D><<<grid_for(b), kWarps * 32, smem, st>>>(*p, b, obs, mu, value, xn_out, h1_out, h2_out, h3_out, g_mlp_dbg); \
+    } while (0)
+    if (is_shipped(p, 32)) AGX_FWD(S32);
+    else if (is_shipped(p, 48)) AGX_FWD(S48);
+    else AGX_FWD(Dims);
+#undef AGX_FWD
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_forward: launch failed");
 }
 
@@ -525,15 +563,22 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
     const int pf = partial_floats(p);
     float* w_partials = workspace;
     float* b_partials = workspace + (int64_t)kWgradGrid * pf;
-    cudaFuncSetAttribute(agx_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned gb = grid_for(b);
-    agx_mlp_backward_kernel<<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials);
-    int64_t rows = (b + kWgradGrid - 1) / kWgradGrid;  // 2 CTAs per SM: no shared memory, more warps to hide the L2 latency
+    int64_t rows = (b + kWgradGrid - 1) / kWgradGrid;
     rows = (rows + 7) / 8 * 8;
-    const unsigned gw = (unsigned)((b + rows - 1) / rows);
-    agx_mlp_wgrad_kernel<<<gw, kWarps * 32, 0, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf);
+    const unsigned n_slabs = (unsigned)((b + rows - 1) / rows), gw = n_slabs * kWgradSplit;
+#define AGX_BWD(D)                                                                                                       \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(agx_mlp_backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        agx_mlp_backward_kernel<D><<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials); \
+        agx_mlp_wgrad_kernel<D><<<gw, kWarps * 32, 0, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf);   \
+    } while (0)
+    if (is_shipped(p, 32)) AGX_BWD(S32);
+    else if (is_shipped(p, 48)) AGX_BWD(S48);
+    else AGX_BWD(Dims);
+#undef AGX_BWD
     const unsigned gr = (unsigned)((pf + kBiasSlots + 255) / 256);
-    agx_mlp_wgrad_reduce_kernel<<<gr, 256, 0, st>>>(*p, *g, w_partials, (int)gw, pf, b_partials, (int)gb);
+    agx_mlp_wgrad_reduce_kernel<<<gr, 256, 0, st>>>(*p, *g, w_partials, (int)n_slabs, pf, b_partials, (int)gb);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward: launch failed");
 }
 
