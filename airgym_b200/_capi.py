@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagx.so")
+# AGX_LIB: tuning runs (scripts/kbench.py) point this at an alternative build of the same sources
+LIB_PATH = os.environ.get("AGX_LIB") or os.path.join(_HERE, "libagx.so")
 
 AGX_MAX_ACTIONS = 5
 AGX_CTRL_STATE_MAX = 12

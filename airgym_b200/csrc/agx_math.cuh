@@ -169,9 +169,12 @@ AGX_HD U4 philox_block(const PhiloxCtx& c, uint32_t stream_id, uint32_t blk) {
 }
 AGX_HD float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
 
-AGX_HD void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
-    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;  // (0,1]
-    const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;         // [0,1)
+// Box-Muller on the two 16-bit halves of one Philox word: radius from the high half (u1 in (0,1], |z| <= 4.71),
+// angle from the low half.  One 128-bit Philox block therefore yields 8 normals; sensor-noise quality, documented in
+// DESIGN.md §4 (the reference draws torch.randn; the stream is builder-defined either way).
+AGX_HD void box_muller16(uint32_t w, float* z0, float* z1) {
+    const float u1 = (float)((w >> 16) + 1u) * 1.52587890625e-5f;  // (0,1]
+    const float u2 = (float)(w & 0xFFFFu) * 1.52587890625e-5f;     // [0,1)
     float s, c;
 #if defined(__CUDA_ARCH__)
     // SFU path (MUFU.LG2 / MUFU.SIN / MUFU.COS): abs error ~2^-21 on N(0,1) draws, far below the noise itself
@@ -186,27 +189,51 @@ AGX_HD void box_muller(uint32_t a, uint32_t b, float* z0, float* z1) {
 
 // `count` uniforms of stream `sid` (0: pre-step reset, 1: post-step reset)
 AGX_HD void philox_uniforms(const PhiloxCtx& c, uint32_t sid, int count, float* u) {
-    for (int b = 0; b * 4 < count; ++b) {
+#pragma unroll
+    for (int b = 0; b < AGX_RESET_DRAWS_MAX / 4; ++b) {
+        if (b * 4 >= count) break;
         const U4 r = philox_block(c, sid, (uint32_t)b);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
         for (int j = 0; j < 4; ++j)
             if (b * 4 + j < count) u[b * 4 + j] = u32_to_unit(w[j]);
     }
 }
-// `count` (<= 20) standard normals of stream 2
+// `count` (<= 24) standard normals of stream 2: block b → normals [8b, 8b+8)
 AGX_HD void philox_normals(const PhiloxCtx& c, int count, float* z) {
 #pragma unroll
-    for (int b = 0; b < 5; ++b) {
-        if (b * 4 >= count) break;
+    for (int b = 0; b < 3; ++b) {
+        if (b * 8 >= count) break;
         const U4 r = philox_block(c, 2u, (uint32_t)b);
-        float n0, n1, n2, n3;
-        box_muller(r.x, r.y, &n0, &n1);
-        box_muller(r.z, r.w, &n2, &n3);
-        const float n[4] = {n0, n1, n2, n3};
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (b * 4 + j < count) z[b * 4 + j] = n[j];
+        for (int j = 0; j < 4; ++j) {
+            float n0, n1;
+            box_muller16(w[j], &n0, &n1);
+            if (b * 8 + 2 * j < count) z[b * 8 + 2 * j] = n0;
+            if (b * 8 + 2 * j + 1 < count) z[b * 8 + 2 * j + 1] = n1;
+        }
     }
+}
+
+// matrix_to_quaternion(euler_angles_to_matrix(a,'XYZ')) in closed form: q = qx(a0) * qy(a1) * qz(a2) (Hamilton, half
+// angles), standardised to w >= 0 like pytorch3d.  Same rotation as matrix_to_quat(euler_xyz_to_matrix()) to fp32
+// rounding, at 3 sincos instead of 6 sin/cos + 4 sqrt + 4 divisions (reset paths only; hovering.py:323-324).
+AGX_HD Q4 euler_xyz_to_quat(float a0, float a1, float a2) {
+    float s0, c0, s1, c1, s2, c2;
+#if defined(__CUDA_ARCH__)
+    sincosf(0.5f * a0, &s0, &c0); sincosf(0.5f * a1, &s1, &c1); sincosf(0.5f * a2, &s2, &c2);
+#else
+    s0 = sinf(0.5f * a0); c0 = cosf(0.5f * a0); s1 = sinf(0.5f * a1); c1 = cosf(0.5f * a1);
+    s2 = sinf(0.5f * a2); c2 = cosf(0.5f * a2);
+#endif
+    Q4 q;
+    q.w = c0 * c1 * c2 - s0 * s1 * s2;
+    q.x = s0 * c1 * c2 + c0 * s1 * s2;
+    q.y = c0 * s1 * c2 - s0 * c1 * s2;
+    q.z = c0 * c1 * s2 + s0 * s1 * c2;
+    if (q.w < 0.0f) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+    return q;
 }
 
 // ---- reset samplers ---------------------------------------------------------------------------------
@@ -227,9 +254,7 @@ AGX_HD void reset_sample_balloon(const float* u, float* s, float* aux) {
     const float a0 = 0.1f * urange(u[6], -kPi, kPi);
     const float a1 = 0.1f * urange(u[7], 0.0f, kPi);
     const float a2 = 0.2f * urange(u[8], -kPi, kPi);
-    float m[9];
-    euler_xyz_to_matrix(a0, a1, a2, m);
-    const Q4 q = matrix_to_quat(m);
+    const Q4 q = euler_xyz_to_quat(a0, a1, a2);
     s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
     s[7] = 0.5f * urange(u[9], -1.0f, 1.0f);
     s[8] = 0.5f * urange(u[10], -1.0f, 1.0f);
@@ -241,7 +266,8 @@ AGX_HD void reset_sample_balloon(const float* u, float* s, float* aux) {
 }
 
 template <int TASK>
-AGX_HD void reset_sample(const float* u, float* s) {
+AGX_HD void reset_sample(const float* u, float* s, float* aux) {
+    if (TASK == AGX_TASK_BALLOON) { reset_sample_balloon(u, s, aux); return; }
     float a0, a1, a2;
     if (TASK == AGX_TASK_TRACKING) {
         s[0] = 0.1f * urange(u[0], -1.0f, 1.0f);
@@ -258,9 +284,7 @@ AGX_HD void reset_sample(const float* u, float* s) {
         a1 = 0.01f * urange(u[4], -kPi, kPi);
         a2 = 0.05f * urange(u[5], -kPi, kPi);
     }
-    float m[9];
-    euler_xyz_to_matrix(a0, a1, a2, m);
-    const Q4 q = matrix_to_quat(m);
+    const Q4 q = euler_xyz_to_quat(a0, a1, a2);
     s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
     s[7] = 0.5f * urange(u[6], -1.0f, 1.0f);
     s[8] = 0.5f * urange(u[7], -1.0f, 1.0f);
@@ -475,6 +499,10 @@ AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, f
     s[10] = ww.x; s[11] = ww.y; s[12] = ww.z;
 }
 
+// uniforms one reset_idx consumes (== AgxParams.reset_draws, checked at the C ABI)
+template <int TASK>
+struct ResetDraws { static constexpr int kD = (TASK == AGX_TASK_BALLOON) ? 15 : 12; };
+
 // ---- random source: explicit rows (parity mode) or Philox (perf mode) ---------------------------------
 struct RandSrc {
     const float* reset_row;  // [2,D] or nullptr
@@ -516,12 +544,9 @@ struct EnvRegs {
     float aux[AGX_AUX_MAX];      // task state beyond the drone (balloon: ball xyz, previous drone xyz, collision flag)
 };
 
-template <int TASK>
-AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e) {
-    float u[AGX_RESET_DRAWS_MAX];
-    draw_reset(rnd, which, P.reset_draws, u);
-    if (TASK == AGX_TASK_BALLOON) reset_sample_balloon(u, e.s, e.aux);
-    else reset_sample<TASK>(u, e.s);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+// Bookkeeping half of reset_idx (hovering.py:332-335): the sampled state/aux are supplied by the caller (the kernel
+// computes them warp-cooperatively, the host build serially).
+AGX_HD void reset_apply(const AgxParams& P, EnvRegs& e) {
     e.progress = 0;
 #pragma unroll
     for (int i = 0; i < AGX_MAX_ACTIONS; ++i) e.pa[i] = 0.0f;
@@ -529,6 +554,14 @@ AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs&
 #pragma unroll
         for (int i = 0; i < AGX_CTRL_STATE_MAX; ++i) e.cs[i] = 0.0f;
     }
+}
+
+template <int TASK>
+AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e) {
+    float u[AGX_RESET_DRAWS_MAX];
+    draw_reset(rnd, which, ResetDraws<TASK>::kD, u);
+    reset_sample<TASK>(u, e.s, e.aux);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+    reset_apply(P, e);
 }
 
 // Tracking.compute_traj_lemniscate (tracking.py:194-200), point k of 10
@@ -558,13 +591,12 @@ AGX_HD void scaled_noise(const AgxParams& P, const RandSrc& rnd, float* z) {
     for (int i = 15; i < 18; ++i) z[i] = P.noise_sigma[3] * z[i];
 }
 
+// Everything between the two reset_idx passes of one step: the caller has already applied the pre-step reset
+// (hovering.py:209-211, quirk Q1) to `e` when e.pending, and applies the end-of-step reset when e.reset comes back set.
 template <int TASK, int MODE>
-AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, EnvRegs& e, float* obs) {
+AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs) {
     constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
     constexpr bool kThrustMode = (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI);
-
-    // -- pre_physics_step: resets pending from the previous step (hovering.py:209-211, quirk Q1)
-    if (e.pending) do_reset<TASK>(P, rnd, 0, e);
 
     // -- action shaping (hovering.py:212-216).  Customized family (customized.py:226-232): the remap mutates
     //    self.actions in place but the clamp result only feeds the controller, so reward / pre_actions / the
@@ -767,10 +799,21 @@ AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, Env
 #pragma unroll
     for (int i = 0; i < A; ++i) e.pa[i] = e.a[i];
 
-    // -- end-of-step reset_idx (hovering.py:300-302): fresh draw, reset_buf stays 1, progress 0
-    if (reset) do_reset<TASK>(P, rnd, 1, e);
+}
 
-    e.timeout = (e.progress > (int64_t)P.max_episode_length) ? 1 : 0;  // hovering.py:304
+// time_out_buf (hovering.py:304), evaluated after the end-of-step reset zeroed progress
+AGX_HD void env_finish(const AgxParams& P, EnvRegs& e) {
+    e.timeout = (e.progress > (int64_t)P.max_episode_length) ? 1 : 0;
+}
+
+// The whole step for one env, serially (host build of tests/hostsim; the kernel interleaves the same pieces with its
+// warp-cooperative reset sampling).
+template <int TASK, int MODE>
+AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, EnvRegs& e, float* obs) {
+    if (e.pending) do_reset<TASK>(P, rnd, 0, e);  // pre_physics_step (hovering.py:209-211, quirk Q1)
+    env_core<TASK, MODE>(P, z, e, obs);
+    if (e.reset) do_reset<TASK>(P, rnd, 1, e);    // end-of-step reset_idx (hovering.py:300-302): reset_buf stays 1
+    env_finish(P, e);
 }
 
 }  // namespace agx

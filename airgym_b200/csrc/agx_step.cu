@@ -93,6 +93,79 @@ struct TaskTraits<AGX_TASK_TRACKING> { static constexpr int kObs = 48; };
 template <>
 struct TaskTraits<AGX_TASK_BALLOON> { static constexpr int kObs = 18; };
 
+// ---- warp-cooperative reset sampling ---------------------------------------------------------------------
+// Resets are rare per env (~2 % of env-steps under random actions) but common per warp (~50 % of warps hold at least one
+// resetting lane), so a per-lane `if (reset) sample()` makes half of all warps walk the whole sampler — Philox blocks,
+// sincos, quaternion — for one or two live lanes (measured: 43 % of the step time at 4 M envs).  Instead the warp packs
+// its resetting lanes into items and spends 4 lanes on each: lane `sub` of an item draws Philox block `sub` (or copies
+// the explicit draws) into shared memory, lane 0 of the item turns the uniforms into the new root-state row, written
+// straight into the CTA's state tile; task state (aux) returns through the same scratch row.  Up to 8 items per pass.
+struct WarpScratch {
+    float u[8][AGX_RESET_DRAWS_MAX];  // per item: uniforms in, aux out
+    uint8_t src[32];                  // item → lane
+};
+
+template <int TASK>
+__device__ __forceinline__ void warp_reset(const AgxStepIO& io, bool need, int which, uint64_t step, int64_t warp_env0,
+                                           float* s_state_warp, WarpScratch& ws, float* aux) {
+    using namespace agx;
+    constexpr int D = ResetDraws<TASK>::kD;
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
+    if (mask == 0u) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int n_items = __popc(mask);
+    const int my_item = __popc(mask & ((1u << lane) - 1u));
+    if (need) ws.src[my_item] = (uint8_t)lane;
+    __syncwarp();
+    const int slot = lane >> 2, sub = lane & 3;
+    for (int base = 0; base < n_items; base += 8) {
+        const int item = base + slot;
+        int src = 0;
+        if (item < n_items) {
+            src = ws.src[item];
+            const int64_t env = warp_env0 + src;
+            if (io.rand_reset) {
+                const float* row = io.rand_reset + (env * 2 + which) * (int64_t)D;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (sub * 4 + j < D) ws.u[slot][sub * 4 + j] = row[sub * 4 + j];
+            } else if (sub * 4 < D) {
+                PhiloxCtx ph;
+                const uint64_t genv = (uint64_t)(io.env_offset + env);
+                ph.k0 = (uint32_t)io.seed; ph.k1 = (uint32_t)(io.seed >> 32);
+                ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
+                ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
+                const U4 r = philox_block(ph, (uint32_t)which, (uint32_t)sub);
+                ws.u[slot][sub * 4 + 0] = u32_to_unit(r.x);
+                ws.u[slot][sub * 4 + 1] = u32_to_unit(r.y);
+                ws.u[slot][sub * 4 + 2] = u32_to_unit(r.z);
+                ws.u[slot][sub * 4 + 3] = u32_to_unit(r.w);
+            }
+        }
+        __syncwarp();
+        if (item < n_items && sub == 0) {
+            float u[AGX_RESET_DRAWS_MAX], st[13], ax[AGX_AUX_MAX];
+#pragma unroll
+            for (int i = 0; i < D; ++i) u[i] = ws.u[slot][i];
+#pragma unroll
+            for (int i = 0; i < AGX_AUX_MAX; ++i) ax[i] = 0.0f;
+            reset_sample<TASK>(u, st, ax);
+#pragma unroll
+            for (int i = 0; i < 13; ++i) s_state_warp[src * 13 + i] = st[i];
+            if (TASK == AGX_TASK_BALLOON) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) ws.u[slot][i] = ax[i];
+            }
+        }
+        __syncwarp();
+        if (TASK == AGX_TASK_BALLOON && need && my_item >= base && my_item < base + 8) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) aux[i] = ws.u[my_item - base][i];  // ball xyz, pre_root_positions = 0
+        }
+        __syncwarp();
+    }
+}
+
 // ---- the fused step kernel ----------------------------------------------------------------------------
 template <int TASK, int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
@@ -107,6 +180,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     __shared__ __align__(128) float s_state[BLOCK * 13];
     __shared__ __align__(128) float s_obs[BLOCK * OL::kStride];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ WarpScratch s_ws[BLOCK / 32];
 
     const int tid = threadIdx.x;
     const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
@@ -116,73 +190,102 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     const int64_t env = tile0 + tid;
     const bool active = tid < tile_n;
 
-    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; no global memory is
-    // touched before the previous grid has completed and flushed.  (No-op when launched without the attribute.)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-    // ---- stage the state tile into shared memory
-    if (bulk) {
-        if (tid == 0) {
-            mbar_init(&s_bar, 1);
-            mbar_expect_tx(&s_bar, BLOCK * 13 * 4);
-            bulk_g2s(s_state, io.state + tile0 * 13, BLOCK * 13 * 4, &s_bar);
-        }
-    } else {
-        const float* src = io.state + tile0 * 13;
-        for (int i = tid; i < tile_n * 13; i += BLOCK) s_state[i] = src[i];
-    }
-
-    // ---- coalesced per-env loads (overlap with the bulk copy in flight)
     EnvRegs e;
-    if (active) {
-        if (A == 4) {
-            const float4 a4 = reinterpret_cast<const float4*>(io.action)[env];
-            const float4 p4 = reinterpret_cast<const float4*>(io.prev_action)[env];
-            e.a[0] = a4.x; e.a[1] = a4.y; e.a[2] = a4.z; e.a[3] = a4.w; e.a[4] = 0.0f;
-            e.pa[0] = p4.x; e.pa[1] = p4.y; e.pa[2] = p4.z; e.pa[3] = p4.w; e.pa[4] = 0.0f;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) { e.a[i] = io.action[env * 5 + i]; e.pa[i] = io.prev_action[env * 5 + i]; }
-        }
-#pragma unroll
-        for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
-        e.progress = io.progress[env];
-        e.pending = io.reset[env] != 0;
-        if (TASK == AGX_TASK_BALLOON) {
-            const float4 x0 = reinterpret_cast<const float4*>(io.aux)[env * 2], x1 = reinterpret_cast<const float4*>(io.aux)[env * 2 + 1];
-            e.aux[0] = x0.x; e.aux[1] = x0.y; e.aux[2] = x0.z; e.aux[3] = x0.w;
-            e.aux[4] = x1.x; e.aux[5] = x1.y; e.aux[6] = x1.z; e.aux[7] = x1.w;
-        }
-    }
-    // Philox step index: device counter (graph replay) or launch argument.  Every CTA takes a ticket AFTER its read
-    // (data dependency through `zero`); the CTA holding the last ticket bumps the counter at the end.
-    uint64_t step = io.step;
-    unsigned long long ticket = 0;
-    if (io.step_dev) {
-        step = *reinterpret_cast<const volatile uint64_t*>(io.step_dev);
-        if (tid == 0) {
-            unsigned int zero;
-            asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)step));
-            ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
-        }
-    }
-
-    // Random source + observation noise: needs only (seed, env id, step) — evaluated while the loads above fly.
     RandSrc rnd;
     float z[AGX_NOISE_DRAWS];
-    if (active) {
-        rnd.reset_row = io.rand_reset ? io.rand_reset + env * (int64_t)(2 * P.reset_draws) : nullptr;
-        rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
-        const uint64_t genv = (uint64_t)(io.env_offset + env);
-        rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
-        rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
-        rnd.ph.step_lo = (uint32_t)step; rnd.ph.step_hi = (uint32_t)(step >> 32);
-        scaled_noise(P, rnd, z);
-        // keep the consumers of the loads below this point: the compiler would otherwise hoist the first use of the
-        // action registers above the noise code and park every warp on the load latency before doing useful work
+    uint64_t step = io.step;
+    unsigned long long ticket = 0;
+
+    // ---- stage the state tile into shared memory + coalesced per-env loads (which overlap the bulk copy in flight)
+    auto load_inputs = [&]() {
+        if (bulk) {
+            if (tid == 0) {
+                mbar_init(&s_bar, 1);
+                mbar_expect_tx(&s_bar, BLOCK * 13 * 4);
+                bulk_g2s(s_state, io.state + tile0 * 13, BLOCK * 13 * 4, &s_bar);
+            }
+        } else {
+            const float* src = io.state + tile0 * 13;
+            for (int i = tid; i < tile_n * 13; i += BLOCK) s_state[i] = src[i];
+        }
+        if (active) {
+            if (A == 4) {
+                const float4 a4 = reinterpret_cast<const float4*>(io.action)[env];
+                const float4 p4 = reinterpret_cast<const float4*>(io.prev_action)[env];
+                e.a[0] = a4.x; e.a[1] = a4.y; e.a[2] = a4.z; e.a[3] = a4.w; e.a[4] = 0.0f;
+                e.pa[0] = p4.x; e.pa[1] = p4.y; e.pa[2] = p4.z; e.pa[3] = p4.w; e.pa[4] = 0.0f;
+            } else {
 #pragma unroll
-        for (int i = 0; i < AGX_MAX_ACTIONS; ++i) asm volatile("" : "+f"(e.a[i]), "+f"(e.pa[i]));
+                for (int i = 0; i < 5; ++i) { e.a[i] = io.action[env * 5 + i]; e.pa[i] = io.prev_action[env * 5 + i]; }
+            }
+#pragma unroll
+            for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
+            e.progress = io.progress[env];
+            e.pending = io.reset[env] != 0;
+            if (TASK == AGX_TASK_BALLOON) {
+                const float4 x0 = reinterpret_cast<const float4*>(io.aux)[env * 2], x1 = reinterpret_cast<const float4*>(io.aux)[env * 2 + 1];
+                e.aux[0] = x0.x; e.aux[1] = x0.y; e.aux[2] = x0.z; e.aux[3] = x0.w;
+                e.aux[4] = x1.x; e.aux[5] = x1.y; e.aux[6] = x1.z; e.aux[7] = x1.w;
+            }
+        }
+    };
+    // Philox step index: device counter (graph replay) or launch argument.  Every CTA takes a ticket AFTER its read
+    // (data dependency through `zero`); the CTA holding the last ticket — every other CTA has read by then — bumps it.
+    auto take_step = [&]() {
+        if (io.step_dev) {
+            step = *reinterpret_cast<const volatile uint64_t*>(io.step_dev);
+            if (tid == 0) {
+                unsigned int zero;
+                asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)step));
+                ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
+            }
+        }
+    };
+    auto bump_step = [&]() {
+        if (io.step_dev && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
+            io.step_dev[1] = 0;
+            io.step_dev[0] = step + 1;
+            __threadfence();
+        }
+    };
+    // Observation noise: needs only (seed, env id, step), not the env state.
+    auto make_noise = [&]() {
+        if (active) {
+            rnd.reset_row = nullptr;  // reset draws are taken by warp_reset
+            rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
+            const uint64_t genv = (uint64_t)(io.env_offset + env);
+            rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
+            rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
+            rnd.ph.step_lo = (uint32_t)step; rnd.ph.step_hi = (uint32_t)(step >> 32);
+            scaled_noise(P, rnd, z);
+        }
+    };
+
+    if (pdl_mode == 3) {
+        // Programmatic dependent launch, noise-first: this grid may start while the previous kernel of the stream is
+        // still running.  The step counter, the ticket and the noise touch nothing that kernel writes (its own counter
+        // bump precedes its launch_dependents), so a third of the step's instructions run under its tail; every other
+        // global access waits for its completion + flush.
+        take_step();
+        if (!io.rand_noise) make_noise();
+        bump_step();
+        if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // after this CTA's (possible) bump
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        load_inputs();
+        if (io.rand_noise) make_noise();  // explicit draws may come from the previous kernel
+    } else {
+        // (griddepcontrol.* are no-ops when launched without the attribute.)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        load_inputs();
+        take_step();
+        make_noise();  // evaluated while the loads above fly
+        if (active) {
+            // keep the consumers of the loads below this point: the compiler would otherwise hoist the first use of the
+            // action registers above the noise code and park every warp on the load latency before doing useful work
+#pragma unroll
+            for (int i = 0; i < AGX_MAX_ACTIONS; ++i) asm volatile("" : "+f"(e.a[i]), "+f"(e.pa[i]));
+        }
     }
 
     if (bulk) {
@@ -192,15 +295,29 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         __syncthreads();
     }
 
+    // ---- pre_physics_step reset of the envs flagged last step (hovering.py:209-211, quirk Q1): new rows land in the tile
+    const int warp = tid >> 5;
+    const int64_t warp_env0 = tile0 + warp * 32;
+    warp_reset<TASK>(io, active && e.pending, 0, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
+
     if (active) {
 #pragma unroll
         for (int i = 0; i < 13; ++i) e.s[i] = s_state[tid * 13 + i];
+        if (e.pending) reset_apply(P, e);
 
-        env_step<TASK, MODE>(P, rnd, z, e, &s_obs[tid * OL::kStride]);
+        env_core<TASK, MODE>(P, z, e, &s_obs[tid * OL::kStride]);
         if (pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
 #pragma unroll
         for (int i = 0; i < 13; ++i) s_state[tid * 13 + i] = e.s[i];
+    }
+    __syncwarp();
+    // ---- end-of-step reset_idx (hovering.py:300-302): fresh rows overwrite the tile, reset_buf stays 1, progress 0
+    warp_reset<TASK>(io, active && e.reset, 1, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
+
+    if (active) {
+        if (e.reset) reset_apply(P, e);
+        env_finish(P, e);
 
         // ---- coalesced per-env stores
         if (A == 4) {
@@ -262,10 +379,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         }
     }
     if (bulk && tid == 0) bulk_wait_read0();  // smem must stay alive until the bulk stores have read it
-    if (io.step_dev && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
-        io.step_dev[1] = 0;
-        io.step_dev[0] = step + 1;
-    }
+    if (pdl_mode != 3) bump_step();
 }
 
 // ---- standalone reset_idx kernel -------------------------------------------------------------------------
@@ -295,10 +409,10 @@ __global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_
     if (TASK == AGX_TASK_BALLOON) {
         float ax[AGX_AUX_MAX];
         for (int i = 0; i < AGX_AUX_MAX; ++i) ax[i] = aux[env * AGX_AUX_MAX + i];
-        reset_sample_balloon(u, s, ax);
+        reset_sample<TASK>(u, s, ax);
         for (int i = 0; i < AGX_AUX_MAX; ++i) aux[env * AGX_AUX_MAX + i] = ax[i];
     } else {
-        reset_sample<TASK>(u, s);
+        reset_sample<TASK>(u, s, nullptr);
     }
     for (int i = 0; i < 13; ++i) state[env * 13 + i] = s[i];
     for (int i = 0; i < P.num_actions; ++i) prev_action[env * P.num_actions + i] = 0.0f;
@@ -392,7 +506,7 @@ int agx_set_option(const char* key, int value) {
     }
     if (!strcmp(key, "use_bulk")) { g_use_bulk = value ? 1 : 0; return AGX_OK; }
     if (!strcmp(key, "pdl")) {
-        if (value < 0 || value > 2) return fail(AGX_ERR_ARG, "agx_set_option: pdl must be 0|1|2%s");
+        if (value < 0 || value > 3) return fail(AGX_ERR_ARG, "agx_set_option: pdl must be 0..3%s");
         g_pdl = value;
         return AGX_OK;
     }
