@@ -25,6 +25,38 @@ struct V3 { float x, y, z; };
 struct Q4 { float x, y, z, w; };  // xyzw, like the reference state row (hovering.py:75)
 
 AGX_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// Division / square root of the step.  Device: MUFU.RCP + FMUL (div.approx.ftz, <= 2 ulp for |b| in [2^-126, 2^126]; IEEE
+// results for b = 0 / inf / NaN operands, so quirk Q5's 0/0 = NaN survives) and MUFU.SQRT / MUFU.RSQ (sqrt.approx.ftz:
+// a subnormal argument counts as 0).  `x / y` itself would compile to div.full's range-scaling sequence (~8 SASS
+// instructions per divide, 54 of the 974 main-path instructions per warp in the round-1 capture).  Host build: exact.
+AGX_HD float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
+    return a / b;
+#endif
+}
+AGX_HD float fsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+AGX_HD float frsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 AGX_HD float sq(float x) { return x * x; }
 AGX_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 AGX_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -34,13 +66,13 @@ AGX_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 AGX_HD V3 cross(V3 a, V3 b) {
     return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-AGX_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
+AGX_HD float norm(V3 a) { return fsqrt(dot(a, a)); }
 
 // ---- rotation conventions of pytorch3d.transforms [EXT] restated ------------------
 
 // quaternion_to_matrix on (w,x,y,z) = (q.w,q.x,q.y,q.z); row-major 3x3; 2/|q|^2 scaling.
 AGX_HD void quat_to_matrix(Q4 q, float* m) {
-    const float two_s = 2.0f / (q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    const float two_s = fdiv(2.0f, q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
     m[0] = 1.0f - two_s * (q.y * q.y + q.z * q.z);
     m[1] = two_s * (q.x * q.y - q.z * q.w);
     m[2] = two_s * (q.x * q.z + q.y * q.w);
@@ -64,7 +96,7 @@ AGX_HD void euler_xyz_to_matrix(float a0, float a1, float a2, float* m) {
     m[6] = a20 * c2 + a21 * s2;  m[7] = a21 * c2 - a20 * s2;  m[8] = a22;
 }
 
-AGX_HD float sqrt_pos(float x) { return x > 0.0f ? sqrtf(x) : 0.0f; }
+AGX_HD float sqrt_pos(float x) { return x > 0.0f ? fsqrt(x) : 0.0f; }
 
 // matrix_to_quaternion: max-of-four-candidates, returns xyzw with w >= 0 (standardised).
 AGX_HD Q4 matrix_to_quat(const float* m) {
@@ -77,16 +109,16 @@ AGX_HD Q4 matrix_to_quat(const float* m) {
     float w, x, y, z, d;
     if (qa0 >= qa1 && qa0 >= qa2 && qa0 >= qa3) {
         d = 2.0f * (qa0 > 0.1f ? qa0 : 0.1f);
-        w = qa0 * qa0 / d; x = (m21 - m12) / d; y = (m02 - m20) / d; z = (m10 - m01) / d;
+        const float id = fdiv(1.0f, d); w = qa0 * qa0 * id; x = (m21 - m12) * id; y = (m02 - m20) * id; z = (m10 - m01) * id;
     } else if (qa1 >= qa2 && qa1 >= qa3) {
         d = 2.0f * (qa1 > 0.1f ? qa1 : 0.1f);
-        w = (m21 - m12) / d; x = qa1 * qa1 / d; y = (m10 + m01) / d; z = (m02 + m20) / d;
+        const float id = fdiv(1.0f, d); w = (m21 - m12) * id; x = qa1 * qa1 * id; y = (m10 + m01) * id; z = (m02 + m20) * id;
     } else if (qa2 >= qa3) {
         d = 2.0f * (qa2 > 0.1f ? qa2 : 0.1f);
-        w = (m02 - m20) / d; x = (m10 + m01) / d; y = qa2 * qa2 / d; z = (m12 + m21) / d;
+        const float id = fdiv(1.0f, d); w = (m02 - m20) * id; x = (m10 + m01) * id; y = qa2 * qa2 * id; z = (m12 + m21) * id;
     } else {
         d = 2.0f * (qa3 > 0.1f ? qa3 : 0.1f);
-        w = (m10 - m01) / d; x = (m20 + m02) / d; y = (m21 + m12) / d; z = qa3 * qa3 / d;
+        const float id = fdiv(1.0f, d); w = (m10 - m01) * id; x = (m20 + m02) * id; y = (m21 + m12) * id; z = qa3 * qa3 * id;
     }
     Q4 q;
     if (w < 0.0f) { q.x = -x; q.y = -y; q.z = -z; q.w = -w; }
@@ -105,8 +137,8 @@ AGX_HD Q4 qmul(Q4 a, Q4 b) {
 }
 AGX_HD Q4 qconj(Q4 a) { Q4 r; r.x = -a.x; r.y = -a.y; r.z = -a.z; r.w = a.w; return r; }
 AGX_HD Q4 qnormalize(Q4 a) {
-    const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
-    Q4 r; r.x = a.x / n; r.y = a.y / n; r.z = a.z / n; r.w = a.w / n; return r;
+    const float in = frsqrt(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
+    Q4 r; r.x = a.x * in; r.y = a.y * in; r.z = a.z * in; r.w = a.w * in; return r;
 }
 // third column of the rotation matrix of a unit quaternion (body z in world)
 AGX_HD V3 quat_body_z(Q4 q) {
@@ -173,16 +205,18 @@ AGX_HD float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.96046447753906
 // angle from the low half.  One 128-bit Philox block therefore yields 8 normals; sensor-noise quality, documented in
 // DESIGN.md §4 (the reference draws torch.randn; the stream is builder-defined either way).
 AGX_HD void box_muller16(uint32_t w, float* z0, float* z1) {
-    const float u1 = (float)((w >> 16) + 1u) * 1.52587890625e-5f;  // (0,1]
-    const float u2 = (float)(w & 0xFFFFu) * 1.52587890625e-5f;     // [0,1)
-    float s, c;
+    const uint32_t hi = (w >> 16) + 1u, lo = w & 0xFFFFu;  // u1 = hi / 65536 in (0,1], u2 = lo / 65536 in [0,1)
+    float s, c, r;
 #if defined(__CUDA_ARCH__)
-    // SFU path (MUFU.LG2 / MUFU.SIN / MUFU.COS): abs error ~2^-21 on N(0,1) draws, far below the noise itself
-    const float r = sqrtf(-2.0f * __logf(u1));
-    __sincosf(kTwoPi * u2, &s, &c);
+    // MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS (u1 >= 2^-16 is never subnormal, so the .ftz forms are exact
+    // equivalents): abs error ~2^-21 on N(0,1) draws, far below the noise itself
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)hi * 1.52587890625e-5f));
+    r = fsqrt(lg * -1.3862943611198906f);  // -2 ln u1 = -2 ln2 * log2 u1 >= 0
+    __sincosf((float)lo * 9.5873799242852576e-5f, &s, &c);
 #else
-    const float r = sqrtf(-2.0f * logf(u1));
-    s = sinf(kTwoPi * u2); c = cosf(kTwoPi * u2);
+    r = sqrtf(-2.0f * logf((float)hi * 1.52587890625e-5f));
+    s = sinf((float)lo * 9.5873799242852576e-5f); c = cosf((float)lo * 9.5873799242852576e-5f);
 #endif
     *z0 = r * c; *z1 = r * s;
 }
@@ -317,9 +351,9 @@ AGX_HD V3 rate_loop(const AgxParams& P, V3 w_sp, V3 w_b, float* cs) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float e = wsp[i] - wb[i];
-        const float wdot = (wb[i] - cs[3 + i]) / P.dt;
+        const float wdot = fdiv(wb[i] - cs[3 + i], P.dt);
         tau[i] = P.rate_p[i] * e + cs[i] - P.rate_d[i] * wdot;
-        const float ef = e / P.rate_i_fade;
+        const float ef = fdiv(e, P.rate_i_fade);
         float fade = 1.0f - ef * ef;
         fade = fade < 0.0f ? 0.0f : fade;
         cs[i] = clampf(cs[i] + fade * P.rate_i[i] * e * P.dt, -P.rate_int_lim, P.rate_int_lim);
@@ -368,7 +402,7 @@ AGX_HD void velocity_loop(const AgxParams& P, V3 v_sp, float yaw_sp, V3 v, float
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float e = vsp[i] - vv[i];
-        const float vdot = (vv[i] - cs[9 + i]) / P.dt;
+        const float vdot = fdiv(vv[i] - cs[9 + i], P.dt);
         acc[i] = P.vel_p[i] * e + cs[6 + i] - P.vel_d[i] * vdot;
         cs[6 + i] = clampf(cs[6 + i] + P.vel_i[i] * e * P.dt, -P.vel_int_lim[i], P.vel_int_lim[i]);
         cs[9 + i] = vv[i];
@@ -376,17 +410,18 @@ AGX_HD void velocity_loop(const AgxParams& P, V3 v_sp, float yaw_sp, V3 v, float
     float fx = acc[0], fy = acc[1], fz = acc[2] + P.gravity;
     const float fz_min = 0.1f * P.gravity;
     fz = fz < fz_min ? fz_min : fz;
-    const float h = sqrtf(fx * fx + fy * fy);
+    const float h = fsqrt(fx * fx + fy * fy);
     const float hmax = fz * P.tilt_max_tan;
-    if (h > hmax) { const float k = hmax / h; fx = fx * k; fy = fy * k; }
-    const float fn = sqrtf(fx * fx + fy * fy + fz * fz);
-    const V3 bz = v3(fx / fn, fy / fn, fz / fn);
-    *thrust = clampf(P.hover_thrust * fn / P.gravity, P.thr_min, P.thr_max);
+    if (h > hmax) { const float k = fdiv(hmax, h); fx = fx * k; fy = fy * k; }
+    const float fn = fsqrt(fx * fx + fy * fy + fz * fz);
+    const float ifn = fdiv(1.0f, fn);
+    const V3 bz = v3(fx * ifn, fy * ifn, fz * ifn);
+    *thrust = clampf(fdiv(P.hover_thrust * fn, P.gravity), P.thr_min, P.thr_max);
     // bodyzToAttitude: x axis from the yaw heading, orthogonalised against body z
     const V3 yc = v3(-sinf(yaw_sp), cosf(yaw_sp), 0.0f);
     V3 bx = cross(yc, bz);
     const float bxn = norm(bx);
-    bx = v3(bx.x / bxn, bx.y / bxn, bx.z / bxn);
+    { const float ib = fdiv(1.0f, bxn); bx = v3(bx.x * ib, bx.y * ib, bx.z * ib); }
     const V3 by = cross(bz, bx);
     const float m[9] = {bx.x, by.x, bz.x, bx.y, by.y, bz.y, bx.z, by.z, bz.z};
     *q_sp = matrix_to_quat(m);
@@ -444,7 +479,7 @@ AGX_HD Deriv body_deriv(const AgxParams& P, V3 v, Q4 q, V3 w, float fz_over_m, V
     d.dq.w = 0.5f * (-q.x * w.x - q.y * w.y - q.z * w.z);
     const V3 Iw = v3(P.inertia[0] * w.x, P.inertia[1] * w.y, P.inertia[2] * w.z);
     const V3 g = cross(w, Iw);
-    d.dw = v3((tau.x - g.x) / P.inertia[0], (tau.y - g.y) / P.inertia[1], (tau.z - g.z) / P.inertia[2]);
+    d.dw = v3(fdiv(tau.x - g.x, P.inertia[0]), fdiv(tau.y - g.y, P.inertia[1]), fdiv(tau.z - g.z, P.inertia[2]));
     return d;
 }
 
@@ -459,7 +494,7 @@ AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, f
     V3 p = v3(s[0], s[1], s[2]);
     Q4 q; q.x = s[3]; q.y = s[4]; q.z = s[5]; q.w = s[6];
     V3 v = v3(s[7], s[8], s[9]);  // w: body rates R(q)^T w_world, computed once by the caller
-    const float fz_over_m = (thrust[0] + thrust[1] + thrust[2] + thrust[3]) / P.mass;
+    const float fz_over_m = fdiv(thrust[0] + thrust[1] + thrust[2] + thrust[3], P.mass);
     const V3 tau = v3(P.arm * (-thrust[0] + thrust[1] + thrust[2] - thrust[3]),
                       P.arm * (-thrust[0] + thrust[1] - thrust[2] + thrust[3]), tau_z);
     const float h = P.dt;
@@ -477,7 +512,7 @@ AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, f
         const Deriv k3 = body_deriv(P, v + (0.5f * h) * k2.dv, qaxpy(q, 0.5f * h, k2.dq),
                                     w + (0.5f * h) * k2.dw, fz_over_m, tau);
         const Deriv k4 = body_deriv(P, v + h * k3.dv, qaxpy(q, h, k3.dq), w + h * k3.dw, fz_over_m, tau);
-        const float h6 = h / 6.0f;
+        const float h6 = h * (1.0f / 6.0f);
         p = p + h6 * (k1.dp + 2.0f * k2.dp + 2.0f * k3.dp + k4.dp);
         v = v + h6 * (k1.dv + 2.0f * k2.dv + 2.0f * k3.dv + k4.dv);
         w = w + h6 * (k1.dw + 2.0f * k2.dw + 2.0f * k3.dw + k4.dw);
@@ -490,9 +525,9 @@ AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, f
     quat_to_matrix(q, Rnew);
     V3 ww = mat_mul_v(Rnew, w);  // back to world-frame angular velocity (IsaacGym root-state convention)
     const float vn = norm(v);
-    if (vn > P.max_lin_vel) v = (P.max_lin_vel / vn) * v;
+    if (vn > P.max_lin_vel) v = fdiv(P.max_lin_vel, vn) * v;
     const float wn = norm(ww);
-    if (wn > P.max_ang_vel) ww = (P.max_ang_vel / wn) * ww;
+    if (wn > P.max_ang_vel) ww = fdiv(P.max_ang_vel, wn) * ww;
     s[0] = p.x; s[1] = p.y; s[2] = p.z;
     s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
     s[7] = v.x; s[8] = v.y; s[9] = v.z;
@@ -569,7 +604,7 @@ AGX_HD V3 lemniscate(int64_t progress, int k, float dt) {
     const float t = (float)(progress + 5 * k) * dt * 0.25f;
     const float st = sinf(t), ct = cosf(t);
     const float den = 1.0f + ct * ct;
-    return v3(3.0f * st / den, 3.0f * st * ct / den, 1.0f);
+    { const float id = fdiv(1.0f, den); return v3(3.0f * st * id, 3.0f * st * ct * id, 1.0f); }
 }
 
 // Observation noise draws, already scaled by sigma (hovering.py:350-353).  Independent of the env state, so the
@@ -694,9 +729,9 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
         const V3 rel = ball - p;
         const float check = norm(rel);
         const float nrm = check > 1e-12f ? check : 1e-12f;  // F.normalize eps
-        const float dir_yaw = atan2f(rel.y / nrm, rel.x / nrm);
+        const float dir_yaw = atan2f(fdiv(rel.y, nrm), fdiv(rel.x, nrm));
         const float yd_b = fabsf(yaw_diff(yaw, dir_yaw));
-        const float yaw_r = 1.0f / (1.0f + sq(1.6f * yd_b));
+        const float yaw_r = fdiv(1.0f, 1.0f + sq(1.6f * yd_b));
         const V3 prev = v3(e.aux[3], e.aux[4], e.aux[5]);
         const float guidance = 30.0f * (norm(ball - prev) - check);
         const float ups_r = 0.5f * sq((up_z + 1.0f) / 2.0f);
@@ -705,7 +740,7 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
 #pragma unroll
         for (int i = 0; i < A; ++i) { sa += ar[i] * ar[i]; sd += sq(ar[i] - e.pa[i]); }
         const float effort_b = 0.1f * expf(-sa);
-        const float smooth = 0.1f * expf(-sqrtf(sd));
+        const float smooth = 0.1f * expf(-fsqrt(sd));
         reward = guidance + yaw_r + hit_r + smooth + ups_r + effort_b;
         reset = (e.progress >= (int64_t)(P.max_episode_length - 1)) ? 1 : 0;
         if (ar[A - 1] < -1.0f) reset = 1;
@@ -737,26 +772,26 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
         float ss = 0.0f;
 #pragma unroll
         for (int i = 0; i < A; ++i) ss += d[i] * d[i];
-        cont = 0.2f * expf(-sqrtf(ss));
+        cont = 0.2f * expf(-fsqrt(ss));
     } else {
         float ss = 0.0f;
 #pragma unroll
         for (int i = 0; i < A - 1; ++i) ss += d[i] * d[i];
         if (TASK == AGX_TASK_TRACKING)
-            cont = 0.1f * expf(-sqrtf(ss)) + 0.5f / (1.0f + sq(2.0f * d[A - 1]));
+            cont = 0.1f * expf(-fsqrt(ss)) + fdiv(0.5f, 1.0f + sq(2.0f * d[A - 1]));
         else
-            cont = 0.2f * expf(-sqrtf(ss)) + 0.5f / (1.0f + sq(3.0f * d[A - 1]));
+            cont = 0.2f * expf(-fsqrt(ss)) + fdiv(0.5f, 1.0f + sq(3.0f * d[A - 1]));
         thrust_r = 0.1f * (1.0f - fabsf(0.1533f - e.a[A - 1]));
     }
-    const float yd = yaw_diff(P.target_yaw, yaw) / kPi;
+    const float yd = yaw_diff(P.target_yaw, yaw) * (1.0f / kPi);
     const float wz2 = w.z * w.z;
     const float ups_r = sq((up_z + 1.0f) / 2.0f);
     if (TASK == AGX_TASK_TRACKING) {
         const V3 dd = ref0 - p;
         const float dist = norm(dd);
-        const float dist_r = 1.0f / (1.0f + sq(1.8f * dist));
-        const float yaw_r = 1.0f / (1.0f + sq(4.0f * yd));
-        const float spin_r = 1.0f / (1.0f + sq(2.0f * wz2));
+        const float dist_r = fdiv(1.0f, 1.0f + sq(1.8f * dist));
+        const float yaw_r = fdiv(1.0f, 1.0f + sq(4.0f * yd));
+        const float spin_r = fdiv(1.0f, 1.0f + sq(2.0f * wz2));
         reward = cont + effort;
         if (kThrustMode) reward = reward + thrust_r;
         reward = reward + dist_r + dist_r * (spin_r + yaw_r + ups_r);
@@ -767,13 +802,13 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
     } else {
         const V3 rel = v3(P.target[9] - p.x, P.target[10] - p.y, P.target[11] - p.z);
         const float pd = norm(rel);
-        const float pos_r = 0.7f / (1.0f + sq(1.6f * pd));
+        const float pos_r = fdiv(0.7f, 1.0f + sq(1.6f * pd));
         const float vn = norm(v);
-        const float dp = (rel.x / pd) * (v.x / vn) + (rel.y / pd) * (v.y / vn) + (rel.z / pd) * (v.z / vn);
+        const float dp = fdiv(rel.x, pd) * fdiv(v.x, vn) + fdiv(rel.y, pd) * fdiv(v.y, vn) + fdiv(rel.z, pd) * fdiv(v.z, vn);
         const float ang = fabsf(acosf(clampf(dp, -1.0f, 1.0f)));
-        const float veld = 0.1f * expf(-ang / kPi);
-        const float yaw_r = 1.0f / (1.0f + sq(3.0f * yd));
-        const float spin_r = 1.0f / (1.0f + sq(3.0f * wz2));
+        const float veld = 0.1f * expf(-ang * (1.0f / kPi));
+        const float yaw_r = fdiv(1.0f, 1.0f + sq(3.0f * yd));
+        const float spin_r = fdiv(1.0f, 1.0f + sq(3.0f * wz2));
         reward = cont + effort;
         if (kThrustMode) reward = reward + thrust_r;
         reward = reward + pos_r + pos_r * (veld + ups_r + spin_r + yaw_r);

@@ -69,6 +69,9 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* src_gmem, uint32_t bytes) {  // bytes % 16 == 0, src 16-B aligned
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -76,6 +79,28 @@ __device__ __forceinline__ void bulk_wait_read0() {
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+#ifdef AGX_TIMELINE
+// Tuning builds only (scripts/timeline.py): per-CTA phase stamps {globaltimer ns, clock64} x 6 phases + smid.
+__device__ unsigned long long g_timeline[8192 * 16];
+__device__ __forceinline__ void tl_stamp(int phase) {
+    if (threadIdx.x == 0 && blockIdx.x < 8192) {
+        unsigned long long t, c;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+        g_timeline[blockIdx.x * 16 + phase * 2] = t;
+        g_timeline[blockIdx.x * 16 + phase * 2 + 1] = c;
+        if (phase == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_timeline[blockIdx.x * 16 + 14] = smid;
+        }
+    }
+}
+#define TL(p) tl_stamp(p)
+#else
+#define TL(p)
+#endif
 
 template <int NOBS>
 struct ObsLayout {
@@ -167,8 +192,11 @@ __device__ __forceinline__ void warp_reset(const AgxStepIO& io, bool need, int w
 }
 
 // ---- the fused step kernel ----------------------------------------------------------------------------
+#ifndef AGX_MIN_CTAS
+#define AGX_MIN_CTAS 1
+#endif
 template <int TASK, int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, AGX_MIN_CTAS)
 agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ AgxStepIO io, const int64_t n,
                 const int kflags) {  // bit0: TMA bulk staging, bits1-2: PDL trigger point (0 none, 1 start, 2 pre-store)
     using namespace agx;
@@ -190,8 +218,8 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     const int64_t env = tile0 + tid;
     const bool active = tid < tile_n;
 
+    TL(0);
     EnvRegs e;
-    RandSrc rnd;
     float z[AGX_NOISE_DRAWS];
     uint64_t step = io.step;
     unsigned long long ticket = 0;
@@ -251,6 +279,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     // Observation noise: needs only (seed, env id, step), not the env state.
     auto make_noise = [&]() {
         if (active) {
+            RandSrc rnd;
             rnd.reset_row = nullptr;  // reset draws are taken by warp_reset
             rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
             const uint64_t genv = (uint64_t)(io.env_offset + env);
@@ -266,20 +295,35 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         // still running.  The step counter, the ticket and the noise touch nothing that kernel writes (its own counter
         // bump precedes its launch_dependents), so a third of the step's instructions run under its tail; every other
         // global access waits for its completion + flush.
+        // L2 is the GPU's point of coherence, so prefetching this tile's inputs into it is a pure hint whatever the
+        // running predecessor still writes: the DRAM reads of step t+1 overlap the compute phase of step t, and the
+        // loads after the wait hit L2.
+        if (tile_n == BLOCK && tid < 5 + K) {
+            if (tid == 0) prefetch_l2(io.state + tile0 * 13, BLOCK * 13 * 4);
+            else if (tid == 1) prefetch_l2(io.action + tile0 * A, BLOCK * A * 4);
+            else if (tid == 2) prefetch_l2(io.prev_action + tile0 * A, BLOCK * A * 4);
+            else if (tid == 3) prefetch_l2(io.progress + tile0, BLOCK * 8);
+            else if (tid == 4) prefetch_l2(io.reset + tile0, BLOCK * 8);
+            else if ((n & 3) == 0) prefetch_l2(io.ctrl_state + (int64_t)(tid - 5) * n + tile0, BLOCK * 4);  // plane rows 16-B aligned
+        }
         take_step();
         if (!io.rand_noise) make_noise();
         bump_step();
         if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // after this CTA's (possible) bump
+        TL(1);
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        TL(2);
         load_inputs();
         if (io.rand_noise) make_noise();  // explicit draws may come from the previous kernel
     } else {
         // (griddepcontrol.* are no-ops when launched without the attribute.)
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        TL(1);
         if (pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         load_inputs();
         take_step();
         make_noise();  // evaluated while the loads above fly
+        TL(2);
         if (active) {
             // keep the consumers of the loads below this point: the compiler would otherwise hoist the first use of the
             // action registers above the noise code and park every warp on the load latency before doing useful work
@@ -295,6 +339,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         __syncthreads();
     }
 
+    TL(3);
     // ---- pre_physics_step reset of the envs flagged last step (hovering.py:209-211, quirk Q1): new rows land in the tile
     const int warp = tid >> 5;
     const int64_t warp_env0 = tile0 + warp * 32;
@@ -347,6 +392,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     }
 
     // ---- tiles leave shared memory
+    TL(4);
     if (bulk) {
         fence_async_smem();  // generic-proxy smem writes → visible to the async (TMA) proxy
         __syncthreads();
@@ -380,6 +426,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     }
     if (bulk && tid == 0) bulk_wait_read0();  // smem must stay alive until the bulk stores have read it
     if (pdl_mode != 3) bump_step();
+    TL(5);
 }
 
 // ---- standalone reset_idx kernel -------------------------------------------------------------------------
@@ -440,7 +487,9 @@ __global__ void agx_philox_fill_kernel(float* out, int64_t n, int width, int str
 
 int g_block = 128;
 int g_use_bulk = 1;
-int g_pdl = 0;  // measured slower on B200 (13.8 vs 12.1 us/step at 65 536 envs): off by default
+int g_pdl = -1;  // -1 auto: noise-first PDL (mode 3) for grids of at most ~one wave, where the kernel boundary dominates
+                 // (65 536 envs: 10.3 -> 7.9 us/step); off for multi-wave grids, where early CTAs only steal slots (4 M envs: 357 -> 402 us)
+int g_sm_count = 0;
 
 template <typename Kernel>
 cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, const AgxParams& P,
@@ -450,10 +499,19 @@ cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, 
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
+    int pdl = g_pdl;
+    if (pdl < 0) {
+        if (g_sm_count == 0) {
+            int dev = 0, sms = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) g_sm_count = sms;
+            if (g_sm_count <= 0) g_sm_count = 148;
+        }
+        pdl = ((uint64_t)grid * block <= (uint64_t)g_sm_count * 512u) ? 3 : 0;
+    }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
-    const int kflags = (g_use_bulk ? 1 : 0) | ((g_pdl & 3) << 1);
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1);
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, P, io, n, kflags);
@@ -493,6 +551,11 @@ bool misaligned(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 1
 extern "C" {
 
 int agx_version(void) { return AGX_VERSION; }
+#ifdef AGX_TIMELINE
+int agx_debug_timeline(unsigned long long* host_out, int n_entries) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * n_entries);
+}
+#endif
 const char* agx_error_string(void) { return g_err; }
 int agx_sizeof_params(void) { return (int)sizeof(AgxParams); }
 int agx_sizeof_step_io(void) { return (int)sizeof(AgxStepIO); }
@@ -506,7 +569,7 @@ int agx_set_option(const char* key, int value) {
     }
     if (!strcmp(key, "use_bulk")) { g_use_bulk = value ? 1 : 0; return AGX_OK; }
     if (!strcmp(key, "pdl")) {
-        if (value < 0 || value > 3) return fail(AGX_ERR_ARG, "agx_set_option: pdl must be 0..3%s");
+        if (value < -1 || value > 3) return fail(AGX_ERR_ARG, "agx_set_option: pdl must be -1 (auto) or 0..3%s");
         g_pdl = value;
         return AGX_OK;
     }

@@ -151,9 +151,12 @@ const char* agx_error_string(void);   /* thread-local text of the last error */
 int         agx_sizeof_params(void);  /* sizeof(AgxParams): lets a binding check its struct mirror */
 int         agx_sizeof_step_io(void);
 
-/* Tuning knobs (process-wide): "block" = 64|128 threads per CTA, "use_bulk" = 0|1 (TMA bulk-copy
- * staging vs cooperative copies), "pdl" = 0|1 (programmatic dependent launch: the next step's prologue overlaps
- * this step's tail; stream order of all memory effects is unchanged). */
+/* Tuning knobs (process-wide): "block" = 64|128 threads per CTA, "use_bulk" = 0|1 (TMA bulk-copy staging vs
+ * cooperative copies), "pdl" = programmatic dependent launch of agx_step: -1 auto (default: mode 3 for grids of at most
+ * about one wave, else off), 0 off, 1 trigger at entry / wait at entry, 2 trigger before the stores, 3 noise-first — the
+ * step's state-independent prologue (Philox counter, observation noise, L2 prefetch hints for its inputs) runs while the
+ * previous kernel of the stream is still executing; every global read or write of caller data happens after
+ * griddepcontrol.wait, so stream order of all memory effects is unchanged. */
 int agx_set_option(const char* key, int value);
 
 /* Fill `p` with the defaults of (task, ctl_mode): replaces the reference's cfg classes + the

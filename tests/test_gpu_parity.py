@@ -167,7 +167,7 @@ def test_philox_stream_matches_host_build():
         if sid < 2:
             assert np.array_equal(out.cpu().numpy(), ref)
         else:
-            assert_close(out.cpu(), ref, "normals", rtol=1e-4, atol=3e-5)  # SFU lg2/sin/cos (~2^-21 abs) vs libm
+            assert_close(out.cpu(), ref, "normals", rtol=1e-4, atol=1e-4)  # SFU lg2/sin/cos (~2^-21 abs; r = sqrt(-2 ln u1) amplifies it at small r) vs libm
 
 
 def test_philox_mode_equals_explicit_mode():
