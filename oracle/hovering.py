@@ -351,5 +351,7 @@ class TrackingOracle(HoveringOracle):
 
 def make_oracle(spec: QuadSpec, num_envs: int, dtype=torch.float32, rng="torch"):
     from .customized import BalloonOracle
+    from .image_tasks import AvoidOracle, PlanningOracle
 
-    return {"hovering": HoveringOracle, "tracking": TrackingOracle, "balloon": BalloonOracle}[spec.task](spec, num_envs, dtype, rng)
+    return {"hovering": HoveringOracle, "tracking": TrackingOracle, "balloon": BalloonOracle, "avoid": AvoidOracle,
+            "planning": PlanningOracle}[spec.task](spec, num_envs, dtype, rng)

@@ -79,6 +79,8 @@ class QuadSpec:
         if self.episode_length_s == 24.0:  # *_config.py episode_length_s
             self.episode_length_s = {"tracking": 36.0, "balloon": 8.0, "avoid": 6.0, "planning": 16.0}.get(self.task, 24.0)
         self.act_lo, self.act_hi = _limits(self.task, self.ctl_mode)
+        if self.task == "avoid":  # avoid_config.py:11: hover target at z = 1
+            self.target_state = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0]
 
     @property
     def num_actions(self) -> int:
@@ -112,4 +114,4 @@ class QuadSpec:
 
     @property
     def reset_draws(self) -> int:
-        return {"balloon": 15}.get(self.task, 12)
+        return {"balloon": 15, "avoid": 11, "planning": 124}.get(self.task, 12)

@@ -36,6 +36,7 @@ from oracle import QuadSpec, make_oracle  # noqa: E402
 from oracle import rotations as ORot  # noqa: E402
 from oracle.px4_controller import ParallelControl  # noqa: E402
 from oracle.rigid_body import simulate  # noqa: E402
+from oracle import scene as OScene  # noqa: E402
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -77,6 +78,7 @@ def install_stubs():
     sys.modules["pytorch3d"].transforms = sys.modules["pytorch3d.transforms"]
 
     mod("rospy")
+    mod("cv2", normalize=lambda *a, **k: None, applyColorMap=lambda *a, **k: None, NORM_MINMAX=0, CV_8UC1=0, COLORMAP_PLASMA=0)
     mod("matplotlib")  # airgym/utils/__init__.py imports a plotting Logger; not on the path
     mod("matplotlib.pyplot")
 
@@ -133,14 +135,33 @@ class FakeGym:
         rotor = f[:, 1:5, 2].to(torch.float32)
         tau_z = t[:, 1:5, 2].sum(-1).to(torch.float32)
         simulate(self.spec, self.env.root_states, rotor, tau_z)
+        if self.spec.task == "avoid":  # the thrown cube's flight (PhysX in the reference; oracle/scene.py here)
+            OScene.cube_step(self.env.object_states[:, 0:3], self.env.object_states[:, 7:10], self.spec.dt, self.spec.gravity)
 
     def refresh_actor_root_state_tensor(self, sim): pass
 
+    def _trees(self):
+        a = self.env.env_asset_root_states
+        yaw = 2.0 * torch.atan2(a[:, 1:, 5], a[:, 1:, 6])  # the simulator only knows the quaternion
+        return (a[:, 1:, 0:2], yaw)
+
     def refresh_net_contact_force_tensor(self, sim):
-        # builder-defined stand-in for PhysX's net contact force (oracle/customized.py refresh_contact_forces)
-        hit = self.env.root_states[:, 2] < 0.2
-        self.env.contact_forces.zero_()
-        self.env.contact_forces[hit, 2] = 1.0
+        # builder-defined stand-in for PhysX's net contact force (oracle/scene.py drone_contacts)
+        env, task = self.env, self.spec.task
+        kw = {"cube": env.object_states[:, 0:3]} if task == "avoid" else ({"trees": self._trees()} if task == "planning" else {})
+        hit = OScene.drone_contacts(env.root_states[:, 0:3], **kw)
+        env.contact_forces.zero_()
+        env.contact_forces[hit, 2] = 1.0
+
+    def render_all_camera_sensors(self, sim):
+        # builder-defined stand-in for IsaacGym's depth camera: camera_tensors[i] is [H,W] of NEGATIVE planar depth, -inf = no hit
+        env, task = self.env, self.spec.task
+        kw = {"cube": env.object_states[:, 0:3]} if task == "avoid" else {"trees": self._trees(), "ball": env.goal_states[:, 0:3]}
+        d = OScene.render_depth(env.root_states[:, 0:3], env.root_states[:, 3:7], **kw)  # [N,W,H]
+        env.camera_tensors = [(-d[i]).T.contiguous() for i in range(env.num_envs)]
+
+    def start_access_image_tensors(self, sim): pass
+    def end_access_image_tensors(self, sim): pass
 
     def set_actor_root_state_tensor(self, sim, tensor): pass
     def fetch_results(self, sim, flag): pass
@@ -161,6 +182,14 @@ def make_reference_env(task, mode, N, ctl_state, episode_length_s=None):
         import airgym.envs.task.balloon as ref_bal
         from airgym.envs.task.balloon_config import BalloonCfg
         cls, cfg = ref_bal.Balloon, BalloonCfg()
+    elif task == "avoid":
+        import airgym.envs.task.avoid as ref_avd
+        from airgym.envs.task.avoid_config import AvoidCfg
+        cls, cfg = ref_avd.Avoid, AvoidCfg()
+    elif task == "planning":
+        import airgym.envs.task.planning as ref_pln
+        from airgym.envs.task.planning_config import PlanningCfg
+        cls, cfg = ref_pln.Planning, PlanningCfg()
     else:
         cls, cfg = (ref_hov.Hovering, HoveringCfg()) if task == "hovering" else (ref_trk.Tracking, TrackingCfg())
     if episode_length_s is not None:
@@ -179,7 +208,7 @@ def make_reference_env(task, mode, N, ctl_state, episode_length_s=None):
     env.time_out_buf = torch.zeros(N, dtype=torch.bool)
     env.progress_buf = torch.zeros(N, dtype=torch.long)
     env.extras = {}
-    n_actors = 2 if task == "balloon" else 1
+    n_actors = {"balloon": 2, "avoid": 2, "planning": 42}.get(task, 1)
     env.vec_root_tensor = torch.zeros(N, n_actors, 13)
     env.vec_root_tensor[:, :, 6] = 1.0
     env.root_tensor = env.vec_root_tensor
@@ -222,8 +251,43 @@ def make_reference_env(task, mode, N, ctl_state, episode_length_s=None):
         env.collisions = torch.zeros(N)
         env.enable_onboard_cameras = False
         env.counter = 0
+    if task in ("avoid", "planning"):  # Customized.__init__ (customized.py:57-143) + Avoid/Planning.__init__ attribute set-up
+        env.num_assets = n_actors - 1
+        env.env_asset_root_states = env.vec_root_tensor[:, 1:1 + env.num_assets, :]
+        env.pre_root_positions = torch.zeros(N, 3)
+        env.pre_root_linvels = torch.zeros(N, 3)
+        env.pre_root_angvels = torch.zeros(N, 3)
+        env.contact_forces = torch.zeros(N, 3)
+        env.collisions = torch.zeros(N)
+        env.enable_onboard_cameras = True
+        env.cam_resolution, env.cam_channel = (212, 120), 1
+        env.full_camera_array = torch.zeros(N, 1, 212, 120)
+        env.camera_tensors = [torch.zeros(120, 212) for _ in range(N)]
+        env.counter = 0
+        if task == "avoid":
+            env.object_states = env.env_asset_root_states[:, 0, :]
+            env.object_positions = env.object_states[..., 0:3]
+            env.object_quats = env.object_states[..., 3:7]
+            env.object_linvels = env.object_states[..., 7:10]
+            env.object_angvels = env.object_states[..., 10:13]
+        else:
+            env.goal_states = env.env_asset_root_states[:, 0, :]
+            env.goal_positions = env.goal_states[..., 0:3]
+            env.goal_quats = env.goal_states[..., 3:7]
+            env.prev_related_dist = torch.zeros(N)
     env.gym = FakeGym(env, spec)
     return env, spec
+
+
+def ref_aux_matrix(task, ref):
+    a = torch.zeros(ref.num_envs, 8)
+    if task == "avoid":
+        a[:, 0:3], a[:, 3:6], a[:, 6] = ref.object_positions, ref.object_linvels, ref.collisions
+    else:
+        # col 7 (esdf_dist) is left to the oracle: Planning.reset_idx overwrites the attribute of ALL envs with 10 whenever any
+        # env resets (planning.py:136) — a dead store, step() recomputes it from the image before every use (:162-163)
+        a[:, 0:3], a[:, 3:6], a[:, 6], a[:, 7] = ref.goal_positions, ref.pre_root_positions, ref.collisions, float("inf")
+    return a
 
 
 def action_sequence(mode, N, A, T, gen):
@@ -251,6 +315,9 @@ def run_case(task, mode, N, T, seed, ctl_state, episode_length_s=None, tag=""):
     for t in range(T):
         a = acts[t].clone()
         obs, _, rew, reset, extras = ref.step(a)
+        image = None
+        if isinstance(obs, dict):
+            image, obs = obs["image"].clone(), obs["observation"]
         info = extras["item_reward_info"]
         MISSING = float("inf")  # keys the kernel exports but the reference's dict lacks: filled from the oracle below
         terms = torch.stack([info[k].to(torch.float32) if torch.is_tensor(info.get(k)) else torch.full((N,), float(info.get(k, MISSING)))
@@ -259,6 +326,9 @@ def run_case(task, mode, N, T, seed, ctl_state, episode_length_s=None, tag=""):
                             progress=ref.progress_buf.clone(), timeout=extras["time_outs"].clone(),
                             actions=ref.actions.clone().to(torch.float32), pre_actions=ref.pre_actions.clone().to(torch.float32),
                             cmd=ref.cmd_thrusts.clone().to(torch.float32), terms=terms, action_in_after=a.clone()))
+        if image is not None:
+            ref_out[-1]["image"] = image
+            ref_out[-1]["aux"] = ref_aux_matrix(task, ref)
     # oracle run, same seed → must agree; its recorded draws go into the fixture
     torch.manual_seed(seed)
     worst = 0.0
@@ -268,8 +338,13 @@ def run_case(task, mode, N, T, seed, ctl_state, episode_length_s=None, tag=""):
         orc.step(a)
         o = dict(state=orc.root_states, obs=orc.obs_buf, rew=orc.rew_buf, actions=orc.actions, pre_actions=orc.pre_actions,
                  cmd=orc.cmd_thrusts, terms=orc.reward_terms_matrix(), action_in_after=a)
+        if task in ("avoid", "planning"):
+            o["image"] = orc.full_camera_array
+            o["aux"] = orc.aux_matrix()
         r = ref_out[t]
         r["terms"] = torch.where(torch.isinf(r["terms"]), o["terms"], r["terms"])
+        if "aux" in r:
+            r["aux"] = torch.where(torch.isinf(r["aux"]), o["aux"], r["aux"])
         for k, v in o.items():
             rv = r[k]
             same_nan = torch.isnan(v) == torch.isnan(rv)
@@ -288,7 +363,14 @@ def run_case(task, mode, N, T, seed, ctl_state, episode_length_s=None, tag=""):
             rec[k].append(r[k].numpy())
         if hasattr(orc, "aux_matrix"):
             rec.setdefault("aux", []).append(orc.aux_matrix().numpy())
-            ref_aux = torch.cat((ref.balloon_positions, ref.pre_root_positions, ref.collisions.unsqueeze(1)), 1)
+        if task in ("avoid", "planning"):
+            rec.setdefault("rendered", []).append(np.array(orc.rendered))
+            if orc.rendered:
+                rec.setdefault("image", []).append(r["image"].numpy())
+                for kk in ("add", "mul", "kern"):
+                    rec.setdefault("img_" + kk, []).append(orc.last_image_draws[kk].numpy().copy())
+            if task == "planning":
+                rec.setdefault("assets", []).append(orc.asset_matrix().numpy())
         rec["draw_reset"].append(orc.last_draws["reset"].numpy().copy())
         rec["draw_noise"].append(orc.last_draws["noise"].numpy().copy())
     out = {k: np.stack(v) for k, v in rec.items()}
@@ -310,7 +392,12 @@ def main():
         return orig_to(self, *a, **kw)
 
     torch.Tensor.to = to_cpu
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"  # "image": only the avoid/planning cases
     try:
+        if which == "image":
+            run_case("avoid", "rate", 2, 9, 21, ctl_state, episode_length_s=0.07)   # time-outs at step 6; renders at 4, 8
+            run_case("planning", "rate", 2, 9, 23, ctl_state)                      # renders at steps 4, 8
+            return
         for mode in ("rate", "prop", "atti", "vel", "pos"):
             run_case("hovering", mode, 16, 24, 7, ctl_state)
         run_case("hovering", "rate", 16, 30, 11, ctl_state, episode_length_s=0.12, tag="_short")  # time-out resets (Q1)
@@ -319,6 +406,8 @@ def main():
         run_case("tracking", "vel", 16, 30, 3, ctl_state, episode_length_s=0.12, tag="_short")
         for mode in ("rate", "vel"):
             run_case("balloon", mode, 16, 40, 9, ctl_state)
+        run_case("avoid", "rate", 2, 9, 21, ctl_state, episode_length_s=0.07)   # time-outs at step 6; renders at 4, 8
+        run_case("planning", "rate", 2, 9, 23, ctl_state)                      # renders at steps 4, 8
     finally:
         torch.Tensor.to = orig_to
 

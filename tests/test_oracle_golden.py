@@ -15,9 +15,20 @@ def test_oracle_matches_reference_trajectory(name):
     spec.episode_length_s = max_len * spec.dt + 1e-9
     assert spec.max_episode_length == max_len
     orc = make_oracle(spec, N, rng="explicit")
+    r_idx = 0
     for t in range(T):
         a = torch.from_numpy(g["action_in"][t].copy())
-        orc.step(a, torch.from_numpy(g["draw_reset"][t]), torch.from_numpy(g["draw_noise"][t]))
+        if task in ("avoid", "planning"):  # image tasks: the image noise of a render step is part of the explicit draws
+            img = None
+            if g["rendered"][t]:
+                img = {k: torch.from_numpy(g["img_" + k][r_idx]) for k in ("add", "mul", "kern")}
+            orc.step(a, torch.from_numpy(g["draw_reset"][t]), torch.from_numpy(g["draw_noise"][t]), img)
+            if g["rendered"][t]:
+                assert_close(orc.full_camera_array, g["image"][r_idx], f"{name} t={t} image", rtol=1e-5, atol=2e-5)
+                r_idx += 1
+            assert_close(orc.aux_matrix(), g["aux"][t], f"{name} t={t} aux", rtol=1e-5, atol=2e-5)
+        else:
+            orc.step(a, torch.from_numpy(g["draw_reset"][t]), torch.from_numpy(g["draw_noise"][t]))
         assert_close(orc.root_states, g["state"][t], f"{name} t={t} state", rtol=1e-5, atol=2e-6)
         assert_close(orc.obs_buf, g["obs"][t], f"{name} t={t} obs", rtol=1e-5, atol=2e-6)
         ra = 6e-5 if task == "balloon" else 2e-6  # balloon: 30x guidance amplification (tests/util.py task_tols)
