@@ -19,6 +19,10 @@ TASK_IDS = {"hovering": 0, "tracking": 1, "balloon": 2, "avoid": 3, "planning": 
 CTL_IDS = {"pos": 0, "vel": 1, "atti": 2, "rate": 3, "prop": 4}
 FLAG_MUTATE_ACTIONS, FLAG_CTRL_RESET, FLAG_NO_NOISE, FLAG_RESET_ON_COLLISION = 1, 2, 4, 8
 AGX_AUX_MAX = 8
+AGX_REWARD_TERMS = 12
+AGX_NUM_TREES, AGX_NUM_ASSETS, AGX_ASSET_ROW, AGX_PLANNING_DRAWS = 40, 41, 164, 124
+AGX_CAM_W, AGX_CAM_H = 212, 120
+PHASE_FUSED, PHASE_PHYSICS, PHASE_TASK = 0, 1, 2
 INT_RK4, INT_EULER = 0, 1
 
 _f3 = C.c_float * 3
@@ -56,6 +60,15 @@ class AgxStepIO(C.Structure):
         ("obs", C.c_void_p), ("reward", C.c_void_p), ("cmd", C.c_void_p), ("reward_terms", C.c_void_p),
         ("aux", C.c_void_p), ("rand_reset", C.c_void_p), ("rand_noise", C.c_void_p),
         ("seed", C.c_uint64), ("step", C.c_uint64), ("step_dev", C.c_void_p), ("env_offset", C.c_int64),
+        ("assets", C.c_void_p), ("trees", C.c_void_p), ("phase", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class AgxRenderIO(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p), ("aux", C.c_void_p), ("assets", C.c_void_p), ("trees", C.c_void_p), ("image", C.c_void_p),
+        ("rand_add", C.c_void_p), ("rand_mul", C.c_void_p), ("rand_kern", C.c_void_p),
+        ("seed", C.c_uint64), ("step", C.c_uint64), ("env_offset", C.c_int64),
     ]
 
 
@@ -95,8 +108,10 @@ def bind(lib):
     lib.agx_step.argtypes = [C.POINTER(AgxParams), C.c_int64, C.POINTER(AgxStepIO), C.c_void_p]
     lib.agx_reset_idx.argtypes = [
         C.POINTER(AgxParams), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
     ]
+    lib.agx_render_depth.argtypes = [C.POINTER(AgxParams), C.c_int64, C.POINTER(AgxRenderIO), C.c_void_p]
+    lib.agx_sizeof_render_io.restype = C.c_int
     lib.agx_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
     lib.agx_gae.argtypes = [C.c_int64, C.c_int, C.c_float, C.c_float] + [C.c_void_p] * 8
     lib.agx_ppo_workspace_floats.restype = C.c_int64
@@ -110,7 +125,7 @@ def bind(lib):
 
 
 EXPORTS = (
-    "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_set_option",
+    "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_sizeof_render_io", "agx_render_depth", "agx_set_option",
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
 )
@@ -129,7 +144,8 @@ def load():
             "(nvcc -gencode arch=compute_100a,code=sm_100a). airgym_b200 has no CPU fallback."
         )
     lib = bind(C.CDLL(LIB_PATH))
-    if lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO):
+    if (lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO)
+            or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO)):
         raise ImportError("libagx.so struct layout differs from airgym_b200/_capi.py (rebuild the library)")
     _lib = lib
     return lib

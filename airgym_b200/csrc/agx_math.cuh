@@ -299,9 +299,181 @@ AGX_HD void reset_sample_balloon(const float* u, float* s, float* aux) {
     aux[3] = 0.0f; aux[4] = 0.0f; aux[5] = 0.0f;  // pre_root_positions[env_ids] = 0 (balloon.py:90)
 }
 
+// ---- scene stand-ins for IsaacGym cameras / PhysX contacts (builder-defined; oracle/scene.py is the restatement) ----
+constexpr float kDroneRadius = 0.2f;   // robots/X152b/model.urdf:13-18 collision sphere
+constexpr float kBallRadius = 0.2f;    // balls/ball/model.urdf
+constexpr float kCubeHalf = 0.15f;     // cubes/1x1: +-1 mesh scaled 0.15
+constexpr float kCamFar = 5.0f;        // avoid_config.py:60 far_plane
+constexpr float kCamF = 111.70069f;    // (212 / 2) / tan(87 deg / 2): focal length in pixels
+constexpr float kTMin = 1e-3f;
+constexpr float kInf = __builtin_huge_valf();  // +inf
+
+struct Capsule { V3 c, a; float r, h; };  // capped cylinder: centre, unit axis, radius, half length (world frame)
+
+// tree `j` of an env: asset-frame table row (centre xyz, axis xyz, radius, half length) placed at (x, y, 0), yawed by (cy, sy)
+AGX_HD Capsule place_tree(const float* t, float x, float y, float cy, float sy) {
+    Capsule k;
+    k.c = v3(cy * t[0] - sy * t[1] + x, sy * t[0] + cy * t[1] + y, t[2]);
+    k.a = v3(cy * t[3] - sy * t[4], sy * t[3] + cy * t[4], t[5]);
+    k.r = t[6];
+    k.h = t[7];
+    return k;
+}
+
+AGX_HD float hit_ground(V3 o, V3 d) {
+    const float t = fdiv(-o.z, d.z);
+    return (d.z < 0.0f && t > kTMin) ? t : kInf;
+}
+AGX_HD float hit_sphere(V3 o, V3 d, V3 c, float r) {
+    const V3 oc = o - c;
+    const float a = dot(d, d), b = dot(d, oc), cc = dot(oc, oc) - r * r;
+    const float disc = b * b - a * cc;
+    const float t = fdiv(-b - fsqrt(disc > 0.0f ? disc : 0.0f), a);
+    return (disc > 0.0f && t > kTMin) ? t : kInf;
+}
+AGX_HD float hit_box(V3 o, V3 d, V3 c, float half) {
+    const float ix = fdiv(1.0f, d.x), iy = fdiv(1.0f, d.y), iz = fdiv(1.0f, d.z);
+    const float ax = (c.x - half - o.x) * ix, bx = (c.x + half - o.x) * ix;
+    const float ay = (c.y - half - o.y) * iy, by = (c.y + half - o.y) * iy;
+    const float az = (c.z - half - o.z) * iz, bz = (c.z + half - o.z) * iz;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return (tn <= tf && tn > kTMin) ? tn : kInf;
+}
+AGX_HD float hit_capsule(V3 o, V3 d, const Capsule& k) {  // side wall, then the end cap facing the ray
+    const V3 oc = o - k.c;
+    const float card = dot(k.a, d), caoc = dot(k.a, oc);
+    const float A = dot(d, d) - card * card;
+    const float B = dot(oc, d) - caoc * card;
+    const float C = dot(oc, oc) - caoc * caoc - k.r * k.r;
+    const float disc = B * B - A * C;
+    if (!(disc > 0.0f)) return kInf;
+    const float sq = fsqrt(disc);
+    const float t = fdiv(-B - sq, A);
+    const float y = caoc + t * card;
+    const float side = (fabsf(y) < k.h && t > kTMin) ? t : kInf;
+    const float tc = fdiv((y < 0.0f ? -k.h : k.h) - caoc, card);
+    const float cap = (fabsf(B + A * tc) < sq && tc > kTMin) ? tc : kInf;
+    return fminf(side, cap);
+}
+// drone collision sphere vs a tree, the tree taken as a capsule (segment distance)
+AGX_HD bool touch_capsule(V3 p, const Capsule& k) {
+    const V3 rel = p - k.c;
+    float s = dot(rel, k.a);
+    s = s < -k.h ? -k.h : (s > k.h ? k.h : s);
+    const V3 q = rel - s * k.a;
+    return norm(q) < k.r + kDroneRadius;
+}
+AGX_HD bool touch_box(V3 p, V3 c, float half) {
+    const float qx = fmaxf(fabsf(p.x - c.x) - half, 0.0f), qy = fmaxf(fabsf(p.y - c.y) - half, 0.0f),
+                qz = fmaxf(fabsf(p.z - c.z) - half, 0.0f);
+    return fsqrt(qx * qx + qy * qy + qz * qz) < kDroneRadius;
+}
+// one dt of the thrown cube (avoid.py leaves its flight to PhysX): semi-implicit Euler, rests where it lands; cubes parked at
+// x = -999 (avoid.py:124-129) stay.  c = [px py pz vx vy vz]
+AGX_HD void cube_step(float* c, float dt, float g) {
+    if (c[0] == -999.0f) return;
+    const float vz = c[5] - g * dt;
+    float px = c[0] + c[3] * dt, py = c[1] + c[4] * dt, pz = c[2] + vz * dt;
+    float vx = c[3], vy = c[4], vzz = vz;
+    if (pz < kCubeHalf) { pz = kCubeHalf; vx = 0.0f; vy = 0.0f; vzz = 0.0f; }
+    c[0] = px; c[1] = py; c[2] = pz; c[3] = vx; c[4] = vy; c[5] = vzz;
+}
+
+// ---- depth camera (builder-defined stand-in for IsaacGym's camera sensor; oracle/scene.py camera_rays) ----
+struct Camera { V3 o; float R[9]; };
+AGX_HD Camera make_camera(const float* s) {  // s = root-state row; unit quaternion assumed (1 - 2(yy+zz) form, like the oracle)
+    Camera c;
+    const float x = s[3], y = s[4], z = s[5], w = s[6];
+    c.R[0] = 1.0f - 2.0f * (y * y + z * z); c.R[1] = 2.0f * (x * y - z * w); c.R[2] = 2.0f * (x * z + y * w);
+    c.R[3] = 2.0f * (x * y + z * w); c.R[4] = 1.0f - 2.0f * (x * x + z * z); c.R[5] = 2.0f * (y * z - x * w);
+    c.R[6] = 2.0f * (x * z - y * w); c.R[7] = 2.0f * (y * z + x * w); c.R[8] = 1.0f - 2.0f * (x * x + y * y);
+    const V3 off = mat_mul_v(c.R, v3(0.15f, 0.0f, 0.1f));  // local_transform.p (avoid_config.py:66)
+    c.o = v3(s[0] + off.x, s[1] + off.y, s[2] + off.z);
+    return c;
+}
+// world direction of pixel (u, v), u along the width (to the left is +y body), v down; x_cam component = 1 so the ray
+// parameter IS the planar depth
+AGX_HD V3 pixel_dir(const Camera& c, int u, int v) {
+    const float dy = fdiv((float)(AGX_CAM_W / 2) - (float)u - 0.5f, kCamF);
+    const float dz = fdiv((float)(AGX_CAM_H / 2) - (float)v - 0.5f, kCamF);
+    return mat_mul_v(c.R, v3(1.0f, dy, dz));
+}
+// customized.py:402-404: beyond the far plane = no hit = +inf; clip at 4.5 m; / 4.5
+AGX_HD float normalize_depth(float t) {
+    if (t > kCamFar) t = kInf;
+    t = t > 4.5f ? 4.5f : t;
+    t = t < 0.0f ? 0.0f : t;
+    return t / 4.5f;
+}
+// can the capsule show up in the image at all? (bounding sphere vs the far-plane frustum's bounding sphere / camera plane)
+AGX_HD bool capsule_visible(const Camera& c, const Capsule& k) {
+    const V3 rel = k.c - c.o;
+    const float reach = k.h + k.r;
+    if (norm(rel) - reach > 7.5f) return false;  // 5 m far plane x |d|max = 1.475
+    const V3 fwd = v3(c.R[0], c.R[3], c.R[6]);
+    return dot(rel, fwd) + k.h * fabsf(dot(k.a, fwd)) + k.r > 0.0f;
+}
+
+// Avoid.reset_idx (avoid.py:91-158) on the 11 compact draws [u_mode, theta, aim xyz, x, y, z, roll, pitch, yaw]
+// (zero-weighted reference draws dropped).  aux = [cube xyz | cube linvel xyz | collisions | pad].
+AGX_HD void reset_sample_avoid(const float* u, float* s, float* aux) {
+    if (u[0] < 0.8f) {  // thrown at the hover point (avoid.py:104-117, calculate_object_velocity :58-89)
+        const float theta = (kPi / 6.0f) * urange(u[1], -1.0f, 1.0f);
+        const float cx = 4.2f * cosf(theta), cy = 4.2f * sinf(theta), cz = 1.4f;
+        const float tx = 0.3f * urange(u[2], -1.0f, 1.0f) + 0.0f, ty = 0.3f * urange(u[3], -1.0f, 1.0f) + 0.0f,
+                    tz = 0.3f * urange(u[4], -1.0f, 1.0f) + 1.0f;
+        const float dx = tx - cx, dy = ty - cy;
+        const float dxy = sqrtf(dx * dx + dy * dy);
+        const float t = dxy / 4.5f;
+        aux[0] = cx; aux[1] = cy; aux[2] = cz;
+        aux[3] = (dx / dxy) * 4.5f;
+        aux[4] = (dy / dxy) * 4.5f;
+        aux[5] = (tz - cz + 4.905f * (t * t)) / t;
+    } else {
+        aux[0] = -999.0f; aux[1] = -999.0f; aux[2] = 0.0f;
+        aux[3] = 0.0f; aux[4] = 0.0f; aux[5] = 0.0f;
+    }
+    s[0] = 0.2f * urange(u[5], -1.0f, 1.0f) + 0.0f;
+    s[1] = 0.2f * urange(u[6], -1.0f, 1.0f) + 0.0f;
+    s[2] = 0.2f * urange(u[7], -1.0f, 1.0f) + 1.0f;
+    const Q4 q = euler_xyz_to_quat(0.01f * urange(u[8], -kPi, kPi), 0.01f * urange(u[9], -kPi, kPi), 0.05f * urange(u[10], -kPi, kPi));
+    s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+#pragma unroll
+    for (int i = 7; i < 13; ++i) s[i] = 0.0f;
+}
+
+// Planning.reset_idx (planning.py:63-136): draw d of the 124 compact draws [asset x(41) | y(41) | yaw(41) | goal y] → its slot(s)
+// in the env's asset row [x(41) | y(41) | cos yaw(41) | sin yaw(41)].  The goal fix-up (asset 0 = the ball: x = 8.5,
+// y = 1.5 U(-1,1)) must be applied AFTER all 124 draws are placed: planning_goal_fixup.
+AGX_HD void planning_place_draw(int d, float u, float* row) {
+    if (d < AGX_NUM_ASSETS) row[d] = 8.0f * urange(u, -1.0f, 1.0f) + 0.0f;             // LENGTH
+    else if (d < 2 * AGX_NUM_ASSETS) row[d] = 4.0f * urange(u, -1.0f, 1.0f) + 0.0f;    // WIDTH
+    else if (d < 3 * AGX_NUM_ASSETS) {
+        const float yaw = urange(u, -kPi, kPi);
+        row[d] = cosf(yaw);
+        row[d + AGX_NUM_ASSETS] = sinf(yaw);
+    }
+}
+// goal + drone pose from the last draw; aux = [goal xyz | pre_root_positions xyz | collisions | esdf_dist]
+AGX_HD void planning_goal_fixup(float u_goal, float* row, float* s, float* aux) {
+    const float gy = 1.5f * urange(u_goal, -1.0f, 1.0f) + 0.0f;
+    row[0] = 8.5f;
+    row[AGX_NUM_ASSETS] = gy;
+    aux[0] = 8.5f; aux[1] = gy; aux[2] = 1.5f;
+    aux[3] = 0.0f; aux[4] = 0.0f; aux[5] = 0.0f;  // pre_root_positions[env_ids] = 0 (planning.py:119)
+    s[0] = -8.5f; s[1] = 0.0f; s[2] = 1.5f;
+    const float yaw0 = atan2f(gy - 0.0f, 8.5f - (-8.5f));  // compute_direction_angle (planning.py:86-99)
+    const Q4 q = euler_xyz_to_quat(0.0f, 0.0f, yaw0);
+    s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+#pragma unroll
+    for (int i = 7; i < 13; ++i) s[i] = 0.0f;
+}
+
 template <int TASK>
 AGX_HD void reset_sample(const float* u, float* s, float* aux) {
     if (TASK == AGX_TASK_BALLOON) { reset_sample_balloon(u, s, aux); return; }
+    if (TASK == AGX_TASK_AVOID) { reset_sample_avoid(u, s, aux); return; }
     float a0, a1, a2;
     if (TASK == AGX_TASK_TRACKING) {
         s[0] = 0.1f * urange(u[0], -1.0f, 1.0f);
@@ -536,7 +708,9 @@ AGX_HD void integrate(const AgxParams& P, float* s, V3 w, const float* thrust, f
 
 // uniforms one reset_idx consumes (== AgxParams.reset_draws, checked at the C ABI)
 template <int TASK>
-struct ResetDraws { static constexpr int kD = (TASK == AGX_TASK_BALLOON) ? 15 : 12; };
+struct ResetDraws {  // planning (124 draws) has its own sampler: planning_place_draw / planning_goal_fixup
+    static constexpr int kD = (TASK == AGX_TASK_BALLOON) ? 15 : (TASK == AGX_TASK_AVOID ? 11 : (TASK == AGX_TASK_PLANNING ? AGX_PLANNING_DRAWS : 12));
+};
 
 // ---- random source: explicit rows (parity mode) or Philox (perf mode) ---------------------------------
 struct RandSrc {
@@ -575,8 +749,9 @@ struct EnvRegs {
     float a_last_remap;          // out: 0.5+0.5a of the last action column (Q4 write-back)
     float rew;
     float cmd[4];
-    float terms[9];
-    float aux[AGX_AUX_MAX];      // task state beyond the drone (balloon: ball xyz, previous drone xyz, collision flag)
+    float terms[AGX_REWARD_TERMS];
+    float aux[AGX_AUX_MAX];      // task state beyond the drone — balloon: ball xyz, previous drone xyz, collision flag; avoid: cube xyz,
+                                 // cube linvel xyz, collision flag; planning: goal xyz, previous drone xyz, collision flag, esdf_dist
 };
 
 // Bookkeeping half of reset_idx (hovering.py:332-335): the sampled state/aux are supplied by the caller (the kernel
@@ -591,11 +766,38 @@ AGX_HD void reset_apply(const AgxParams& P, EnvRegs& e) {
     }
 }
 
+// what the planning task needs beyond EnvRegs: this env's asset row (in/out) and the tree table
+struct SceneRef { float* assets_row; const float* trees; };
+
+// Planning.reset_idx, serially (host build, standalone reset_idx kernel): 124 draws = 31 Philox blocks of stream `which`
+AGX_HD void reset_planning_serial(const RandSrc& r, int which, float* s, float* aux, float* row) {
+    float u_goal = 0.0f;
+    for (int b = 0; b < AGX_PLANNING_DRAWS / 4; ++b) {
+        float u[4];
+        if (r.reset_row) {
+            for (int j = 0; j < 4; ++j) u[j] = r.reset_row[which * AGX_PLANNING_DRAWS + b * 4 + j];
+        } else {
+            const U4 w = philox_block(r.ph, (uint32_t)which, (uint32_t)b);
+            u[0] = u32_to_unit(w.x); u[1] = u32_to_unit(w.y); u[2] = u32_to_unit(w.z); u[3] = u32_to_unit(w.w);
+        }
+        for (int j = 0; j < 4; ++j) {
+            const int d = b * 4 + j;
+            if (d == AGX_PLANNING_DRAWS - 1) u_goal = u[j];
+            else planning_place_draw(d, u[j], row);
+        }
+    }
+    planning_goal_fixup(u_goal, row, s, aux);
+}
+
 template <int TASK>
-AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e) {
-    float u[AGX_RESET_DRAWS_MAX];
-    draw_reset(rnd, which, ResetDraws<TASK>::kD, u);
-    reset_sample<TASK>(u, e.s, e.aux);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+AGX_HD void do_reset(const AgxParams& P, const RandSrc& rnd, int which, EnvRegs& e, const SceneRef& sc) {
+    if (TASK == AGX_TASK_PLANNING) {
+        reset_planning_serial(rnd, which, e.s, e.aux, sc.assets_row);
+    } else {
+        float u[AGX_RESET_DRAWS_MAX];
+        draw_reset(rnd, which, ResetDraws<TASK>::kD, u);
+        reset_sample<TASK>(u, e.s, e.aux);  // root_states[ids] = initial (zeros + identity quat) then overwritten
+    }
     reset_apply(P, e);
 }
 
@@ -626,10 +828,13 @@ AGX_HD void scaled_noise(const AgxParams& P, const RandSrc& rnd, float* z) {
     for (int i = 15; i < 18; ++i) z[i] = P.noise_sigma[3] * z[i];
 }
 
-// Everything between the two reset_idx passes of one step: the caller has already applied the pre-step reset
-// (hovering.py:209-211, quirk Q1) to `e` when e.pending, and applies the end-of-step reset when e.reset comes back set.
+// The step between its two reset_idx passes, in two halves (the depth-camera tasks render between them on a render step,
+// customized.py:318-325).  The caller has already applied the pre-step reset (hovering.py:209-211, quirk Q1) to `e` when
+// e.pending, and applies the end-of-step reset when e.reset comes back set.
+//
+// env_phys: action shaping, controller cascade, rigid body, progress += 1, object flight and contacts.  R leaves as R(q_new).
 template <int TASK, int MODE>
-AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs) {
+AGX_HD void env_phys(const AgxParams& P, EnvRegs& e, const SceneRef& sc, float* R) {
     constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
     constexpr bool kThrustMode = (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI);
 
@@ -656,7 +861,6 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
     if (e.s[6] < 0.0f) { e.s[3] = -e.s[3]; e.s[4] = -e.s[4]; e.s[5] = -e.s[5]; e.s[6] = -e.s[6]; }
 
     // -- body rates, shared by the controller and the integrator
-    float R[9];
     {
         Q4 q0; q0.x = e.s[3]; q0.y = e.s[4]; q0.z = e.s[5]; q0.w = e.s[6];
         quat_to_matrix(q0, R);
@@ -677,10 +881,138 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
 
     e.progress += 1;  // hovering.py:297
 
+    // Customized family from here on sees the remapped-but-unclamped actions only
+    if (kCustom) {
+#pragma unroll
+        for (int i = 0; i < A; ++i) e.a[i] = ar[i];
+        // -- object flight + check_collisions (customized.py:393-397), builder-defined contact model: the drone's r = 0.2
+        //    collision sphere (model.urdf:13-18) against the ground plane, the thrown cube (avoid), the tree capsules (planning);
+        //    the balloon / goal ball never collide.
+        const V3 pn = v3(e.s[0], e.s[1], e.s[2]);
+        bool hit = pn.z < P.collision_radius;
+        if (TASK == AGX_TASK_AVOID) {
+            cube_step(e.aux, P.dt, P.gravity);
+            hit = hit || touch_box(pn, v3(e.aux[0], e.aux[1], e.aux[2]), kCubeHalf);
+        }
+        if (TASK == AGX_TASK_PLANNING) {
+            const float* row = sc.assets_row;
+            for (int j = 1; j < AGX_NUM_ASSETS; ++j) {
+                const float dx = pn.x - row[j], dy = pn.y - row[AGX_NUM_ASSETS + j];
+                if (dx * dx + dy * dy > 9.0f) continue;  // tree bounding cylinder: r + lean < 1.9 m from its root
+                const Capsule k = place_tree(sc.trees + (j - 1) * 8, row[j], row[AGX_NUM_ASSETS + j], row[2 * AGX_NUM_ASSETS + j],
+                                             row[3 * AGX_NUM_ASSETS + j]);
+                hit = hit || touch_capsule(pn, k);
+            }
+        }
+        e.aux[6] = hit ? 1.0f : 0.0f;
+    }
+}
+
+// yaw-aligned local frame of the depth-camera tasks (avoid.py:203-226): W = Rz(yaw)^T, yaw = atan2(R10, R00)
+struct LocalFrame { float c, s; float eul[3]; V3 v, w; };
+AGX_HD LocalFrame local_frame(const float* R, V3 v, V3 w) {
+    LocalFrame f;
+    const float yaw = atan2f(R[3], R[0]);
+    f.c = cosf(yaw); f.s = sinf(yaw);
+    const float m00 = f.c * R[0] + f.s * R[3], m01 = f.c * R[1] + f.s * R[4], m02 = f.c * R[2] + f.s * R[5];
+    const float m12 = -f.s * R[2] + f.c * R[5], m22 = R[8];
+    f.eul[0] = atan2f(-m12, m22); f.eul[1] = asinf(m02); f.eul[2] = atan2f(-m01, m00);  // matrix_to_euler_angles(W R, 'XYZ')
+    f.v = v3(f.c * v.x + f.s * v.y, -f.s * v.x + f.c * v.y, v.z);
+    f.w = v3(f.c * w.x + f.s * w.y, -f.s * w.x + f.c * w.y, w.z);
+    return f;
+}
+
+// env_task: observations, reward, termination flags, pre_actions.  R = R(q) of the current state.
+template <int TASK, int MODE>
+AGX_HD void env_task(const AgxParams& P, const float* z, EnvRegs& e, const float* R, float* obs) {
+    constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
+    constexpr bool kThrustMode = (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI);
+    constexpr bool kImageTask = (TASK == AGX_TASK_AVOID || TASK == AGX_TASK_PLANNING);
+    const float* ar = e.a;  // Customized family: remapped, unclamped (env_phys left them in e.a)
+
     // -- compute_observations + add_noise (hovering.py:337-358; tracking.py:202-214); z = sigma * N(0,1)
     const V3 p = v3(e.s[0], e.s[1], e.s[2]);
     const V3 v = v3(e.s[7], e.s[8], e.s[9]);
     const V3 w = v3(e.s[10], e.s[11], e.s[12]);
+    int reset;
+    float reward;
+    Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
+    const float up_z = (2.0f * q.w * q.w - 1.0f) + q.z * q.z * 2.0f;  // quat_axis(q,2)[2] (hovering.py:464-481)
+    const float yaw = atan2f(-R[1], R[0]);  // pytorch3d matrix_to_euler_angles(.,'XYZ')[2] (quirk Q6)
+    if (kImageTask) {
+        const LocalFrame lf = local_frame(R, v, w);
+        const float collided = e.aux[6];
+        float sa = 0.0f, sd_all = 0.0f, sd_rate = 0.0f;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+            sa += ar[i] * ar[i];
+            sd_all += sq(ar[i] - e.pa[i]);
+            if (i < A - 1) sd_rate += sq(ar[i] - e.pa[i]);
+        }
+        const float ups_r = sq((up_z + 1.0f) / 2.0f);
+        obs[3] = lf.eul[0]; obs[4] = lf.eul[1]; obs[5] = lf.eul[2];
+        obs[6] = lf.v.x; obs[7] = lf.v.y; obs[8] = lf.v.z;
+        obs[9] = lf.w.x; obs[10] = lf.w.y; obs[11] = lf.w.z;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) obs[12 + i] = ar[i];  // actions_local aliases the tensor pre_physics_step remapped (avoid.py:162,226)
+        if (TASK == AGX_TASK_AVOID) {  // avoid.py:203-295
+            obs[0] = p.x - P.target[9]; obs[1] = p.y - P.target[10]; obs[2] = p.z - P.target[11];
+            const V3 rel = v3(P.target[9] - p.x, P.target[10] - p.y, P.target[11] - p.z);
+            const float heading = yaw_diff(P.target_yaw, yaw);
+            const float distance = fsqrt(rel.x * rel.x + rel.y * rel.y + rel.z * rel.z + heading * heading);
+            const float pose_r = fdiv(1.0f, 1.0f + sq(1.6f * distance));
+            const float spin_r = fdiv(1.0f, 1.0f + sq(w.z * w.z));
+            const float effort_r = 0.1f * expf(-sa);
+            const float thrust_r = 0.05f * (1.0f - fabsf(0.1533f - ar[A - 1]));
+            const float smooth_r = 0.1f * expf(-fsqrt(sd_rate));
+            const float alive_r = collided > 0.0f ? -500.0f : 0.5f;
+            reward = pose_r + pose_r * (ups_r + spin_r) + effort_r + smooth_r + thrust_r + alive_r;
+            reset = (e.progress >= (int64_t)(P.max_episode_length - 1)) ? 1 : 0;
+            if (p.z < 0.3f) reset = 1;
+            if (p.z > 1.7f) reset = 1;
+            if (norm(rel) > 2.0f) reset = 1;
+            if (up_z < 0.0f) reset = 1;
+            e.terms[0] = pose_r; e.terms[1] = ups_r; e.terms[2] = spin_r; e.terms[3] = effort_r; e.terms[4] = smooth_r;
+            e.terms[5] = thrust_r; e.terms[6] = alive_r; e.terms[7] = 0.0f; e.terms[8] = reward;
+        } else {  // planning.py:186-307
+            const V3 goal = v3(e.aux[0], e.aux[1], e.aux[2]);
+            const V3 fg = goal - p;
+            const V3 pdl = v3(lf.c * fg.x + lf.s * fg.y, -lf.s * fg.x + lf.c * fg.y, fg.z);
+            const float n = norm(pdl);
+            const V3 gd = v3(fdiv(pdl.x, n), fdiv(pdl.y, n), fdiv(pdl.z, n));
+            const float related = norm(fg);
+            obs[0] = gd.x; obs[1] = gd.y; obs[2] = gd.z;
+            const float cont = 0.2f * norm(lf.w) + 0.2f * fsqrt(sd_all);
+            const float thrust_r = 0.5f * (1.0f - fabsf(0.1533f - ar[A - 1]));
+            const V3 prev = v3(e.aux[3], e.aux[4], e.aux[5]);
+            const float forward_r = 0.1f * (norm(goal - prev) - related);
+            const float heading_r = gd.x * 1.0f + gd.y * 0.0f + gd.z * 0.0f;
+            const float speed_r = -0.5f * (1.0f - expf(-2.0f * sq(lf.v.x - 1.0f)));
+            const float z_r = fminf(fminf(p.z - 1.8f, 0.0f), 1.2f - p.z);
+            const float esdf = e.aux[7];
+            const float esdf_r = 0.5f * (1.0f - expf(-0.5f * sq(esdf)));
+            const float alive_r = esdf > 0.3f ? 0.0f : -1.0f;
+            const bool reach = related < 0.3f;
+            const float reach_r = reach ? 200.0f : 0.0f;
+            reward = cont + forward_r + alive_r + esdf_r + ups_r + z_r + speed_r + heading_r + thrust_r + reach_r;
+            reset = 0;
+            if (p.z < 1.5f - 0.3f) reset = 1;
+            if (p.z > 1.5f + 0.3f) reset = 1;
+            if (p.x < -8.0f - 0.5f) reset = 1;
+            if (p.x > 8.0f + 0.5f) reset = 1;
+            if (p.y < -4.0f) reset = 1;
+            if (p.y > 4.0f) reset = 1;
+            if (collided > 0.0f) reset = 1;
+            if (reach) reset = 1;
+            if (heading_r < 0.25f) reset = 1;
+            if (e.progress >= (int64_t)(P.max_episode_length - 1)) reset = 1;
+            e.aux[3] = p.x; e.aux[4] = p.y; e.aux[5] = p.z;  // pre_root_positions = root_positions.clone()
+            e.terms[0] = cont; e.terms[1] = heading_r; e.terms[2] = speed_r; e.terms[3] = forward_r; e.terms[4] = alive_r;
+            e.terms[5] = ups_r; e.terms[6] = z_r; e.terms[7] = esdf_r; e.terms[8] = thrust_r; e.terms[9] = reach_r;
+            e.terms[10] = reward;
+        }
+        if ((P.flags & AGX_FLAG_RESET_ON_COLLISION) && collided > 0.0f) reset = 1;  // customized.py:328-330
+    } else {
     float o[18];
 #pragma unroll
     for (int i = 0; i < 9; ++i) o[i] = R[i] + z[i];
@@ -718,11 +1050,6 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
         for (int i = 0; i < 18; ++i) obs[i] = o[i] - P.target[i];  // hovering.py:356
     }
 
-    int reset;
-    float reward;
-    Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
-    const float up_z = (2.0f * q.w * q.w - 1.0f) + q.z * q.z * 2.0f;  // quat_axis(q,2)[2] (hovering.py:464-481)
-    const float yaw = atan2f(-R[1], R[0]);  // pytorch3d matrix_to_euler_angles(.,'XYZ')[2] (quirk Q6)
     if (TASK == AGX_TASK_BALLOON) {
         // -- Balloon.compute_quadcopter_reward (balloon.py:159-225) on the remapped, unclamped actions
         const V3 ball = v3(e.aux[0], e.aux[1], e.aux[2]);
@@ -751,10 +1078,7 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
         if (p.z < 0.5f) reset = 1;
         if (p.z > 1.5f) reset = 1;
         if (check < 0.1f) reset = 1;
-        // check_collisions (customized.py:393-397) — builder-defined contact model: the drone's r = 0.2 collision sphere
-        // (model.urdf:13-18) against the ground plane; the ball shares the drone's collision mask and never collides.
-        const float collided = p.z < P.collision_radius ? 1.0f : 0.0f;
-        e.aux[6] = collided;
+        const float collided = e.aux[6];  // check_collisions ran in env_phys
         if ((P.flags & AGX_FLAG_RESET_ON_COLLISION) && collided > 0.0f) reset = 1;  // customized.py:328-330
         e.aux[3] = p.x; e.aux[4] = p.y; e.aux[5] = p.z;  // pre_root_positions = root_positions.clone()
         e.terms[0] = guidance; e.terms[1] = hit_r; e.terms[2] = smooth; e.terms[3] = effort_b; e.terms[4] = ups_r;
@@ -823,17 +1147,21 @@ AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, float* obs)
     if (MODE == AGX_CTL_ATTI && e.a[0] < 0.0f) reset = 1;  // hovering.py:442-444
     }  // !balloon
     e.terms[8] = reward;
+    }  // !image task
     e.rew = reward;
     e.reset = reset;
 
     // -- pre_actions = actions.clone() (hovering.py:369); `e.a` leaves as the env's `actions` attribute
-    if (kCustom) {
-#pragma unroll
-        for (int i = 0; i < A; ++i) e.a[i] = ar[i];
-    }
 #pragma unroll
     for (int i = 0; i < A; ++i) e.pa[i] = e.a[i];
+}
 
+// both halves back to back (every task on a step without a render)
+template <int TASK, int MODE>
+AGX_HD void env_core(const AgxParams& P, const float* z, EnvRegs& e, const SceneRef& sc, float* obs) {
+    float R[9];
+    env_phys<TASK, MODE>(P, e, sc, R);
+    env_task<TASK, MODE>(P, z, e, R, obs);
 }
 
 // time_out_buf (hovering.py:304), evaluated after the end-of-step reset zeroed progress
@@ -844,10 +1172,18 @@ AGX_HD void env_finish(const AgxParams& P, EnvRegs& e) {
 // The whole step for one env, serially (host build of tests/hostsim; the kernel interleaves the same pieces with its
 // warp-cooperative reset sampling).
 template <int TASK, int MODE>
-AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, EnvRegs& e, float* obs) {
-    if (e.pending) do_reset<TASK>(P, rnd, 0, e);  // pre_physics_step (hovering.py:209-211, quirk Q1)
-    env_core<TASK, MODE>(P, z, e, obs);
-    if (e.reset) do_reset<TASK>(P, rnd, 1, e);    // end-of-step reset_idx (hovering.py:300-302): reset_buf stays 1
+AGX_HD void env_step(const AgxParams& P, const RandSrc& rnd, const float* z, EnvRegs& e, const SceneRef& sc, float* obs, int phase) {
+    float R[9];
+    if (phase != AGX_PHASE_TASK) {
+        if (e.pending) do_reset<TASK>(P, rnd, 0, e, sc);  // pre_physics_step (hovering.py:209-211, quirk Q1)
+        env_phys<TASK, MODE>(P, e, sc, R);
+        if (phase == AGX_PHASE_PHYSICS) return;
+    } else {
+        Q4 q; q.x = e.s[3]; q.y = e.s[4]; q.z = e.s[5]; q.w = e.s[6];
+        quat_to_matrix(q, R);
+    }
+    env_task<TASK, MODE>(P, z, e, R, obs);
+    if (e.reset) do_reset<TASK>(P, rnd, 1, e, sc);    // end-of-step reset_idx (hovering.py:300-302): reset_buf stays 1
     env_finish(P, e);
 }
 

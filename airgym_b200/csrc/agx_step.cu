@@ -1,4 +1,5 @@
-// agx_step.cu — fused env-step kernels for sm_100a + the C ABI declared in include/agx.h.
+// agx_step.cu — the C ABI declared in include/agx.h for the env path (the kernel template lives in
+// agx_step_kernel.cuh and is instantiated per task in agx_step_<task>.cu).
 //
 // One thread = one env.  A CTA owns a tile of BLOCK consecutive envs:
 //   * the [BLOCK,13] root-state rows (52-B rows, not 16-B aligned individually) are one contiguous,
@@ -16,458 +17,37 @@
 
 #include "agx.h"
 #include "agx_math.cuh"
+#include "agx_step_kernel.cuh"
 
 namespace {
-
 thread_local char g_err[512] = "";
+}  // namespace
 
-int fail(int code, const char* fmt, const char* detail = "") {
+namespace agxk {
+int g_block = 128;
+int g_use_bulk = 1;
+int g_pdl = -1;  // -1 auto: noise-first PDL (mode 3) for grids of at most ~one wave, where the kernel boundary dominates
+                 // (65 536 envs: 10.3 -> 7.9 us/step); off for multi-wave grids, where early CTAs only steal slots (4 M envs: 357 -> 402 us)
+int g_sm_count = 0;
+
+int fail(int code, const char* fmt, const char* detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
 }
 
-}  // namespace
+// one translation unit per task (agx_step_<task>.cu)
+extern template int agx_dispatch_task<AGX_TASK_HOVERING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+extern template int agx_dispatch_task<AGX_TASK_TRACKING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+extern template int agx_dispatch_task<AGX_TASK_BALLOON>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+extern template int agx_dispatch_task<AGX_TASK_AVOID>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+extern template int agx_dispatch_task<AGX_TASK_PLANNING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+}  // namespace agxk
+
+using namespace agxk;
 
 int agx_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
 namespace {
-
-// ---- PTX wrappers: mbarrier + TMA bulk copies ---------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* src_gmem, uint32_t bytes) {  // bytes % 16 == 0, src 16-B aligned
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-#ifdef AGX_TIMELINE
-// Tuning builds only (scripts/timeline.py): per-CTA phase stamps {globaltimer ns, clock64} x 6 phases + smid.
-__device__ unsigned long long g_timeline[8192 * 16];
-__device__ __forceinline__ void tl_stamp(int phase) {
-    if (threadIdx.x == 0 && blockIdx.x < 8192) {
-        unsigned long long t, c;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
-        g_timeline[blockIdx.x * 16 + phase * 2] = t;
-        g_timeline[blockIdx.x * 16 + phase * 2 + 1] = c;
-        if (phase == 0) {
-            unsigned int smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_timeline[blockIdx.x * 16 + 14] = smid;
-        }
-    }
-}
-#define TL(p) tl_stamp(p)
-#else
-#define TL(p)
-#endif
-
-template <int NOBS>
-struct ObsLayout {
-    // dense rows only when the row stride in words is conflict-light (18 → 2-way); else pad to odd
-    static constexpr bool kDense = (NOBS == 18);
-    static constexpr int kStride = kDense ? NOBS : (NOBS | 1);
-};
-
-template <int TASK>
-struct TaskTraits;
-template <>
-struct TaskTraits<AGX_TASK_HOVERING> { static constexpr int kObs = 18; };
-template <>
-struct TaskTraits<AGX_TASK_TRACKING> { static constexpr int kObs = 48; };
-template <>
-struct TaskTraits<AGX_TASK_BALLOON> { static constexpr int kObs = 18; };
-
-// ---- warp-cooperative reset sampling ---------------------------------------------------------------------
-// Resets are rare per env (~2 % of env-steps under random actions) but common per warp (~50 % of warps hold at least one
-// resetting lane), so a per-lane `if (reset) sample()` makes half of all warps walk the whole sampler — Philox blocks,
-// sincos, quaternion — for one or two live lanes (measured: 43 % of the step time at 4 M envs).  Instead the warp packs
-// its resetting lanes into items and spends 4 lanes on each: lane `sub` of an item draws Philox block `sub` (or copies
-// the explicit draws) into shared memory, lane 0 of the item turns the uniforms into the new root-state row, written
-// straight into the CTA's state tile; task state (aux) returns through the same scratch row.  Up to 8 items per pass.
-struct WarpScratch {
-    float u[8][AGX_RESET_DRAWS_MAX];  // per item: uniforms in, aux out
-    uint8_t src[32];                  // item → lane
-};
-
-template <int TASK>
-__device__ __forceinline__ void warp_reset(const AgxStepIO& io, bool need, int which, uint64_t step, int64_t warp_env0,
-                                           float* s_state_warp, WarpScratch& ws, float* aux) {
-    using namespace agx;
-    constexpr int D = ResetDraws<TASK>::kD;
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
-    if (mask == 0u) return;  // warp-uniform
-    const int lane = threadIdx.x & 31;
-    const int n_items = __popc(mask);
-    const int my_item = __popc(mask & ((1u << lane) - 1u));
-    if (need) ws.src[my_item] = (uint8_t)lane;
-    __syncwarp();
-    const int slot = lane >> 2, sub = lane & 3;
-    for (int base = 0; base < n_items; base += 8) {
-        const int item = base + slot;
-        int src = 0;
-        if (item < n_items) {
-            src = ws.src[item];
-            const int64_t env = warp_env0 + src;
-            if (io.rand_reset) {
-                const float* row = io.rand_reset + (env * 2 + which) * (int64_t)D;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (sub * 4 + j < D) ws.u[slot][sub * 4 + j] = row[sub * 4 + j];
-            } else if (sub * 4 < D) {
-                PhiloxCtx ph;
-                const uint64_t genv = (uint64_t)(io.env_offset + env);
-                ph.k0 = (uint32_t)io.seed; ph.k1 = (uint32_t)(io.seed >> 32);
-                ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
-                ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
-                const U4 r = philox_block(ph, (uint32_t)which, (uint32_t)sub);
-                ws.u[slot][sub * 4 + 0] = u32_to_unit(r.x);
-                ws.u[slot][sub * 4 + 1] = u32_to_unit(r.y);
-                ws.u[slot][sub * 4 + 2] = u32_to_unit(r.z);
-                ws.u[slot][sub * 4 + 3] = u32_to_unit(r.w);
-            }
-        }
-        __syncwarp();
-        if (item < n_items && sub == 0) {
-            float u[AGX_RESET_DRAWS_MAX], st[13], ax[AGX_AUX_MAX];
-#pragma unroll
-            for (int i = 0; i < D; ++i) u[i] = ws.u[slot][i];
-#pragma unroll
-            for (int i = 0; i < AGX_AUX_MAX; ++i) ax[i] = 0.0f;
-            reset_sample<TASK>(u, st, ax);
-#pragma unroll
-            for (int i = 0; i < 13; ++i) s_state_warp[src * 13 + i] = st[i];
-            if (TASK == AGX_TASK_BALLOON) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) ws.u[slot][i] = ax[i];
-            }
-        }
-        __syncwarp();
-        if (TASK == AGX_TASK_BALLOON && need && my_item >= base && my_item < base + 8) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) aux[i] = ws.u[my_item - base][i];  // ball xyz, pre_root_positions = 0
-        }
-        __syncwarp();
-    }
-}
-
-// ---- the fused step kernel ----------------------------------------------------------------------------
-#ifndef AGX_MIN_CTAS
-#define AGX_MIN_CTAS 1
-#endif
-template <int TASK, int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, AGX_MIN_CTAS)
-agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ AgxStepIO io, const int64_t n,
-                const int kflags) {  // bit0: TMA bulk staging, bits1-2: PDL trigger point (0 none, 1 start, 2 pre-store)
-    using namespace agx;
-    constexpr int A = (MODE == AGX_CTL_ATTI) ? 5 : 4;
-    constexpr int NOBS = TaskTraits<TASK>::kObs;
-    constexpr int K = (MODE == AGX_CTL_PROP) ? 0 : ((MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI) ? 6 : 12);
-    using OL = ObsLayout<NOBS>;
-
-    __shared__ __align__(128) float s_state[BLOCK * 13];
-    __shared__ __align__(128) float s_obs[BLOCK * OL::kStride];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ WarpScratch s_ws[BLOCK / 32];
-
-    const int tid = threadIdx.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
-    const int tile_n = (int)((n - tile0) < (int64_t)BLOCK ? (n - tile0) : (int64_t)BLOCK);
-    const bool bulk = (kflags & 1) && (tile_n == BLOCK);  // CTA-uniform
-    const int pdl_mode = (kflags >> 1) & 3;
-    const int64_t env = tile0 + tid;
-    const bool active = tid < tile_n;
-
-    TL(0);
-    EnvRegs e;
-    float z[AGX_NOISE_DRAWS];
-    uint64_t step = io.step;
-    unsigned long long ticket = 0;
-
-    // ---- stage the state tile into shared memory + coalesced per-env loads (which overlap the bulk copy in flight)
-    auto load_inputs = [&]() {
-        if (bulk) {
-            if (tid == 0) {
-                mbar_init(&s_bar, 1);
-                mbar_expect_tx(&s_bar, BLOCK * 13 * 4);
-                bulk_g2s(s_state, io.state + tile0 * 13, BLOCK * 13 * 4, &s_bar);
-            }
-        } else {
-            const float* src = io.state + tile0 * 13;
-            for (int i = tid; i < tile_n * 13; i += BLOCK) s_state[i] = src[i];
-        }
-        if (active) {
-            if (A == 4) {
-                const float4 a4 = reinterpret_cast<const float4*>(io.action)[env];
-                const float4 p4 = reinterpret_cast<const float4*>(io.prev_action)[env];
-                e.a[0] = a4.x; e.a[1] = a4.y; e.a[2] = a4.z; e.a[3] = a4.w; e.a[4] = 0.0f;
-                e.pa[0] = p4.x; e.pa[1] = p4.y; e.pa[2] = p4.z; e.pa[3] = p4.w; e.pa[4] = 0.0f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) { e.a[i] = io.action[env * 5 + i]; e.pa[i] = io.prev_action[env * 5 + i]; }
-            }
-#pragma unroll
-            for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
-            e.progress = io.progress[env];
-            e.pending = io.reset[env] != 0;
-            if (TASK == AGX_TASK_BALLOON) {
-                const float4 x0 = reinterpret_cast<const float4*>(io.aux)[env * 2], x1 = reinterpret_cast<const float4*>(io.aux)[env * 2 + 1];
-                e.aux[0] = x0.x; e.aux[1] = x0.y; e.aux[2] = x0.z; e.aux[3] = x0.w;
-                e.aux[4] = x1.x; e.aux[5] = x1.y; e.aux[6] = x1.z; e.aux[7] = x1.w;
-            }
-        }
-    };
-    // Philox step index: device counter (graph replay) or launch argument.  Every CTA takes a ticket AFTER its read
-    // (data dependency through `zero`); the CTA holding the last ticket — every other CTA has read by then — bumps it.
-    auto take_step = [&]() {
-        if (io.step_dev) {
-            step = *reinterpret_cast<const volatile uint64_t*>(io.step_dev);
-            if (tid == 0) {
-                unsigned int zero;
-                asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)step));
-                ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
-            }
-        }
-    };
-    auto bump_step = [&]() {
-        if (io.step_dev && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
-            io.step_dev[1] = 0;
-            io.step_dev[0] = step + 1;
-            __threadfence();
-        }
-    };
-    // Observation noise: needs only (seed, env id, step), not the env state.
-    auto make_noise = [&]() {
-        if (active) {
-            RandSrc rnd;
-            rnd.reset_row = nullptr;  // reset draws are taken by warp_reset
-            rnd.noise_row = io.rand_noise ? io.rand_noise + env * (int64_t)AGX_NOISE_DRAWS : nullptr;
-            const uint64_t genv = (uint64_t)(io.env_offset + env);
-            rnd.ph.k0 = (uint32_t)io.seed; rnd.ph.k1 = (uint32_t)(io.seed >> 32);
-            rnd.ph.env_lo = (uint32_t)genv; rnd.ph.env_hi = (uint32_t)(genv >> 32);
-            rnd.ph.step_lo = (uint32_t)step; rnd.ph.step_hi = (uint32_t)(step >> 32);
-            scaled_noise(P, rnd, z);
-        }
-    };
-
-    if (pdl_mode == 3) {
-        // Programmatic dependent launch, noise-first: this grid may start while the previous kernel of the stream is
-        // still running.  The step counter, the ticket and the noise touch nothing that kernel writes (its own counter
-        // bump precedes its launch_dependents), so a third of the step's instructions run under its tail; every other
-        // global access waits for its completion + flush.
-        // L2 is the GPU's point of coherence, so prefetching this tile's inputs into it is a pure hint whatever the
-        // running predecessor still writes: the DRAM reads of step t+1 overlap the compute phase of step t, and the
-        // loads after the wait hit L2.
-        if (tile_n == BLOCK && tid < 5 + K) {
-            if (tid == 0) prefetch_l2(io.state + tile0 * 13, BLOCK * 13 * 4);
-            else if (tid == 1) prefetch_l2(io.action + tile0 * A, BLOCK * A * 4);
-            else if (tid == 2) prefetch_l2(io.prev_action + tile0 * A, BLOCK * A * 4);
-            else if (tid == 3) prefetch_l2(io.progress + tile0, BLOCK * 8);
-            else if (tid == 4) prefetch_l2(io.reset + tile0, BLOCK * 8);
-            else if ((n & 3) == 0) prefetch_l2(io.ctrl_state + (int64_t)(tid - 5) * n + tile0, BLOCK * 4);  // plane rows 16-B aligned
-        }
-        take_step();
-        if (!io.rand_noise) make_noise();
-        bump_step();
-        if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // after this CTA's (possible) bump
-        TL(1);
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        TL(2);
-        load_inputs();
-        if (io.rand_noise) make_noise();  // explicit draws may come from the previous kernel
-    } else {
-        // (griddepcontrol.* are no-ops when launched without the attribute.)
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        TL(1);
-        if (pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        load_inputs();
-        take_step();
-        make_noise();  // evaluated while the loads above fly
-        TL(2);
-        if (active) {
-            // keep the consumers of the loads below this point: the compiler would otherwise hoist the first use of the
-            // action registers above the noise code and park every warp on the load latency before doing useful work
-#pragma unroll
-            for (int i = 0; i < AGX_MAX_ACTIONS; ++i) asm volatile("" : "+f"(e.a[i]), "+f"(e.pa[i]));
-        }
-    }
-
-    if (bulk) {
-        __syncthreads();  // barrier init visible to all waiters
-        mbar_wait(&s_bar, 0);
-    } else {
-        __syncthreads();
-    }
-
-    TL(3);
-    // ---- pre_physics_step reset of the envs flagged last step (hovering.py:209-211, quirk Q1): new rows land in the tile
-    const int warp = tid >> 5;
-    const int64_t warp_env0 = tile0 + warp * 32;
-    warp_reset<TASK>(io, active && e.pending, 0, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
-
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < 13; ++i) e.s[i] = s_state[tid * 13 + i];
-        if (e.pending) reset_apply(P, e);
-
-        env_core<TASK, MODE>(P, z, e, &s_obs[tid * OL::kStride]);
-        if (pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-#pragma unroll
-        for (int i = 0; i < 13; ++i) s_state[tid * 13 + i] = e.s[i];
-    }
-    __syncwarp();
-    // ---- end-of-step reset_idx (hovering.py:300-302): fresh rows overwrite the tile, reset_buf stays 1, progress 0
-    warp_reset<TASK>(io, active && e.reset, 1, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
-
-    if (active) {
-        if (e.reset) reset_apply(P, e);
-        env_finish(P, e);
-
-        // ---- coalesced per-env stores
-        if (A == 4) {
-            reinterpret_cast<float4*>(io.actions_out)[env] = make_float4(e.a[0], e.a[1], e.a[2], e.a[3]);
-            reinterpret_cast<float4*>(io.prev_action)[env] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) { io.actions_out[env * 5 + i] = e.a[i]; io.prev_action[env * 5 + i] = e.pa[i]; }
-        }
-        if ((P.flags & AGX_FLAG_MUTATE_ACTIONS) && (MODE == AGX_CTL_RATE || MODE == AGX_CTL_ATTI))
-            io.action[env * A + (A - 1)] = e.a_last_remap;
-#pragma unroll
-        for (int k = 0; k < K; ++k) io.ctrl_state[(int64_t)k * n + env] = e.cs[k];
-        if (TASK == AGX_TASK_BALLOON) {
-            reinterpret_cast<float4*>(io.aux)[env * 2] = make_float4(e.aux[0], e.aux[1], e.aux[2], e.aux[3]);
-            reinterpret_cast<float4*>(io.aux)[env * 2 + 1] = make_float4(e.aux[4], e.aux[5], e.aux[6], e.aux[7]);
-        }
-        io.progress[env] = e.progress;
-        io.reset[env] = (int64_t)e.reset;
-        io.timeout[env] = (uint8_t)e.timeout;
-        io.reward[env] = e.rew;
-        if (io.cmd) reinterpret_cast<float4*>(io.cmd)[env] = make_float4(e.cmd[0], e.cmd[1], e.cmd[2], e.cmd[3]);
-        if (io.reward_terms) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) io.reward_terms[(int64_t)k * n + env] = e.terms[k];
-        }
-    }
-
-    // ---- tiles leave shared memory
-    TL(4);
-    if (bulk) {
-        fence_async_smem();  // generic-proxy smem writes → visible to the async (TMA) proxy
-        __syncthreads();
-        if (tid == 0) {
-            bulk_s2g(io.state + tile0 * 13, s_state, BLOCK * 13 * 4);
-            if (OL::kDense) bulk_s2g(io.obs + tile0 * NOBS, s_obs, BLOCK * NOBS * 4);
-            bulk_commit();
-        }
-    } else {
-        __syncthreads();
-        float* dst = io.state + tile0 * 13;
-        for (int i = tid; i < tile_n * 13; i += BLOCK) dst[i] = s_state[i];
-    }
-    if (!(bulk && OL::kDense)) {
-        float* dst = io.obs + tile0 * NOBS;
-        if (OL::kDense) {
-            for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i];
-        } else if (tile_n == BLOCK) {  // padded rows → dense float4 stores (BLOCK*NOBS % 4 == 0)
-            for (int i4 = tid; i4 < BLOCK * NOBS / 4; i4 += BLOCK) {
-                float4 v;
-                const int i = i4 * 4;
-                v.x = s_obs[i + i / NOBS];
-                v.y = s_obs[(i + 1) + (i + 1) / NOBS];
-                v.z = s_obs[(i + 2) + (i + 2) / NOBS];
-                v.w = s_obs[(i + 3) + (i + 3) / NOBS];
-                reinterpret_cast<float4*>(dst)[i4] = v;
-            }
-        } else {
-            for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i + i / NOBS];
-        }
-    }
-    if (bulk && tid == 0) bulk_wait_read0();  // smem must stay alive until the bulk stores have read it
-    if (pdl_mode != 3) bump_step();
-    TL(5);
-}
-
-// ---- standalone reset_idx kernel -------------------------------------------------------------------------
-template <int TASK>
-__global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_t n, int64_t m,
-                                     const int64_t* __restrict__ env_ids, float* state, float* prev_action,
-                                     float* ctrl_state, int64_t* progress, int64_t* reset, float* aux,
-                                     const float* __restrict__ rand, uint64_t seed, uint64_t step,
-                                     int64_t env_offset) {
-    using namespace agx;
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const int64_t env = env_ids[j];
-    if (env < 0 || env >= n) return;
-    float u[AGX_RESET_DRAWS_MAX];
-    if (rand) {
-        for (int i = 0; i < P.reset_draws; ++i) u[i] = rand[j * P.reset_draws + i];
-    } else {
-        PhiloxCtx ph;
-        const uint64_t genv = (uint64_t)(env_offset + env);
-        ph.k0 = (uint32_t)seed; ph.k1 = (uint32_t)(seed >> 32);
-        ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
-        ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
-        philox_uniforms(ph, 3u, P.reset_draws, u);  // stream 3: standalone reset_idx
-    }
-    float s[13];
-    if (TASK == AGX_TASK_BALLOON) {
-        float ax[AGX_AUX_MAX];
-        for (int i = 0; i < AGX_AUX_MAX; ++i) ax[i] = aux[env * AGX_AUX_MAX + i];
-        reset_sample<TASK>(u, s, ax);
-        for (int i = 0; i < AGX_AUX_MAX; ++i) aux[env * AGX_AUX_MAX + i] = ax[i];
-    } else {
-        reset_sample<TASK>(u, s, nullptr);
-    }
-    for (int i = 0; i < 13; ++i) state[env * 13 + i] = s[i];
-    for (int i = 0; i < P.num_actions; ++i) prev_action[env * P.num_actions + i] = 0.0f;
-    if ((P.flags & AGX_FLAG_CTRL_RESET) && ctrl_state)
-        for (int k = 0; k < P.ctrl_state_dim; ++k) ctrl_state[(int64_t)k * n + env] = 0.0f;
-    progress[env] = 0;
-    reset[env] = 1;
-}
 
 __global__ void agx_philox_fill_kernel(float* out, int64_t n, int width, int stream_id, uint64_t seed,
                                        uint64_t step, int64_t env_offset) {
@@ -485,63 +65,6 @@ __global__ void agx_philox_fill_kernel(float* out, int64_t n, int width, int str
     for (int i = 0; i < width; ++i) out[env * width + i] = v[i];
 }
 
-int g_block = 128;
-int g_use_bulk = 1;
-int g_pdl = -1;  // -1 auto: noise-first PDL (mode 3) for grids of at most ~one wave, where the kernel boundary dominates
-                 // (65 536 envs: 10.3 -> 7.9 us/step); off for multi-wave grids, where early CTAs only steal slots (4 M envs: 357 -> 402 us)
-int g_sm_count = 0;
-
-template <typename Kernel>
-cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, const AgxParams& P,
-                      const AgxStepIO& io, int64_t n) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    int pdl = g_pdl;
-    if (pdl < 0) {
-        if (g_sm_count == 0) {
-            int dev = 0, sms = 0;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) g_sm_count = sms;
-            if (g_sm_count <= 0) g_sm_count = 148;
-        }
-        pdl = ((uint64_t)grid * block <= (uint64_t)g_sm_count * 512u) ? 3 : 0;
-    }
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1);
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k, P, io, n, kflags);
-}
-
-template <int TASK, int MODE>
-int launch_step(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st) {
-    if (n == 0) return AGX_OK;
-    cudaError_t err;
-    if (g_block == 64) {
-        err = launch_ex(agx_step_kernel<TASK, MODE, 64>, (unsigned)((n + 63) / 64), 64, st, P, io, n);
-    } else {
-        err = launch_ex(agx_step_kernel<TASK, MODE, 128>, (unsigned)((n + 127) / 128), 128, st, P, io, n);
-    }
-    if (err == cudaSuccess) err = cudaGetLastError();
-    if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_step launch: %s", cudaGetErrorString(err));
-    return AGX_OK;
-}
-
-template <int TASK>
-int dispatch_mode(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st) {
-    switch (P.ctl_mode) {
-        case AGX_CTL_POS: return launch_step<TASK, AGX_CTL_POS>(P, n, io, st);
-        case AGX_CTL_VEL: return launch_step<TASK, AGX_CTL_VEL>(P, n, io, st);
-        case AGX_CTL_ATTI: return launch_step<TASK, AGX_CTL_ATTI>(P, n, io, st);
-        case AGX_CTL_RATE: return launch_step<TASK, AGX_CTL_RATE>(P, n, io, st);
-        case AGX_CTL_PROP: return launch_step<TASK, AGX_CTL_PROP>(P, n, io, st);
-        default: return fail(AGX_ERR_ARG, "agx_step: unknown ctl_mode%s");
-    }
-}
 
 bool misaligned(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
@@ -551,14 +74,10 @@ bool misaligned(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 1
 extern "C" {
 
 int agx_version(void) { return AGX_VERSION; }
-#ifdef AGX_TIMELINE
-int agx_debug_timeline(unsigned long long* host_out, int n_entries) {
-    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * n_entries);
-}
-#endif
 const char* agx_error_string(void) { return g_err; }
 int agx_sizeof_params(void) { return (int)sizeof(AgxParams); }
 int agx_sizeof_step_io(void) { return (int)sizeof(AgxStepIO); }
+int agx_sizeof_render_io(void) { return (int)sizeof(AgxRenderIO); }
 
 int agx_set_option(const char* key, int value) {
     if (!key) return fail(AGX_ERR_ARG, "agx_set_option: null key%s");
@@ -578,24 +97,26 @@ int agx_set_option(const char* key, int value) {
 
 int agx_params_default(AgxParams* p, int task, int ctl_mode) {
     if (!p) return fail(AGX_ERR_ARG, "agx_params_default: null params%s");
-    if (task != AGX_TASK_HOVERING && task != AGX_TASK_TRACKING && task != AGX_TASK_BALLOON)
-        return fail(AGX_ERR_UNSUPPORTED, "agx_params_default: task not built yet%s");
+    if (task < AGX_TASK_HOVERING || task > AGX_TASK_PLANNING) return fail(AGX_ERR_ARG, "agx_params_default: unknown task%s");
+    const bool image_task = (task == AGX_TASK_AVOID || task == AGX_TASK_PLANNING);
+    if (image_task && ctl_mode == AGX_CTL_ATTI)
+        return fail(AGX_ERR_UNSUPPORTED, "agx_params_default: avoid/planning have no atti mode (obs[12:16] holds the 4 actions, avoid.py:226)%s");
     if (ctl_mode < AGX_CTL_POS || ctl_mode > AGX_CTL_PROP) return fail(AGX_ERR_ARG, "agx_params_default: bad ctl_mode%s");
     memset(p, 0, sizeof(*p));
     const double pi = 3.14159265358979323846;
     p->task = task;
     p->ctl_mode = ctl_mode;
     p->num_actions = (ctl_mode == AGX_CTL_ATTI) ? 5 : 4;
-    p->num_obs = (task == AGX_TASK_TRACKING) ? 48 : 18;
+    p->num_obs = (task == AGX_TASK_TRACKING) ? 48 : (image_task ? 16 : 18);
     p->integrator = AGX_INT_RK4;
     p->flags = AGX_FLAG_MUTATE_ACTIONS;  // (collision flag for the Customized family is added below)
     p->dt = 0.01f;
-    const double episode_s = (task == AGX_TASK_TRACKING) ? 36.0 : (task == AGX_TASK_BALLOON ? 8.0 : 24.0);  // *_config.py episode_length_s
+    const double episode_s = (task == AGX_TASK_TRACKING) ? 36.0 : (task == AGX_TASK_BALLOON ? 8.0 : (task == AGX_TASK_AVOID ? 6.0 : (task == AGX_TASK_PLANNING ? 16.0 : 24.0)));  // *_config.py episode_length_s
     p->max_episode_length = (int)(episode_s / 0.01);
     p->ctrl_state_dim = (ctl_mode == AGX_CTL_PROP) ? 0 : ((ctl_mode == AGX_CTL_RATE || ctl_mode == AGX_CTL_ATTI) ? 6 : 12);
-    p->reset_draws = (task == AGX_TASK_BALLOON) ? 15 : 12;
+    p->reset_draws = (task == AGX_TASK_BALLOON) ? 15 : (task == AGX_TASK_AVOID ? 11 : (task == AGX_TASK_PLANNING ? AGX_PLANNING_DRAWS : 12));
     p->collision_radius = 0.2f;
-    if (task == AGX_TASK_BALLOON) p->flags |= AGX_FLAG_RESET_ON_COLLISION;  // balloon_config.py:19
+    if (task == AGX_TASK_BALLOON || task == AGX_TASK_AVOID) p->flags |= AGX_FLAG_RESET_ON_COLLISION;  // balloon_config.py:19, avoid_config.py:19 (planning: False)
     p->gravity = 9.81f;
     const double m_base = 0.585, m_prop = 0.004, arm = 0.05374, hz = 0.024;
     p->mass = (float)(m_base + 4.0 * m_prop);
@@ -642,6 +163,7 @@ int agx_params_default(AgxParams* p, int task, int ctl_mode) {
     p->thr_max = 1.0f;
     const float tgt[18] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 18; ++i) p->target[i] = tgt[i];
+    if (task == AGX_TASK_AVOID) p->target[11] = 1.0f;  // avoid_config.py:11: hover target at z = 1
     p->target_yaw = 0.0f;  // atan2(-0, 1)
     p->noise_sigma[0] = 1e-3f; p->noise_sigma[1] = 5e-3f; p->noise_sigma[2] = 2e-2f; p->noise_sigma[3] = 4e-1f;
     return AGX_OK;
@@ -660,25 +182,40 @@ int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream) {
         if (misaligned(q)) return fail(AGX_ERR_ALIGN, "agx_step: buffer not 16-byte aligned%s");
     const int want_actions = (p->ctl_mode == AGX_CTL_ATTI) ? 5 : 4;
     if (p->num_actions != want_actions) return fail(AGX_ERR_ARG, "agx_step: num_actions does not match ctl_mode%s");
-    if (p->reset_draws < 12 || p->reset_draws > AGX_RESET_DRAWS_MAX) return fail(AGX_ERR_ARG, "agx_step: bad reset_draws%s");
+    {
+        const int want = (p->task == AGX_TASK_BALLOON) ? 15 : (p->task == AGX_TASK_AVOID ? 11 : (p->task == AGX_TASK_PLANNING ? AGX_PLANNING_DRAWS : 12));
+        if (p->reset_draws != want) return fail(AGX_ERR_ARG, "agx_step: reset_draws does not match the task%s");
+    }
+    const bool image_task = (p->task == AGX_TASK_AVOID || p->task == AGX_TASK_PLANNING);
+    if (io->phase < AGX_PHASE_FUSED || io->phase > AGX_PHASE_TASK || (!image_task && io->phase != AGX_PHASE_FUSED))
+        return fail(AGX_ERR_ARG, "agx_step: bad phase (only avoid/planning split the step)%s");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (p->task) {
         case AGX_TASK_HOVERING:
             if (p->num_obs != 18) return fail(AGX_ERR_ARG, "agx_step: hovering needs num_obs=18%s");
-            return dispatch_mode<AGX_TASK_HOVERING>(*p, n, *io, st);
+            return agx_dispatch_task<AGX_TASK_HOVERING>(*p, n, *io, st);
         case AGX_TASK_TRACKING:
             if (p->num_obs != 48) return fail(AGX_ERR_ARG, "agx_step: tracking needs num_obs=48%s");
-            return dispatch_mode<AGX_TASK_TRACKING>(*p, n, *io, st);
+            return agx_dispatch_task<AGX_TASK_TRACKING>(*p, n, *io, st);
         case AGX_TASK_BALLOON:
             if (p->num_obs != 18) return fail(AGX_ERR_ARG, "agx_step: balloon needs num_obs=18%s");
             if (!io->aux || misaligned(io->aux)) return fail(AGX_ERR_ARG, "agx_step: balloon needs a 16-byte aligned aux buffer%s");
-            return dispatch_mode<AGX_TASK_BALLOON>(*p, n, *io, st);
-        default: return fail(AGX_ERR_UNSUPPORTED, "agx_step: task not built yet%s");
+            return agx_dispatch_task<AGX_TASK_BALLOON>(*p, n, *io, st);
+        case AGX_TASK_AVOID:
+            if (p->num_obs != 16) return fail(AGX_ERR_ARG, "agx_step: avoid needs num_obs=16%s");
+            if (!io->aux || misaligned(io->aux)) return fail(AGX_ERR_ARG, "agx_step: avoid needs a 16-byte aligned aux buffer%s");
+            return agx_dispatch_task<AGX_TASK_AVOID>(*p, n, *io, st);
+        case AGX_TASK_PLANNING:
+            if (p->num_obs != 16) return fail(AGX_ERR_ARG, "agx_step: planning needs num_obs=16%s");
+            if (!io->aux || misaligned(io->aux)) return fail(AGX_ERR_ARG, "agx_step: planning needs a 16-byte aligned aux buffer%s");
+            if (!io->assets || misaligned(io->assets) || !io->trees) return fail(AGX_ERR_ARG, "agx_step: planning needs the assets and trees buffers%s");
+            return agx_dispatch_task<AGX_TASK_PLANNING>(*p, n, *io, st);
+        default: return fail(AGX_ERR_UNSUPPORTED, "agx_step: unknown task%s");
     }
 }
 
 int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_ids, float* state,
-                  float* prev_action, float* ctrl_state, int64_t* progress, int64_t* reset, float* aux,
+                  float* prev_action, float* ctrl_state, int64_t* progress, int64_t* reset, float* aux, float* assets,
                   const float* rand, uint64_t seed, uint64_t step, int64_t env_offset, void* stream) {
     if (!p || !env_ids || !state || !prev_action || !progress || !reset) return fail(AGX_ERR_ARG, "agx_reset_idx: null argument%s");
     if (n < 0 || m < 0) return fail(AGX_ERR_ARG, "agx_reset_idx: negative size%s");
@@ -687,16 +224,24 @@ int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_i
     const unsigned grid = (unsigned)((m + 127) / 128);
     if (p->task == AGX_TASK_HOVERING)
         agx_reset_idx_kernel<AGX_TASK_HOVERING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
-                                                                      progress, reset, aux, rand, seed, step, env_offset);
+                                                                      progress, reset, aux, assets, rand, seed, step, env_offset);
     else if (p->task == AGX_TASK_TRACKING)
         agx_reset_idx_kernel<AGX_TASK_TRACKING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
-                                                                      progress, reset, aux, rand, seed, step, env_offset);
+                                                                      progress, reset, aux, assets, rand, seed, step, env_offset);
     else if (p->task == AGX_TASK_BALLOON) {
         if (!aux) return fail(AGX_ERR_ARG, "agx_reset_idx: balloon needs aux%s");
         agx_reset_idx_kernel<AGX_TASK_BALLOON><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
-                                                                     progress, reset, aux, rand, seed, step, env_offset);
+                                                                     progress, reset, aux, assets, rand, seed, step, env_offset);
+    } else if (p->task == AGX_TASK_AVOID) {
+        if (!aux) return fail(AGX_ERR_ARG, "agx_reset_idx: avoid needs aux%s");
+        agx_reset_idx_kernel<AGX_TASK_AVOID><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
+                                                                   progress, reset, aux, assets, rand, seed, step, env_offset);
+    } else if (p->task == AGX_TASK_PLANNING) {
+        if (!aux || !assets) return fail(AGX_ERR_ARG, "agx_reset_idx: planning needs aux and assets%s");
+        agx_reset_idx_kernel<AGX_TASK_PLANNING><<<grid, 128, 0, st>>>(*p, n, m, env_ids, state, prev_action, ctrl_state,
+                                                                      progress, reset, aux, assets, rand, seed, step, env_offset);
     } else
-        return fail(AGX_ERR_UNSUPPORTED, "agx_reset_idx: task not built yet%s");
+        return fail(AGX_ERR_UNSUPPORTED, "agx_reset_idx: unknown task%s");
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_reset_idx launch: %s", cudaGetErrorString(err));
     return AGX_OK;

@@ -68,7 +68,7 @@ class Hovering(BaseTask):
         self.actions = torch.zeros(N, A, device=dev, dtype=torch.float32)
         self.pre_actions = torch.zeros(N, A, device=dev, dtype=torch.float32)
         self.ctrl_state = torch.zeros(max(P.ctrl_state_dim, 1), N, device=dev, dtype=torch.float32)
-        self._reward_terms = torch.zeros(9, N, device=dev, dtype=torch.float32) if bk.reward_terms else None
+        self._reward_terms = torch.zeros(_capi.AGX_REWARD_TERMS, N, device=dev, dtype=torch.float32) if bk.reward_terms else None
         self._step_dev = torch.zeros(2, device=dev, dtype=torch.int64)  # {global step, CTA ticket}
         self.rng_seed = int(cfg.seed) if int(getattr(cfg, "seed", -1)) >= 0 else int(torch.initial_seed() & 0x7FFFFFFF)
         self.env_offset = 0  # global id of env 0 (multi-GPU shards set this)
@@ -134,7 +134,7 @@ class Hovering(BaseTask):
         _capi.check(self._lib.agx_reset_idx(
             C.byref(self.params), self.num_envs, m, env_ids.data_ptr(), self.root_states.data_ptr(),
             self.pre_actions.data_ptr(), self.ctrl_state.data_ptr() if self.params.ctrl_state_dim > 0 else None,
-            self.progress_buf.data_ptr(), self.reset_buf.data_ptr(), None,
+            self.progress_buf.data_ptr(), self.reset_buf.data_ptr(), None, None,
             rand.data_ptr() if rand is not None else None, self.rng_seed, self.counter, self.env_offset,
             C.c_void_p(stream)), "agx_reset_idx")
 

@@ -59,5 +59,5 @@ class Balloon(Hovering):
         _capi.check(self._lib.agx_reset_idx(
             C.byref(self.params), self.num_envs, m, env_ids.data_ptr(), self.root_states.data_ptr(), self.pre_actions.data_ptr(),
             self.ctrl_state.data_ptr() if self.params.ctrl_state_dim > 0 else None, self.progress_buf.data_ptr(),
-            self.reset_buf.data_ptr(), self.aux.data_ptr(), rand.data_ptr() if rand is not None else None, self.rng_seed,
+            self.reset_buf.data_ptr(), self.aux.data_ptr(), None, rand.data_ptr() if rand is not None else None, self.rng_seed,
             self.counter, self.env_offset, C.c_void_p(stream)), "agx_reset_idx")

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AGX_VERSION 100
+#define AGX_VERSION 110
 
 enum AgxError {
     AGX_OK = 0,
@@ -67,6 +67,22 @@ enum AgxFlags {
 #define AGX_RESET_DRAWS_MAX 16
 #define AGX_NOISE_DRAWS 18
 #define AGX_AUX_MAX 8           /* floats of per-env task state in AgxStepIO.aux */
+#define AGX_REWARD_TERMS 12     /* planes of AgxStepIO.reward_terms (9 used by hovering/tracking/balloon/avoid, 11 by planning) */
+#define AGX_NUM_TREES 40        /* `thin` group assets of the planning task (planning_config.py:74-78) */
+#define AGX_NUM_ASSETS 41       /* goal ball + trees, in the reference's asset order (asset_manager.py:79-152) */
+#define AGX_ASSET_ROW 164       /* floats per env in AgxStepIO.assets: x[41] | y[41] | cos(yaw)[41] | sin(yaw)[41] */
+#define AGX_PLANNING_DRAWS 124  /* uniforms of one Planning.reset_idx: asset x[41] | y[41] | yaw[41] | goal y */
+#define AGX_CAM_W 212           /* depth camera (avoid_config.py:55-68): width, height, horizontal fov 87 deg, far plane 5 m, */
+#define AGX_CAM_H 120           /* mounted at body (0.15, 0, 0.1); images are stored width-major [W,H] like the reference's */
+                                /* full_camera_array (customized.py:144,402) */
+
+/* agx_step phases for the depth-camera tasks: the reference renders between gym.simulate and compute_reward
+ * (customized.py:318-325), so on a render step the fused step is split around agx_render_depth */
+enum AgxPhase {
+    AGX_PHASE_FUSED = 0,   /* everything (all tasks; avoid/planning on the 3 of 4 steps without a render) */
+    AGX_PHASE_PHYSICS = 1, /* pre-step reset, action shaping, controller, rigid body, object flight, contacts, progress += 1 */
+    AGX_PHASE_TASK = 2     /* observations, reward, termination, end-of-step reset, time-outs */
+};
 
 /* Everything the fused step needs that is not per-env data.  Mirrors the reference's nested cfg
  * classes (hovering_config.py:8-69), URDF constants (assets/robots/X152b/model.urdf) and the
@@ -75,7 +91,8 @@ typedef struct AgxParams {
     int32_t task;              /* AgxTask */
     int32_t ctl_mode;          /* AgxCtlMode */
     int32_t num_actions;       /* 5 for atti else 4 (hovering.py:46) */
-    int32_t num_obs;           /* 18 hovering/balloon, 48 tracking, 16 avoid/planning */
+    int32_t num_obs;           /* 18 hovering/balloon, 48 tracking, 16 avoid/planning (atti is not available there: the
+                                  reference writes its [N,A] actions into obs[12:16], avoid.py:226) */
     int32_t integrator;        /* AgxIntegrator */
     int32_t flags;             /* AgxFlags bit set */
     int32_t max_episode_length;/* int(episode_length_s / dt) (hovering.py:48) */
@@ -132,7 +149,7 @@ typedef struct AgxStepIO {
     float*   obs;          /* [N,num_obs] out: reference obs_buf                               */
     float*   reward;       /* [N]    out: reference rew_buf                                    */
     float*   cmd;          /* [N,4]  out: reference cmd_thrusts, or NULL                       */
-    float*   reward_terms; /* [9,N]  out: reference item_reward_info planes, or NULL           */
+    float*   reward_terms; /* [AGX_REWARD_TERMS,N] out: reference item_reward_info planes, or NULL */
     float*   aux;          /* [N,AGX_AUX_MAX] task state in/out, or NULL for hovering/tracking.  Balloon: ball xyz (balloon_states
                               positions), previous drone xyz (pre_root_positions), collision flag (collisions), pad */
     const float* rand_reset; /* [N,2,D] U[0,1) draws for the pre-/post-step reset, or NULL → Philox */
@@ -143,7 +160,28 @@ typedef struct AgxStepIO {
                               step_dev[0] instead of `step` and the last CTA to retire increments it, so a
                               captured CUDA graph can be replayed without re-baking the step index */
     int64_t  env_offset;   /* global id of env 0 of this shard (partition-invariant RNG, §8e) */
+    float*   assets;       /* [N,AGX_ASSET_ROW] planning only: world placement of the goal ball + 40 trees (in/out: rewritten on reset) */
+    const float* trees;    /* [AGX_NUM_TREES,8] planning only: cylinder table, asset frame: centre xyz, unit axis xyz, radius, half length */
+    int32_t  phase;        /* AgxPhase (avoid/planning); must be 0 for the other tasks */
+    int32_t  _pad;
 } AgxStepIO;
+
+/* Depth camera + post-processing of one render step (replaces IsaacGym's camera sensor and Customized.dump_images,
+ * customized.py:386-435): analytic ray cast of the ground plane, the thrown cube (avoid) or the 40 tree cylinders + goal ball
+ * (planning) → planar depth clipped at 4.5 m / 4.5 → + N(0,0.1) clamped to [0, max] → x N(1,0.3) clamped to [0, max] →
+ * 5x5 correlation with a random kernel (randint(0,256)/256, zero padding).  Run between the PHYSICS and TASK phases. */
+typedef struct AgxRenderIO {
+    const float* state;    /* [N,13] root states after the physics phase */
+    float*       aux;      /* [N,AGX_AUX_MAX] task state: cube / goal position in; column 7 out = min over the image (Planning esdf_dist, planning.py:162-163) */
+    const float* assets;   /* [N,AGX_ASSET_ROW] planning, else NULL */
+    const float* trees;    /* [AGX_NUM_TREES,8] planning, else NULL */
+    float*       image;    /* [N,AGX_CAM_W,AGX_CAM_H] out: reference full_camera_array[:,0] */
+    const float* rand_add; /* [N,W,H] the additive noise samples, or NULL → Philox stream 4 */
+    const float* rand_mul; /* [N,W,H] the multiplicative noise samples (mean 1), or NULL → Philox stream 4 */
+    const float* rand_kern;/* [N,25]  the blur kernel, or NULL → Philox stream 5 */
+    uint64_t seed, step;
+    int64_t  env_offset;
+} AgxRenderIO;
 
 /* library info */
 int         agx_version(void);
@@ -169,11 +207,14 @@ int agx_params_default(AgxParams* p, int task, int ctl_mode);
  * for AGX_TASK_TRACKING additionally tracking.py:159-296. */
 int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream);
 
+int agx_render_depth(const AgxParams* p, int64_t n, const AgxRenderIO* io, void* stream);
+int agx_sizeof_render_io(void);
+
 /* reset_idx(env_ids) as a standalone call (hovering.py:310-335, tracking.py:159-192):
  * env_ids [m] int64 device pointer; rand [m,D] U[0,1) draws in env_ids order or NULL → Philox. */
 int agx_reset_idx(const AgxParams* p, int64_t n, int64_t m, const int64_t* env_ids,
                   float* state, float* prev_action, float* ctrl_state, int64_t* progress,
-                  int64_t* reset, float* aux, const float* rand, uint64_t seed, uint64_t step,
+                  int64_t* reset, float* aux, float* assets, const float* rand, uint64_t seed, uint64_t step,
                   int64_t env_offset, void* stream);
 
 /* Fill out[n, width] with the library's Philox4x32-10 stream `stream_id` (0 pre-reset uniforms,

@@ -425,13 +425,14 @@ class PlanningOracle(ImageTaskOracle):
         a[:, 0:3] = self.goal_positions
         a[:, 3:6] = self.pre_root_positions
         a[:, 6] = self.collisions
-        a[:, 7] = self.esdf_dist
+        a[:, 7] = self.full_camera_array.reshape(self.num_envs, -1).min(dim=1).values  # = esdf_dist once a step has run
         return a
 
     def asset_matrix(self):
-        """[N,124] in the layout of the kernel's asset table: x (41), y (41), yaw (41), pad — world frame."""
-        a = torch.zeros(self.num_envs, 124)
+        """[N,164] in the layout of the kernel's asset row: x (41) | y (41) | cos yaw (41) | sin yaw (41) — world frame."""
+        a = torch.zeros(self.num_envs, 164)
         a[:, 0:41] = self.env_asset_root_states[:, :, 0]
         a[:, 41:82] = self.env_asset_root_states[:, :, 1]
-        a[:, 82:123] = self.asset_yaw
+        a[:, 82:123] = torch.cos(self.asset_yaw)
+        a[:, 123:164] = torch.sin(self.asset_yaw)
         return a

@@ -21,6 +21,7 @@ def build(force=False):
                                "-o", _SO, src])
     lib = C.CDLL(_SO)
     lib.hostsim_step.argtypes = [C.POINTER(_capi.AgxParams), C.c_int64, C.POINTER(_capi.AgxStepIO)]
+    lib.hostsim_render.argtypes = [C.POINTER(_capi.AgxParams), C.c_int64, C.POINTER(_capi.AgxRenderIO)]
     lib.hostsim_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64]
     return lib
 
@@ -42,10 +43,23 @@ class HostEnv:
         self.obs = np.zeros((n, params.num_obs), np.float32)
         self.reward = np.zeros(n, np.float32)
         self.cmd = np.zeros((n, 4), np.float32)
-        self.terms = np.zeros((9, n), np.float32)
+        self.terms = np.zeros((_capi.AGX_REWARD_TERMS, n), np.float32)
         self.aux = np.zeros((n, _capi.AGX_AUX_MAX), np.float32)
+        self.assets = np.zeros((n, _capi.AGX_ASSET_ROW), np.float32)
+        self.trees = np.load(os.path.join(_ROOT, "airgym_b200", "assets", "thin_trees.npy"))[:_capi.AGX_NUM_TREES].copy()
+        self.image = np.zeros((n, _capi.AGX_CAM_W, _capi.AGX_CAM_H), np.float32)
 
-    def step(self, action, rand_reset=None, rand_noise=None, seed=0, step=0, env_offset=0):
+    def render(self, rand_add, rand_mul, rand_kern):
+        """Host twin of agx_render_depth (explicit noise)."""
+        io = _capi.AgxRenderIO()
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._keep_r = (rand_add, rand_mul, rand_kern)
+        io.state, io.aux, io.assets, io.trees, io.image = ptr(self.state), ptr(self.aux), ptr(self.assets), ptr(self.trees), ptr(self.image)
+        io.rand_add, io.rand_mul, io.rand_kern = ptr(rand_add), ptr(rand_mul), ptr(rand_kern)
+        rc = self.lib.hostsim_render(C.byref(self.P), self.n, C.byref(io))
+        assert rc == 0, rc
+
+    def step(self, action, rand_reset=None, rand_noise=None, seed=0, step=0, env_offset=0, phase=0):
         io = _capi.AgxStepIO()
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         self._keep = (action, rand_reset, rand_noise)
@@ -54,6 +68,7 @@ class HostEnv:
         io.obs, io.reward, io.cmd, io.reward_terms = ptr(self.obs), ptr(self.reward), ptr(self.cmd), ptr(self.terms)
         io.rand_reset, io.rand_noise = ptr(rand_reset), ptr(rand_noise)
         io.aux = ptr(self.aux)
+        io.assets, io.trees, io.phase = ptr(self.assets), ptr(self.trees), phase
         io.seed, io.step, io.env_offset = seed, step, env_offset
         rc = self.lib.hostsim_step(C.byref(self.P), self.n, C.byref(io))
         assert rc == 0, rc

@@ -23,13 +23,14 @@ def test_library_exports_every_declared_symbol(built):
     assert set(names) == set(_capi.EXPORTS), (names, _capi.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f"libagx.so does not export {n}"
-    assert lib.agx_version() == 100
+    assert lib.agx_version() == 110
 
 
 def test_struct_mirrors_match_library(built):
     lib = _capi.load()
     assert lib.agx_sizeof_params() == C.sizeof(_capi.AgxParams)
     assert lib.agx_sizeof_step_io() == C.sizeof(_capi.AgxStepIO)
+    assert lib.agx_sizeof_render_io() == C.sizeof(_capi.AgxRenderIO)
 
 
 def test_error_paths_return_codes_not_exceptions(built):
@@ -37,7 +38,8 @@ def test_error_paths_return_codes_not_exceptions(built):
     p = _capi.AgxParams()
     assert lib.agx_params_default(C.byref(p), 0, 99) == -1
     assert b"ctl_mode" in lib.agx_error_string()
-    assert lib.agx_params_default(C.byref(p), 4, 3) == -4  # planning: kernels not built yet
+    assert lib.agx_params_default(C.byref(p), 4, 2) == -4  # planning/avoid have no atti mode (the reference cannot run it either)
+    assert lib.agx_params_default(C.byref(p), 5, 3) == -1  # unknown task
     assert lib.agx_params_default(C.byref(p), 0, 3) == 0
     io = _capi.AgxStepIO()
     assert lib.agx_step(C.byref(p), 8, C.byref(io), None) == -1  # null buffers
@@ -48,10 +50,12 @@ def test_error_paths_return_codes_not_exceptions(built):
         _capi.check(-1, "x")
 
 
-@pytest.mark.parametrize("task", ["hovering", "tracking", "balloon"])
+@pytest.mark.parametrize("task", ["hovering", "tracking", "balloon", "avoid", "planning"])
 @pytest.mark.parametrize("mode", ["pos", "vel", "atti", "rate", "prop"])
 def test_params_default_equals_oracle_spec(built, task, mode):
     """The constants are written down twice (agx_params_default in C, oracle/spec.py); they must agree."""
+    if task in ("avoid", "planning") and mode == "atti":
+        pytest.skip("no atti mode for the depth-camera tasks")
     P = _capi.default_params(task, mode)
     s = QuadSpec(task=task, ctl_mode=mode)
     f32 = lambda x: C.c_float(x).value
