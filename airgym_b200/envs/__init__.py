@@ -1,10 +1,14 @@
 """Task registry contents — same task names as the reference (airgym/envs/__init__.py:5-87).
-Tasks whose kernels are not built yet are listed in PENDING and raise on make_env."""
+Names in PENDING raise on make_env."""
 from ..utils.task_registry import task_registry
 from .base.hovering import Hovering
 from .base.hovering_config import HoveringCfg
+from .task.avoid import Avoid
+from .task.avoid_config import AvoidCfg
 from .task.balloon import Balloon
 from .task.balloon_config import BalloonCfg
+from .task.planning import Planning
+from .task.planning_config import PlanningCfg
 from .task.tracking import Tracking
 from .task.tracking_config import TrackingCfg
 
@@ -12,8 +16,10 @@ TASK_CONFIGS = [
     {"name": "hovering", "config_class": HoveringCfg, "task_class": Hovering},
     {"name": "tracking", "config_class": TrackingCfg, "task_class": Tracking},
     {"name": "balloon", "config_class": BalloonCfg, "task_class": Balloon},
+    {"name": "avoid", "config_class": AvoidCfg, "task_class": Avoid},
+    {"name": "planning", "config_class": PlanningCfg, "task_class": Planning},
 ]
-PENDING = ("customized", "avoid", "planning")
+PENDING = ("customized",)  # the reference's bare Customized base has an empty reward (customized.py:462-474): not a trainable task
 
 
 def register_tasks():
