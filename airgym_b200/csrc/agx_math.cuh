@@ -406,13 +406,32 @@ AGX_HD float normalize_depth(float t) {
     t = t < 0.0f ? 0.0f : t;
     return t / 4.5f;
 }
-// can the capsule show up in the image at all? (bounding sphere vs the far-plane frustum's bounding sphere / camera plane)
-AGX_HD bool capsule_visible(const Camera& c, const Capsule& k) {
+// Image columns [u0, u1] a capsule can touch (conservative), or u0 > u1 when it cannot show up at all.  The segment is
+// clipped to the half space 5 cm in front of the camera plane, its end points are projected to pixel columns and the band is
+// padded by the projected radius (at the clipped segment's nearest depth, x2 for the perspective stretch off-axis) + 2 px.
+AGX_HD void capsule_columns(const Camera& c, const Capsule& k, int* u0, int* u1) {
+    *u0 = 1; *u1 = 0;
     const V3 rel = k.c - c.o;
-    const float reach = k.h + k.r;
-    if (norm(rel) - reach > 7.5f) return false;  // 5 m far plane x |d|max = 1.475
-    const V3 fwd = v3(c.R[0], c.R[3], c.R[6]);
-    return dot(rel, fwd) + k.h * fabsf(dot(k.a, fwd)) + k.r > 0.0f;
+    if (norm(rel) - (k.h + k.r) > 7.5f) return;  // 5 m far plane x |d|max = 1.475
+    const V3 fwd = v3(c.R[0], c.R[3], c.R[6]), left = v3(c.R[1], c.R[4], c.R[7]);
+    const float xc = dot(rel, fwd), yc = dot(rel, left), xa = dot(k.a, fwd), ya = dot(k.a, left);
+    float s0 = -k.h, s1 = k.h;                    // segment parameter range with x_cam(s) = xc + s xa >= near
+    const float near = 0.05f;
+    if (xc + s0 * xa < near) {
+        if (xc + s1 * xa < near) { if (xc + k.h * fabsf(xa) + k.r <= 0.0f) return; *u0 = 0; *u1 = AGX_CAM_W - 1; return; }
+        s0 = (near - xc) / xa;
+    } else if (xc + s1 * xa < near) {
+        s1 = (near - xc) / xa;
+    }
+    const float xa0 = xc + s0 * xa, xa1 = xc + s1 * xa;
+    const float ua = (float)(AGX_CAM_W / 2) - 0.5f - kCamF * (yc + s0 * ya) / xa0;
+    const float ub = (float)(AGX_CAM_W / 2) - 0.5f - kCamF * (yc + s1 * ya) / xa1;
+    const float xmin = fmaxf(fminf(xa0, xa1) - k.r, near);
+    const float pad = 2.0f * kCamF * k.r / xmin + 2.0f;
+    const float lo = fminf(ua, ub) - pad, hi = fmaxf(ua, ub) + pad;
+    if (hi < 0.0f || lo > (float)(AGX_CAM_W - 1)) return;
+    *u0 = lo < 0.0f ? 0 : (int)lo;
+    *u1 = hi > (float)(AGX_CAM_W - 1) ? AGX_CAM_W - 1 : (int)hi;
 }
 
 // Avoid.reset_idx (avoid.py:91-158) on the 11 compact draws [u_mode, theta, aim xyz, x, y, z, roll, pitch, yaw]

@@ -44,6 +44,7 @@ template <int TASK>
 __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_constant__ AgxRenderIO io, const int64_t n) {
     extern __shared__ __align__(16) float s_img[];  // [W][H]
     __shared__ Capsule s_caps[AGX_NUM_TREES];
+    __shared__ int s_u0[AGX_NUM_TREES], s_u1[AGX_NUM_TREES];  // image-column band of each listed capsule
     __shared__ int s_ncaps;
     __shared__ float s_red[kThreads / 32];
     __shared__ float s_kern[28];
@@ -79,27 +80,47 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
         const int j = tid + 1;
         const Capsule k = place_tree(io.trees + tid * 8, row[j], row[AGX_NUM_ASSETS + j], row[2 * AGX_NUM_ASSETS + j],
                                      row[3 * AGX_NUM_ASSETS + j]);
-        if (capsule_visible(cam, k)) s_caps[atomicAdd(&s_ncaps, 1)] = k;
+        int u0, u1;
+        capsule_columns(cam, k, &u0, &u1);
+        if (u0 <= u1) {
+            const int slot = atomicAdd(&s_ncaps, 1);
+            s_caps[slot] = k; s_u0[slot] = u0; s_u1[slot] = u1;
+        }
     }
     __syncthreads();
     const int ncaps = s_ncaps;
+    bool ball_near = false;  // CTA-uniform: the goal ball can only show up within the far plane's reach
+    if (TASK == AGX_TASK_PLANNING) ball_near = norm(obj - cam.o) - kBallRadius < 7.5f;
 
     // ---- pass 1: ray cast (4 consecutive v per thread: one u, float4-aligned)
     float lmax = 0.0f;
     for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
         const int u = i4 / AGX_CAM_H, v0 = i4 - u * AGX_CAM_H;
         float val[4];
+        V3 d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const V3 d = pixel_dir(cam, u, v0 + j);
-            float t = hit_ground(cam.o, d);
-            if (TASK == AGX_TASK_PLANNING) {
-                for (int c = 0; c < ncaps; ++c) t = fminf(t, hit_capsule(cam.o, d, s_caps[c]));
-                t = fminf(t, hit_sphere(cam.o, d, obj, kBallRadius));
-            } else {
-                t = fminf(t, hit_box(cam.o, d, obj, kCubeHalf));
+            d[j] = pixel_dir(cam, u, v0 + j);
+            val[j] = hit_ground(cam.o, d[j]);
+        }
+        if (TASK == AGX_TASK_PLANNING) {
+            for (int c = 0; c < ncaps; ++c) {
+                if (u < s_u0[c] || u > s_u1[c]) continue;  // this column cannot see capsule c
+                const Capsule k = s_caps[c];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) val[j] = fminf(val[j], hit_capsule(cam.o, d[j], k));
             }
-            val[j] = normalize_depth(t);
+            if (ball_near) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) val[j] = fminf(val[j], hit_sphere(cam.o, d[j], obj, kBallRadius));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[j] = fminf(val[j], hit_box(cam.o, d[j], obj, kCubeHalf));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            val[j] = normalize_depth(val[j]);
             lmax = fmaxf(lmax, val[j]);
         }
         *reinterpret_cast<float4*>(&s_img[i4]) = make_float4(val[0], val[1], val[2], val[3]);
@@ -154,12 +175,15 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
         for (int i = 0; i < 5; ++i) {
             const int uu = u + i - 2;
             if (uu < 0 || uu >= AGX_CAM_W) continue;
+            // the 8 inputs v0-2 .. v0+5 of this row sit inside the three aligned float4 groups v0-4 .. v0+7
             float rowv[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int vv = v0 + c - 2;
-                rowv[c] = (vv >= 0 && vv < AGX_CAM_H) ? s_img[uu * AGX_CAM_H + vv] : 0.0f;
-            }
+            const float* rp = &s_img[uu * AGX_CAM_H + v0];
+            const float4 mid = *reinterpret_cast<const float4*>(rp);
+            float4 lo = make_float4(0.0f, 0.0f, 0.0f, 0.0f), hi = lo;
+            if (v0 > 0) lo = *reinterpret_cast<const float4*>(rp - 4);
+            if (v0 + 4 < AGX_CAM_H) hi = *reinterpret_cast<const float4*>(rp + 4);
+            rowv[0] = lo.z; rowv[1] = lo.w; rowv[2] = mid.x; rowv[3] = mid.y; rowv[4] = mid.z; rowv[5] = mid.w;
+            rowv[6] = hi.x; rowv[7] = hi.y;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
 #pragma unroll

@@ -25,22 +25,30 @@ def child(spec):
     from airgym_b200.envs.base.hovering_config import HoveringCfg
     from airgym_b200.envs.task.tracking import Tracking
     from airgym_b200.envs.task.tracking_config import TrackingCfg
+    from airgym_b200.envs.task.avoid import Avoid
+    from airgym_b200.envs.task.avoid_config import AvoidCfg
+    from airgym_b200.envs.task.planning import Planning
+    from airgym_b200.envs.task.planning_config import PlanningCfg
+
+    CLS = {"hovering": (Hovering, HoveringCfg), "tracking": (Tracking, TrackingCfg), "avoid": (Avoid, AvoidCfg),
+           "planning": (Planning, PlanningCfg)}
 
     n, steps = int(spec.get("n", 65536)), int(spec.get("steps", 2000))
     for k, v in spec.items():
         if k.startswith("opt."):
             _capi.check(_capi.load().agx_set_option(k[4:].encode(), int(v)), k)
-    reps = max(2, (8 << 16) // n)
     task, mode = spec.get("task", "hovering"), spec.get("mode", "rate")
+    reps = max(2, (8 << 16) // n) if task in ("hovering", "tracking") else 1  # image tasks: 101 KB of image per env
+    render_only = spec.get("render_only", "0") == "1"
     envs, acts = [], []
     g = torch.Generator(device="cuda").manual_seed(5678)
     for r in range(reps):
-        cfg = TrackingCfg() if task == "tracking" else HoveringCfg()
+        cfg = CLS[task][1]()
         cfg.env.num_envs, cfg.env.ctl_mode, cfg.seed = n, mode, 1234 + r
         cfg.backend.reward_terms = False
         cfg.backend.export_cmd_thrusts = False
         cfg.backend.mutate_input_actions = False
-        env = (Tracking if task == "tracking" else Hovering)(cfg, None, None, "cuda:0", True)
+        env = CLS[task][0](cfg, None, None, "cuda:0", True)
         if spec.get("noise", "1") == "0":
             env.params.flags |= _capi.FLAG_NO_NOISE
         envs.append(env)
@@ -54,13 +62,22 @@ def child(spec):
             if mode == "prop":
                 a[:] = 0.1537
         acts.append(a)
+    if task in ("avoid", "planning") and mode == "rate":
+        for a in acts:
+            a[:, 3] = a[:, 3] * 0.1 - 0.69  # near hover: episodes last
     for i in range(50):
         envs[i % reps].step(acts[i % reps])
     torch.cuda.synchronize()
     chunk = torch.cuda.CUDAGraph()
     with torch.cuda.graph(chunk):
         for r in range(reps):
-            envs[r].step(acts[r])
+            if render_only:
+                envs[r].render_cameras()
+            elif task in ("avoid", "planning"):
+                for _ in range(4):  # one camera period: 3 fused steps + 1 split step with a render
+                    envs[r].step(acts[r])
+            else:
+                envs[r].step(acts[r])
     for _ in range(30):
         chunk.replay()
     torch.cuda.synchronize()
@@ -75,6 +92,8 @@ def child(spec):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / (steps // reps * reps))
         rates.append(float(envs[0].reset_buf.float().mean()))
+    if task in ("avoid", "planning") and not render_only:
+        best /= 4
     print(json.dumps({"us_per_step": round(best, 3), "algo_GBs": round(288 * n / best / 1e3, 1),
                       "reset_frac": round(sum(rates) / len(rates), 4)}), flush=True)
 

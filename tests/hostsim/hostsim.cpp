@@ -94,12 +94,15 @@ extern "C" int hostsim_render(const AgxParams* p, int64_t n, const AgxRenderIO* 
         const float* aux = io->aux + env * AGX_AUX_MAX;
         const V3 obj = v3(aux[0], aux[1], aux[2]);
         std::vector<Capsule> caps;
+        std::vector<int> cu0, cu1;
         if (p->task == AGX_TASK_PLANNING) {
             const float* row = io->assets + env * (int64_t)AGX_ASSET_ROW;
             for (int j = 1; j < AGX_NUM_ASSETS; ++j) {
                 const Capsule k = place_tree(io->trees + (j - 1) * 8, row[j], row[AGX_NUM_ASSETS + j], row[2 * AGX_NUM_ASSETS + j],
                                              row[3 * AGX_NUM_ASSETS + j]);
-                if (capsule_visible(cam, k)) caps.push_back(k);
+                int u0, u1;
+                capsule_columns(cam, k, &u0, &u1);
+                if (u0 <= u1) { caps.push_back(k); cu0.push_back(u0); cu1.push_back(u1); }
             }
         }
         float m = 0.0f;
@@ -108,7 +111,8 @@ extern "C" int hostsim_render(const AgxParams* p, int64_t n, const AgxRenderIO* 
                 const V3 d = pixel_dir(cam, u, v);
                 float t = hit_ground(cam.o, d);
                 if (p->task == AGX_TASK_PLANNING) {
-                    for (const Capsule& k : caps) t = fminf(t, hit_capsule(cam.o, d, k));
+                    for (size_t c = 0; c < caps.size(); ++c)
+                        if (u >= cu0[c] && u <= cu1[c]) t = fminf(t, hit_capsule(cam.o, d, caps[c]));
                     t = fminf(t, hit_sphere(cam.o, d, obj, kBallRadius));
                 } else {
                     t = fminf(t, hit_box(cam.o, d, obj, kCubeHalf));
