@@ -31,3 +31,16 @@ class RunningMeanStd(nn.Module):
         if denorm:
             return torch.sqrt(var + self.epsilon) * torch.clamp(x, min=-5.0, max=5.0) + mean
         return torch.clamp((x - mean) / torch.sqrt(var + self.epsilon), min=-5.0, max=5.0)
+
+
+class RunningMeanStdObs(nn.Module):
+    """Per-key RunningMeanStd for dict observations (lib/core/running_mean_std.py:84-95): state_dict keys
+    `running_mean_std.<key>.{running_mean,running_var,count}`."""
+
+    def __init__(self, insize, epsilon=1e-05):
+        assert isinstance(insize, dict)
+        super().__init__()
+        self.running_mean_std = nn.ModuleDict({k: RunningMeanStd(tuple(v), epsilon) for k, v in insize.items()})
+
+    def forward(self, input, denorm=False):
+        return {k: self.running_mean_std[k](v, denorm) for k, v in input.items()}

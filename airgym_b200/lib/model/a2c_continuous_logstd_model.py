@@ -11,7 +11,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import _capi
-from ..core.running_mean_std import RunningMeanStd
+from ..core.running_mean_std import RunningMeanStd, RunningMeanStdObs
+from ..network.cnn import CNNFeatureExtractor
 
 _ACTS = {"elu": F.elu, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "sin": torch.sin}
 
@@ -40,16 +41,25 @@ class ModelA2CContinuousLogStd(nn.Module):
     def __init__(self, params, keys):
         super().__init__()
         net = params["network"]
-        if net.get("separate", False) or "cnn" in net or "vae" in net or "resnet" in net:
-            raise NotImplementedError("only the non-separate MLP network of ppo_hovering/tracking.yaml is built in this round")
+        if net.get("separate", False) or "vae" in net or "resnet" in net:
+            raise NotImplementedError("built: the non-separate MLP network (ppo_hovering/tracking/balloon.yaml) and the non-separate "
+                                      "CNN network (ppo_avoid/planning.yaml); separate critics, resnet and vae encoders are not")
         self.actions_num = keys["actions_num"]
         input_shape = keys["input_shape"]
+        self.has_cnn = "cnn" in net
+        if self.has_cnn != isinstance(input_shape, dict):
+            raise ValueError("a `cnn` network needs a dict observation space {'image','observation'} (env_config use_image: True) and vice versa")
         self.normalize_value = params["config"].get("normalize_value", False)
         self.normalize_input = params["config"].get("normalize_input", False)
         self.value_size = params["config"].get("value_size", 1)
         units, act = net["mlp"]["units"], net["mlp"]["activation"]
         assert net["space"]["continuous"].get("fixed_sigma", True), "fixed_sigma: True is the only shipped configuration"
-        self.actor_mlp = MLP(input_shape[0], units, act)
+        if self.has_cnn:  # a2c_continuous_logstd_model.py:30-32
+            self.feature_dim = int(net["cnn"]["output_dim"])
+            self.actor_cnn = CNNFeatureExtractor(feature_dim=self.feature_dim)
+            self.actor_mlp = MLP(input_shape["observation"][0] + self.feature_dim, units, act)
+        else:
+            self.actor_mlp = MLP(input_shape[0], units, act)
         self.mu = nn.Linear(units[-1], self.actions_num)
         self.mu.weight.data.mul_(0.1)
         self.mu.bias.data.mul_(0.0)
@@ -60,7 +70,11 @@ class ModelA2CContinuousLogStd(nn.Module):
         if self.normalize_value:
             self.value_mean_std = RunningMeanStd((self.value_size,))
         if self.normalize_input:
-            self.running_mean_std = RunningMeanStd(tuple(input_shape))
+            if self.has_cnn:  # the vector part is normalised AFTER the CNN features are appended (:73-78)
+                shapes = {"image": tuple(input_shape["image"]), "observation": (input_shape["observation"][0] + self.feature_dim,)}
+                self.running_mean_std = RunningMeanStdObs(shapes)
+            else:
+                self.running_mean_std = RunningMeanStd(tuple(input_shape))
         self.flat_params = self.flat_grads = None
 
     # ---- flat parameter / gradient storage ------------------------------------------------------------------------
@@ -99,7 +113,8 @@ class ModelA2CContinuousLogStd(nn.Module):
         P.w_mu, P.b_mu = self.mu.weight.data_ptr(), self.mu.bias.data_ptr()
         P.w_value, P.b_value = self.value_head.weight.data_ptr(), self.value_head.bias.data_ptr()
         if self.normalize_input:
-            P.in_mean, P.in_var = self.running_mean_std.running_mean.data_ptr(), self.running_mean_std.running_var.data_ptr()
+            rms = self.running_mean_std.running_mean_std["observation"] if self.has_cnn else self.running_mean_std
+            P.in_mean, P.in_var = rms.running_mean.data_ptr(), rms.running_var.data_ptr()
         return P
 
     def fused_heads(self, obs, mu_out, value_out, keep=None):
@@ -148,8 +163,27 @@ class ModelA2CContinuousLogStd(nn.Module):
     def denorm_value(self, value):
         return self.value_mean_std(value, denorm=True) if self.normalize_value else value
 
+    def trunk_input(self, obs):
+        """CNN network: [observation | cnn(norm(image))] (:141-145), un-normalised — what the MLP trunk's input
+        normalisation (`running_mean_std.observation`) then sees."""
+        img = obs["image"]
+        if self.normalize_input:
+            with torch.no_grad():
+                img = self.running_mean_std.running_mean_std["image"](img)
+        return torch.cat((obs["observation"], self.actor_cnn(img)), dim=-1)
+
     def heads(self, obs):
-        h = self.actor_mlp(self.norm_obs(obs))
+        if self.has_cnn:
+            x = self.trunk_input(obs)
+            if self.normalize_input:
+                with torch.no_grad():
+                    xn = self.running_mean_std.running_mean_std["observation"](x.detach())
+                # normalisation is applied under no_grad in the reference too (base_model.py:29-31): the CNN gets no gradient
+                # through it — the features reach the trunk only through this detached, normalised copy
+                x = xn
+            h = self.actor_mlp(x)
+        else:
+            h = self.actor_mlp(self.norm_obs(obs))
         return self.mu(h), self.value_head(h)
 
     @staticmethod

@@ -64,7 +64,14 @@ class Runner:
         return agent.train()
 
     def run_play(self, args):
-        raise NotImplementedError("the player (lib/agent/players.py) is a later §8(f) row")
+        print("Started to play")  # torch_runner.py:86-90
+        from .agent.players import PpoPlayerContinuous
+
+        player = PpoPlayerContinuous(self.params)
+        if args.get("checkpoint"):
+            player.restore(args["checkpoint"])
+        self.player = player
+        return player.run()
 
     def run(self, args):
         if args.get("play") and not args.get("train"):

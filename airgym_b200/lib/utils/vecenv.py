@@ -29,13 +29,17 @@ class AirGymRLGPUEnv:
         kwargs.setdefault("seed", 0)
         self.env, self.env_cfg = task_registry.make_env(config_name, args=Namespace(**kwargs))
 
+    def _obs(self, obs):
+        # the camera tasks always return the dict; without use_image the policy only sees the vector part
+        return obs["observation"] if (isinstance(obs, dict) and not self.use_image) else obs
+
     def step(self, actions):  # ExtractObsWrapper.step: drop the privileged observations (vecenv.py:59-67)
         obs, _priv, rewards, dones, infos = self.env.step(actions)
-        return obs, rewards, dones, infos
+        return self._obs(obs), rewards, dones, infos
 
     def reset(self):
         obs, _priv = self.env.reset()
-        return obs
+        return self._obs(obs)
 
     def get_number_of_agents(self):
         return 1
@@ -44,7 +48,12 @@ class AirGymRLGPUEnv:
         info = {k: v for k, v in type(self.env_cfg.env).__dict__.items() if not k.startswith("__") and not callable(v)}
         n = self.env.num_actions
         info["action_space"] = Box(-np.ones(n, np.float32), np.ones(n, np.float32))
-        info["observation_space"] = Box(np.full(self.env.num_obs, -np.inf, np.float32), np.full(self.env.num_obs, np.inf, np.float32))
+        vec = Box(np.full(self.env.num_obs, -np.inf, np.float32), np.full(self.env.num_obs, np.inf, np.float32))
+        if self.use_image:  # vecenv.py:93-98: Dict{'image': Box(0,1,(C,W,H)), 'observation': Box}
+            shp = (self.env.cam_channel, self.env.cam_resolution[0], self.env.cam_resolution[1])
+            info["observation_space"] = {"image": Box(np.zeros(shp, np.float32), np.ones(shp, np.float32)), "observation": vec}
+        else:
+            info["observation_space"] = vec
         return info
 
     def get_env_state(self):

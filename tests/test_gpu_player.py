@@ -1,0 +1,61 @@
+"""Player / checkpoint compatibility: the reference's shipped policy checkpoint
+(trained/planning_cnn_rate.pth, stripped to its model state dict by tests/golden/make_golden_ckpt.py) loads key for key into
+the B200 model and plays in the B200 Planning env through the reference's `--play` entry point."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+CKPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "planning_cnn_rate_model.pth")
+
+PARAMS = {
+    "algo": {"name": "a2c_continuous"}, "model": {"name": "continuous_a2c_logstd"},
+    "network": {"name": "actor_critic", "separate": False, "space": {"continuous": {"fixed_sigma": True}},
+                "mlp": {"units": [64, 128, 64], "activation": "elu"}, "cnn": {"output_dim": 30}},
+    "config": {"env_name": "planning", "env_config": {"use_image": True, "ctl_mode": "rate", "seed": 1}, "name": "ppo_planning",
+               "normalize_input": True, "normalize_value": True, "num_actors": 64, "clip_actions": True, "reward_shaper": {"scale_value": 0.1},
+               "player": {"games_num": 64, "deterministic": True, "print_stats": False, "max_steps": 60}},
+}
+
+
+def test_reference_checkpoint_loads_and_plays():
+    from airgym_b200.lib.torch_runner import Runner
+
+    r = Runner()
+    r.load({"params": copy.deepcopy(PARAMS)})
+    av_reward, av_steps = r.run({"play": True, "train": False, "checkpoint": CKPT})
+    model = r.player.model
+    ck = torch.load(CKPT, weights_only=False)["model"]
+    assert set(model.state_dict().keys()) == set(ck.keys())  # the reference's .pth key layout, key for key
+    for k, v in ck.items():
+        assert torch.allclose(model.state_dict()[k].cpu().double(), v.double(), rtol=1e-6, atol=1e-7), k
+    assert r.player.games_played >= 64 and av_steps > 1 and torch.isfinite(torch.tensor(av_reward))
+    # the model's forward is the reference's: [obs16 | cnn(norm(image))] -> norm -> MLP -> mu (a2c_continuous_logstd_model.py:139-150)
+    obs = r.player.env.reset()
+    with torch.no_grad():
+        res = model({"is_train": False, "obs": obs})
+        img = model.running_mean_std.running_mean_std["image"](obs["image"])
+        x = torch.cat((obs["observation"], model.actor_cnn(img)), -1)
+        h = model.actor_mlp(model.running_mean_std.running_mean_std["observation"](x))
+    assert torch.allclose(res["mus"], model.mu(h), atol=1e-6)
+
+
+def test_pretrained_mlp_checkpoint_initialises_cnn_policy(tmp_path):
+    """players.py:387-428: an MLP-only checkpoint (obs 46 wide) fills everything but the CNN."""
+    from airgym_b200.lib.agent.players import PpoPlayerContinuous
+
+    ck = torch.load(CKPT, weights_only=False)
+    w = {k: v for k, v in ck["model"].items() if "cnn" not in k and "image" not in k}
+    w = {k.replace("running_mean_std.running_mean_std.observation.", "running_mean_std."): v for k, v in w.items()}
+    fn = str(tmp_path / "mlp_only.pth")
+    torch.save({"model": w}, fn)
+    p = copy.deepcopy(PARAMS)
+    pl = PpoPlayerContinuous(p)
+    before = pl.model.actor_cnn.fc.weight.clone()
+    pl.restore(fn)
+    assert torch.equal(pl.model.actor_cnn.fc.weight, before)
+    assert torch.allclose(pl.model.mu.weight.cpu(), ck["model"]["mu.weight"])
+    assert torch.allclose(pl.model.running_mean_std.running_mean_std["observation"].running_mean.cpu(),
+                          ck["model"]["running_mean_std.running_mean_std.observation.running_mean"])
