@@ -60,7 +60,9 @@ class A2CAgent:
             self.env.set_seed(self.env.rng_seed, env_offset=self.global_rank * self.num_actors)
         self.env_info = self.vec_env.get_env_info()
         self.value_size = 1
-        self.obs_shape = self.env_info["observation_space"].shape
+        space = self.env_info["observation_space"]
+        self.has_cnn = isinstance(space, dict)  # avoid / planning with env_config use_image: True (ppo_avoid/planning.yaml)
+        self.obs_shape = {k: v.shape for k, v in space.items()} if self.has_cnn else space.shape
         self.actions_num = self.env_info["action_space"].shape[0]
         dev = self.ppo_device
         self.actions_low = torch.from_numpy(self.env_info["action_space"].low.copy()).float().to(dev)
@@ -105,13 +107,21 @@ class A2CAgent:
         self.nn_dir = os.path.join(self.experiment_dir, "nn")
         if self.global_rank == 0:
             os.makedirs(self.nn_dir, exist_ok=True)
-        self.use_cuda_graph = config.get("use_cuda_graph", True)
+        self.use_cuda_graph = config.get("use_cuda_graph", not self.has_cnn)  # the cuDNN encoder is run eagerly by default
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
         self.algo_observer = config.get("features", {}).get("observer", None)
 
         keys = {"actions_num": self.actions_num, "input_shape": self.obs_shape, "num_seqs": self.num_actors,
                 "value_size": 1, "normalize_value": self.normalize_value, "normalize_input": self.normalize_input}
         self.model = ModelA2CContinuousLogStd(params, keys).to(dev)
+        if self.has_cnn:
+            # The reference normalises the trunk input under no_grad (base_model.py:29-31), so its CNN never receives a gradient:
+            # the encoder is a fixed feature extractor.  The agent therefore encodes each observation ONCE, when it arrives
+            # (eval-mode BatchNorm), and everything downstream — rollout buffer, fused MLP kernels, update — works on the
+            # 46-wide trunk input [obs16 | cnn(norm(image))] instead of 101 KB images per sample.  (Deviation, DESIGN.md §9: the
+            # reference re-encodes the minibatch images in train mode — BatchNorm batch statistics — during the update.)
+            self.image_shape = self.obs_shape["image"]
+            self.obs_shape = (self.obs_shape["observation"][0] + self.model.feature_dim,)
         self.flat_params, self.flat_grads = self.model.flatten_parameters(extra_grad_slots=_capi.AGX_PPO_STATS)
         self.n_params = self.model.num_flat
         self.stats = self.flat_grads[self.n_params:]  # loss statistics ride behind the grads through the all-reduce
@@ -167,8 +177,24 @@ class A2CAgent:
             return rescale_actions(self.actions_low, self.actions_high, torch.clamp(actions, -1.0, 1.0))
         return actions
 
+    def _trunk_rms(self):
+        rms = self.model.running_mean_std
+        return rms.running_mean_std["observation"] if self.has_cnn else rms
+
+    def _ingest(self, obs, update_image_rms=True):
+        """What the policy trunk sees of an env observation: the vector itself, or [obs16 | cnn(norm(image))]."""
+        if not self.has_cnn:
+            return obs
+        with torch.no_grad():
+            self.model.eval()
+            if self.normalize_input and update_image_rms:  # running_mean_std.image sees every image once, like the reference's
+                img = obs["image"]                         # first mini-epoch does (a2c_continuous.py:130-131)
+                self._rms_update(self.model.running_mean_std.running_mean_std["image"], img.reshape(img.shape[0], -1),
+                                 shape=self.image_shape)
+            return self.model.trunk_input(obs)
+
     def env_reset(self):
-        self.obs.copy_(self.vec_env.reset())
+        self.obs.copy_(self._ingest(self.vec_env.reset(), update_image_rms=False))
         return self.obs
 
     def _rollout_step(self, n):
@@ -191,7 +217,7 @@ class A2CAgent:
         if self.value_bootstrap and "time_outs" in infos:
             shaped = shaped + self.gamma * res["values"].squeeze(-1) * infos["time_outs"].float()
         b["rewards"][:, n] = shaped
-        self.obs.copy_(obs)
+        self.obs.copy_(self._ingest(obs))
         self.dones.copy_(dones)
         # episode statistics, on device (the reference keeps a 100-game window on the host, a2c_base.py:680-695)
         self.current_rewards += rewards
@@ -245,11 +271,21 @@ class A2CAgent:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
-    def _rms_update(self, rms, x):
+    def _rms_update(self, rms, x, shape=None):
         """RunningMeanStd train-mode update; with >1 rank the batch moments are merged across ranks first so that
         replicas keep identical statistics (the reference keeps per-rank statistics)."""
         x64 = x.double()
         n = x.shape[0]
+        if shape is not None:  # flattened image batch: moments back in the buffer's shape
+            var, mean = torch.var_mean(x64, dim=0)
+            if self.multi_gpu and self.world_size > 1:
+                s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
+                self._allreduce(s)
+                k, n = x.shape[1], n * self.world_size
+                mean = s[:k] / n
+                var = (s[k:] - n * mean * mean) / (n - 1)
+            rms.update_from_moments(mean.reshape(shape), var.reshape(shape), n)
+            return
         if self.multi_gpu and self.world_size > 1:
             s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
             self._allreduce(s)
@@ -301,7 +337,7 @@ class A2CAgent:
         obs = b["obses"].view(-1, *self.obs_shape)[sl]
         if self.normalize_input and update_rms:
             with torch.no_grad():
-                self._rms_update(self.model.running_mean_std, obs)
+                self._rms_update(self._trunk_rms(), obs)
         self.model.eval()  # statistics are updated explicitly above; forward only normalises
         if self.fused_mlp:
             self.model.fused_heads(obs, self.mb_mu, self.mb_value, keep=self.keep)
@@ -391,7 +427,10 @@ class A2CAgent:
         self.env_reset()
         if self.multi_gpu and self.world_size > 1:
             dist.broadcast(self.flat_params, 0)  # flat-tensor broadcast instead of a pickled state_dict (:188-192)
-            for rms in (getattr(self.model, "running_mean_std", None), getattr(self.model, "value_mean_std", None)):
+            rmss = [getattr(self.model, "value_mean_std", None)]
+            if self.normalize_input:
+                rmss += list(self.model.running_mean_std.running_mean_std.values()) if self.has_cnn else [self.model.running_mean_std]
+            for rms in rmss:
                 if rms is not None:
                     for t in (rms.running_mean, rms.running_var, rms.count):
                         dist.broadcast(t, 0)

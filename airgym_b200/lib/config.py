@@ -1,5 +1,5 @@
-"""Default PPO configurations with the schema and values of the reference's yamls (scripts/config/ppo_hovering.yaml:1-73,
-ppo_tracking.yaml — identical except name/env_name/max_epochs 300).  The reference's yaml files load unchanged through
+"""Default PPO configurations with the schema and values of the reference's yamls (scripts/config/ppo_hovering.yaml:1-73;
+ppo_tracking / ppo_balloon / ppo_avoid / ppo_planning.yaml differ in the fields default_ppo_config sets).  The reference's yaml files load unchanged through
 `scripts/runner.py --config <file>`; these defaults exist so the package runs without them."""
 import copy
 
@@ -35,6 +35,16 @@ def default_ppo_config(task: str = "hovering"):
     c["env_name"], c["name"] = task, f"ppo_{task}"
     if task == "tracking":
         c["max_epochs"] = 300
+    elif task == "balloon":  # ppo_balloon.yaml
+        c.update(num_actors=64, horizon_length=32)
+    elif task == "avoid":  # ppo_avoid.yaml:23-57
+        cfg["params"]["network"]["cnn"] = {"output_dim": 30}
+        c["env_config"]["use_image"] = True
+        c.update(horizon_length=64, max_epochs=20000)
+    elif task == "planning":  # ppo_planning.yaml:31-66
+        cfg["params"]["network"]["cnn"] = {"output_dim": 30}
+        c["env_config"]["use_image"] = True
+        c.update(max_epochs=1000, save_frequency=20)
     return cfg
 
 

