@@ -69,7 +69,9 @@ def child(spec):
         envs[i % reps].step(acts[i % reps])
     torch.cuda.synchronize()
     chunk = torch.cuda.CUDAGraph()
+    passes = int(spec.get("chunk", 1))  # passes over the replicas per captured graph
     with torch.cuda.graph(chunk):
+      for _ in range(passes):
         for r in range(reps):
             if render_only:
                 envs[r].render_cameras()
@@ -86,11 +88,11 @@ def child(spec):
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps // reps):
+        for _ in range(steps // (reps * passes)):
             chunk.replay()
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e3 / (steps // reps * reps))
+        best = min(best, e0.elapsed_time(e1) * 1e3 / (steps // (reps * passes) * reps * passes))
         rates.append(float(envs[0].reset_buf.float().mean()))
     if task in ("avoid", "planning") and not render_only:
         best /= 4
