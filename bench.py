@@ -24,6 +24,10 @@ NUM_ENVS = 65536
 REPLICAS = 8
 GRAPH_PASSES = 8  # the timed loop replays graphs of REPLICAS x GRAPH_PASSES = 64 step launches
 ALGO_BYTES_PER_ENV_STEP = 288  # reads 113 B + writes 174 B (Hovering/CTBR fp32)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of agx_step_kernel<hovering, rate, 128> at 65 536 envs, from the
+# `ncu --set full` capture in profiles/r1_agx_step_hovering_rate_ncu_raw.csv (2 launches: 8.18 MB read, 1.28 / 0 MB written — the
+# 11.5 MB of outputs stay in the 126 MB L2 within one launch and are written back later)
+NCU_DRAM_BYTES_PER_LAUNCH = 8.82e6
 WORKLOAD = "Hovering, 65536 envs/GPU, CTBR (ctl_mode=rate), fused step kernel"
 
 
@@ -247,26 +251,42 @@ def time_e2e_loop(env, num_envs, steps, warmup, dist):
     obs_h = torch.empty(num_envs, env.num_obs).pin_memory()
     rew_h = torch.empty(num_envs).pin_memory()
     rst_h = torch.empty(num_envs, dtype=torch.long).pin_memory()
-    a_dev = torch.empty(num_envs, 4, device="cuda")
+    a_dev = [torch.empty(num_envs, 4, device="cuda") for _ in range(2)]  # double-buffered: the H2D of step t+1 rides under the D2H of step t
     h2d = a_host.numel() * 4
     d2h = obs_h.numel() * 4 + rew_h.numel() * 4 + rst_h.numel() * 8
+    main = torch.cuda.current_stream()
+    copy_in = torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_step = [torch.cuda.Event() for _ in range(2)]
 
-    def one():
-        a_dev.copy_(a_host, non_blocking=True)
-        obs, _, rew, rst, _ = env.step(a_dev)
+    def stage(t):  # host -> device copy of step t's actions, on the copy stream (PCIe is full duplex)
+        with torch.cuda.stream(copy_in):
+            copy_in.wait_event(ev_step[t % 2])  # the step that last read this buffer has run
+            a_dev[t % 2].copy_(a_host, non_blocking=True)
+            ev_in[t % 2].record(copy_in)
+
+    def one(t):
+        main.wait_event(ev_in[t % 2])
+        obs, _, rew, rst, _ = env.step(a_dev[t % 2])
+        ev_step[t % 2].record(main)
+        stage(t + 1)
         obs_h.copy_(obs, non_blocking=True)
         rew_h.copy_(rew, non_blocking=True)
         rst_h.copy_(rst, non_blocking=True)
 
-    for _ in range(max(3, min(warmup, 20))):
-        one()
+    for e in ev_step:
+        e.record(main)
+    stage(0)
+    nw = max(3, min(warmup, 20))
+    for t in range(nw):
+        one(t)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        one()
+    for t in range(nw, nw + steps):
+        one(t)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -351,11 +371,13 @@ def run_ours(args):
                    "launch": f"CUDA graph replay ({REPLICAS * GRAPH_PASSES} step launches per graph), programmatic dependent launch "
                              "(noise-first, agx.h 'pdl' auto)", "options": opts, "parallelism": f"env-sharded x{world}, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if N == NUM_ENVS else None, "traffic_unit": "B/launch (ncu dram read+write; algorithmic: "
+                     f"{ALGO_BYTES_PER_ENV_STEP * N} B/launch)", "peak_source": peak_src,
                      "note": f"{ALGO_BYTES_PER_ENV_STEP} algorithmic B/env-step x {N} envs / (timed region / launches), i.e. launch gaps included"},
         "e2e": {"value": world * N * e2e_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "path": "env.step() via ctypes C ABI; pinned host actions in, obs+reward+reset out to pinned host"},
+                "path": "env.step() via ctypes C ABI; pinned host actions in (copy stream, overlapping the previous step's read-back), "
+                        "obs+reward+reset out to pinned host; every step moves all three"},
         "gpu_launches": K,
         "clocks": clocks,
     }
