@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from ... import _capi
 from ..core.running_mean_std import RunningMeanStd, RunningMeanStdObs
 from ..network.cnn import CNNFeatureExtractor
+from ..network.vae_image_encoder import VAEImageEncoder
 
 _ACTS = {"elu": F.elu, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "sin": torch.sin}
 
@@ -41,20 +42,26 @@ class ModelA2CContinuousLogStd(nn.Module):
     def __init__(self, params, keys):
         super().__init__()
         net = params["network"]
-        if net.get("separate", False) or "vae" in net or "resnet" in net:
+        if net.get("separate", False) or "resnet" in net:
             raise NotImplementedError("built: the non-separate MLP network (ppo_hovering/tracking/balloon.yaml) and the non-separate "
-                                      "CNN network (ppo_avoid/planning.yaml); separate critics, resnet and vae encoders are not")
+                                      "CNN / VAE networks (ppo_avoid/planning.yaml); separate critics and the resnet encoder are not")
         self.actions_num = keys["actions_num"]
         input_shape = keys["input_shape"]
-        self.has_cnn = "cnn" in net
+        self.has_vae = "vae" in net and "cnn" not in net  # a2c_continuous_logstd_model.py:27-35: resnet > cnn > vae
+        self.has_cnn = "cnn" in net or self.has_vae        # "has an image encoder in front of the trunk"
         if self.has_cnn != isinstance(input_shape, dict):
-            raise ValueError("a `cnn` network needs a dict observation space {'image','observation'} (env_config use_image: True) and vice versa")
+            raise ValueError("a `cnn`/`vae` network needs a dict observation space {'image','observation'} (env_config use_image: True) and vice versa")
         self.normalize_value = params["config"].get("normalize_value", False)
         self.normalize_input = params["config"].get("normalize_input", False)
         self.value_size = params["config"].get("value_size", 1)
         units, act = net["mlp"]["units"], net["mlp"]["activation"]
         assert net["space"]["continuous"].get("fixed_sigma", True), "fixed_sigma: True is the only shipped configuration"
-        if self.has_cnn:  # a2c_continuous_logstd_model.py:30-32
+        if self.has_vae:  # :33-35 — a frozen, pre-trained encoder: a plain attribute in the reference (its weights are not part of
+            enc = VAEImageEncoder(net["vae"])   # the policy's state_dict), so it is kept out of the module registry here too
+            self.feature_dim = enc.latent_dim
+            object.__setattr__(self, "actor_enc", enc)
+            self.actor_mlp = MLP(input_shape["observation"][0] + self.feature_dim, units, act)
+        elif self.has_cnn:  # :30-32
             self.feature_dim = int(net["cnn"]["output_dim"])
             self.actor_cnn = CNNFeatureExtractor(feature_dim=self.feature_dim)
             self.actor_mlp = MLP(input_shape["observation"][0] + self.feature_dim, units, act)
@@ -170,7 +177,14 @@ class ModelA2CContinuousLogStd(nn.Module):
         if self.normalize_input:
             with torch.no_grad():
                 img = self.running_mean_std.running_mean_std["image"](img)
-        return torch.cat((obs["observation"], self.actor_cnn(img)), dim=-1)
+        feat = self.actor_enc.encode(img) if self.has_vae else self.actor_cnn(img)
+        return torch.cat((obs["observation"], feat), dim=-1)
+
+    def _apply(self, fn, *a, **k):  # .to(device) / .cuda(): the unregistered VAE encoder follows the module
+        out = super()._apply(fn, *a, **k)
+        if getattr(self, "has_vae", False):
+            self.actor_enc._apply(fn)
+        return out
 
     def heads(self, obs):
         if self.has_cnn:
