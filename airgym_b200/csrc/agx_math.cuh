@@ -399,7 +399,9 @@ AGX_HD Camera make_camera(const float* s) {  // s = root-state row; unit quatern
 AGX_HD V3 pixel_dir(const Camera& c, int u, int v) {
     const float dy = fdiv((float)(AGX_CAM_W / 2) - (float)u - 0.5f, kCamF);
     const float dz = fdiv((float)(AGX_CAM_H / 2) - (float)v - 0.5f, kCamF);
-    return mat_mul_v(c.R, v3(1.0f, dy, dz));
+    // R (1, dy, dz) as (R[:,0] + dy R[:,1]) + dz R[:,2]: the render kernel hoists the first half out of its 4-pixel groups
+    return v3(fmaf(c.R[2], dz, fmaf(c.R[1], dy, c.R[0])), fmaf(c.R[5], dz, fmaf(c.R[4], dy, c.R[3])),
+              fmaf(c.R[8], dz, fmaf(c.R[7], dy, c.R[6])));
 }
 // customized.py:402-404: beyond the far plane = no hit = +inf; clip at 4.5 m; / 4.5
 AGX_HD float normalize_depth(float t) {

@@ -92,15 +92,40 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
     bool ball_near = false;  // CTA-uniform: the goal ball can only show up within the far plane's reach
     if (TASK == AGX_TASK_PLANNING) ball_near = norm(obj - cam.o) - kBallRadius < 7.5f;
 
-    // ---- pass 1: ray cast (4 consecutive v per thread: one u, float4-aligned)
+    // ---- pass 1: ray cast (4 consecutive v per thread: one u, float4-aligned).  d(u,v) = R (1, dy(u), dz(v)) = A(u) + dz(v) R[:,2]
+    // CTA-uniform screen band of the cube's bounding sphere (r = sqrt(3) x half extent): a parked / far cube cannot show up at
+    // all, a flying one covers a few dozen columns and rows
+    int cu0 = 1, cu1 = 0, cv0 = 1, cv1 = 0;
+    if (TASK == AGX_TASK_AVOID) {
+        const float rad = 1.7320508f * kCubeHalf;
+        const V3 rel = obj - cam.o;
+        if (norm(rel) - rad < 7.5f) {
+            const float xc = dot(rel, v3(cam.R[0], cam.R[3], cam.R[6])), yc = dot(rel, v3(cam.R[1], cam.R[4], cam.R[7])),
+                        zc = dot(rel, v3(cam.R[2], cam.R[5], cam.R[8]));
+            if (xc + rad > 0.0f) {
+                cu0 = 0; cu1 = AGX_CAM_W - 1; cv0 = 0; cv1 = AGX_CAM_H - 1;
+                if (xc - rad > 0.05f) {  // entirely in front of the camera plane: tight band (x2 radius for the perspective stretch)
+                    const float inv = kCamF / (xc - rad), uc = (float)(AGX_CAM_W / 2) - 0.5f - kCamF * yc / xc,
+                                vc = (float)(AGX_CAM_H / 2) - 0.5f - kCamF * zc / xc, pad = 2.0f * rad * inv + fabsf(yc) * rad * inv / xc + 2.0f,
+                                padv = 2.0f * rad * inv + fabsf(zc) * rad * inv / xc + 2.0f;
+                    cu0 = max(0, (int)floorf(uc - pad)); cu1 = min(AGX_CAM_W - 1, (int)ceilf(uc + pad));
+                    cv0 = max(0, (int)floorf(vc - padv)); cv1 = min(AGX_CAM_H - 1, (int)ceilf(vc + padv));
+                }
+            }
+        }
+    }
+    const V3 col2 = v3(cam.R[2], cam.R[5], cam.R[8]);
     float lmax = 0.0f;
     for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
         const int u = i4 / AGX_CAM_H, v0 = i4 - u * AGX_CAM_H;
+        const float dy = fdiv((float)(AGX_CAM_W / 2) - (float)u - 0.5f, kCamF);
+        const V3 A = v3(fmaf(cam.R[1], dy, cam.R[0]), fmaf(cam.R[4], dy, cam.R[3]), fmaf(cam.R[7], dy, cam.R[6]));
         float val[4];
         V3 d[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            d[j] = pixel_dir(cam, u, v0 + j);
+            const float dz = fdiv((float)(AGX_CAM_H / 2) - (float)(v0 + j) - 0.5f, kCamF);
+            d[j] = v3(fmaf(col2.x, dz, A.x), fmaf(col2.y, dz, A.y), fmaf(col2.z, dz, A.z));
             val[j] = hit_ground(cam.o, d[j]);
         }
         if (TASK == AGX_TASK_PLANNING) {
@@ -114,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 4; ++j) val[j] = fminf(val[j], hit_sphere(cam.o, d[j], obj, kBallRadius));
             }
-        } else {
+        } else if (u >= cu0 && u <= cu1 && v0 + 3 >= cv0 && v0 <= cv1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) val[j] = fminf(val[j], hit_box(cam.o, d[j], obj, kCubeHalf));
         }
@@ -127,47 +152,63 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
     }
     const float m0 = block_reduce(lmax, true, s_red);
 
-    // ---- pass 2: additive noise; pass 3: multiplicative noise (the two normals of a pixel share one Philox word)
-    for (int pass = 0; pass < 2; ++pass) {
-        const float hi = pass == 0 ? m0 : lmax;  // lmax holds the block max of the previous pass (set below)
-        float pmax = 0.0f;
-        for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
-            float4 x = *reinterpret_cast<float4*>(&s_img[i4]);
-            float nz[4];
-            const float* ex = pass == 0 ? io.rand_add : io.rand_mul;
-            if (ex) {
-                const float4 r = *reinterpret_cast<const float4*>(ex + env * (int64_t)kPix + i4);
-                nz[0] = r.x; nz[1] = r.y; nz[2] = r.z; nz[3] = r.w;
-            } else {
-                const U4 w = philox_block(ph, 4u, (uint32_t)(i4 >> 2));
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float z0, z1;
-                    box_muller16(ww[j], &z0, &z1);
-                    nz[j] = pass == 0 ? 0.1f * z0 : 0.3f * z1 + 1.0f;  // torch.normal(0, .1) / torch.normal(1, .3)
-                }
-            }
-            float y[4] = {x.x, x.y, x.z, x.w};
+    // ---- pass 2: + N(0,0.1), clamp to [0, m0].  In Philox mode one word yields BOTH normals of a pixel: the multiplicative
+    // factor 1 + 0.3 z1 is parked in this env's slice of the OUTPUT image (global memory the kernel owns until pass 4 overwrites
+    // it; 2 CTAs x 148 SMs x 101 KB stay in L2) instead of re-deriving Philox + Box-Muller in pass 3.
+    float* out = io.image + env * (int64_t)kPix;
+    float pmax = 0.0f;
+    for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
+        const float4 x = *reinterpret_cast<float4*>(&s_img[i4]);
+        float add[4];
+        if (io.rand_add) {
+            const float4 r = *reinterpret_cast<const float4*>(io.rand_add + env * (int64_t)kPix + i4);
+            add[0] = r.x; add[1] = r.y; add[2] = r.z; add[3] = r.w;
+        } else {
+            const U4 w = philox_block(ph, 4u, (uint32_t)(i4 >> 2));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            float mul[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float t = pass == 0 ? y[j] + nz[j] : y[j] * nz[j];
-                t = t < 0.0f ? 0.0f : t;  // torch.clamp(., 0, max)
-                t = t > hi ? hi : t;
-                y[j] = t;
-                pmax = fmaxf(pmax, t);
+                float z0, z1;
+                box_muller16(ww[j], &z0, &z1);
+                add[j] = 0.1f * z0;            // torch.normal(0, .1)
+                mul[j] = fmaf(0.3f, z1, 1.0f);  // torch.normal(1, .3)
             }
-            *reinterpret_cast<float4*>(&s_img[i4]) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(out + i4) = make_float4(mul[0], mul[1], mul[2], mul[3]);
         }
-        lmax = block_reduce(pmax, true, s_red);
+        float y[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = y[j] + add[j];
+            t = t < 0.0f ? 0.0f : t;  // torch.clamp(., 0, max)
+            t = t > m0 ? m0 : t;
+            y[j] = t;
+            pmax = fmaxf(pmax, t);
+        }
+        *reinterpret_cast<float4*>(&s_img[i4]) = make_float4(y[0], y[1], y[2], y[3]);
     }
+    const float m1 = block_reduce(pmax, true, s_red);
+
+    // ---- pass 3: x N(1,0.3), clamp to [0, m1] (each thread reads back the factors it parked itself: no fence needed)
+    const float* mul_src = io.rand_mul ? io.rand_mul + env * (int64_t)kPix : out;
+    for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
+        const float4 x = *reinterpret_cast<float4*>(&s_img[i4]);
+        const float4 r = *reinterpret_cast<const float4*>(mul_src + i4);
+        float y[4] = {x.x * r.x, x.y * r.y, x.z * r.z, x.w * r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            y[j] = y[j] < 0.0f ? 0.0f : y[j];
+            y[j] = y[j] > m1 ? m1 : y[j];
+        }
+        *reinterpret_cast<float4*>(&s_img[i4]) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+    __syncthreads();  // pass 4 reads neighbours written by other threads, and overwrites the parked factors
 
     // ---- pass 4: 5x5 correlation, zero padding (F.conv2d(padding=2) on the [212,120] plane) → global, block min
     float kk[25];
 #pragma unroll
     for (int i = 0; i < 25; ++i) kk[i] = s_kern[i];
     float lmin = kInf;
-    float* out = io.image + env * (int64_t)kPix;
     for (int i4 = tid * 4; i4 < kPix; i4 += kThreads * 4) {
         const int u = i4 / AGX_CAM_H, v0 = i4 - u * AGX_CAM_H;
         float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
