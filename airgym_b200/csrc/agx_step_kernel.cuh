@@ -239,7 +239,7 @@ __device__ __forceinline__ void warp_reset(const AgxStepIO& io, bool need, int w
 
 // ---- the fused step kernel ----------------------------------------------------------------------------
 #ifndef AGX_MIN_CTAS
-#define AGX_MIN_CTAS 1
+#define AGX_MIN_CTAS 5  // <= 102 registers: 5 CTAs (20 warps) per SM; hovering/rate needs 96 unspilled, the widest modes spill 16 B
 #endif
 template <int TASK, int MODE, int BLOCK, int PHASE>
 __global__ void __launch_bounds__(BLOCK, AGX_MIN_CTAS)

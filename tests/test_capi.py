@@ -44,6 +44,13 @@ def test_error_paths_return_codes_not_exceptions(built):
     io = _capi.AgxStepIO()
     assert lib.agx_step(C.byref(p), 8, C.byref(io), None) == -1  # null buffers
     assert lib.agx_step(C.byref(p), -1, C.byref(io), None) == -1
+    rio = _capi.AgxRenderIO()
+    assert lib.agx_render_depth(C.byref(p), 8, C.byref(rio), None) == -1  # null buffers
+    assert lib.agx_render_depth(None, 8, C.byref(rio), None) == -1
+    io.phase = 1
+    assert lib.agx_step(C.byref(p), 0, C.byref(io), None) == -1  # hovering has no phases (and null buffers)
+    io.phase = 0
+    assert lib.agx_set_option(b"pdl", 7) == -1 and lib.agx_set_option(b"pdl", -1) == 0
     assert lib.agx_set_option(b"block", 100) == -1
     assert lib.agx_set_option(b"block", 128) == 0
     with pytest.raises(_capi.AgxError):
