@@ -296,6 +296,188 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
     }
 }
 
+// ---- forward on the 5th-generation tensor cores (tcgen05 + TMEM) ---------------------------------------------------------------
+// One CTA = 128 threads = one 128-row tile of the batch at a time (persistent over tiles).  Each layer is ONE accumulation chain of
+// tcgen05.mma.cta_group::1.kind::tf32 instructions (M = 128, N = layer width, K = 8 per instruction) issued by a single thread:
+// A = the activations of the previous layer, B = the layer's weights, both K-major in the canonical no-swizzle shared-memory
+// layout ([K/4 chunks][rows/8][8 rows][16 B]: LBO = byte stride between the two 16-B K-chunks of an instruction, SBO = byte stride
+// between 8-row groups; validated by scripts/micro/umma_probe.cu), D = fp32 accumulators in tensor memory.  Completion reaches the
+// 128 epilogue threads through tcgen05.commit → mbarrier; thread r owns row r = TMEM lane r: tcgen05.ld, + bias, ELU, and the
+// result goes straight back into shared memory as the next layer's A operand (16-byte chunk stores, conflict-free) and, when
+// training, to HBM for the backward.  TMEM columns: layer 1 → [0,64), layer 2 → [64,192), layer 3 → [192,256), heads → [0,16).
+// The mma.sync kernel above spends 44 us on a 32 768-row minibatch (legacy-MMA issue bound); SASS of this one shows UTCMMA / LDTM.
+namespace tc {
+constexpr int kM = 128, kH1 = 64, kH2 = 128, kH3 = 64;
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__host__ __device__ inline int canon(int r, int k, int rows) { return (((k >> 2) * (rows >> 3) + (r >> 3)) * 8 + (r & 7)) * 4 + (k & 3); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);  // version 1 (Blackwell), no swizzle
+}
+// D[128, N] (+)= A[128, K] * B[N, K]^T, issued by ONE thread
+__device__ __forceinline__ void gemm(uint32_t a_base, uint32_t b_base, int N, int K, uint32_t tmem_d) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+    const uint32_t lboA = (kM / 8) * 128, lboB = (uint32_t)(N / 8) * 128;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t da = smem_desc(a_base + ks * 2 * lboA, lboA, 128), db = smem_desc(b_base + ks * 2 * lboB, lboB, 128);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(s32(bar)),
+                 "r"(parity)
+                 : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// make this thread's generic-proxy shared-memory writes visible to the tensor core, and order its TMEM reads before the barrier
+__device__ __forceinline__ void publish_and_sync() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// epilogue of one hidden layer for this thread's row: TMEM cols [col0, col0 + W) → + bias → ELU → next A operand (+ HBM copy)
+template <int W>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ bias, float* a_next, int r,
+                                                float* __restrict__ keep_row) {
+#pragma unroll
+    for (int c0 = 0; c0 < W; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_row + (uint32_t)(col0 + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = elu(v[i] + bias[c0 + i]);
+        if (keep_row) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(keep_row + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(a_next + canon(r, c0 + i, kM)) = make_float4(tf32r(v[i]), tf32r(v[i + 1]), tf32r(v[i + 2]), tf32r(v[i + 3]));
+    }
+}
+
+template <int IN_PAD>
+__global__ void __launch_bounds__(kM, 1)
+agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs, float* __restrict__ mu,
+                          float* __restrict__ value, float* __restrict__ xn_out, float* __restrict__ h1_out, float* __restrict__ h2_out,
+                          float* __restrict__ h3_out) {
+    // shared memory carve (floats); every operand base is 128-byte aligned
+    float* w1 = g_smem;                       // [64 x IN_PAD] canonical
+    float* w2 = w1 + kH1 * IN_PAD;            // [128 x 64]
+    float* w3 = w2 + kH2 * kH1;               // [64 x 128]
+    float* wh = w3 + kH3 * kH2;               // [16 x 64]
+    float* bia = wh + kOutPad * kH3;          // b1 | b2 | b3 | heads = 64 + 128 + 64 + 16
+    float* nrm = bia + (kH1 + kH2 + kH3 + kOutPad);  // input mean | 1 / sqrt(var + eps): 2 x IN_PAD
+    float* X = nrm + 2 * IN_PAD;              // [128 x 128]: A0 (normalised input), later A2
+    float* Y = X + kM * kH2;                  // [128 x 64]:  A1, later A3
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, A = P.actions_num, in_dim = P.in_dim;
+
+    for (int i = tid; i < kH1 * IN_PAD; i += kM) { const int n = i / IN_PAD, k = i % IN_PAD; w1[canon(n, k, kH1)] = k < in_dim ? tf32r(P.w1[n * in_dim + k]) : 0.0f; }
+    for (int i = tid; i < kH2 * kH1; i += kM) w2[canon(i / kH1, i % kH1, kH2)] = tf32r(P.w2[i]);
+    for (int i = tid; i < kH3 * kH2; i += kM) w3[canon(i / kH2, i % kH2, kH3)] = tf32r(P.w3[i]);
+    for (int i = tid; i < kOutPad * kH3; i += kM) {
+        const int n = i / kH3, k = i % kH3;
+        wh[canon(n, k, kOutPad)] = n < A ? tf32r(P.w_mu[n * kH3 + k]) : (n == A ? tf32r(P.w_value[k]) : 0.0f);
+    }
+    for (int i = tid; i < kH1; i += kM) bia[i] = P.b1[i];
+    for (int i = tid; i < kH2; i += kM) bia[kH1 + i] = P.b2[i];
+    for (int i = tid; i < kH3; i += kM) bia[kH1 + kH2 + i] = P.b3[i];
+    for (int i = tid; i < kOutPad; i += kM) bia[kH1 + kH2 + kH3 + i] = i < A ? P.b_mu[i] : (i == A ? P.b_value[0] : 0.0f);
+    for (int i = tid; i < IN_PAD; i += kM) {
+        const bool on = P.in_mean && i < in_dim;
+        nrm[i] = on ? (float)P.in_mean[i] : 0.0f;
+        nrm[IN_PAD + i] = on ? sqrtf((float)P.in_var[i] + 1e-5f) : 1.0f;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync();
+    const uint32_t tmem = tmem_base, tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const int64_t n_tiles = (B + kM - 1) / kM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * kM + tid;
+        const bool ok = row < B;
+        // normalised input row (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80) → A0
+#pragma unroll
+        for (int c0 = 0; c0 < IN_PAD; c0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + i;
+                float x = 0.0f;
+                if (ok && c < in_dim) {
+                    x = obs[row * in_dim + c];
+                    if (P.in_mean) {
+                        x = (x - nrm[c]) / nrm[IN_PAD + c];
+                        x = x < -5.0f ? -5.0f : (x > 5.0f ? 5.0f : x);
+                    }
+                }
+                v[i] = x;
+            }
+            if (xn_out && ok) *reinterpret_cast<float4*>(xn_out + row * IN_PAD + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(X + canon(tid, c0, kM)) = make_float4(tf32r(v[0]), tf32r(v[1]), tf32r(v[2]), tf32r(v[3]));
+        }
+        publish_and_sync();
+        if (tid == 0) { gemm(s32(X), s32(w1), kH1, IN_PAD, tmem + 0); commit(&bar); }
+        wait(&bar, phase); phase ^= 1;
+        hidden_epilogue<kH1>(tmem_row, 0, bia, Y, tid, (h1_out && ok) ? h1_out + row * kH1 : nullptr);
+        publish_and_sync();
+        if (tid == 0) { gemm(s32(Y), s32(w2), kH2, kH1, tmem + 64); commit(&bar); }
+        wait(&bar, phase); phase ^= 1;
+        hidden_epilogue<kH2>(tmem_row, 64, bia + kH1, X, tid, (h2_out && ok) ? h2_out + row * kH2 : nullptr);
+        publish_and_sync();
+        if (tid == 0) { gemm(s32(X), s32(w3), kH3, kH2, tmem + 192); commit(&bar); }
+        wait(&bar, phase); phase ^= 1;
+        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Y, tid, (h3_out && ok) ? h3_out + row * kH3 : nullptr);
+        publish_and_sync();
+        if (tid == 0) { gemm(s32(Y), s32(wh), kOutPad, kH3, tmem + 0); commit(&bar); }
+        wait(&bar, phase); phase ^= 1;
+        {
+            float v[16];
+            tmem_ld16(tmem_row + 0u, v);
+            if (ok) {
+                const float* bh = bia + kH1 + kH2 + kH3;
+                for (int a = 0; a < A; ++a) mu[row * A + a] = v[a] + bh[a];
+                float val = v[4] + bh[4];
+                if (A == 5) val = v[5] + bh[5];
+                value[row] = val;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+template <int IN_PAD>
+constexpr size_t smem_bytes_tc() {
+    return sizeof(float) * (size_t)(kH1 * IN_PAD + kH2 * kH1 + kH3 * kH2 + kOutPad * kH3 + (kH1 + kH2 + kH3 + kOutPad) + 2 * IN_PAD + kM * kH2 + kM * kH3);
+}
+}  // namespace tc
+
 // ---- backward: activation-gradient chain + bias-gradient partials ----------------------------------------------------------------
 template <class D>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -456,6 +638,142 @@ agx_mlp_wgrad_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t 
     }
 }
 
+// ---- wgrad, staged: the fragment loads above walk dz / activation rows with a 4-byte stride pattern straight from L2
+// (79 us per 32 768-row minibatch in the round-1 launch list, 7x its HBM time).  Here the CTA streams its slab through shared
+// memory in 16-row stages with cp.async (16-byte chunks, fully coalesced, double buffered: the copy of stage s+1 flies under the
+// MMAs of stage s) and the warps read their fragments from padded rows (stride = width + 8 floats: the 32 lanes of an A or B
+// fragment hit 32 different banks).  Same work units, same partial layout → same reduce kernel.
+constexpr int kStageRows = 32;
+// Units split BY LAYER between the two CTAs of a slab, so each stages only the four arrays its layers touch:
+// half 0: layer 2 (dz2, h1) + heads (dout, h3) = 9 units; half 1: layer 3 (dz3, h2) + layer 1 (dz1, xn) = 12 units (shipped network).
+template <class D>
+__device__ inline int build_units_by_layer(const D& d, int warp, int half, WUnit (&u)[kMaxUnits]) {
+    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
+    const int layers[2][2] = {{1, 3}, {2, 0}};
+    int n = 0, q = 0;
+    for (int k = 0; k < 2; ++k) {
+        const int l = layers[half][k];
+        for (int o0 = 0; o0 < outs[l]; o0 += 16)
+            for (int i0 = 0; i0 < ins[l]; i0 += 64, ++q)
+                if (q % kWarps == warp && n < kMaxUnits) {
+                    u[n].layer = l; u[n].o0 = o0; u[n].i0 = i0; u[n].nt = (ins[l] - i0) >= 64 ? 8 : (ins[l] - i0) / 8; ++n;
+                }
+    }
+    return n;
+}
+// floats of one stage buffer: the larger of the two halves' four arrays, rows padded by 8 floats
+template <class D>
+struct StageLayout {
+    static constexpr int half0 = kStageRows * ((D::h2 + 8) + (kOutPad + 8) + (D::h1 + 8) + (D::h3 + 8));     // dz2, dout, h1, h3
+    static constexpr int half1 = kStageRows * ((D::h3 + 8) + (D::h1 + 8) + (D::h2 + 8) + (D::in_pad + 8));   // dz3, dz1, h2, xn
+    static constexpr int floats = half0 > half1 ? half0 : half1;
+};
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+    const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled (rows past the end of the slab)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+template <class D>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+agx_mlp_wgrad_staged_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, int64_t rows_per_cta, const float* __restrict__ xn,
+                            const float* __restrict__ h1, const float* __restrict__ h2, const float* __restrict__ h3,
+                            const float* __restrict__ dz1, const float* __restrict__ dz2, const float* __restrict__ dz3,
+                            const float* __restrict__ dout, float* __restrict__ partials, int partial_floats) {
+    using L = StageLayout<D>;
+    const D d = dims_of<D>(P);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* srcs[8] = {dz1, dz2, dz3, dout, xn, h1, h2, h3};
+    const int widths[8] = {D::h1, D::h2, D::h3, kOutPad, D::in_pad, D::h1, D::h2, D::h3};
+    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3};
+    WUnit un[kMaxUnits];
+    const int slab = blockIdx.x / kWgradSplit, half = blockIdx.x % kWgradSplit;
+    const int n_units = build_units_by_layer(d, warp, half, un);
+    float acc[kMaxUnits][8][4];
+#pragma unroll
+    for (int q = 0; q < kMaxUnits; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[q][j][0] = 0.0f; acc[q][j][1] = 0.0f; acc[q][j][2] = 0.0f; acc[q][j][3] = 0.0f; }
+    const int64_t r_begin = (int64_t)slab * rows_per_cta;
+    int64_t r_end = r_begin + rows_per_cta;
+    if (r_end > B) r_end = B;
+    const int n_stages = (int)((r_end - r_begin + kStageRows - 1) / kStageRows);
+    // arrays this half needs, as indices into srcs: [dz of layer A, dz of layer B, activation of A, activation of B]
+    const int need[2][4] = {{1, 3, 5, 7}, {2, 0, 6, 4}};  // half 0: dz2, dout, h1, h3 (layers 2 + heads); half 1: dz3, dz1, h2, xn
+    const int layer_a = half == 0 ? 1 : 2;
+    int offs[4];
+    offs[0] = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) offs[k] = offs[k - 1] + kStageRows * (widths[need[half][k - 1]] + 8);
+
+    auto issue = [&](int s) {  // stage s → buffer s & 1
+        float* buf = g_smem + (s & 1) * L::floats;
+        const int64_t r0 = r_begin + (int64_t)s * kStageRows;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = need[half][k];
+            const int w4 = widths[a] / 4, chunks = kStageRows * w4;
+            for (int c = threadIdx.x; c < chunks; c += kWarps * 32) {
+                const int row = c / w4, col = (c - row * w4) * 4;
+                const bool ok = r0 + row < r_end;
+                cp_async16(buf + offs[k] + row * (widths[a] + 8) + col, srcs[a] + (ok ? (r0 + row) * widths[a] + col : 0), ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (n_stages > 0) issue(0);
+    for (int s = 0; s < n_stages; ++s) {
+        if (s + 1 < n_stages) {
+            issue(s + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* buf = g_smem + (s & 1) * L::floats;
+#pragma unroll
+        for (int kk = 0; kk < kStageRows; kk += 8) {
+#pragma unroll
+            for (int q = 0; q < kMaxUnits; ++q) {
+                if (q < n_units) {
+                    const int l = un[q].layer, ldo = outs[l] + 8, ldi = ins[l] + 8;
+                    const int idx = (l == layer_a) ? 0 : 1;
+                    const float* dz = buf + offs[idx] + kk * ldo + un[q].o0;
+                    const float* a_ = buf + offs[2 + idx] + kk * ldi + un[q].i0;
+                    float a[4];
+                    a[0] = tf32r(dz[(t)*ldo + g]);       a[1] = tf32r(dz[(t)*ldo + g + 8]);
+                    a[2] = tf32r(dz[(t + 4) * ldo + g]); a[3] = tf32r(dz[(t + 4) * ldo + g + 8]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < un[q].nt) {
+                            const float b0 = tf32r(a_[t * ldi + 8 * j + g]), b1 = tf32r(a_[(t + 4) * ldi + 8 * j + g]);
+                            mma_tf32(acc[q][j], a, b0, b1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with this buffer before stage s+2 overwrites it
+    }
+    float* mine = partials + (int64_t)slab * partial_floats;
+#pragma unroll
+    for (int q = 0; q < kMaxUnits; ++q) {
+        if (q < n_units) {
+            const int l = un[q].layer;
+            int base = 0;
+            for (int m = 0; m < l; ++m) base += outs[m] * ins[m];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < un[q].nt) {
+                    const int c = un[q].i0 + 8 * j + 2 * t;
+                    *reinterpret_cast<float2*>(&mine[base + (un[q].o0 + g) * ins[l] + c]) = make_float2(acc[q][j][0], acc[q][j][1]);
+                    *reinterpret_cast<float2*>(&mine[base + (un[q].o0 + g + 8) * ins[l] + c]) = make_float2(acc[q][j][2], acc[q][j][3]);
+                }
+            }
+        }
+    }
+}
+
 // deterministic reduction of the per-CTA partials + scatter into the caller's parameter-gradient tensors
 __global__ void agx_mlp_wgrad_reduce_kernel(const __grid_constant__ AgxMlpParams P, const __grid_constant__ AgxMlpGrads G,
                                             const float* __restrict__ partials, int n_cta_w, int partial_floats,
@@ -513,6 +831,8 @@ using S48 = SDims<48, 64, 128, 64>;  // tracking (48 obs)
 bool is_shipped(const AgxMlpParams* p, int in_pad) { return p->in_pad == in_pad && p->h1 == 64 && p->h2 == 128 && p->h3 == 64; }
 constexpr int kGridMax = 148;
 int g_mlp_dbg = 0;
+int g_fwd_tc = 1;        // agx_mlp_debug(4/5): tcgen05 forward off/on (A/B against the mma.sync kernel)
+int g_wgrad_staged = 1;  // agx_mlp_debug(2/3) switches the staged weight-gradient kernel off/on (A/B)
 constexpr int kWgradGrid = 148;  // batch slabs; each slab is walked by kWgradSplit CTAs
 unsigned grid_for(int64_t B) {
     const int64_t tiles = (B + kRows - 1) / kRows;
@@ -525,7 +845,13 @@ unsigned grid_for(int64_t B) {
 
 extern "C" {
 
-void agx_mlp_debug(int v) { g_mlp_dbg = v; }
+void agx_mlp_debug(int v) {
+    if (v == 2) g_wgrad_staged = 0;
+    else if (v == 3) g_wgrad_staged = 1;
+    else if (v == 4) g_fwd_tc = 0;
+    else if (v == 5) g_fwd_tc = 1;
+    else g_mlp_dbg = v;
+}
 
 int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
                     float* h1_out, float* h2_out, float* h3_out, void* stream) {
@@ -538,10 +864,20 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
         cudaFuncSetAttribute(agx_mlp_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         agx_mlp_forward_kernel<D><<<grid_for(b), kWarps * 32, smem, st>>>(*p, b, obs, mu, value, xn_out, h1_out, h2_out, h3_out, g_mlp_dbg); \
     } while (0)
-    if (is_shipped(p, 32)) AGX_FWD(S32);
-    else if (is_shipped(p, 48)) AGX_FWD(S48);
+#define AGX_FWD_TC(PAD)                                                                                                                  \
+    do {                                                                                                                                 \
+        constexpr int kSm = (int)tc::smem_bytes_tc<PAD>();                                                                               \
+        cudaFuncSetAttribute(tc::agx_mlp_forward_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                      \
+        const int64_t tiles = (b + tc::kM - 1) / tc::kM;                                                                                 \
+        tc::agx_mlp_forward_tc_kernel<PAD><<<(unsigned)(tiles < kGridMax ? tiles : kGridMax), tc::kM, kSm, st>>>(*p, b, obs, mu, value, xn_out, \
+                                                                                                                 h1_out, h2_out, h3_out); \
+    } while (0)
+    const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
+    if (is_shipped(p, 32)) { if (g_fwd_tc && keep_aligned) AGX_FWD_TC(32); else AGX_FWD(S32); }
+    else if (is_shipped(p, 48)) { if (g_fwd_tc && keep_aligned) AGX_FWD_TC(48); else AGX_FWD(S48); }
     else AGX_FWD(Dims);
 #undef AGX_FWD
+#undef AGX_FWD_TC
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_forward: launch failed");
 }
 
@@ -571,12 +907,27 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
     do {                                                                                                                 \
         cudaFuncSetAttribute(agx_mlp_backward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         agx_mlp_backward_kernel<D><<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials); \
-        agx_mlp_wgrad_kernel<D><<<gw, kWarps * 32, 0, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf);   \
+        AGX_WGRAD(D);                                                                                                    \
     } while (0)
-    if (is_shipped(p, 32)) AGX_BWD(S32);
-    else if (is_shipped(p, 48)) AGX_BWD(S48);
-    else AGX_BWD(Dims);
+#define AGX_WGRAD(D) agx_mlp_wgrad_kernel<D><<<gw, kWarps * 32, 0, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf)
+#define AGX_WGRAD_STAGED(D)                                                                                              \
+    do {                                                                                                                 \
+        constexpr int kSm = 2 * StageLayout<D>::floats * (int)sizeof(float);                                             \
+        cudaFuncSetAttribute(agx_mlp_wgrad_staged_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);          \
+        agx_mlp_wgrad_staged_kernel<D><<<gw, kWarps * 32, kSm, st>>>(*p, b, rows, xn, h1, h2, h3, dz1, dz2, dz3, dout, w_partials, pf); \
+    } while (0)
+    if (is_shipped(p, 32)) {
+        cudaFuncSetAttribute(agx_mlp_backward_kernel<S32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        agx_mlp_backward_kernel<S32><<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials);
+        if (g_wgrad_staged) AGX_WGRAD_STAGED(S32); else AGX_WGRAD(S32);
+    } else if (is_shipped(p, 48)) {
+        cudaFuncSetAttribute(agx_mlp_backward_kernel<S48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        agx_mlp_backward_kernel<S48><<<gb, kWarps * 32, smem, st>>>(*p, b, grad_mu, grad_value, h1, h2, h3, dz1, dz2, dz3, dout, b_partials);
+        if (g_wgrad_staged) AGX_WGRAD_STAGED(S48); else AGX_WGRAD(S48);
+    } else AGX_BWD(Dims);
 #undef AGX_BWD
+#undef AGX_WGRAD
+#undef AGX_WGRAD_STAGED
     const unsigned gr = (unsigned)((pf + kBiasSlots + 255) / 256);
     agx_mlp_wgrad_reduce_kernel<<<gr, 256, 0, st>>>(*p, *g, w_partials, (int)n_slabs, pf, b_partials, (int)gb);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward: launch failed");

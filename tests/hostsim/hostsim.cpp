@@ -88,7 +88,7 @@ extern "C" int hostsim_step(const AgxParams* p, int64_t n, const AgxStepIO* io) 
 // Host twin of agx_render_kernel (airgym_b200/csrc/agx_render.cu): same per-pixel functions, explicit noise only.
 extern "C" int hostsim_render(const AgxParams* p, int64_t n, const AgxRenderIO* io) {
     const int W = AGX_CAM_W, H = AGX_CAM_H;
-    std::vector<float> img(W * H), tmp(W * H);
+    std::vector<float> img(W * H);
     for (int64_t env = 0; env < n; ++env) {
         const Camera cam = make_camera(io->state + env * 13);
         const float* aux = io->aux + env * AGX_AUX_MAX;

@@ -76,7 +76,6 @@ def test_ppo_trains_on_image_tasks(task):
     cfg["params"]["seed"] = 1
     r = Runner()
     r.load(cfg)
-    agent_cls_before = None
     r.run({"train": True})
     ag = r.agent
     assert ag.has_cnn and ag.obs_shape == (46,)
