@@ -309,7 +309,7 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
 namespace tc {
 constexpr int kM = 128, kH1 = 64, kH2 = 128, kH3 = 64;
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__host__ __device__ inline int canon(int r, int k, int rows) { return (((k >> 2) * (rows >> 3) + (r >> 3)) * 8 + (r & 7)) * 4 + (k & 3); }
+__host__ __device__ inline int canon(int r, int k, int rows) { return ((k >> 2) * rows + r) * 4 + (k & 3); }  // rows % 8 == 0
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);  // version 1 (Blackwell), no swizzle
@@ -390,12 +390,38 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, A = P.actions_num, in_dim = P.in_dim;
 
-    for (int i = tid; i < kH1 * IN_PAD; i += kM) { const int n = i / IN_PAD, k = i % IN_PAD; w1[canon(n, k, kH1)] = k < in_dim ? tf32r(P.w1[n * in_dim + k]) : 0.0f; }
-    for (int i = tid; i < kH2 * kH1; i += kM) w2[canon(i / kH1, i % kH1, kH2)] = tf32r(P.w2[i]);
-    for (int i = tid; i < kH3 * kH2; i += kM) w3[canon(i / kH2, i % kH2, kH3)] = tf32r(P.w3[i]);
-    for (int i = tid; i < kOutPad * kH3; i += kM) {
-        const int n = i / kH3, k = i % kH3;
-        wh[canon(n, k, kOutPad)] = n < A ? tf32r(P.w_mu[n * kH3 + k]) : (n == A ? tf32r(P.w_value[k]) : 0.0f);
+    // weights → canonical layout, TF32-rounded.  canon(n, k, N) = ((k / 4) * N + n) * 4 + k % 4: one 16-byte chunk per (row, K-chunk);
+    // the loads of a batch of chunks are issued together (an un-unrolled load→store loop would serialise ~150 L2 round trips)
+    auto stage4 = [&](float* dst, const float* __restrict__ src, int N, int K) {  // src rows 16-byte aligned (K % 4 == 0)
+        const int chunks = N * (K >> 2);
+        for (int i0 = tid; i0 < chunks; i0 += kM * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kM;
+                if (i < chunks) { const int kc = i / N, n = i - kc * N; v[u] = *reinterpret_cast<const float4*>(src + n * K + kc * 4); }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kM;
+                if (i < chunks) *reinterpret_cast<float4*>(dst + i * 4) = make_float4(tf32r(v[u].x), tf32r(v[u].y), tf32r(v[u].z), tf32r(v[u].w));
+            }
+        }
+    };
+    stage4(w2, P.w2, kH2, kH1);
+    stage4(w3, P.w3, kH3, kH2);
+    {   // w1: in_dim (18 / 48 / 46) columns per row, zero padded to IN_PAD; heads: [w_mu (A rows) | w_value | 0] as a 16-row operand
+        constexpr int kPer = (kH1 * IN_PAD + kM - 1) / kM;
+        float v[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) { const int i = tid + u * kM, n = i / IN_PAD, k = i - n * IN_PAD; v[u] = (i < kH1 * IN_PAD && k < in_dim) ? P.w1[n * in_dim + k] : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) { const int i = tid + u * kM, n = i / IN_PAD, k = i - n * IN_PAD; if (i < kH1 * IN_PAD) w1[canon(n, k, kH1)] = tf32r(v[u]); }
+        float h[kOutPad * kH3 / kM];
+#pragma unroll
+        for (int u = 0; u < kOutPad * kH3 / kM; ++u) { const int i = tid + u * kM, n = i / kH3, k = i - n * kH3; h[u] = n < A ? P.w_mu[n * kH3 + k] : (n == A ? P.w_value[k] : 0.0f); }
+#pragma unroll
+        for (int u = 0; u < kOutPad * kH3 / kM; ++u) { const int i = tid + u * kM, n = i / kH3, k = i - n * kH3; wh[canon(n, k, kOutPad)] = tf32r(h[u]); }
     }
     for (int i = tid; i < kH1; i += kM) bia[i] = P.b1[i];
     for (int i = tid; i < kH2; i += kM) bia[kH1 + i] = P.b2[i];
@@ -831,7 +857,7 @@ using S48 = SDims<48, 64, 128, 64>;  // tracking (48 obs)
 bool is_shipped(const AgxMlpParams* p, int in_pad) { return p->in_pad == in_pad && p->h1 == 64 && p->h2 == 128 && p->h3 == 64; }
 constexpr int kGridMax = 148;
 int g_mlp_dbg = 0;
-int g_fwd_tc = 1;        // agx_mlp_debug(4/5): tcgen05 forward off/on (A/B against the mma.sync kernel)
+int g_fwd_tc = 1;        // tcgen05 forward: 0 off, 1 inference calls only (default), 2 always — agx_mlp_debug(4/5/6)
 int g_wgrad_staged = 1;  // agx_mlp_debug(2/3) switches the staged weight-gradient kernel off/on (A/B)
 constexpr int kWgradGrid = 148;  // batch slabs; each slab is walked by kWgradSplit CTAs
 unsigned grid_for(int64_t B) {
@@ -850,6 +876,7 @@ void agx_mlp_debug(int v) {
     else if (v == 3) g_wgrad_staged = 1;
     else if (v == 4) g_fwd_tc = 0;
     else if (v == 5) g_fwd_tc = 1;
+    else if (v == 6) g_fwd_tc = 2;
     else g_mlp_dbg = v;
 }
 
@@ -873,8 +900,12 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
                                                                                                                  h1_out, h2_out, h3_out); \
     } while (0)
     const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
-    if (is_shipped(p, 32)) { if (g_fwd_tc && keep_aligned) AGX_FWD_TC(32); else AGX_FWD(S32); }
-    else if (is_shipped(p, 48)) { if (g_fwd_tc && keep_aligned) AGX_FWD_TC(48); else AGX_FWD(S48); }
+    // measured (scripts/mlp_bench.py, B200): tcgen05 31.7 / 56.4 us vs mma.sync 33.1 / 59.0 us at 32 768 / 65 536 rows without the
+    // kept activations (rollout), 37.3 vs 33.5 us with them (update: the row-per-thread epilogue's HBM stores) → default per case
+    const bool w_aligned = (((uintptr_t)p->w2 | (uintptr_t)p->w3) & 15u) == 0;  // the tcgen05 kernel stages W2 / W3 with 16-byte loads
+    const bool use_tc = keep_aligned && w_aligned && (g_fwd_tc == 2 || (g_fwd_tc == 1 && !xn_out));
+    if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }
+    else if (is_shipped(p, 48)) { if (use_tc) AGX_FWD_TC(48); else AGX_FWD(S48); }
     else AGX_FWD(Dims);
 #undef AGX_FWD
 #undef AGX_FWD_TC

@@ -491,7 +491,7 @@ class A2CAgent:
             k = prm.numel()
             state[idx] = {"step": self.opt_step.clone().float().squeeze(), "exp_avg": self.exp_avg[off:off + k].view_as(prm).clone(),
                           "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(prm).clone()}
-            off += k
+            off += (k + 3) // 4 * 4  # parameters sit 16-byte aligned in the flat buffers (model.flatten_parameters)
         groups = [{"lr": self.last_lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": self.hyper.weight_decay,
                    "amsgrad": False, "params": list(range(len(names)))}]
         return {"model": {k: v.clone() for k, v in self.model.state_dict().items()}, "epoch": self.epoch_num, "frame": self.frame,
@@ -500,6 +500,7 @@ class A2CAgent:
     def set_full_state_weights(self, weights, set_epoch=True):
         sd = weights["model"]
         with torch.no_grad():
+            self.flat_params.zero_()  # alignment padding between parameters stays zero
             for k, v in self.model.state_dict().items():
                 v.copy_(sd[k])  # in place: parameters stay views of the flat buffer
         if set_epoch:
@@ -514,7 +515,7 @@ class A2CAgent:
                     self.exp_avg[off:off + k].copy_(s["exp_avg"].reshape(-1))
                     self.exp_avg_sq[off:off + k].copy_(s["exp_avg_sq"].reshape(-1))
                     self.opt_step.fill_(int(s["step"]))
-                off += k
+                off += (k + 3) // 4 * 4
             self.last_lr = float(opt["param_groups"][0]["lr"])
             self.lr_dev.fill_(self.last_lr)
         self.last_mean_rewards = weights.get("last_mean_rewards", -1000000000)

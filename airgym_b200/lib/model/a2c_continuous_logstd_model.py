@@ -89,9 +89,10 @@ class ModelA2CContinuousLogStd(nn.Module):
         """Re-home every parameter (and a pre-allocated grad) as a view of one flat buffer; `extra_grad_slots` floats
         are appended to the grad buffer so scalars (the KL) can ride along in the same all-reduce."""
         ps = list(self.parameters())
-        n = sum(p.numel() for p in ps)
+        al = lambda k: (k + 3) // 4 * 4  # every parameter starts 16-byte aligned (vector loads / bulk copies in the kernels)
+        n = sum(al(p.numel()) for p in ps)
         dev = ps[0].device
-        flat = torch.empty(n, device=dev, dtype=torch.float32)
+        flat = torch.zeros(n, device=dev, dtype=torch.float32)
         grads = torch.zeros(n + extra_grad_slots, device=dev, dtype=torch.float32)
         off = 0
         for p in ps:
@@ -99,7 +100,7 @@ class ModelA2CContinuousLogStd(nn.Module):
             flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = flat[off:off + k].view_as(p.data)
             p.grad = grads[off:off + k].view_as(p.data)
-            off += k
+            off += al(k)
         self.flat_params, self.flat_grads, self.num_flat = flat, grads, n
         return flat, grads
 

@@ -31,7 +31,15 @@ if __name__ == "__main__":
         keep = tuple(torch.zeros(B, d, device="cuda") for d in dims)
         dz = tuple(torch.zeros(B, d, device="cuda") for d in dims[1:]); dout = torch.zeros(B, 16, device="cuda")
         gmu, gv = torch.randn(B, A, device="cuda"), torch.randn(B, device="cuda")
+        import ctypes
+        from airgym_b200 import _capi
+        dbg = _capi.load().agx_mlp_debug
+        dbg.argtypes = [ctypes.c_int]
         with torch.no_grad():
+            dbg(4)  # legacy mma.sync forward
+            out[f"mma_sync_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
+            out[f"mma_sync_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
+            dbg(5)  # tcgen05 forward (default)
             out[f"fused_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"fused_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
             out[f"fused_bwd_wgrad_B{B}_us"] = timeit(lambda: model.fused_backward(gmu, gv, keep, dz, dout, ws))

@@ -220,7 +220,23 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
     dims = model.fused_keep_dims()
     keep = tuple(torch.zeros(B, d, device="cuda") for d in dims)
     mu, value = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda")
-    model.fused_heads(obs, mu, value, keep=keep)
+    import ctypes
+    dbg = _capi.load().agx_mlp_debug
+    dbg.argtypes = [ctypes.c_int]
+    # every forward implementation: mma.sync, tcgen05 for inference calls (default), tcgen05 with kept activations
+    for mode, with_keep in ((4, True), (5, False), (6, True), (5, True)):
+        dbg(mode)
+        mu.zero_(); value.zero_()
+        for k in keep:
+            k.zero_()
+        model.fused_heads(obs, mu, value, keep=keep if with_keep else None)
+        assert_close(mu.cpu(), mu_ref.detach().cpu(), f"mu (mode {mode})", rtol=5e-3, atol=2e-3)
+        assert_close(value.cpu(), v_ref.detach().squeeze(-1).cpu(), f"value (mode {mode})", rtol=5e-3, atol=2e-3)
+        if with_keep:
+            assert_close(keep[0][:, :OBS].cpu(), model.norm_obs(obs).cpu(), "normalised input", rtol=1e-6, atol=1e-6)
+            with torch.no_grad():
+                h1_ref = torch.nn.functional.elu(model.actor_mlp.layers[0](model.norm_obs(obs)))
+            assert_close(keep[1].cpu(), h1_ref.cpu(), f"h1 (mode {mode})", rtol=5e-3, atol=3e-3)
     assert_close(mu.cpu(), mu_ref.detach().cpu(), "mu", rtol=5e-3, atol=2e-3)
     assert_close(value.cpu(), v_ref.detach().squeeze(-1).cpu(), "value", rtol=5e-3, atol=2e-3)
     assert_close(keep[0][:, :OBS].cpu(), model.norm_obs(obs).cpu(), "normalised input", rtol=1e-6, atol=1e-6)
