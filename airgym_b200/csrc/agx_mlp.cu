@@ -315,12 +315,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)1 << 46);  // version 1 (Blackwell), no swizzle
 }
 // D[128, N] (+)= A[128, K] * B[N, K]^T, issued by ONE thread
-__device__ __forceinline__ void gemm(uint32_t a_base, uint32_t b_base, int N, int K, uint32_t tmem_d) {
+__device__ __forceinline__ void gemm(uint32_t a_base, uint32_t b_base, int N, int K, uint32_t tmem_d, bool accumulate_first = false) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
     const uint32_t lboA = (kM / 8) * 128, lboB = (uint32_t)(N / 8) * 128;
     for (int ks = 0; ks < K / 8; ++ks) {
         const uint64_t da = smem_desc(a_base + ks * 2 * lboA, lboA, 128), db = smem_desc(b_base + ks * 2 * lboB, lboB, 128);
-        const uint32_t acc = ks > 0 ? 1u : 0u;
+        const uint32_t acc = (ks > 0 || accumulate_first) ? 1u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
                      "l"(da), "l"(db), "r"(idesc), "r"(acc)
                      : "memory");
@@ -335,11 +335,12 @@ __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
                  : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// make this thread's generic-proxy shared-memory writes visible to the tensor core, and order its TMEM reads before the barrier
-__device__ __forceinline__ void publish_and_sync() {
+// make this thread's generic-proxy shared-memory writes visible to the tensor core, and order its TMEM reads before the barrier;
+// the barrier is the 128-thread named barrier of this thread's tile group (id 1 or 2), or the whole CTA (id 0)
+__device__ __forceinline__ void publish_and_sync(int bar_id, int nthreads) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -361,19 +362,25 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, con
         float v[16];
         tmem_ld16(tmem_row + (uint32_t)(col0 + c0), v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = elu(v[i] + bias[c0 + i]);
+        for (int i = 0; i < 16; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c0 + i);  // broadcast LDS.128
+            v[i] = elu(v[i] + b.x); v[i + 1] = elu(v[i + 1] + b.y); v[i + 2] = elu(v[i + 2] + b.z); v[i + 3] = elu(v[i + 3] + b.w);
+        }
         if (keep_row) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(keep_row + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(a_next + canon(r, c0 + i, kM)) = make_float4(tf32r(v[i]), tf32r(v[i + 1]), tf32r(v[i + 2]), tf32r(v[i + 3]));
+            // fp32 bit patterns go in as they are: kind::tf32 reads the top 19 bits (truncation, <= 1 tf32 ulp; the weights were rounded
+            // once at staging) — cvt.rna.tf32 is a ~6-instruction software sequence on sm_100 and was 30 % of this kernel
+            *reinterpret_cast<float4*>(a_next + canon(r, c0 + i, kM)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
 }
 
+constexpr int kThreads = 2 * kM;  // two 128-thread tile groups per CTA: the MMA / barrier latency of one hides under the epilogue of the other
 template <int IN_PAD>
-__global__ void __launch_bounds__(kM, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs, float* __restrict__ mu,
                           float* __restrict__ value, float* __restrict__ xn_out, float* __restrict__ h1_out, float* __restrict__ h2_out,
                           float* __restrict__ h3_out) {
@@ -383,27 +390,28 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
     float* w3 = w2 + kH2 * kH1;               // [64 x 128]
     float* wh = w3 + kH3 * kH2;               // [16 x 64]
     float* bia = wh + kOutPad * kH3;          // b1 | b2 | b3 | heads = 64 + 128 + 64 + 16
-    float* nrm = bia + (kH1 + kH2 + kH3 + kOutPad);  // input mean | 1 / sqrt(var + eps): 2 x IN_PAD
-    float* X = nrm + 2 * IN_PAD;              // [128 x 128]: A0 (normalised input), later A2
-    float* Y = X + kM * kH2;                  // [128 x 64]:  A1, later A3
-    __shared__ __align__(8) uint64_t bar;
+    float* nrm = bia + (kH1 + kH2 + kH3 + kOutPad);  // input mean | sqrt(var + eps): 2 x IN_PAD
+    float* act = nrm + 2 * IN_PAD;            // per group: Pbuf [128 x 64] (A0, A2[:, :64], A3) | Qbuf [128 x 64] (A1, A2[:, 64:])
+    __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base;
-    const int tid = threadIdx.x, warp = tid >> 5, A = P.actions_num, in_dim = P.in_dim;
-
+    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all >> 7, tid = tid_all & (kM - 1), A = P.actions_num, in_dim = P.in_dim;
+    float* Pbuf = act + group * (2 * kM * kH1);
+    float* Qbuf = Pbuf + kM * kH1;
+    uint64_t* bar = &bars[group];
     // weights → canonical layout, TF32-rounded.  canon(n, k, N) = ((k / 4) * N + n) * 4 + k % 4: one 16-byte chunk per (row, K-chunk);
     // the loads of a batch of chunks are issued together (an un-unrolled load→store loop would serialise ~150 L2 round trips)
     auto stage4 = [&](float* dst, const float* __restrict__ src, int N, int K) {  // src rows 16-byte aligned (K % 4 == 0)
         const int chunks = N * (K >> 2);
-        for (int i0 = tid; i0 < chunks; i0 += kM * 8) {
+        for (int i0 = tid_all; i0 < chunks; i0 += kThreads * 8) {
             float4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * kM;
+                const int i = i0 + u * kThreads;
                 if (i < chunks) { const int kc = i / N, n = i - kc * N; v[u] = *reinterpret_cast<const float4*>(src + n * K + kc * 4); }
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * kM;
+                const int i = i0 + u * kThreads;
                 if (i < chunks) *reinterpret_cast<float4*>(dst + i * 4) = make_float4(tf32r(v[u].x), tf32r(v[u].y), tf32r(v[u].z), tf32r(v[u].w));
             }
         }
@@ -411,43 +419,46 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
     stage4(w2, P.w2, kH2, kH1);
     stage4(w3, P.w3, kH3, kH2);
     {   // w1: in_dim (18 / 48 / 46) columns per row, zero padded to IN_PAD; heads: [w_mu (A rows) | w_value | 0] as a 16-row operand
-        constexpr int kPer = (kH1 * IN_PAD + kM - 1) / kM;
+        constexpr int kPer = (kH1 * IN_PAD + kThreads - 1) / kThreads;
         float v[kPer];
 #pragma unroll
-        for (int u = 0; u < kPer; ++u) { const int i = tid + u * kM, n = i / IN_PAD, k = i - n * IN_PAD; v[u] = (i < kH1 * IN_PAD && k < in_dim) ? P.w1[n * in_dim + k] : 0.0f; }
+        for (int u = 0; u < kPer; ++u) { const int i = tid_all + u * kThreads, n = i / IN_PAD, k = i - n * IN_PAD; v[u] = (i < kH1 * IN_PAD && k < in_dim) ? P.w1[n * in_dim + k] : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < kPer; ++u) { const int i = tid + u * kM, n = i / IN_PAD, k = i - n * IN_PAD; if (i < kH1 * IN_PAD) w1[canon(n, k, kH1)] = tf32r(v[u]); }
-        float h[kOutPad * kH3 / kM];
+        for (int u = 0; u < kPer; ++u) { const int i = tid_all + u * kThreads, n = i / IN_PAD, k = i - n * IN_PAD; if (i < kH1 * IN_PAD) w1[canon(n, k, kH1)] = tf32r(v[u]); }
+        float h[kOutPad * kH3 / kThreads];
 #pragma unroll
-        for (int u = 0; u < kOutPad * kH3 / kM; ++u) { const int i = tid + u * kM, n = i / kH3, k = i - n * kH3; h[u] = n < A ? P.w_mu[n * kH3 + k] : (n == A ? P.w_value[k] : 0.0f); }
+        for (int u = 0; u < kOutPad * kH3 / kThreads; ++u) { const int i = tid_all + u * kThreads, n = i / kH3, k = i - n * kH3; h[u] = n < A ? P.w_mu[n * kH3 + k] : (n == A ? P.w_value[k] : 0.0f); }
 #pragma unroll
-        for (int u = 0; u < kOutPad * kH3 / kM; ++u) { const int i = tid + u * kM, n = i / kH3, k = i - n * kH3; wh[canon(n, k, kOutPad)] = tf32r(h[u]); }
+        for (int u = 0; u < kOutPad * kH3 / kThreads; ++u) { const int i = tid_all + u * kThreads, n = i / kH3, k = i - n * kH3; wh[canon(n, k, kOutPad)] = tf32r(h[u]); }
     }
-    for (int i = tid; i < kH1; i += kM) bia[i] = P.b1[i];
-    for (int i = tid; i < kH2; i += kM) bia[kH1 + i] = P.b2[i];
-    for (int i = tid; i < kH3; i += kM) bia[kH1 + kH2 + i] = P.b3[i];
-    for (int i = tid; i < kOutPad; i += kM) bia[kH1 + kH2 + kH3 + i] = i < A ? P.b_mu[i] : (i == A ? P.b_value[0] : 0.0f);
-    for (int i = tid; i < IN_PAD; i += kM) {
+    for (int i = tid_all; i < kH1; i += kThreads) bia[i] = P.b1[i];
+    for (int i = tid_all; i < kH2; i += kThreads) bia[kH1 + i] = P.b2[i];
+    for (int i = tid_all; i < kH3; i += kThreads) bia[kH1 + kH2 + i] = P.b3[i];
+    for (int i = tid_all; i < kOutPad; i += kThreads) bia[kH1 + kH2 + kH3 + i] = i < A ? P.b_mu[i] : (i == A ? P.b_value[0] : 0.0f);
+    for (int i = tid_all; i < IN_PAD; i += kThreads) {
         const bool on = P.in_mean && i < in_dim;
         nrm[i] = on ? (float)P.in_mean[i] : 0.0f;
         nrm[IN_PAD + i] = on ? sqrtf((float)P.in_var[i] + 1e-5f) : 1.0f;
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
+    if (tid_all == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(256u) : "memory");
+    if (warp_all == 0) {  // the whole tensor memory: 256 columns per tile group
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    publish_and_sync();
-    const uint32_t tmem = tmem_base, tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    publish_and_sync(0, kThreads);
+    const uint32_t tmem = tmem_base + (uint32_t)(group * 256);                      // this group's columns
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp_all & 3) * 32) << 16);       // a warp reaches TMEM lanes 32 (warp % 4) ..
+    const int gbar = 1 + group;
     uint32_t phase = 0;
     const int64_t n_tiles = (B + kM - 1) / kM;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + group; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
         const int64_t row = tile * kM + tid;
         const bool ok = row < B;
-        // normalised input row (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80) → A0
+        // normalised input row (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80) → A0 in Pbuf
 #pragma unroll
         for (int c0 = 0; c0 < IN_PAD; c0 += 4) {
             float v[4];
@@ -465,23 +476,28 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
                 v[i] = x;
             }
             if (xn_out && ok) *reinterpret_cast<float4*>(xn_out + row * IN_PAD + c0) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(X + canon(tid, c0, kM)) = make_float4(tf32r(v[0]), tf32r(v[1]), tf32r(v[2]), tf32r(v[3]));
+            *reinterpret_cast<float4*>(Pbuf + canon(tid, c0, kM)) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        publish_and_sync();
-        if (tid == 0) { gemm(s32(X), s32(w1), kH1, IN_PAD, tmem + 0); commit(&bar); }
-        wait(&bar, phase); phase ^= 1;
-        hidden_epilogue<kH1>(tmem_row, 0, bia, Y, tid, (h1_out && ok) ? h1_out + row * kH1 : nullptr);
-        publish_and_sync();
-        if (tid == 0) { gemm(s32(Y), s32(w2), kH2, kH1, tmem + 64); commit(&bar); }
-        wait(&bar, phase); phase ^= 1;
-        hidden_epilogue<kH2>(tmem_row, 64, bia + kH1, X, tid, (h2_out && ok) ? h2_out + row * kH2 : nullptr);
-        publish_and_sync();
-        if (tid == 0) { gemm(s32(X), s32(w3), kH3, kH2, tmem + 192); commit(&bar); }
-        wait(&bar, phase); phase ^= 1;
-        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Y, tid, (h3_out && ok) ? h3_out + row * kH3 : nullptr);
-        publish_and_sync();
-        if (tid == 0) { gemm(s32(Y), s32(wh), kOutPad, kH3, tmem + 0); commit(&bar); }
-        wait(&bar, phase); phase ^= 1;
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Pbuf), s32(w1), kH1, IN_PAD, tmem + 0); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && ok) ? h1_out + row * kH1 : nullptr);            // A1 → Qbuf
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Qbuf), s32(w2), kH2, kH1, tmem + 64); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        // layer 2's 128 columns leave in two halves so that A2 never needs more than the two 32 KB buffers: the first half goes to
+        // Pbuf and layer 3 starts on it (K-steps 0..7) while the epilogue of the second half fills Qbuf (A1 is dead by now)
+        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && ok) ? h2_out + row * kH2 : nullptr);
+        publish_and_sync(gbar, kM);
+        if (tid == 0) gemm(s32(Pbuf), s32(w3), kH3, kH1, tmem + 192);
+        hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, (h2_out && ok) ? h2_out + row * kH2 + kH1 : nullptr);
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Qbuf), s32(w3) + 8 * 2 * (kH3 / 8) * 128, kH3, kH1, tmem + 192, true); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, (h3_out && ok) ? h3_out + row * kH3 : nullptr);  // A3 → Pbuf
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Pbuf), s32(wh), kOutPad, kH3, tmem + 0); commit(bar); }
+        wait(bar, phase); phase ^= 1;
         {
             float v[16];
             tmem_ld16(tmem_row + 0u, v);
@@ -496,11 +512,11 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    if (warp_all == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 template <int IN_PAD>
 constexpr size_t smem_bytes_tc() {
-    return sizeof(float) * (size_t)(kH1 * IN_PAD + kH2 * kH1 + kH3 * kH2 + kOutPad * kH3 + (kH1 + kH2 + kH3 + kOutPad) + 2 * IN_PAD + kM * kH2 + kM * kH3);
+    return sizeof(float) * (size_t)(kH1 * IN_PAD + kH2 * kH1 + kH3 * kH2 + kOutPad * kH3 + (kH1 + kH2 + kH3 + kOutPad) + 2 * IN_PAD + 2 * (2 * kM * kH1));
 }
 }  // namespace tc
 
@@ -895,9 +911,9 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
     do {                                                                                                                                 \
         constexpr int kSm = (int)tc::smem_bytes_tc<PAD>();                                                                               \
         cudaFuncSetAttribute(tc::agx_mlp_forward_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                      \
-        const int64_t tiles = (b + tc::kM - 1) / tc::kM;                                                                                 \
-        tc::agx_mlp_forward_tc_kernel<PAD><<<(unsigned)(tiles < kGridMax ? tiles : kGridMax), tc::kM, kSm, st>>>(*p, b, obs, mu, value, xn_out, \
-                                                                                                                 h1_out, h2_out, h3_out); \
+        const int64_t pairs = ((b + tc::kM - 1) / tc::kM + 1) / 2;                                                                       \
+        tc::agx_mlp_forward_tc_kernel<PAD><<<(unsigned)(pairs < kGridMax ? pairs : kGridMax), tc::kThreads, kSm, st>>>(*p, b, obs, mu, value,  \
+                                                                                                                       xn_out, h1_out, h2_out, h3_out); \
     } while (0)
     const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
     // measured (scripts/mlp_bench.py, B200): tcgen05 31.7 / 56.4 us vs mma.sync 33.1 / 59.0 us at 32 768 / 65 536 rows without the

@@ -39,7 +39,9 @@ if __name__ == "__main__":
             dbg(4)  # legacy mma.sync forward
             out[f"mma_sync_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"mma_sync_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
-            dbg(5)  # tcgen05 forward (default)
+            dbg(6)  # tcgen05 forward also when the activations are kept
+            out[f"tcgen05_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
+            dbg(5)  # default: tcgen05 for inference calls
             out[f"fused_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"fused_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
             out[f"fused_bwd_wgrad_B{B}_us"] = timeit(lambda: model.fused_backward(gmu, gv, keep, dz, dout, ws))
