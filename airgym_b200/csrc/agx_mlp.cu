@@ -873,7 +873,7 @@ using S48 = SDims<48, 64, 128, 64>;  // tracking (48 obs)
 bool is_shipped(const AgxMlpParams* p, int in_pad) { return p->in_pad == in_pad && p->h1 == 64 && p->h2 == 128 && p->h3 == 64; }
 constexpr int kGridMax = 148;
 int g_mlp_dbg = 0;
-int g_fwd_tc = 1;        // tcgen05 forward: 0 off, 1 inference calls only (default), 2 always — agx_mlp_debug(4/5/6)
+int g_fwd_tc = 2;        // tcgen05 forward: 0 off (mma.sync kernel), 1 inference calls only, 2 always (default) — agx_mlp_debug(4/5/6)
 int g_wgrad_staged = 1;  // agx_mlp_debug(2/3) switches the staged weight-gradient kernel off/on (A/B)
 constexpr int kWgradGrid = 148;  // batch slabs; each slab is walked by kWgradSplit CTAs
 unsigned grid_for(int64_t B) {
@@ -916,8 +916,8 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
                                                                                                                        xn_out, h1_out, h2_out, h3_out); \
     } while (0)
     const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
-    // measured (scripts/mlp_bench.py, B200): tcgen05 31.7 / 56.4 us vs mma.sync 33.1 / 59.0 us at 32 768 / 65 536 rows without the
-    // kept activations (rollout), 37.3 vs 33.5 us with them (update: the row-per-thread epilogue's HBM stores) → default per case
+    // measured (scripts/mlp_bench.py, B200, 32 768 / 65 536 rows): tcgen05 20.6 / 33.5 us vs mma.sync 32.9 / 58.7 us without the kept
+    // activations (rollout), 28.4 / 49.0 vs 33.5 / 63.1 us with them (update)
     const bool w_aligned = (((uintptr_t)p->w2 | (uintptr_t)p->w3) & 15u) == 0;  // the tcgen05 kernel stages W2 / W3 with 16-byte loads
     const bool use_tc = keep_aligned && w_aligned && (g_fwd_tc == 2 || (g_fwd_tc == 1 && !xn_out));
     if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }

@@ -107,7 +107,8 @@ class A2CAgent:
         self.nn_dir = os.path.join(self.experiment_dir, "nn")
         if self.global_rank == 0:
             os.makedirs(self.nn_dir, exist_ok=True)
-        self.use_cuda_graph = config.get("use_cuda_graph", not self.has_cnn)  # the cuDNN encoder is run eagerly by default
+        # camera tasks run eagerly: the render cadence (every cam_every-th step) and the encoder-feature cache are host-side decisions
+        self.use_cuda_graph = config.get("use_cuda_graph", True) and not self.has_cnn
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
         self.algo_observer = config.get("features", {}).get("observer", None)
 
@@ -121,6 +122,7 @@ class A2CAgent:
             # 46-wide trunk input [obs16 | cnn(norm(image))] instead of 101 KB images per sample.  (Deviation, DESIGN.md §9: the
             # reference re-encodes the minibatch images in train mode — BatchNorm batch statistics — during the update.)
             self.image_shape = self.obs_shape["image"]
+            self._img_cache = None
             self.obs_shape = (self.obs_shape["observation"][0] + self.model.feature_dim,)
         self.flat_params, self.flat_grads = self.model.flatten_parameters(extra_grad_slots=_capi.AGX_PPO_STATS)
         self.n_params = self.model.num_flat
@@ -187,11 +189,27 @@ class A2CAgent:
             return obs
         with torch.no_grad():
             self.model.eval()
-            if self.normalize_input and update_image_rms:  # running_mean_std.image sees every image once, like the reference's
-                img = obs["image"]                         # first mini-epoch does (a2c_continuous.py:130-131)
-                self._rms_update(self.model.running_mean_std.running_mean_std["image"], img.reshape(img.shape[0], -1),
-                                 shape=self.image_shape)
-            return self.model.trunk_input(obs)
+            # the camera refreshes every cam_every-th step (customized.py:318-321): between renders the image tensor — and with a
+            # frozen encoder its features — do not change, so the CNN runs once per render and the image statistics are merged
+            # from the cached batch moments on the steps in between (same counts as the reference's per-sample update)
+            fresh = self._img_cache is None or self.env.counter % self.env.cam_every == 0
+            if fresh:
+                img = obs["image"]
+                var, mean = torch.var_mean(img.reshape(img.shape[0], -1), dim=0)
+                feat = self.model.encode_image(img)
+                self._img_cache = (feat, mean.double().reshape(self.image_shape), var.double().reshape(self.image_shape), img.shape[0])
+            feat, mean, var, n = self._img_cache
+            if self.normalize_input and update_image_rms:
+                if self.multi_gpu and self.world_size > 1:  # merge the per-rank moments: [n mean, n (var (n-1)/n + mean^2)]
+                    s = torch.stack((mean * n, var * (n - 1) + mean * mean * n))
+                    self._allreduce(s)
+                    nt = n * self.world_size
+                    gmean = s[0] / nt
+                    gvar = (s[1] - nt * gmean * gmean) / (nt - 1)
+                    self.model.running_mean_std.running_mean_std["image"].update_from_moments(gmean, gvar, nt)
+                else:
+                    self.model.running_mean_std.running_mean_std["image"].update_from_moments(mean, var, n)
+            return torch.cat((obs["observation"], feat), dim=-1)
 
     def env_reset(self):
         self.obs.copy_(self._ingest(self.vec_env.reset(), update_image_rms=False))
@@ -271,21 +289,11 @@ class A2CAgent:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
-    def _rms_update(self, rms, x, shape=None):
+    def _rms_update(self, rms, x):
         """RunningMeanStd train-mode update; with >1 rank the batch moments are merged across ranks first so that
         replicas keep identical statistics (the reference keeps per-rank statistics)."""
-        x64 = x.double()
         n = x.shape[0]
-        if shape is not None:  # flattened image batch: moments back in the buffer's shape
-            var, mean = torch.var_mean(x64, dim=0)
-            if self.multi_gpu and self.world_size > 1:
-                s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
-                self._allreduce(s)
-                k, n = x.shape[1], n * self.world_size
-                mean = s[:k] / n
-                var = (s[k:] - n * mean * mean) / (n - 1)
-            rms.update_from_moments(mean.reshape(shape), var.reshape(shape), n)
-            return
+        x64 = x.double()
         if self.multi_gpu and self.world_size > 1:
             s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
             self._allreduce(s)

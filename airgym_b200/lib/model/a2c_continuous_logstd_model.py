@@ -171,6 +171,13 @@ class ModelA2CContinuousLogStd(nn.Module):
     def denorm_value(self, value):
         return self.value_mean_std(value, denorm=True) if self.normalize_value else value
 
+    def encode_image(self, img):
+        """features of the (normalised) depth image: CNN (:141-142) or the frozen VAE encoder's means (:146-147)"""
+        if self.normalize_input:
+            with torch.no_grad():
+                img = self.running_mean_std.running_mean_std["image"](img)
+        return self.actor_enc.encode(img) if self.has_vae else self.actor_cnn(img)
+
     def trunk_input(self, obs):
         """CNN network: [observation | cnn(norm(image))] (:141-145), un-normalised — what the MLP trunk's input
         normalisation (`running_mean_std.observation`) then sees."""

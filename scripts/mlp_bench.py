@@ -41,7 +41,7 @@ if __name__ == "__main__":
             out[f"mma_sync_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
             dbg(6)  # tcgen05 forward also when the activations are kept
             out[f"tcgen05_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
-            dbg(5)  # default: tcgen05 for inference calls
+            dbg(6)  # default: tcgen05 always
             out[f"fused_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"fused_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
             out[f"fused_bwd_wgrad_B{B}_us"] = timeit(lambda: model.fused_backward(gmu, gv, keep, dz, dout, ws))

@@ -223,8 +223,8 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
     import ctypes
     dbg = _capi.load().agx_mlp_debug
     dbg.argtypes = [ctypes.c_int]
-    # every forward implementation: mma.sync, tcgen05 for inference calls (default), tcgen05 with kept activations
-    for mode, with_keep in ((4, True), (5, False), (6, True), (5, True)):
+    # every forward implementation: mma.sync (4), tcgen05 for inference calls only (5), tcgen05 always (6 = default, last)
+    for mode, with_keep in ((4, True), (5, False), (5, True), (6, False), (6, True)):
         dbg(mode)
         mu.zero_(); value.zero_()
         for k in keep:
