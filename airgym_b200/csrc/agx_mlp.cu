@@ -10,6 +10,7 @@
 // In forward/backward each warp owns a tile of 16 samples end to end (no block-level sync after the weights are staged);
 // shared-memory leading dimensions are padded (+4 / +8 floats) so that the fragment loads are bank-conflict free.
 #include <cuda_runtime.h>
+#include <string.h>
 #include <stdint.h>
 
 #include "agx.h"
@@ -224,12 +225,11 @@ template <class D>
 __global__ void __launch_bounds__(kWarps * 32)
 agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs,
                        float* __restrict__ mu, float* __restrict__ value, float* __restrict__ xn_out,
-                       float* __restrict__ h1_out, float* __restrict__ h2_out, float* __restrict__ h3_out, int dbg) {
+                       float* __restrict__ h1_out, float* __restrict__ h2_out, float* __restrict__ h3_out) {
     const D d = dims_of<D>(P);
     const SmemW W = carve_weights(d, 4);  // ld ≡ 4 (mod 32): conflict-free B fragments of X · W^T
-    if (!(dbg & 1)) stage_weights(P, d, W);
+    stage_weights(P, d, W);
     __syncthreads();
-    if (dbg & 2) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bufA = W.end + warp * (2 * kRows * kActLd), bufB = bufA + kRows * kActLd;  // ping-pong tiles of this warp
     float n_mean[kU], n_sd[kU];  // this lane's input columns: mean and sqrt(var + eps) as float
@@ -265,19 +265,19 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
             }
         }
         __syncwarp();
-        if (!(dbg & 8)) gemm16<true>(bufA, W.w1, W.ld1, d.in_pad, d.h1, bufB, lane);
+        gemm16<true>(bufA, W.w1, W.ld1, d.in_pad, d.h1, bufB, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufB, W.b1, d.h1, lane, h1_out, row0, rows_valid);
+        bias_elu_tile(bufB, W.b1, d.h1, lane, h1_out, row0, rows_valid);
         __syncwarp();
-        if (!(dbg & 8)) gemm16<true>(bufB, W.w2, W.ld2, d.h1, d.h2, bufA, lane);
+        gemm16<true>(bufB, W.w2, W.ld2, d.h1, d.h2, bufA, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufA, W.b2, d.h2, lane, h2_out, row0, rows_valid);
+        bias_elu_tile(bufA, W.b2, d.h2, lane, h2_out, row0, rows_valid);
         __syncwarp();
-        if (!(dbg & 8)) gemm16<true>(bufA, W.w3, W.ld3, d.h2, d.h3, bufB, lane);
+        gemm16<true>(bufA, W.w3, W.ld3, d.h2, d.h3, bufB, lane);
         __syncwarp();
-        if (!(dbg & 4)) bias_elu_tile(bufB, W.b3, d.h3, lane, h3_out, row0, rows_valid);
+        bias_elu_tile(bufB, W.b3, d.h3, lane, h3_out, row0, rows_valid);
         __syncwarp();
-        if (!(dbg & 8)) gemm16<true>(bufB, W.wh, W.ldh, d.h3, kOutPad, bufA, lane);
+        gemm16<true>(bufB, W.wh, W.ldh, d.h3, kOutPad, bufA, lane);
         __syncwarp();
         {
             const int c = lane & 15;
@@ -816,29 +816,44 @@ agx_mlp_wgrad_staged_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, i
     }
 }
 
-// deterministic reduction of the per-CTA partials + scatter into the caller's parameter-gradient tensors
-__global__ void agx_mlp_wgrad_reduce_kernel(const __grid_constant__ AgxMlpParams P, const __grid_constant__ AgxMlpGrads G,
-                                            const float* __restrict__ partials, int n_cta_w, int partial_floats,
-                                            const float* __restrict__ bias_partials, int n_cta_b) {
+// deterministic reduction of the per-CTA partials + scatter into the caller's parameter-gradient tensors.
+// A CTA owns 32 consecutive elements; warp w adds partials w, w + 8, w + 16, ... (independent coalesced 128-B loads, ~19 per
+// thread at 148 slabs instead of a 148-long dependent chain), then warp 0 adds the 8 group sums in group order.
+constexpr int kRedGroups = 8;
+__global__ void __launch_bounds__(32 * kRedGroups)
+agx_mlp_wgrad_reduce_kernel(const __grid_constant__ AgxMlpParams P, const __grid_constant__ AgxMlpGrads G,
+                            const float* __restrict__ partials, int n_cta_w, int partial_floats,
+                            const float* __restrict__ bias_partials, int n_cta_b) {
+    __shared__ float s_sum[kRedGroups][32];
     const Dims d = dims_of<Dims>(P);
-    const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3}, real_in[4] = {d.in_dim, d.h1, d.h2, d.h3};
-    float* gw[3] = {G.gw1, G.gw2, G.gw3};
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < partial_floats) {
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    const bool is_w = e < partial_floats, is_b = !is_w && e - partial_floats < kBiasSlots;
+    const float* src = is_w ? partials + e : bias_partials + (e - partial_floats);
+    const int64_t pitch = is_w ? partial_floats : kBiasSlots;
+    const int count = is_w ? n_cta_w : (is_b ? n_cta_b : 0);
+    float s = 0.0f;
+#pragma unroll 8
+    for (int c = grp; c < count; c += kRedGroups) s += src[(int64_t)c * pitch];
+    s_sum[grp][lane] = s;
+    __syncthreads();
+    if (grp != 0) return;
+    s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kRedGroups; ++k) s += s_sum[k][lane];
+    if (is_w) {
+        const int outs[4] = {d.h1, d.h2, d.h3, kOutPad}, ins[4] = {d.in_pad, d.h1, d.h2, d.h3}, real_in[4] = {d.in_dim, d.h1, d.h2, d.h3};
+        float* gw[3] = {G.gw1, G.gw2, G.gw3};
         int l = 0, base = 0;
         while (l < 3 && e >= base + outs[l] * ins[l]) { base += outs[l] * ins[l]; ++l; }
         const int o = (e - base) / ins[l], i = (e - base) % ins[l];
-        float s = 0.0f;
-        for (int c = 0; c < n_cta_w; ++c) s += partials[(int64_t)c * partial_floats + e];
         if (i < real_in[l]) {
             if (l < 3) gw[l][o * real_in[l] + i] = s;
             else if (o < d.a) G.gw_mu[o * d.h3 + i] = s;
             else if (o == d.a) G.gw_value[i] = s;
         }
-    } else if (e - partial_floats < kBiasSlots) {
+    } else if (is_b) {
         const int i = e - partial_floats;
-        float s = 0.0f;
-        for (int c = 0; c < n_cta_b; ++c) s += bias_partials[(int64_t)c * kBiasSlots + i];
         const int seg = i / kMaxW, c = i % kMaxW;
         if (seg == 0 && c < d.h1) G.gb1[c] = s;
         else if (seg == 1 && c < d.h2) G.gb2[c] = s;
@@ -872,9 +887,8 @@ using S32 = SDims<32, 64, 128, 64>;  // hovering / balloon (18 obs) with the shi
 using S48 = SDims<48, 64, 128, 64>;  // tracking (48 obs)
 bool is_shipped(const AgxMlpParams* p, int in_pad) { return p->in_pad == in_pad && p->h1 == 64 && p->h2 == 128 && p->h3 == 64; }
 constexpr int kGridMax = 148;
-int g_mlp_dbg = 0;
-int g_fwd_tc = 2;        // tcgen05 forward: 0 off (mma.sync kernel), 1 inference calls only, 2 always (default) — agx_mlp_debug(4/5/6)
-int g_wgrad_staged = 1;  // agx_mlp_debug(2/3) switches the staged weight-gradient kernel off/on (A/B)
+int g_fwd_tc = 2;        // tcgen05 forward: 0 off (mma.sync kernel), 1 inference calls only, 2 always (default) — agx_set_option("mlp_forward")
+int g_wgrad_staged = 1;  // agx_set_option("mlp_wgrad_staged") switches the staged weight-gradient kernel off/on (A/B)
 constexpr int kWgradGrid = 148;  // batch slabs; each slab is walked by kWgradSplit CTAs
 unsigned grid_for(int64_t B) {
     const int64_t tiles = (B + kRows - 1) / kRows;
@@ -887,13 +901,15 @@ unsigned grid_for(int64_t B) {
 
 extern "C" {
 
-void agx_mlp_debug(int v) {
-    if (v == 2) g_wgrad_staged = 0;
-    else if (v == 3) g_wgrad_staged = 1;
-    else if (v == 4) g_fwd_tc = 0;
-    else if (v == 5) g_fwd_tc = 1;
-    else if (v == 6) g_fwd_tc = 2;
-    else g_mlp_dbg = v;
+// agx_set_option keys owned by this translation unit: returns 1 when handled, 0 for an unknown key, -1 for a bad value
+int agx_internal_mlp_option(const char* key, int value) {
+    if (!strcmp(key, "mlp_forward")) {  // 0 TF32 mma.sync kernel, 1 tcgen05 for inference calls only, 2 tcgen05 always (default)
+        if (value < 0 || value > 2) return -1;
+        g_fwd_tc = value;
+        return 1;
+    }
+    if (!strcmp(key, "mlp_wgrad_staged")) { g_wgrad_staged = value ? 1 : 0; return 1; }
+    return 0;
 }
 
 int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
@@ -905,7 +921,7 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
 #define AGX_FWD(D)                                                                                                      \
     do {                                                                                                                \
         cudaFuncSetAttribute(agx_mlp_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        agx_mlp_forward_kernel<D><<<grid_for(b), kWarps * 32, smem, st>>>(*p, b, obs, mu, value, xn_out, h1_out, h2_out, h3_out, g_mlp_dbg); \
+        agx_mlp_forward_kernel<D><<<grid_for(b), kWarps * 32, smem, st>>>(*p, b, obs, mu, value, xn_out, h1_out, h2_out, h3_out); \
     } while (0)
 #define AGX_FWD_TC(PAD)                                                                                                                  \
     do {                                                                                                                                 \
@@ -975,8 +991,8 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
 #undef AGX_BWD
 #undef AGX_WGRAD
 #undef AGX_WGRAD_STAGED
-    const unsigned gr = (unsigned)((pf + kBiasSlots + 255) / 256);
-    agx_mlp_wgrad_reduce_kernel<<<gr, 256, 0, st>>>(*p, *g, w_partials, (int)n_slabs, pf, b_partials, (int)gb);
+    const unsigned gr = (unsigned)((pf + kBiasSlots + 31) / 32);
+    agx_mlp_wgrad_reduce_kernel<<<gr, 32 * kRedGroups, 0, st>>>(*p, *g, w_partials, (int)n_slabs, pf, b_partials, (int)gb);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward: launch failed");
 }
 

@@ -2,6 +2,8 @@
 // All three are bandwidth-/latency-trivial next to the env step; the point of fusing them is to remove the hundreds
 // of tiny torch launches and every host sync (.item()) from the update loop so that it can live in one CUDA graph.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
 #include <stdio.h>
 
 #include "agx.h"
@@ -77,21 +79,36 @@ agx_ppo_loss_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t b, const flo
 #pragma unroll
     for (int i = 0; i < kPartial; ++i) acc[i] = 0.0f;
     const float inv_b = 1.0f / (float)b;
+    const bool vec4 = ((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(actions) | reinterpret_cast<uintptr_t>(old_mu) |
+                        reinterpret_cast<uintptr_t>(old_sigma) | reinterpret_cast<uintptr_t>(grad_mu)) & 15) == 0;
     for (int64_t s = (int64_t)blockIdx.x * kLossBlock + threadIdx.x; s < b; s += (int64_t)gridDim.x * kLossBlock) {
         float m[agx::kMaxAct], ac[agx::kMaxAct], om[agx::kMaxAct], os[agx::kMaxAct];
 #pragma unroll
-        for (int i = 0; i < agx::kMaxAct; ++i) {
-            if (i < A) { m[i] = mu[s * A + i]; ac[i] = actions[s * A + i]; om[i] = old_mu[s * A + i]; os[i] = old_sigma[s * A + i]; }
-            else { m[i] = 0; ac[i] = 0; om[i] = 0; os[i] = 1; }
+        for (int i = A; i < agx::kMaxAct; ++i) { m[i] = 0; ac[i] = 0; om[i] = 0; os[i] = 1; }
+        if (A == 4 && vec4) {  // one 16-B access per row and array
+            const float4 a = reinterpret_cast<const float4*>(mu)[s], c = reinterpret_cast<const float4*>(actions)[s];
+            const float4 d = reinterpret_cast<const float4*>(old_mu)[s], f = reinterpret_cast<const float4*>(old_sigma)[s];
+            m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; ac[0] = c.x; ac[1] = c.y; ac[2] = c.z; ac[3] = c.w;
+            om[0] = d.x; om[1] = d.y; om[2] = d.z; om[3] = d.w; os[0] = f.x; os[1] = f.y; os[2] = f.z; os[3] = f.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < A; ++i) { m[i] = mu[s * A + i]; ac[i] = actions[s * A + i]; om[i] = old_mu[s * A + i]; os[i] = old_sigma[s * A + i]; }
         }
         agx::PpoSampleOut o;
         agx::ppo_sample(hp, A, m, ls, value[s], ac, old_neglogp[s], adv[s], returns[s], om, os, o);
 #pragma unroll
-        for (int i = 0; i < A; ++i) {
-            grad_mu[s * A + i] = o.g_mu[i] * inv_b;
-            old_mu[s * A + i] = m[i];          // PPODataset.update_mu_sigma
-            old_sigma[s * A + i] = sig[i];
-            acc[5 + i] += o.g_logstd[i];
+        for (int i = 0; i < A; ++i) acc[5 + i] += o.g_logstd[i];
+        if (A == 4 && vec4) {
+            reinterpret_cast<float4*>(grad_mu)[s] = make_float4(o.g_mu[0] * inv_b, o.g_mu[1] * inv_b, o.g_mu[2] * inv_b, o.g_mu[3] * inv_b);
+            reinterpret_cast<float4*>(old_mu)[s] = make_float4(m[0], m[1], m[2], m[3]);  // PPODataset.update_mu_sigma
+            reinterpret_cast<float4*>(old_sigma)[s] = make_float4(sig[0], sig[1], sig[2], sig[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < A; ++i) {
+                grad_mu[s * A + i] = o.g_mu[i] * inv_b;
+                old_mu[s * A + i] = m[i];          // PPODataset.update_mu_sigma
+                old_sigma[s * A + i] = sig[i];
+            }
         }
         grad_value[s] = o.g_value * inv_b;
         acc[0] += o.a_loss; acc[1] += o.c_loss; acc[2] += o.entropy; acc[3] += o.b_loss; acc[4] += o.kl;
@@ -116,43 +133,59 @@ agx_ppo_loss_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t b, const flo
     __syncthreads();
     if (s_last) {  // fixed-order final reduction → bitwise reproducible
         __threadfence();
-        if (threadIdx.x < 5 + A) {
+        for (int i = warp; i < 5 + A; i += kLossBlock / 32) {  // one warp per statistic: strided partial sums, then a fixed xor tree
             float v = 0.0f;
-            for (unsigned int c = 0; c < gridDim.x; ++c) v += partials[(int64_t)c * kPartial + threadIdx.x];
-            if (threadIdx.x < 5) stats[threadIdx.x] = v * inv_b;
-            else grad_logstd[threadIdx.x - 5] = v * inv_b - hp.entropy_coef;  // d(-coef * mean entropy)/d logstd_i = -coef
+            for (unsigned int c = lane; c < gridDim.x; c += 32) v += __ldcg(partials + (int64_t)c * kPartial + i);
+            v = warp_sum(v);
+            if (lane == 0) {
+                if (i < 5) stats[i] = v * inv_b;
+                else grad_logstd[i - 5] = v * inv_b - hp.entropy_coef;  // d(-coef * mean entropy)/d logstd_i = -coef
+            }
         }
         if (threadIdx.x == 0) *ticket = 0;
     }
 }
 
-// ---- fused grad-scale + clip_grad_norm_ + Adam + adaptive LR (single CTA) ------------------------------------------
+// ---- fused grad-scale + clip_grad_norm_ + Adam + adaptive LR (one thread-block cluster) ---------------------------
+// One SM's load/store path bounds a single-CTA version (4 arrays in, 3 out through one SM: 17 us for 47 k parameters), so the
+// update runs as ONE cluster of 8 CTAs: each CTA reduces the squared norm of its interleaved slice, the 8 partial sums are
+// exchanged through distributed shared memory and added in rank order by every thread (deterministic), then each CTA updates
+// its slice.  lr / step are read before the closing cluster barrier and written after it by rank 0.
 constexpr int kAdamBlock = 1024;
-__global__ void __launch_bounds__(kAdamBlock)
+constexpr int kAdamCluster = 8;
+__global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(kAdamBlock)
 agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __restrict__ p, const float* __restrict__ g,
                 float* __restrict__ m, float* __restrict__ v, float* lr_dev, long long* step_dev, const float* kl_dev,
                 float grad_scale, float* norm_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float s_red[kAdamBlock / 32];
-    __shared__ float s_norm;
+    __shared__ float s_part;
+    const int64_t first = (int64_t)cluster.block_rank() * kAdamBlock + threadIdx.x, stride = (int64_t)kAdamCluster * kAdamBlock;
     float ss = 0.0f;
-    for (int64_t i = threadIdx.x; i < n; i += kAdamBlock) { const float x = g[i] * grad_scale; ss += x * x; }
+    for (int64_t i = first; i < n; i += stride) { const float x = g[i] * grad_scale; ss += x * x; }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
     __syncthreads();
     if (threadIdx.x < 32) {
         float t = threadIdx.x < kAdamBlock / 32 ? s_red[threadIdx.x] : 0.0f;
         t = warp_sum(t);
-        if (threadIdx.x == 0) s_norm = sqrtf(t);
+        if (threadIdx.x == 0) s_part = t;
     }
-    __syncthreads();
-    const float norm = s_norm;
+    cluster.sync();
+    float total = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kAdamCluster; ++r) total += *cluster.map_shared_rank(&s_part, r);
+    const float norm = sqrtf(total);
     float clip = 1.0f;
     if (hp.grad_norm > 0.0f) { clip = hp.grad_norm / (norm + 1e-6f); clip = clip > 1.0f ? 1.0f : clip; }  // clip_grad_norm_
     const long long t = step_dev[0] + 1;
     const float lr = lr_dev[0];
+    const float kl = (hp.adaptive_lr && kl_dev) ? kl_dev[0] : 0.0f;
     const float bc1 = 1.0f - powf(hp.beta1, (float)t), bc2 = 1.0f - powf(hp.beta2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-    for (int64_t i = threadIdx.x; i < n; i += kAdamBlock) {
+#pragma unroll 2
+    for (int64_t i = first; i < n; i += stride) {
         float gi = g[i] * grad_scale * clip;
         const float pi = p[i];
         if (hp.weight_decay != 0.0f) gi += hp.weight_decay * pi;
@@ -161,11 +194,11 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __rest
         m[i] = mi; v[i] = vi;
         p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + hp.eps);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    cluster.sync();  // every CTA has read lr / step and every remote s_part read has completed
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
         step_dev[0] = t;
         if (norm_out) *norm_out = norm;
-        if (hp.adaptive_lr && kl_dev) lr_dev[0] = agx::adaptive_lr(lr, kl_dev[0] * grad_scale, hp.kl_threshold);
+        if (hp.adaptive_lr && kl_dev) lr_dev[0] = agx::adaptive_lr(lr, kl * grad_scale, hp.kl_threshold);
     }
 }
 
@@ -213,7 +246,7 @@ int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const 
                   float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale, float* grad_norm_out, void* stream) {
     if (!hp || n_params <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev)
         return fail_ppo(AGX_ERR_ARG, "agx_adam_step: bad argument");
-    agx_adam_kernel<<<1, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    agx_adam_kernel<<<kAdamCluster, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         *hp, n_params, params, grads, exp_avg, exp_avg_sq, lr_dev, reinterpret_cast<long long*>(step_dev), kl_dev, grad_scale,
         grad_norm_out);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_adam_step: launch failed");

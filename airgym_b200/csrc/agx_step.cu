@@ -46,6 +46,7 @@ extern template int agx_dispatch_task<AGX_TASK_PLANNING>(const AgxParams&, int64
 using namespace agxk;
 
 int agx_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+extern "C" int agx_internal_mlp_option(const char* key, int value);  // agx_mlp.cu
 
 namespace {
 
@@ -92,6 +93,9 @@ int agx_set_option(const char* key, int value) {
         g_pdl = value;
         return AGX_OK;
     }
+    const int r = agx_internal_mlp_option(key, value);
+    if (r == 1) return AGX_OK;
+    if (r < 0) return fail(AGX_ERR_ARG, "agx_set_option: bad value for '%s'", key);
     return fail(AGX_ERR_ARG, "agx_set_option: unknown key '%s'", key);
 }
 

@@ -90,6 +90,11 @@ class Hovering(BaseTask):
         self._io = io
 
     # ------------------------------------------------------------------------------------------------------
+    @property
+    def reward_terms_matrix(self):
+        """[AGX_REWARD_TERMS, N] planes behind extras["item_reward_info"], rows in REWARD_KEYS order (None when not exported)."""
+        return self._reward_terms
+
     def _make_reward_info(self):
         if self._reward_terms is None:
             return {}

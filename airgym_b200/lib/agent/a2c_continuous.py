@@ -105,8 +105,14 @@ class A2CAgent:
         self.train_dir = config.get("train_dir", "runs")
         self.experiment_dir = os.path.join(self.train_dir, self.experiment_name)
         self.nn_dir = os.path.join(self.experiment_dir, "nn")
+        self.summaries_dir = os.path.join(self.experiment_dir, "summaries")
+        self.writer = None
         if self.global_rank == 0:
             os.makedirs(self.nn_dir, exist_ok=True)
+            if config.get("write_summaries", True):  # rank 0 only, a2c_base.py:262-267
+                from torch.utils.tensorboard import SummaryWriter
+                os.makedirs(self.summaries_dir, exist_ok=True)
+                self.writer = SummaryWriter(self.summaries_dir)
         # camera tasks run eagerly: the render cadence (every cam_every-th step) and the encoder-feature cache are host-side decisions
         self.use_cuda_graph = config.get("use_cuda_graph", True) and not self.has_cnn
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
@@ -161,6 +167,7 @@ class A2CAgent:
         self.env_actions = f(N, A)
         self.current_rewards, self.current_shaped_rewards, self.current_lengths = f(N), f(N), f(N)
         self.ep_stats = torch.zeros(4, device=dev, dtype=torch.float64)  # Σreward, Σshaped, Σlength, #episodes (per epoch)
+        self.term_keys, self.term_sums = None, None  # per-epoch Σ over envs and steps of extras["item_reward_info"] (observer)
         self.grad_mu, self.grad_value, self.grad_logstd = f(self.minibatch_size, A), f(self.minibatch_size), f(A)
         self.norm_values, self.norm_returns, self.advantages = f(N * H, 1), f(N * H, 1), f(N * H)
         if self.fused_mlp:
@@ -250,6 +257,28 @@ class A2CAgent:
         self.current_rewards *= nd
         self.current_shaped_rewards *= nd
         self.current_lengths *= nd
+        if self.writer is not None:
+            self._observe_reward_terms(infos)
+
+    def _observe_reward_terms(self, infos):
+        """RLGPUAlgoObserver.process_infos (lib/utils/isaacgym_utils.py:66-71) without the per-step host list: the reward terms
+        are summed into one device vector (graph-safe); after_print_stats' mean over all envs and steps is Σ / (N · steps)."""
+        info = infos.get("item_reward_info") if isinstance(infos, dict) else None
+        if not info:
+            return
+        if self.term_keys is None:
+            self.term_keys = [k for k, v in info.items() if isinstance(v, torch.Tensor)]
+            self.term_zero_keys = [k for k, v in info.items() if not isinstance(v, torch.Tensor)]  # scalar 0 entries (quirk Q7)
+            self.term_sums = torch.zeros(len(self.term_keys) + 1, device=self.ppo_device, dtype=torch.float64)
+            keys = list(getattr(self.vec_env.env, "REWARD_KEYS", ()))
+            m = getattr(self.vec_env.env, "reward_terms_matrix", None)  # [K, N], rows in REWARD_KEYS order: one reduction per step
+            self.term_rows = (torch.tensor([keys.index(k) for k in self.term_keys], device=self.ppo_device)
+                              if m is not None and all(k in keys for k in self.term_keys) else None)
+        if self.term_rows is not None:
+            self.term_sums[:-1] += self.vec_env.env.reward_terms_matrix.sum(1)[self.term_rows]
+        else:
+            self.term_sums[:-1] += torch.stack([info[k].float().sum() for k in self.term_keys])
+        self.term_sums[-1] += 1.0
 
     def _fused_policy(self, obs):
         """get_action_values (a2c_base.py:357-369) through the fused MLP kernel; sampling/neglogp as in the model's forward."""
@@ -412,6 +441,8 @@ class A2CAgent:
         """a2c_continuous.py:78-138"""
         t0 = time.time()
         self.ep_stats.zero_()
+        if self.term_sums is not None:
+            self.term_sums.zero_()
         self.play_steps()
         torch.cuda.synchronize()
         t1 = time.time()
@@ -465,6 +496,8 @@ class A2CAgent:
                    "kl": losses[4], "lr": self.last_lr}
             self.history.append(rec)
             should_exit = False
+            if self.writer is not None:
+                self.write_stats(rec, total_time, ep)
             if self.global_rank == 0:
                 if self.print_stats:
                     print(f"fps step and policy inference: {rec['fps_step_inference']:.0f} fps total: {rec['fps_total']:.0f} "
@@ -490,6 +523,40 @@ class A2CAgent:
                 should_exit = bool(flag.item())
             if should_exit:
                 return self.last_mean_rewards, self.epoch_num
+
+    def write_stats(self, rec, total_time, ep):
+        """TensorBoard scalars under the reference's tags: a2c_base.py:318-336 (performance/losses/info), a2c_continuous.py:
+        220-242 (bounds loss, rewards, episode lengths) and the observer's Episode/<reward term> means (isaacgym_utils.py:86-99).
+        step_time is not separable from policy inference inside one graph replay, so performance/step_* repeat play_time."""
+        w, frame, epoch = self.writer, rec["frame"], rec["epoch"]
+        curr_frames = self.batch_size * self.world_size
+        w.add_scalar("performance/step_inference_rl_update_fps", rec["fps_total"], frame)
+        w.add_scalar("performance/step_inference_fps", rec["fps_step_inference"], frame)
+        w.add_scalar("performance/step_fps", curr_frames / rec["play_time"], frame)
+        w.add_scalar("performance/rl_update_time", rec["update_time"], frame)
+        w.add_scalar("performance/step_inference_time", rec["play_time"], frame)
+        w.add_scalar("performance/step_time", rec["play_time"], frame)
+        w.add_scalar("losses/a_loss", rec["a_loss"], frame)
+        w.add_scalar("losses/c_loss", rec["c_loss"], frame)
+        w.add_scalar("losses/entropy", rec["entropy"], frame)
+        w.add_scalar("losses/bounds_loss", rec["b_loss"], frame)
+        w.add_scalar("info/last_lr", rec["lr"], frame)
+        w.add_scalar("info/lr_mul", 1.0, frame)
+        w.add_scalar("info/e_clip", self.hyper.e_clip, frame)
+        w.add_scalar("info/kl", rec["kl"], frame)
+        w.add_scalar("info/epochs", epoch, frame)
+        if self.term_sums is not None:
+            sums = self.term_sums.tolist()
+            denom = max(sums[-1], 1.0) * self.num_actors
+            for k, v in zip(self.term_keys, sums[:-1]):
+                w.add_scalar("Episode/" + k, v / denom, epoch)
+            for k in self.term_zero_keys:
+                w.add_scalar("Episode/" + k, 0.0, epoch)
+        if ep[3] > 0:
+            for tag, val in (("rewards", ep[0] / ep[3]), ("shaped_rewards", ep[1] / ep[3]), ("episode_lengths", ep[2] / ep[3])):
+                w.add_scalar(tag + "/step", val, frame)
+                w.add_scalar(tag + "/iter", val, epoch)
+                w.add_scalar(tag + "/time", val, total_time)
 
     # ---- checkpoints: reference key layout (a2c_base.py:528-577, torch_ext.py:74-84) ------------------------------------------
     def get_full_state_weights(self):

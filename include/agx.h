@@ -194,7 +194,9 @@ int         agx_sizeof_step_io(void);
  * about one wave, else off), 0 off, 1 trigger at entry / wait at entry, 2 trigger before the stores, 3 noise-first — the
  * step's state-independent prologue (Philox counter, observation noise, L2 prefetch hints for its inputs) runs while the
  * previous kernel of the stream is still executing; every global read or write of caller data happens after
- * griddepcontrol.wait, so stream order of all memory effects is unchanged. */
+ * griddepcontrol.wait, so stream order of all memory effects is unchanged.
+ * "mlp_forward" = 0 TF32 mma.sync kernel | 1 tcgen05 + TMEM kernel for inference calls only | 2 tcgen05 always (default);
+ * "mlp_wgrad_staged" = 0|1 (cp.async-staged weight-gradient kernel). */
 int agx_set_option(const char* key, int value);
 
 /* Fill `p` with the defaults of (task, ctl_mode): replaces the reference's cfg classes + the

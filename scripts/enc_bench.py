@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Depth-encoder timing probe (row f3): CNNFeatureExtractor forward on [N,1,212,120] images, eval-mode BatchNorm.
+python scripts/enc_bench.py [--n 8192]  → ms per encode for torch/cuDNN fp32, cuDNN with TF32, and the native kernel if built."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from airgym_b200.lib.network.cnn import CNNFeatureExtractor  # noqa: E402
+
+
+def timed(fn, iters=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=8192)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    net = CNNFeatureExtractor(30).cuda().eval()
+    x = torch.rand(a.n, 1, 212, 120, device="cuda")
+    out = {"n": a.n}
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        out["cudnn_fp32_ms"] = timed(lambda: net(x))
+        torch.backends.cudnn.allow_tf32 = True
+        out["cudnn_tf32_ms"] = timed(lambda: net(x))
+        xc = x.contiguous(memory_format=torch.channels_last)
+        netc = net.to(memory_format=torch.channels_last)
+        out["cudnn_tf32_nhwc_ms"] = timed(lambda: netc(xc))
+        try:
+            from airgym_b200.lib.network.cnn import native_encode
+            ref = net(x[:256])
+            got = native_encode(net, x[:256])
+            out["native_max_abs_err"] = float((got - ref).abs().max())
+            out["native_ms"] = timed(lambda: native_encode(net, x))
+        except ImportError:
+            pass
+    print(json.dumps(out))

@@ -31,17 +31,15 @@ if __name__ == "__main__":
         keep = tuple(torch.zeros(B, d, device="cuda") for d in dims)
         dz = tuple(torch.zeros(B, d, device="cuda") for d in dims[1:]); dout = torch.zeros(B, 16, device="cuda")
         gmu, gv = torch.randn(B, A, device="cuda"), torch.randn(B, device="cuda")
-        import ctypes
         from airgym_b200 import _capi
-        dbg = _capi.load().agx_mlp_debug
-        dbg.argtypes = [ctypes.c_int]
+        dbg = lambda m: _capi.load().agx_set_option(b"mlp_forward", m)
         with torch.no_grad():
-            dbg(4)  # legacy mma.sync forward
+            dbg(0)  # legacy mma.sync forward
             out[f"mma_sync_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"mma_sync_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
-            dbg(6)  # tcgen05 forward also when the activations are kept
+            dbg(2)  # tcgen05 forward also when the activations are kept
             out[f"tcgen05_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
-            dbg(6)  # default: tcgen05 always
+            dbg(2)  # default: tcgen05 always
             out[f"fused_fwd_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val))
             out[f"fused_fwd_keep_B{B}_us"] = timeit(lambda: model.fused_heads(obs, mu, val, keep=keep))
             out[f"fused_bwd_wgrad_B{B}_us"] = timeit(lambda: model.fused_backward(gmu, gv, keep, dz, dout, ws))

@@ -26,7 +26,7 @@ if __name__ == "__main__":
     cfg = scale_minibatch(default_ppo_config(a.task), a.num_envs)
     c = cfg["params"]["config"]
     c.update(max_epochs=a.epochs, use_cuda_graph=not a.no_graph, print_stats=False, save_frequency=0, save_best_after=10**9,
-             train_dir="/tmp/agx_runs", multi_gpu=world > 1)
+             train_dir="/tmp/agx_runs", multi_gpu=world > 1, write_summaries=False)
     c["env_config"].update(ctl_mode=a.ctl_mode, num_envs=a.num_envs, seed=a.seed)
     cfg["params"]["seed"] = a.seed
     r = Runner()

@@ -195,6 +195,18 @@ def test_trainer_end_to_end_learns_and_checkpoints(built, tmp_path, graph, fused
     r.agent.flat_params.add_(1.0)
     r.agent.restore(ck)
     assert torch.equal(r.agent.flat_params, before)
+    # TensorBoard scalars under the reference's tags (a2c_base.py:318-336, isaacgym_utils.py:86-99)
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    r.agent.writer.flush()
+    acc = EventAccumulator(r.agent.summaries_dir)
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    assert {"performance/step_inference_rl_update_fps", "losses/a_loss", "losses/c_loss", "losses/entropy", "losses/bounds_loss",
+            "info/last_lr", "info/kl", "info/epochs", "rewards/step", "rewards/iter", "episode_lengths/step",
+            "Episode/pos_reward", "Episode/ups_reward", "Episode/thrust_reward", "Episode/reward"} <= tags
+    assert len(acc.Scalars("losses/a_loss")) == 12 and acc.Scalars("info/epochs")[-1].step == hist[-1]["frame"]
+    ev = acc.Scalars("Episode/pos_reward")
+    assert len(ev) == 12 and all(np.isfinite(e.value) and 0.0 < e.value <= 1.5 for e in ev)
 
 
 @pytest.mark.parametrize("task,B", [("hovering", 2048), ("tracking", 1000), ("hovering", 65536), ("hovering", 8)])
@@ -220,12 +232,9 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
     dims = model.fused_keep_dims()
     keep = tuple(torch.zeros(B, d, device="cuda") for d in dims)
     mu, value = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda")
-    import ctypes
-    dbg = _capi.load().agx_mlp_debug
-    dbg.argtypes = [ctypes.c_int]
-    # every forward implementation: mma.sync (4), tcgen05 for inference calls only (5), tcgen05 always (6 = default, last)
-    for mode, with_keep in ((4, True), (5, False), (5, True), (6, False), (6, True)):
-        dbg(mode)
+    # every forward implementation: mma.sync (0), tcgen05 for inference calls only (1), tcgen05 always (2 = default, last)
+    for mode, with_keep in ((0, True), (1, False), (1, True), (2, False), (2, True)):
+        _capi.check(_capi.load().agx_set_option(b"mlp_forward", mode))
         mu.zero_(); value.zero_()
         for k in keep:
             k.zero_()
