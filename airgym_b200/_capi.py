@@ -93,6 +93,11 @@ class AgxMlpGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("gw1", "gb1", "gw2", "gb2", "gw3", "gb3", "gw_mu", "gb_mu", "gw_value", "gb_value")]
 
 
+class AgxCnnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "s1", "t1", "w2", "b2", "s2", "t2", "w3", "b3", "s3", "t3", "wfc", "bfc")] + [
+        ("feature_dim", C.c_int32), ("_pad", C.c_int32)]
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -121,6 +126,9 @@ def bind(lib):
     lib.agx_mlp_workspace_floats.argtypes = [C.POINTER(AgxMlpParams)]
     lib.agx_mlp_workspace_floats.restype = C.c_int64
     lib.agx_mlp_backward.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
+    lib.agx_sizeof_cnn_params.restype = C.c_int
+    lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p]
     return lib
 
 
@@ -128,6 +136,7 @@ EXPORTS = (
     "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_sizeof_render_io", "agx_render_depth", "agx_set_option",
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
+    "agx_sizeof_cnn_params", "agx_cnn_encode",
 )
 
 _lib = None
@@ -145,7 +154,7 @@ def load():
         )
     lib = bind(C.CDLL(LIB_PATH))
     if (lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO)
-            or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO)):
+            or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO) or lib.agx_sizeof_cnn_params() != C.sizeof(AgxCnnParams)):
         raise ImportError("libagx.so struct layout differs from airgym_b200/_capi.py (rebuild the library)")
     _lib = lib
     return lib

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from ... import _capi
 from ..core.running_mean_std import RunningMeanStd, RunningMeanStdObs
-from ..network.cnn import CNNFeatureExtractor
+from ..network.cnn import CNNFeatureExtractor, native_encode
 from ..network.vae_image_encoder import VAEImageEncoder
 
 _ACTS = {"elu": F.elu, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "sin": torch.sin}
@@ -172,7 +172,15 @@ class ModelA2CContinuousLogStd(nn.Module):
         return self.value_mean_std(value, denorm=True) if self.normalize_value else value
 
     def encode_image(self, img):
-        """features of the (normalised) depth image: CNN (:141-142) or the frozen VAE encoder's means (:146-147)"""
+        """features of the (normalised) depth image: CNN (:141-142) or the frozen VAE encoder's means (:146-147).  In eval mode
+        on the GPU the CNN is the libagx kernel, with the image normalisation fused into its load."""
+        if (not self.has_vae and self.actor_cnn.native_ok(img)
+                and not (self.normalize_input and self.running_mean_std.training)):
+            if self.normalize_input:
+                rms = self.running_mean_std.running_mean_std["image"]
+                return native_encode(self.actor_cnn, img, rms.running_mean.float().reshape(-1),
+                                     torch.rsqrt(rms.running_var.float() + rms.epsilon).reshape(-1))
+            return native_encode(self.actor_cnn, img)
         if self.normalize_input:
             with torch.no_grad():
                 img = self.running_mean_std.running_mean_std["image"](img)
@@ -181,12 +189,7 @@ class ModelA2CContinuousLogStd(nn.Module):
     def trunk_input(self, obs):
         """CNN network: [observation | cnn(norm(image))] (:141-145), un-normalised — what the MLP trunk's input
         normalisation (`running_mean_std.observation`) then sees."""
-        img = obs["image"]
-        if self.normalize_input:
-            with torch.no_grad():
-                img = self.running_mean_std.running_mean_std["image"](img)
-        feat = self.actor_enc.encode(img) if self.has_vae else self.actor_cnn(img)
-        return torch.cat((obs["observation"], feat), dim=-1)
+        return torch.cat((obs["observation"], self.encode_image(obs["image"])), dim=-1)
 
     def _apply(self, fn, *a, **k):  # .to(device) / .cuda(): the unregistered VAE encoder follows the module
         out = super()._apply(fn, *a, **k)

@@ -2,9 +2,59 @@
 its checkpoints load key for key (lib/network/cnn.py:3-33: `features.{0,3,6}` convolutions 1→16 (5x5, s2) →32 (3x3, s2) →64
 (3x3, s2), each followed by ReLU then BatchNorm2d `features.{2,5,8}`, global average pool, `fc` 64→feature_dim).
 
-The convolutions here are cuDNN's (library calls through torch): SURVEY.md §8(f) row 3 — hand-written tensor-core kernels for
-this encoder are not built yet; the MLP trunk behind it does run on the libagx kernels."""
+Inference (eval-mode BatchNorm — the only mode the trainer uses: the reference's encoder never receives a gradient, DESIGN.md
+§4.4) runs on the libagx kernel `agx_cnn_encode`: one persistent launch, the whole network per env in
+shared memory, fp32 FMA arithmetic, optional fused per-pixel input normalisation.  Train-mode BatchNorm (batch statistics) is
+not on the product path; calling the module in train mode uses torch's library convolutions."""
+import ctypes as C
+
+import torch
 import torch.nn as nn
+
+from airgym_b200 import _capi
+
+
+def encoder_params(net):
+    """AgxCnnParams over the module's own parameter storage (+ the tensors that must outlive the call).  The eval-mode
+    BatchNorm of each block is folded to scale / shift: s = weight / sqrt(running_var + eps), t = bias - running_mean * s."""
+    f, keep = net.features, []
+    p = _capi.AgxCnnParams()
+    for i, (conv, bn) in enumerate(((f[0], f[2]), (f[3], f[5]), (f[6], f[8])), start=1):
+        with torch.no_grad():
+            s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+            t = (bn.bias - bn.running_mean * s).float().contiguous()
+        w, b = conv.weight.detach().contiguous(), conv.bias.detach().contiguous()
+        keep += [w, b, s, t]
+        for name, ten in (("w", w), ("b", b), ("s", s), ("t", t)):
+            setattr(p, f"{name}{i}", ten.data_ptr())
+    wfc, bfc = net.fc.weight.detach().contiguous(), net.fc.bias.detach().contiguous()
+    keep += [wfc, bfc]
+    p.wfc, p.bfc, p.feature_dim = wfc.data_ptr(), bfc.data_ptr(), net.fc.out_features
+    return p, keep
+
+
+def native_encode(net, x, px_mean=None, px_rstd=None, out=None):
+    """features [N, feature_dim] of images x [N,1,212,120] through agx_cnn_encode; px_mean / px_rstd [212*120] fuse the
+    RunningMeanStd normalisation clamp((x - mean) * rstd, +-5) into the image load.  `out` may be a column slice of a wider
+    row-major buffer (the trunk-input rows)."""
+    assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (1, _capi.AGX_CAM_W, _capi.AGX_CAM_H), x.shape
+    x = x.contiguous()
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty(n, net.fc.out_features, device=x.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.shape == (n, net.fc.out_features) and out.stride(1) == 1
+    p, keep = encoder_params(net)
+    if px_mean is not None:
+        px_mean, px_rstd = px_mean.float().contiguous(), px_rstd.float().contiguous()
+        keep += [px_mean, px_rstd]
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    _capi.check(_capi.load().agx_cnn_encode(C.byref(p), n, x.data_ptr(), px_mean.data_ptr() if px_mean is not None else None,
+                                            px_rstd.data_ptr() if px_rstd is not None else None, out.data_ptr(),
+                                            out.stride(0) if n > 0 else net.fc.out_features, st), "agx_cnn_encode")
+    for t in keep:  # the launch is asynchronous: temporaries must not be recycled by another stream before it ran
+        if t.is_cuda:
+            t.record_stream(torch.cuda.current_stream(x.device))
+    return out
 
 
 class CNNFeatureExtractor(nn.Module):
@@ -18,6 +68,15 @@ class CNNFeatureExtractor(nn.Module):
         )
         self.fc = nn.Linear(64, feature_dim)
 
-    def forward(self, x):
+    def native_ok(self, x):
+        return (not self.training and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+                and tuple(x.shape[1:]) == (1, _capi.AGX_CAM_W, _capi.AGX_CAM_H) and self.fc.out_features <= 64)
+
+    def forward_torch(self, x):
         x = self.features(x)
         return self.fc(x.view(x.size(0), -1))
+
+    def forward(self, x):
+        if self.native_ok(x):
+            return native_encode(self, x)
+        return self.forward_torch(x)

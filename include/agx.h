@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AGX_VERSION 110
+#define AGX_VERSION 120
 
 enum AgxError {
     AGX_OK = 0,
@@ -310,6 +310,29 @@ int64_t agx_mlp_workspace_floats(const AgxMlpParams* p);
 int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
                      const float* xn, const float* h1, const float* h2, const float* h3, float* dz1, float* dz2, float* dz3,
                      float* dout, float* workspace, void* stream);
+
+/* ---- depth-image encoder (row f3) ------------------------------------------------------------------------------------
+ * Replaces the forward of lib/network/cnn.py:3-33 (CNNFeatureExtractor: three stride-2 convolutions, each followed by
+ * ReLU then BatchNorm2d, global average pool, Linear 64 -> feature_dim) in EVAL mode, with the per-pixel input
+ * normalisation of lib/core/running_mean_std.py:62-81 fused into the image load.  All pointers are device memory and
+ * hold the PyTorch parameter tensors as they are (OIHW convolution weights); s* / t* are the eval-mode BatchNorm affine
+ * s = weight / sqrt(running_var + eps), t = bias - running_mean * s, prepared by the caller. */
+typedef struct AgxCnnParams {
+    const float *w1, *b1, *s1, *t1; /* features.0 [16,1,5,5], [16]; features.2 scale / shift [16] */
+    const float *w2, *b2, *s2, *t2; /* features.3 [32,16,3,3], [32]; features.5 [32] */
+    const float *w3, *b3, *s3, *t3; /* features.6 [64,32,3,3], [64]; features.8 [64] */
+    const float *wfc, *bfc;         /* fc [feature_dim,64], [feature_dim] */
+    int32_t feature_dim;            /* 1..64 */
+    int32_t _pad;
+} AgxCnnParams;
+int agx_sizeof_cnn_params(void);
+
+/* image [n,1,AGX_CAM_W,AGX_CAM_H] f32 -> features [n, ld_features] (first feature_dim columns written; ld_features lets
+ * the caller write straight into a wider trunk-input row).  px_mean / px_rstd [AGX_CAM_W*AGX_CAM_H] (both or neither):
+ * each pixel becomes clamp((x - mean) * rstd, +-5) before the first convolution.  One persistent launch, fp32 FMA
+ * arithmetic throughout (no TF32), no activation leaves the SM. */
+int agx_cnn_encode(const AgxCnnParams* p, int64_t n, const float* image, const float* px_mean, const float* px_rstd,
+                   float* features, int64_t ld_features, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Depth-encoder timing probe (row f3): CNNFeatureExtractor forward on [N,1,212,120] images, eval-mode BatchNorm.
-python scripts/enc_bench.py [--n 8192]  → ms per encode for torch/cuDNN fp32, cuDNN with TF32, and the native kernel if built."""
+python scripts/enc_bench.py [--n 8192]  → ms per encode for the libagx kernel (with and without the fused input normalisation) and for torch/cuDNN in fp32 and TF32."""
 import argparse
 import json
 import os
@@ -28,6 +28,7 @@ def timed(fn, iters=5):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--skip_cudnn", action="store_true")
     a = ap.parse_args()
     torch.manual_seed(0)
     net = CNNFeatureExtractor(30).cuda().eval()
@@ -35,18 +36,15 @@ if __name__ == "__main__":
     out = {"n": a.n}
     with torch.no_grad():
         torch.backends.cudnn.allow_tf32 = False
-        out["cudnn_fp32_ms"] = timed(lambda: net(x))
-        torch.backends.cudnn.allow_tf32 = True
-        out["cudnn_tf32_ms"] = timed(lambda: net(x))
-        xc = x.contiguous(memory_format=torch.channels_last)
-        netc = net.to(memory_format=torch.channels_last)
-        out["cudnn_tf32_nhwc_ms"] = timed(lambda: netc(xc))
-        try:
-            from airgym_b200.lib.network.cnn import native_encode
-            ref = net(x[:256])
-            got = native_encode(net, x[:256])
-            out["native_max_abs_err"] = float((got - ref).abs().max())
-            out["native_ms"] = timed(lambda: native_encode(net, x))
-        except ImportError:
-            pass
+        from airgym_b200.lib.network.cnn import native_encode
+        ref = net.forward_torch(x[:256])
+        got = native_encode(net, x[:256])
+        out["native_max_abs_err_vs_cudnn_fp32"] = float((got - ref).abs().max())
+        out["native_ms"] = timed(lambda: native_encode(net, x))
+        mean, rstd = torch.rand(212 * 120, device="cuda"), torch.rand(212 * 120, device="cuda") + 0.5
+        out["native_fused_norm_ms"] = timed(lambda: native_encode(net, x, mean, rstd))
+        if not a.skip_cudnn:
+            out["cudnn_fp32_ms"] = timed(lambda: net.forward_torch(x))
+            torch.backends.cudnn.allow_tf32 = True
+            out["cudnn_tf32_ms"] = timed(lambda: net.forward_torch(x))
     print(json.dumps(out))

@@ -26,6 +26,22 @@ def build(force=False):
     return lib
 
 
+_SO_CNN = os.path.join(_HERE, "libhostsim_cnn.so")
+
+
+def build_cnn(force=False):
+    """Host build of the depth-encoder phase functions (airgym_b200/csrc/agx_cnn.cuh) + the schedule replay."""
+    src = os.path.join(_HERE, "hostsim_cnn.cpp")
+    hdr = os.path.join(_ROOT, "airgym_b200", "csrc", "agx_cnn.cuh")
+    if force or not os.path.exists(_SO_CNN) or os.path.getmtime(_SO_CNN) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                               "-I" + os.path.join(_ROOT, "include"), "-I" + os.path.join(_ROOT, "airgym_b200", "csrc"),
+                               "-o", _SO_CNN, src])
+    lib = C.CDLL(_SO_CNN)
+    lib.hostsim_cnn_encode.argtypes = [C.POINTER(_capi.AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    return lib
+
+
 class HostEnv:
     """Numpy-buffer twin of airgym_b200's env state; `step` runs the host build of the kernel body."""
 
