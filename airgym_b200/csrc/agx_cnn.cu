@@ -28,10 +28,10 @@ agx_cnn_encode_kernel(const __grid_constant__ Weights W, int64_t n, const float*
         for (int strip = 0; strip < kStrips; ++strip) {
             load_image_strip(tid, kThreads, img, px_mean, px_rstd, strip, sm);
             __syncthreads();  // image strip complete; the previous strip's partial sums (aliasing the conv1 strip) are consumed
-            if (tid < kTasks1) conv1_task(tid, strip, sm);
+            conv1_task(tid, strip, sm);
             conv1_pads(tid, kThreads, sm);
             __syncthreads();
-            if (tid < kTasks2) conv2_task(tid, strip, sm);
+            conv2_task(tid, strip, sm);
             __syncthreads();
             if (tid < kTasks3) conv3_task(tid, sm);
             __syncthreads();

@@ -40,10 +40,14 @@ constexpr int kR0 = 2 * kR1 + 3;      // image rows (33): local rl <-> image row
 static_assert(kStrips * kG == kH3, "strips must tile conv3");
 // with these offsets every layer reads local input rows 2*r + ky for its local output row r
 
-// padded row lengths (floats).  Column x of a layer lives at x + pad, pad = 2 / 1 / 1; the rest of the row is zero.
+// padded row lengths (floats).  Column x of a layer lives at x + pad, pad = 2 / 4 / 2, so that a task's output pixels start
+// on a 16- / 8-byte boundary (vector stores); the pad columns are zero.
 constexpr int kLd0 = 124;  // image strip: 2 + 120 + 2; a conv1 task reads 12 floats from 8*xg (max 8*14 + 11 = 123)
-constexpr int kLd1 = 64;   // conv1 strip: 1 + 60 + 3; a conv2 task reads 5 floats from 4*xg (max 60)
-constexpr int kLd2 = 33;   // conv2 strip: 1 + 30 + 2, odd so the three rows of a conv3 warp fall in different banks
+constexpr int kPad1 = 4;
+constexpr int kLd1 = 64;   // conv1 strip: 4 + 60; a conv2 task reads column 4*xg + 3 and the aligned float4 at 4*xg + 4 (max 63)
+constexpr int kPad2 = 2;
+constexpr int kLd2 = 34;   // conv2 strip: 2 + 30 + 2; a conv3 task reads 7 floats from 6*xg + 1 (max 31)
+constexpr int kLdP = 68;   // conv3 partial sums: 64 channels per pixel + 4, so the 16-byte stores of a warp's 15 tiles spread over the banks
 
 // task grids (one task = one thread's register tile): pixels-per-task P along a row x C output channels
 constexpr int kP1 = 4, kCt = 8;
@@ -56,7 +60,11 @@ constexpr int kTasks3 = kTiles3 * (kC3 / kCt) * kKs;                      // 15 
 constexpr int kPix3 = kG * kW3;                                           // 45 conv3 pixels per strip
 constexpr int kThreads = 512;
 constexpr int kPoolSlices = kThreads / kC3;                               // 8
-static_assert(kTasks1 <= kThreads && kTasks2 <= kThreads && kTasks3 <= kThreads, "one round per phase");
+// A warp should hold ONE channel group, so that its weight loads are single-address broadcasts: the tasks of a channel group
+// are padded to whole warps (conv1: 225 -> 256 slots x 2 groups, conv2: 105 -> 128 slots x 4 groups = the 512 threads).
+constexpr int kSlots1 = 256, kSlots2 = 128;
+static_assert(kSlots1 * (kC1 / kCt) == kThreads && kSlots2 * (kC2 / kCt) == kThreads && kTasks3 <= kThreads, "one round per phase");
+static_assert(kSlots1 >= kR1 * (kW1 / kP1) && kSlots2 >= kR2 * (kW2 / kP2), "slots cover the tasks");
 
 // shared-memory map (float offsets)
 constexpr int kOffW1 = 0;                                  // [25 taps][16]
@@ -65,12 +73,12 @@ constexpr int kOffW3 = kOffW2 + kC1 * 9 * kC2;             // [32 ci][9 taps][64
 constexpr int kOffAff = kOffW3 + kC2 * 9 * kC3;            // bias | bn scale | bn shift for the three layers
 constexpr int kAff1 = 0, kAff2 = 3 * kC1, kAff3 = 3 * kC1 + 3 * kC2;
 constexpr int kOffImg = kOffAff + 3 * (kC1 + kC2 + kC3);   // [33][124]
-constexpr int kOffA1 = kOffImg + kR0 * kLd0;               // [16][15][64]; conv3's partial sums [4][45][64] alias it
-constexpr int kOffA2 = kOffA1 + kC1 * kR1 * kLd1;          // [32][7][33]
+constexpr int kOffA1 = kOffImg + kR0 * kLd0;               // [16][15][64]; conv3's partial sums [4][45][68] alias it
+constexpr int kOffA2 = kOffA1 + kC1 * kR1 * kLd1;          // [32][7][34]
 constexpr int kOffPool = ((kOffA2 + kC2 * kR2 * kLd2 + 3) / 4) * 4;  // [8][64] + y[64]
 constexpr int kSmemFloats = kOffPool + kPoolSlices * kC3 + kC3;
-static_assert(kKs * kPix3 * kC3 <= kC1 * kR1 * kLd1, "partials must fit the conv1 strip they alias");
-static_assert(kOffImg % 4 == 0 && kOffA1 % 4 == 0 && kOffW2 % 4 == 0 && kOffW3 % 4 == 0 && kOffAff % 4 == 0, "16-byte aligned regions");
+static_assert(kKs * kPix3 * kLdP <= kC1 * kR1 * kLd1, "partials must fit the conv1 strip they alias");
+static_assert(kOffImg % 4 == 0 && kOffA1 % 4 == 0 && kOffA2 % 2 == 0 && kOffW2 % 4 == 0 && kOffW3 % 4 == 0 && kOffAff % 4 == 0, "16-byte aligned regions");
 static_assert(kSmemFloats * 4 <= 227 * 1024, "shared memory budget");
 
 struct Weights {  // raw PyTorch parameter tensors (device pointers), CNNFeatureExtractor layout (cnn.py:8-29)
@@ -142,9 +150,11 @@ AGXC_HD void load_image_strip(int tid, int nthreads, const float* img, const flo
     }
 }
 
-// ---- phase 2: conv1 + ReLU + BN for 15 rows; task = (row, 4-pixel group, 8-channel group) ----------------------------------------
-AGXC_HD void conv1_task(int task, int strip, float* sm) {
-    const int cg = task % (kC1 / kCt), xg = (task / (kC1 / kCt)) % (kW1 / kP1), r = task / ((kC1 / kCt) * (kW1 / kP1));
+// ---- phase 2: conv1 + ReLU + BN for 15 rows; thread = (8-channel group, slot), slot = (row, 4-pixel group) -------------------------
+AGXC_HD void conv1_task(int tid, int strip, float* sm) {
+    const int cg = tid / kSlots1, slot = tid % kSlots1;
+    if (slot >= kR1 * (kW1 / kP1)) return;
+    const int xg = slot % (kW1 / kP1), r = slot / (kW1 / kP1);
     float acc[kP1][kCt];
 #pragma unroll
     for (int p = 0; p < kP1; ++p)
@@ -173,22 +183,29 @@ AGXC_HD void conv1_task(int task, int strip, float* sm) {
 #pragma unroll
     for (int c = 0; c < kCt; ++c) {
         const int ch = cg * kCt + c;
-        float* out = sm + kOffA1 + (ch * kR1 + r) * kLd1 + 1 + kP1 * xg;
+        float o[kP1];
 #pragma unroll
-        for (int p = 0; p < kP1; ++p) out[p] = valid ? relu_bn(acc[p][c], aff[ch], aff[kC1 + ch], aff[2 * kC1 + ch]) : 0.0f;
+        for (int p = 0; p < kP1; ++p) o[p] = valid ? relu_bn(acc[p][c], aff[ch], aff[kC1 + ch], aff[2 * kC1 + ch]) : 0.0f;
+        st4(sm + kOffA1 + (ch * kR1 + r) * kLd1 + kPad1 + kP1 * xg, o[0], o[1], o[2], o[3]);
     }
 }
-// the conv1 strip's pad columns (0 and 61..63) are rewritten every strip: conv3's partial sums alias the region
+// the conv1 strip's pad columns (0..3) are rewritten every strip: conv3's partial sums alias the region
 AGXC_HD void conv1_pads(int tid, int nthreads, float* sm) {
-    for (int i = tid; i < kC1 * kR1 * 4; i += nthreads) {
-        const int j = i & 3, line = i >> 2;
-        sm[kOffA1 + line * kLd1 + (j == 0 ? 0 : kW1 + j)] = 0.0f;
-    }
+    for (int line = tid; line < kC1 * kR1; line += nthreads) st4(sm + kOffA1 + line * kLd1, 0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// ---- phase 3: conv2 + ReLU + BN for 7 rows; task = (row, 2-pixel group, 8-channel group) -----------------------------------------
-AGXC_HD void conv2_task(int task, int strip, float* sm) {
-    const int cg = task % (kC2 / kCt), xg = (task / (kC2 / kCt)) % (kW2 / kP2), r = task / ((kC2 / kCt) * (kW2 / kP2));
+// ---- phase 3: conv2 + ReLU + BN for 7 rows; thread = (8-channel group, slot), slot = (row, 2-pixel group) -------------------------
+AGXC_HD void st2(float* p, float a, float b) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+AGXC_HD void conv2_task(int tid, int strip, float* sm) {
+    const int cg = tid / kSlots2, slot = tid % kSlots2;
+    if (slot >= kR2 * (kW2 / kP2)) return;
+    const int xg = slot % (kW2 / kP2), r = slot / (kW2 / kP2);
     float acc[kP2][kCt];
 #pragma unroll
     for (int p = 0; p < kP2; ++p)
@@ -198,9 +215,9 @@ AGXC_HD void conv2_task(int task, int strip, float* sm) {
     for (int ci = 0; ci < kC1; ++ci) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const float* row = sm + kOffA1 + (ci * kR1 + 2 * r + ky) * kLd1 + 2 * kP2 * xg;
+            const float* row = sm + kOffA1 + (ci * kR1 + 2 * r + ky) * kLd1 + 2 * kP2 * xg + kPad1;  // column 4*xg of conv1
             const F4 a = ld4(row);
-            const float v[5] = {a.x, a.y, a.z, a.w, row[4]};
+            const float v[5] = {row[-1], a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 float w[kCt];
@@ -218,9 +235,10 @@ AGXC_HD void conv2_task(int task, int strip, float* sm) {
 #pragma unroll
     for (int c = 0; c < kCt; ++c) {
         const int ch = cg * kCt + c;
-        float* out = sm + kOffA2 + (ch * kR2 + r) * kLd2 + 1 + kP2 * xg;
+        float o[kP2];
 #pragma unroll
-        for (int p = 0; p < kP2; ++p) out[p] = valid ? relu_bn(acc[p][c], aff[ch], aff[kC2 + ch], aff[2 * kC2 + ch]) : 0.0f;
+        for (int p = 0; p < kP2; ++p) o[p] = valid ? relu_bn(acc[p][c], aff[ch], aff[kC2 + ch], aff[2 * kC2 + ch]) : 0.0f;
+        st2(sm + kOffA2 + (ch * kR2 + r) * kLd2 + kPad2 + kP2 * xg, o[0], o[1]);
     }
 }
 
@@ -239,7 +257,7 @@ AGXC_HD void conv3_task(int task, float* sm) {
         const int ci = ks * (kC2 / kKs) + cl;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const float* row = sm + kOffA2 + (ci * kR2 + 2 * r + ky) * kLd2 + 2 * kP3 * xg;
+            const float* row = sm + kOffA2 + (ci * kR2 + 2 * r + ky) * kLd2 + 2 * kP3 * xg + kPad2 - 1;
             float v[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) v[i] = row[i];
@@ -256,7 +274,7 @@ AGXC_HD void conv3_task(int task, float* sm) {
     }
 #pragma unroll
     for (int p = 0; p < kP3; ++p) {
-        float* out = sm + kOffA1 + ((ks * kPix3) + r * kW3 + kP3 * xg + p) * kC3 + cg * kCt;
+        float* out = sm + kOffA1 + ((ks * kPix3) + r * kW3 + kP3 * xg + p) * kLdP + cg * kCt;
         st4(out, acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
         st4(out + 4, acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
     }
@@ -270,7 +288,7 @@ AGXC_HD float pool_strip(int tid, const float* sm) {
     for (int pix = q; pix < kPix3; pix += kPoolSlices) {
         float v = bias;
 #pragma unroll
-        for (int ks = 0; ks < kKs; ++ks) v += sm[kOffA1 + (ks * kPix3 + pix) * kC3 + c];
+        for (int ks = 0; ks < kKs; ++ks) v += sm[kOffA1 + (ks * kPix3 + pix) * kLdP + c];
         sum += v > 0.0f ? v : 0.0f;
     }
     return sum;

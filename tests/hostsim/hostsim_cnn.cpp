@@ -24,8 +24,8 @@ extern "C" int hostsim_cnn_encode(const AgxCnnParams* p, int64_t n, const float*
         for (int tid = 0; tid < kThreads; ++tid) pooled[tid] = 0.0f;
         for (int strip = 0; strip < kStrips; ++strip) {
             for (int tid = 0; tid < kThreads; ++tid) load_image_strip(tid, kThreads, img, px_mean, px_rstd, strip, sm);
-            for (int tid = 0; tid < kThreads; ++tid) { if (tid < kTasks1) conv1_task(tid, strip, sm); conv1_pads(tid, kThreads, sm); }
-            for (int tid = 0; tid < kThreads; ++tid) if (tid < kTasks2) conv2_task(tid, strip, sm);
+            for (int tid = 0; tid < kThreads; ++tid) { conv1_task(tid, strip, sm); conv1_pads(tid, kThreads, sm); }
+            for (int tid = 0; tid < kThreads; ++tid) conv2_task(tid, strip, sm);
             for (int tid = 0; tid < kThreads; ++tid) if (tid < kTasks3) conv3_task(tid, sm);
             for (int tid = 0; tid < kThreads; ++tid) pooled[tid] += pool_strip(tid, sm);
         }
