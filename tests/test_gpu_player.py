@@ -39,7 +39,8 @@ def test_reference_checkpoint_loads_and_plays():
         img = model.running_mean_std.running_mean_std["image"](obs["image"])
         x = torch.cat((obs["observation"], model.actor_cnn(img)), -1)
         h = model.actor_mlp(model.running_mean_std.running_mean_std["observation"](x))
-    assert torch.allclose(res["mus"], model.mu(h), atol=1e-6)
+    # the model fuses the image normalisation into the encoder kernel ((x - mean) * rsqrt instead of a division): rounding-level differences
+    assert torch.allclose(res["mus"], model.mu(h), atol=1e-4)
 
 
 def test_pretrained_mlp_checkpoint_initialises_cnn_policy(tmp_path):
