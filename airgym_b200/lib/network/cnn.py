@@ -33,10 +33,10 @@ def encoder_params(net):
     return p, keep
 
 
-def native_encode(net, x, px_mean=None, px_rstd=None, out=None):
+def native_encode(net, x, px_mean=None, px_rstd=None, out=None, lib=None):
     """features [N, feature_dim] of images x [N,1,212,120] through agx_cnn_encode; px_mean / px_rstd [212*120] fuse the
     RunningMeanStd normalisation clamp((x - mean) * rstd, +-5) into the image load.  `out` may be a column slice of a wider
-    row-major buffer (the trunk-input rows)."""
+    row-major buffer (the trunk-input rows); `lib` substitutes another build of libagx (tuning variants, scripts/enc_bench.py)."""
     assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape[1:]) == (1, _capi.AGX_CAM_W, _capi.AGX_CAM_H), x.shape
     x = x.contiguous()
     n = x.shape[0]
@@ -48,13 +48,10 @@ def native_encode(net, x, px_mean=None, px_rstd=None, out=None):
         px_mean, px_rstd = px_mean.float().contiguous(), px_rstd.float().contiguous()
         keep += [px_mean, px_rstd]
     st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-    _capi.check(_capi.load().agx_cnn_encode(C.byref(p), n, x.data_ptr(), px_mean.data_ptr() if px_mean is not None else None,
+    _capi.check((lib or _capi.load()).agx_cnn_encode(C.byref(p), n, x.data_ptr(), px_mean.data_ptr() if px_mean is not None else None,
                                             px_rstd.data_ptr() if px_rstd is not None else None, out.data_ptr(),
                                             out.stride(0) if n > 0 else net.fc.out_features, st), "agx_cnn_encode")
-    for t in keep:  # the launch is asynchronous: temporaries must not be recycled by another stream before it ran
-        if t.is_cuda:
-            t.record_stream(torch.cuda.current_stream(x.device))
-    return out
+    return out  # temporaries were allocated on the launch stream: the caching allocator's stream order keeps them alive long enough
 
 
 class CNNFeatureExtractor(nn.Module):

@@ -29,6 +29,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--skip_cudnn", action="store_true")
+    ap.add_argument("--libs", default="", help="comma-separated variant builds of libagx.so (scripts/build_variant.sh) to A/B")
     a = ap.parse_args()
     torch.manual_seed(0)
     net = CNNFeatureExtractor(30).cuda().eval()
@@ -43,6 +44,17 @@ if __name__ == "__main__":
         out["native_ms"] = timed(lambda: native_encode(net, x))
         mean, rstd = torch.rand(212 * 120, device="cuda"), torch.rand(212 * 120, device="cuda") + 0.5
         out["native_fused_norm_ms"] = timed(lambda: native_encode(net, x, mean, rstd))
+        if a.libs:
+            import ctypes as C
+            from airgym_b200 import _capi
+            torch.backends.cudnn.allow_tf32 = False
+            ref = net.forward_torch(x[:296])
+            for path in a.libs.split(","):
+                lib = _capi.bind(C.CDLL(os.path.abspath(path)))
+                got = native_encode(net, x[:296], lib=lib)
+                torch.cuda.synchronize()
+                out[os.path.basename(path)] = {"max_abs_err": float((got - ref).abs().max()),
+                                               "ms": timed(lambda: native_encode(net, x, lib=lib))}
         if not a.skip_cudnn:
             out["cudnn_fp32_ms"] = timed(lambda: net.forward_torch(x))
             torch.backends.cudnn.allow_tf32 = True
