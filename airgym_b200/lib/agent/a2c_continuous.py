@@ -116,6 +116,10 @@ class A2CAgent:
         # camera tasks run eagerly: the render cadence (every cam_every-th step) and the encoder-feature cache are host-side decisions
         self.use_cuda_graph = config.get("use_cuda_graph", True) and not self.has_cnn
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
+        # With more than one rank the passes that contain an all-reduce (dataset statistics, every minibatch of the update) run
+        # eagerly unless this is set: capturing NCCL collectives inside the CUDA graphs is not yet validated on this stack
+        # (DESIGN.md §7); the rollout graph holds no collective and is always replayed.
+        self.graph_collectives = bool(config.get("graph_collectives", False))
         self.algo_observer = config.get("features", {}).get("observer", None)
 
         keys = {"actions_num": self.actions_num, "input_shape": self.obs_shape, "num_seqs": self.num_actors,
@@ -361,9 +365,15 @@ class A2CAgent:
                 adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         self.advantages.copy_(adv)
 
+    def _graph_ok_with_collectives(self):
+        return self.use_cuda_graph and (self.graph_collectives or not (self.multi_gpu and self.world_size > 1))
+
     def prepare_dataset(self):
         with torch.no_grad():
-            self._run_graphed("dataset", self._prepare_dataset)
+            if self._graph_ok_with_collectives():
+                self._run_graphed("dataset", self._prepare_dataset)
+            else:
+                self._prepare_dataset()
 
     # ---- update ---------------------------------------------------------------------------------------------------------
     def _minibatch(self, i, update_rms):
@@ -448,7 +458,7 @@ class A2CAgent:
         t1 = time.time()
         self.prepare_dataset()
         self.epoch_loss_sums.zero_()
-        graph_update = self.use_cuda_graph and not (self.multi_gpu and self.world_size > 1)
+        graph_update = self._graph_ok_with_collectives()
         for mini_ep in range(self.mini_epochs_num):
             first = mini_ep == 0  # input statistics are only updated during the first mini-epoch (:130-131)
             if graph_update:

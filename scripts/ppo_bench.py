@@ -19,6 +19,7 @@ if __name__ == "__main__":
     ap.add_argument("--num_envs", type=int, default=65536)
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--no_graph", action="store_true")
+    ap.add_argument("--graph_collectives", action="store_true", help="multi-GPU: replay the update from graphs with NCCL inside")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--skip", type=int, default=3, help="epochs excluded from the timing (graph capture / warm-up)")
     a = ap.parse_args()
@@ -26,12 +27,15 @@ if __name__ == "__main__":
     cfg = scale_minibatch(default_ppo_config(a.task), a.num_envs)
     c = cfg["params"]["config"]
     c.update(max_epochs=a.epochs, use_cuda_graph=not a.no_graph, print_stats=False, save_frequency=0, save_best_after=10**9,
-             train_dir="/tmp/agx_runs", multi_gpu=world > 1, write_summaries=False)
+             train_dir="/tmp/agx_runs", multi_gpu=world > 1, write_summaries=False,
+             graph_collectives=a.graph_collectives)
     c["env_config"].update(ctl_mode=a.ctl_mode, num_envs=a.num_envs, seed=a.seed)
     cfg["params"]["seed"] = a.seed
+    import contextlib
     r = Runner()
-    r.load(cfg)
-    r.run({"train": True})
+    with contextlib.redirect_stdout(sys.stderr):  # the trainer's own prints (reference wording) must not mix with the JSON line
+        r.load(cfg)
+        r.run({"train": True})
     if int(os.environ.get("RANK", "0")) == 0:
         h = r.agent.history[a.skip:]
         frames = sum(x["frame"] - (r.agent.history[i + a.skip - 1]["frame"] if i + a.skip > 0 else 0) for i, x in enumerate(h))
