@@ -116,6 +116,34 @@ def _calibrate_threads(orc, a):
     return best, avail
 
 
+def cpu_reference_shaped_steps_per_s(num_envs, cores, budget_s=6.0, min_steps=3):
+    """SURVEY.md 8d's second CPU number: the same oracle step, but with the controller called the way the reference's host
+    calls rlPx4Controller (hovering.py:246-250) — float64 numpy marshalling and a single-threaded per-env C loop
+    (oracle/host_loop) — to show what that boundary costs next to the vectorised restatement."""
+    import torch
+
+    from oracle import QuadSpec, make_oracle
+    from oracle.host_loop import HostLoopRateControl
+
+    torch.manual_seed(0)
+    torch.set_num_threads(cores)
+    spec = QuadSpec(task="hovering", ctl_mode="rate")
+    orc = make_oracle(spec, num_envs, rng="torch")
+    orc.controller = HostLoopRateControl(num_envs, spec)
+    a = torch.rand(num_envs, 4) * 2 - 1
+    a[:, 3] = a[:, 3] * 0.2 - 0.6
+    orc.step(a.clone())
+    n, t0 = 0, time.perf_counter()
+    while True:
+        orc.step(a.clone())
+        n += 1
+        el = time.perf_counter() - t0
+        if (el > budget_s and n >= min_steps) or n >= 200:
+            break
+    return num_envs * n / el, (f"{n} oracle steps of {num_envs} envs ({el:.1f} s) with the controller as a single-threaded per-env C "
+                               f"loop behind float64 numpy marshalling (oracle/host_loop); the rest torch CPU fp32 on {cores} threads")
+
+
 def cpu_oracle_steps_per_s(num_envs, budget_s=12.0, min_steps=3):
     """The reference's step() restated (oracle/) timed on this box's host cores: bounded sample."""
     import torch
@@ -384,6 +412,11 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_steps_per_s(N)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        try:  # an extra, informational number: it must never cost the bench line
+            rv, rsample = cpu_reference_shaped_steps_per_s(N, cores)
+            line["cpu_baseline"]["reference_shaped"] = {"value": rv, "unit": "env-steps/s", "sample": rsample}
+        except Exception as exc:  # noqa: BLE001
+            line["cpu_baseline"]["reference_shaped"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
