@@ -439,7 +439,9 @@ class A2CAgent:
         if g == "warm":
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
+            # with collectives inside, the NCCL watchdog thread's event queries must not invalidate this thread's capture
+            mode = "thread_local" if (self.graph_collectives and self.multi_gpu and self.world_size > 1) else "global"
+            with torch.cuda.graph(graph, capture_error_mode=mode):
                 fn(*args)
             self._graphs[key] = graph
             graph.replay()
