@@ -15,22 +15,15 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from tests.util_vae import procedural_images  # noqa: E402
+from tests.util_vae import POLICY_IMAGE_SCALE, policy_inputs  # noqa: E402
 
 REF = "/root/reference"
-sys.path.insert(0, REF)
-from lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd  # noqa: E402
-
 N = 6
-IMAGE_SCALE = 18.0  # the env's depth images after dump_images span roughly [0, 20] (stored image mean of the checkpoint: 9.3)
-
-
-def inputs():
-    g = torch.Generator().manual_seed(7)
-    return procedural_images(N) * IMAGE_SCALE, torch.randn(N, 16, generator=g) * 0.5
-
 
 if __name__ == "__main__":
+    sys.path.insert(0, REF)
+    from lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd  # the reference's own model (build container only)
+
     network = {"name": "actor_critic", "separate": False,
                "space": {"continuous": {"mu_activation": "None", "sigma_activation": "None", "mu_init": {"name": "default"},
                                         "sigma_init": {"name": "const_initializer", "val": 0}, "fixed_sigma": True}},
@@ -42,11 +35,11 @@ if __name__ == "__main__":
     ck = torch.load(os.path.join(REF, "trained", "planning_cnn_rate.pth"), map_location="cpu", weights_only=False)
     model.load_state_dict(ck["model"])
     model.eval()
-    img, obs = inputs()
+    img, obs = policy_inputs(N)
     with torch.no_grad():
         feat = model.actor_cnn(model.norm_image(img))
         res = model({"is_train": True, "prev_actions": torch.zeros(N, 4), "obs": {"image": img, "observation": obs}})
     np.savez_compressed(os.path.join(HERE, "policy_planning_cnn.npz"), cnn_features=feat.numpy(), mus=res["mus"].numpy(),
                         values=res["values"].numpy(), sigmas=res["sigmas"].numpy(), observation=obs.numpy(),
-                        image_scale=np.float32(IMAGE_SCALE))
+                        image_scale=np.float32(POLICY_IMAGE_SCALE))
     print("features", feat.shape, float(feat.abs().mean()), "mus", res["mus"][0].tolist(), "values", res["values"][:3, 0].tolist())

@@ -12,7 +12,7 @@ import torch
 from airgym_b200 import _capi
 from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
 from airgym_b200.lib.network.cnn import encoder_params
-from tests.golden.make_golden_policy import inputs
+from tests.util_vae import policy_inputs as inputs
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

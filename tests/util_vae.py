@@ -13,6 +13,15 @@ def procedural_images(n):
     return img.clamp(0, 1).unsqueeze(1)
 
 
+POLICY_IMAGE_SCALE = 18.0  # the env's depth images after dump_images span roughly [0, 20] (stored image mean of the checkpoint: 9.3)
+
+
+def policy_inputs(n=6):
+    """Inputs of tests/golden/policy_planning_cnn.npz: procedural depth images in the env's range + a seeded observation batch."""
+    g = torch.Generator().manual_seed(7)
+    return procedural_images(n) * POLICY_IMAGE_SCALE, torch.randn(n, 16, generator=g) * 0.5
+
+
 def procedural_state(shapes):
     """Deterministic weights from the parameter name and element index: w = scale * sin(a * i + b), scale ~ 1/sqrt(fan_in)."""
     out = {}
