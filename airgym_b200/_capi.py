@@ -61,6 +61,7 @@ class AgxStepIO(C.Structure):
         ("aux", C.c_void_p), ("rand_reset", C.c_void_p), ("rand_noise", C.c_void_p),
         ("seed", C.c_uint64), ("step", C.c_uint64), ("step_dev", C.c_void_p), ("env_offset", C.c_int64),
         ("assets", C.c_void_p), ("trees", C.c_void_p), ("phase", C.c_int32), ("_pad", C.c_int32),
+        ("reset_u8", C.c_void_p),
     ]
 
 
@@ -98,6 +99,13 @@ class AgxCnnParams(C.Structure):
         ("feature_dim", C.c_int32), ("_pad", C.c_int32)]
 
 
+AGX_IPC_HANDLE_BYTES, AGX_COMM_MAX_RANKS, AGX_F32, AGX_F64 = 64, 8, 0, 1
+
+
+class AgxComm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slot_bytes", C.c_int64), ("region", C.c_void_p * AGX_COMM_MAX_RANKS)]
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -129,6 +137,19 @@ def bind(lib):
     lib.agx_sizeof_cnn_params.restype = C.c_int
     lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]
+    lib.agx_comm_region_bytes.argtypes = [C.c_int, C.c_int64]
+    lib.agx_comm_region_bytes.restype = C.c_int64
+    lib.agx_comm_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.agx_comm_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.agx_comm_close.argtypes = [C.c_void_p]
+    lib.agx_comm_free.argtypes = [C.c_void_p]
+    lib.agx_comm_allreduce.argtypes = [C.POINTER(AgxComm), C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.agx_comm_status.argtypes = [C.POINTER(AgxComm), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+    lib.agx_adam_step_allreduce.argtypes = [C.POINTER(AgxPpoHyper), C.POINTER(AgxComm), C.c_int64, C.c_int64] + [C.c_void_p] * 7 + [
+        C.c_float, C.c_void_p, C.c_void_p]
+    lib.agx_device_numa_node.argtypes = [C.c_int]
+    lib.agx_host_alloc_pinned.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.agx_host_free_pinned.argtypes = [C.c_void_p, C.c_int64]
     return lib
 
 
@@ -137,6 +158,8 @@ EXPORTS = (
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
+    "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",
+    "agx_comm_status", "agx_adam_step_allreduce", "agx_device_numa_node", "agx_host_alloc_pinned", "agx_host_free_pinned",
 )
 
 _lib = None
@@ -169,3 +192,17 @@ def default_params(task: str, ctl_mode: str) -> AgxParams:
     p = AgxParams()
     check(load().agx_params_default(C.byref(p), TASK_IDS[task], CTL_IDS[ctl_mode]), "agx_params_default")
     return p
+
+
+def pinned_host_tensor(nbytes: int, device_index: int):
+    """uint8 CPU tensor over a page-locked buffer placed on the NUMA node of GPU `device_index` (agx_host_alloc_pinned);
+    returns (tensor, info) — keep the tensor alive as long as copies are in flight; the buffer lives until process exit."""
+    import torch
+
+    lib = load()
+    node = int(lib.agx_device_numa_node(device_index))
+    ptr, placed = C.c_void_p(), C.c_int(0)
+    check(lib.agx_host_alloc_pinned(nbytes, node, C.byref(ptr), C.byref(placed)), "agx_host_alloc_pinned")
+    buf = (C.c_ubyte * nbytes).from_address(ptr.value)
+    t = torch.frombuffer(buf, dtype=torch.uint8)
+    return t, {"numa_node": node, "placed": bool(placed.value)}

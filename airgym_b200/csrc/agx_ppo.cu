@@ -5,8 +5,10 @@
 #include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "agx.h"
+#include "agx_comm.cuh"
 #include "agx_ppo_math.cuh"
 
 int agx_internal_fail(int code, const char* msg);  // agx_step.cu: sets the thread-local text behind agx_error_string()
@@ -151,19 +153,36 @@ agx_ppo_loss_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t b, const flo
 // update runs as ONE cluster of 8 CTAs: each CTA reduces the squared norm of its interleaved slice, the 8 partial sums are
 // exchanged through distributed shared memory and added in rank order by every thread (deterministic), then each CTA updates
 // its slice.  lr / step are read before the closing cluster barrier and written after it by rank 0.
-constexpr int kAdamBlock = 1024;
-constexpr int kAdamCluster = 8;
+constexpr int kAdamBlock = agxc::kBlock;
+constexpr int kAdamCluster = agxc::kCluster;
+// COMM = true: the multi-GPU variant — the kernel first all-reduces `g` [n + n_extra] (flat gradients ‖ loss statistics incl. the KL,
+// reference a2c_base.py:293-309 + a2c_continuous.py:112-123) across the ranks through NVLink peer memory (agx_comm.cuh: push into
+// every peer's slot, flag, wait, add the W slots in rank order), writes the sums back into `g` and carries straight on with
+// the norm / clip / Adam / learning-rate rule on them: ONE launch per minibatch instead of NCCL all-reduce + Adam, and bitwise
+// identical parameters on every rank.
+template <bool COMM>
 __global__ void __cluster_dims__(kAdamCluster, 1, 1) __launch_bounds__(kAdamBlock)
-agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __restrict__ p, const float* __restrict__ g,
-                float* __restrict__ m, float* __restrict__ v, float* lr_dev, long long* step_dev, const float* kl_dev,
-                float grad_scale, float* norm_out) {
+agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, const __grid_constant__ AgxComm comm, int64_t n, int64_t n_extra,
+                float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* lr_dev,
+                long long* step_dev, const float* kl_dev, float grad_scale, float* norm_out) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float s_red[kAdamBlock / 32];
     __shared__ float s_part;
     const int64_t first = (int64_t)cluster.block_rank() * kAdamBlock + threadIdx.x, stride = (int64_t)kAdamCluster * kAdamBlock;
     float ss = 0.0f;
-    for (int64_t i = first; i < n; i += stride) { const float x = g[i] * grad_scale; ss += x * x; }
+    unsigned long long seq = 0;
+    if (COMM) {
+        seq = agxc::push_and_wait<float>(comm, g, n + n_extra);
+        const int parity = (int)(seq & 1ull);
+        for (int64_t i = first; i < n + n_extra; i += stride) {
+            const float sum = agxc::reduce_elem<float>(comm, parity, i);
+            g[i] = sum;  // re-read below by this same thread
+            if (i < n) { const float x = sum * grad_scale; ss += x * x; }
+        }
+    } else {
+        for (int64_t i = first; i < n; i += stride) { const float x = g[i] * grad_scale; ss += x * x; }
+    }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
     __syncthreads();
@@ -181,7 +200,9 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __rest
     if (hp.grad_norm > 0.0f) { clip = hp.grad_norm / (norm + 1e-6f); clip = clip > 1.0f ? 1.0f : clip; }  // clip_grad_norm_
     const long long t = step_dev[0] + 1;
     const float lr = lr_dev[0];
-    const float kl = (hp.adaptive_lr && kl_dev) ? kl_dev[0] : 0.0f;
+    // the KL rides in the extra slots of `g`: with COMM it was written by OTHER threads of this cluster above — the cluster
+    // barrier ordered those stores; read it through L2
+    const float kl = (hp.adaptive_lr && kl_dev) ? __ldcg(kl_dev) : 0.0f;
     const float bc1 = 1.0f - powf(hp.beta1, (float)t), bc2 = 1.0f - powf(hp.beta2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
 #pragma unroll 2
@@ -194,11 +215,12 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, int64_t n, float* __rest
         m[i] = mi; v[i] = vi;
         p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + hp.eps);
     }
-    cluster.sync();  // every CTA has read lr / step and every remote s_part read has completed
+    cluster.sync();  // every CTA has read lr / step (and the call counter) and every remote s_part read has completed
     if (cluster.block_rank() == 0 && threadIdx.x == 0) {
         step_dev[0] = t;
         if (norm_out) *norm_out = norm;
         if (hp.adaptive_lr && kl_dev) lr_dev[0] = agx::adaptive_lr(lr, kl * grad_scale, hp.kl_threshold);
+        if (COMM) *static_cast<volatile unsigned long long*>(comm.region[comm.rank]) = seq + 1ull;
     }
 }
 
@@ -246,10 +268,28 @@ int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const 
                   float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale, float* grad_norm_out, void* stream) {
     if (!hp || n_params <= 0 || !params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev)
         return fail_ppo(AGX_ERR_ARG, "agx_adam_step: bad argument");
-    agx_adam_kernel<<<kAdamCluster, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        *hp, n_params, params, grads, exp_avg, exp_avg_sq, lr_dev, reinterpret_cast<long long*>(step_dev), kl_dev, grad_scale,
-        grad_norm_out);
+    AgxComm none;
+    memset(&none, 0, sizeof(none));
+    agx_adam_kernel<false><<<kAdamCluster, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *hp, none, n_params, 0, params, const_cast<float*>(grads), exp_avg, exp_avg_sq, lr_dev, reinterpret_cast<long long*>(step_dev), kl_dev,
+        grad_scale, grad_norm_out);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_adam_step: launch failed");
+}
+
+int agx_adam_step_allreduce(const AgxPpoHyper* hp, const AgxComm* comm, int64_t n_params, int64_t n_extra, float* params, float* grads,
+                            float* exp_avg, float* exp_avg_sq, float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale,
+                            float* grad_norm_out, void* stream) {
+    if (!hp || !comm || n_params <= 0 || n_extra < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev)
+        return fail_ppo(AGX_ERR_ARG, "agx_adam_step_allreduce: bad argument");
+    if (comm->world < 1 || comm->world > AGX_COMM_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world || (comm->slot_bytes & 255) ||
+        (n_params + n_extra) * 4 > comm->slot_bytes)
+        return fail_ppo(AGX_ERR_ARG, "agx_adam_step_allreduce: bad communicator or message larger than its slot");
+    for (int i = 0; i < comm->world; ++i)
+        if (!comm->region[i]) return fail_ppo(AGX_ERR_ARG, "agx_adam_step_allreduce: unmapped peer region");
+    agx_adam_kernel<true><<<kAdamCluster, kAdamBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *hp, *comm, n_params, n_extra, params, grads, exp_avg, exp_avg_sq, lr_dev, reinterpret_cast<long long*>(step_dev), kl_dev, grad_scale,
+        grad_norm_out);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_adam_step_allreduce: launch failed");
 }
 
 }  // extern "C"

@@ -258,6 +258,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     __shared__ __align__(128) float s_obs[BLOCK * OL::kStride];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ WarpScratch s_ws[BLOCK / 32];
+    __shared__ unsigned long long s_step;
 
     const int tid = threadIdx.x;
     const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
@@ -308,22 +309,28 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
             }
         }
     };
-    // Philox step index: device counter (graph replay) or launch argument.  Every CTA takes a ticket AFTER its read
-    // (data dependency through `zero`); the CTA holding the last ticket — every other CTA has read by then — bumps it.
+    // Philox step index: device counter (graph replay) or launch argument.  ONE thread reads the counter (acquire, pairs with the
+    // release store of the previous launch's bump) and takes the CTA's ticket AFTER its read (data dependency through `zero`);
+    // the value reaches the other warps through shared memory, so every thread of the CTA uses the same index even when the
+    // CTA holding the last ticket — every other CTA has read by then — bumps the counter while this CTA's late warps arrive.
     auto take_step = [&]() {
         if (io.step_dev) {
-            step = *reinterpret_cast<const volatile uint64_t*>(io.step_dev);
             if (tid == 0) {
+                unsigned long long s0;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(s0) : "l"(io.step_dev) : "memory");
                 unsigned int zero;
-                asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)step));
+                asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)s0));
                 ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
+                s_step = s0;
             }
+            __syncthreads();
+            step = s_step;
         }
     };
     auto bump_step = [&]() {
         if (io.step_dev && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
             io.step_dev[1] = 0;
-            io.step_dev[0] = step + 1;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(io.step_dev), "l"((unsigned long long)(step + 1)) : "memory");
             __threadfence();
         }
     };
@@ -452,6 +459,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         io.progress[env] = e.progress;
         if (kTask) {
             io.reset[env] = (int64_t)e.reset;
+            if (io.reset_u8) io.reset_u8[env] = (uint8_t)e.reset;
             io.timeout[env] = (uint8_t)e.timeout;
             io.reward[env] = e.rew;
             if (io.reward_terms) {

@@ -28,14 +28,27 @@ class BaseTask:
         self.get_privileged_obs = cfg.env.get_privileged_obs
         self.num_actions = cfg.env.num_actions
 
-        # base_task.py:73-76
-        self.obs_buf = torch.zeros(self.num_envs, self.num_obs, device=dev, dtype=torch.float)
-        self.rew_buf = torch.zeros(self.num_envs, device=dev, dtype=torch.float)
+        # base_task.py:73-76.  obs_buf and rew_buf are views into ONE block [obs | rew | reset flags as bytes] (sections padded
+        # to 256 B), so a caller that ships a step's results to the host reads all three back with a single copy
+        # (`results_block` / `unpack_results`); reset_buf itself stays the reference's int64 tensor.
+        N, no = self.num_envs, self.num_obs
+        al = lambda b: (b + 255) // 256 * 256
+        self._res_off = (0, al(N * no * 4), al(N * no * 4) + al(N * 4))
+        self.results_block = torch.zeros(self._res_off[2] + al(N), device=dev, dtype=torch.uint8)
+        self.obs_buf = self.results_block[: N * no * 4].view(torch.float32).view(N, no)
+        self.rew_buf = self.results_block[self._res_off[1]: self._res_off[1] + N * 4].view(torch.float32)
+        self.reset_u8 = self.results_block[self._res_off[2]: self._res_off[2] + N]
         self.reset_buf = torch.ones(self.num_envs, device=dev, dtype=torch.long)
         self.time_out_buf = torch.zeros(self.num_envs, device=dev, dtype=torch.bool)
         self.extras = {}
         self.viewer = None
         self.enable_viewer_sync = False
+
+    def unpack_results(self, block):
+        """Views (obs [N,num_obs] f32, rew [N] f32, reset [N] u8) of a copy of `results_block` (e.g. in pinned host memory)."""
+        N, no, (o0, o1, o2) = self.num_envs, self.num_obs, self._res_off
+        return (block[o0: o0 + N * no * 4].view(torch.float32).view(N, no), block[o1: o1 + N * 4].view(torch.float32),
+                block[o2: o2 + N])
 
     def get_observations(self):
         return self.obs_buf

@@ -84,6 +84,7 @@ class Hovering(BaseTask):
         io.timeout = self.time_out_buf.data_ptr()
         io.obs = self.obs_buf.data_ptr()
         io.reward = self.rew_buf.data_ptr()
+        io.reset_u8 = self.reset_u8.data_ptr()
         io.cmd = self.cmd_thrusts.data_ptr() if getattr(bk, "export_cmd_thrusts", True) else None
         io.reward_terms = self._reward_terms.data_ptr() if self._reward_terms is not None else None
         io.step_dev = self._step_dev.data_ptr()

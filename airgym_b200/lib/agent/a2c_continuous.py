@@ -19,6 +19,8 @@ import torch
 import torch.distributed as dist
 
 from ... import _capi
+from ...comm import PeerComm
+from ..core.moments import batch_sums, moments_from_sums, sums_from_moments
 from ..model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
 from ..utils import vecenv
 
@@ -116,10 +118,16 @@ class A2CAgent:
         # camera tasks run eagerly: the render cadence (every cam_every-th step) and the encoder-feature cache are host-side decisions
         self.use_cuda_graph = config.get("use_cuda_graph", True) and not self.has_cnn
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
-        # With more than one rank the passes that contain an all-reduce (dataset statistics, every minibatch of the update) run
-        # eagerly unless this is set: capturing NCCL collectives inside the CUDA graphs is not yet validated on this stack
-        # (DESIGN.md §7); the rollout graph holds no collective and is always replayed.
-        self.graph_collectives = bool(config.get("graph_collectives", False))
+        # Collectives of the sharded update.  "peer" (default): libagx kernels over NVLink peer memory — the
+        # per-minibatch all-reduce is fused into the Adam launch (agx_adam_step_allreduce), the per-epoch moments go through
+        # agx_comm_allreduce; everything is stream-ordered and captured in the update / dataset graphs.  "nccl": torch.distributed
+        # all-reduces, captured in the graphs when graph_collectives is set (default) or run eagerly around them.
+        self.comm_kind = config.get("multi_gpu_comm", "peer")
+        if self.comm_kind not in ("peer", "nccl"):
+            raise ValueError(f"multi_gpu_comm must be 'peer' or 'nccl', got {self.comm_kind!r}")
+        self.graph_collectives = bool(config.get("graph_collectives", True))
+        self.comm = None
+        self.noise_table = None  # optional [H, N, A] N(0,1) draws replacing torch.randn in the rollout (explicit randomness, tests)
         self.algo_observer = config.get("features", {}).get("observer", None)
 
         keys = {"actions_num": self.actions_num, "input_shape": self.obs_shape, "num_seqs": self.num_actors,
@@ -143,6 +151,11 @@ class A2CAgent:
         self.opt_step = torch.zeros(1, device=dev, dtype=torch.int64)
         self.grad_norm_dev = torch.zeros(1, device=dev)
         self._lib = _capi.load()
+        if self.multi_gpu and self.world_size > 1 and self.comm_kind == "peer":
+            biggest = self.flat_grads.numel() * 4
+            if self.has_cnn:  # merged image moments: 2 x [C,W,H] float64
+                biggest = max(biggest, 2 * 8 * int(torch.Size(self.image_shape).numel()))
+            self.comm = PeerComm(self.global_rank, self.world_size, biggest, dev)
         self.workspace = torch.zeros(int(self._lib.agx_ppo_workspace_floats()), device=dev)
         hp = _capi.AgxPpoHyper()
         hp.e_clip, hp.critic_coef, hp.entropy_coef = self.e_clip, self.critic_coef, self.entropy_coef
@@ -156,6 +169,9 @@ class A2CAgent:
             self.value_mean_std = self.model.value_mean_std
         self._graphs = {}
         self.init_tensors()
+        if self.algo_observer is not None:  # a2c_base.py:147-148,255
+            self.algo_observer.before_init(base_name, config, self.experiment_name)
+            self.algo_observer.after_init(self)
 
     # ---- buffers --------------------------------------------------------------------------------------------------------
     def init_tensors(self):
@@ -211,12 +227,10 @@ class A2CAgent:
                 self._img_cache = (feat, mean.double().reshape(self.image_shape), var.double().reshape(self.image_shape), img.shape[0])
             feat, mean, var, n = self._img_cache
             if self.normalize_input and update_image_rms:
-                if self.multi_gpu and self.world_size > 1:  # merge the per-rank moments: [n mean, n (var (n-1)/n + mean^2)]
-                    s = torch.stack((mean * n, var * (n - 1) + mean * mean * n))
-                    self._allreduce(s)
+                if self.multi_gpu and self.world_size > 1:  # merge the per-rank moments through their sums
+                    s = self._allreduce(sums_from_moments(mean, var, n).contiguous())
                     nt = n * self.world_size
-                    gmean = s[0] / nt
-                    gvar = (s[1] - nt * gmean * gmean) / (nt - 1)
+                    gmean, gvar = moments_from_sums(s, nt)
                     self.model.running_mean_std.running_mean_std["image"].update_from_moments(gmean, gvar, nt)
                 else:
                     self.model.running_mean_std.running_mean_std["image"].update_from_moments(mean, var, n)
@@ -229,6 +243,7 @@ class A2CAgent:
     def _rollout_step(self, n):
         b = self.buf
         self.model.eval()
+        self._ro_step = n
         if self.fused_mlp:
             res = self._fused_policy(self.obs)
         else:
@@ -291,7 +306,8 @@ class A2CAgent:
         mu = self.ro_mu
         logstd = mu * 0.0 + m.logstd
         sigma = torch.exp(logstd)
-        action = mu + sigma * torch.randn_like(mu)
+        noise = self.noise_table[self._ro_step] if self.noise_table is not None else torch.randn_like(mu)
+        action = mu + sigma * noise
         return {"neglogpacs": m.neglogp(action, mu, sigma, logstd), "values": m.denorm_value(self.ro_value.unsqueeze(-1)),
                 "actions": action, "mus": mu, "sigmas": sigma}
 
@@ -318,24 +334,24 @@ class A2CAgent:
 
     # ---- dataset ----------------------------------------------------------------------------------------------------------
     def _allreduce(self, t):
+        """In-place SUM over the ranks (no-op on one rank)."""
         if self.multi_gpu and self.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            if self.comm is not None and t.dtype in (torch.float32, torch.float64) and t.numel() * t.element_size() <= self.comm.slot_bytes:
+                self.comm.all_reduce(t)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
     def _rms_update(self, rms, x):
         """RunningMeanStd train-mode update; with >1 rank the batch moments are merged across ranks first so that
         replicas keep identical statistics (the reference keeps per-rank statistics)."""
         n = x.shape[0]
-        x64 = x.double()
         if self.multi_gpu and self.world_size > 1:
-            s = torch.cat((x64.sum(0), (x64 * x64).sum(0)))
-            self._allreduce(s)
-            k = x.shape[1]
             n = n * self.world_size
-            mean = s[:k] / n
-            var = (s[k:] - n * mean * mean) / (n - 1)
+            mean, var = moments_from_sums(self._allreduce(batch_sums(x)), n)
+            mean, var = mean.reshape(rms.running_mean.shape), var.reshape(rms.running_mean.shape)
         else:
-            var, mean = torch.var_mean(x64, dim=0)
+            var, mean = torch.var_mean(x.double(), dim=0)
         rms.update_from_moments(mean, var, n)
 
     def _prepare_dataset(self):
@@ -354,19 +370,15 @@ class A2CAgent:
             self.norm_returns.copy_(returns)
         if self.normalize_advantage:
             if self.multi_gpu and self.world_size > 1:  # global moments (north_star: all-reduce of Σadv, Σadv², n)
-                a64 = adv.double()
-                s = torch.stack((a64.sum(), (a64 * a64).sum()))
-                self._allreduce(s)
                 n = adv.numel() * self.world_size
-                mean = s[0] / n
-                std = torch.sqrt((s[1] - n * mean * mean) / (n - 1))
-                adv = ((adv - mean.float()) / (std.float() + 1e-8))
+                mean, var = moments_from_sums(self._allreduce(batch_sums(adv)), n)
+                adv = (adv - mean.float()) / (torch.sqrt(var).float() + 1e-8)
             else:
                 adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         self.advantages.copy_(adv)
 
     def _graph_ok_with_collectives(self):
-        return self.use_cuda_graph and (self.graph_collectives or not (self.multi_gpu and self.world_size > 1))
+        return self.use_cuda_graph and (self.comm is not None or self.graph_collectives or not (self.multi_gpu and self.world_size > 1))
 
     def prepare_dataset(self):
         with torch.no_grad():
@@ -404,6 +416,14 @@ class A2CAgent:
             self.flat_grads[: self.n_params].zero_()
             torch.autograd.backward((mu, value), (self.grad_mu, self.grad_value.view(-1, 1)))
             self.model.logstd.grad += self.grad_logstd
+        if self.comm is not None:  # all-reduce of [grads ‖ stats (KL)] fused into the Adam launch, over NVLink peer memory
+            scale = 1.0 / self.world_size
+            _capi.check(self._lib.agx_adam_step_allreduce(
+                C.byref(self.hyper), C.byref(self.comm.c), self.n_params, _capi.AGX_PPO_STATS, p(self.flat_params), p(self.flat_grads),
+                p(self.exp_avg), p(self.exp_avg_sq), p(self.lr_dev), p(self.opt_step), p(self.stats[4:5]), scale, p(self.grad_norm_dev), st),
+                "agx_adam_step_allreduce")
+            self.epoch_loss_sums += self.stats * scale
+            return
         scale = 1.0
         if self.multi_gpu and self.world_size > 1:
             self._allreduce(self.flat_grads)  # grads ‖ stats (KL) in one message
@@ -439,8 +459,8 @@ class A2CAgent:
         if g == "warm":
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            # with collectives inside, the NCCL watchdog thread's event queries must not invalidate this thread's capture
-            mode = "thread_local" if (self.graph_collectives and self.multi_gpu and self.world_size > 1) else "global"
+            # with a process group alive, the NCCL watchdog thread's event queries must not invalidate this thread's capture
+            mode = "thread_local" if (self.multi_gpu and self.world_size > 1) else "global"
             with torch.cuda.graph(graph, capture_error_mode=mode):
                 fn(*args)
             self._graphs[key] = graph
@@ -470,21 +490,29 @@ class A2CAgent:
         torch.cuda.synchronize()
         t2 = time.time()
         self.last_lr = float(self.lr_dev.item())
+        if self.comm is not None:
+            self.comm.check()  # a collective that timed out on a missing peer raises here instead of training on garbage
         return t1 - t0, t2 - t1, t2 - t0
 
     # ---- driver -----------------------------------------------------------------------------------------------------------
+    def sync_replicas(self):
+        """Rank 0's parameters and normalisation statistics to every rank (a2c_continuous.py:188-192) — one flat-tensor
+        broadcast instead of a pickled state_dict."""
+        if not (self.multi_gpu and self.world_size > 1):
+            return
+        dist.broadcast(self.flat_params, 0)
+        rmss = [getattr(self.model, "value_mean_std", None)]
+        if self.normalize_input:
+            rmss += list(self.model.running_mean_std.running_mean_std.values()) if self.has_cnn else [self.model.running_mean_std]
+        for rms in rmss:
+            if rms is not None:
+                for t in (rms.running_mean, rms.running_var, rms.count):
+                    dist.broadcast(t, 0)
+
     def train(self):
         """a2c_continuous.py:179-294"""
         self.env_reset()
-        if self.multi_gpu and self.world_size > 1:
-            dist.broadcast(self.flat_params, 0)  # flat-tensor broadcast instead of a pickled state_dict (:188-192)
-            rmss = [getattr(self.model, "value_mean_std", None)]
-            if self.normalize_input:
-                rmss += list(self.model.running_mean_std.running_mean_std.values()) if self.has_cnn else [self.model.running_mean_std]
-            for rms in rmss:
-                if rms is not None:
-                    for t in (rms.running_mean, rms.running_var, rms.count):
-                        dist.broadcast(t, 0)
+        self.sync_replicas()
         total_time = 0.0
         self.history = []
         while True:
@@ -510,6 +538,8 @@ class A2CAgent:
             should_exit = False
             if self.writer is not None:
                 self.write_stats(rec, total_time, ep)
+                if self.algo_observer is not None:
+                    self.algo_observer.after_print_stats(self.frame, self.epoch_num, total_time)
             if self.global_rank == 0:
                 if self.print_stats:
                     print(f"fps step and policy inference: {rec['fps_step_inference']:.0f} fps total: {rec['fps_total']:.0f} "

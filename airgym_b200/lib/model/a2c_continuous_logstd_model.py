@@ -198,8 +198,10 @@ class ModelA2CContinuousLogStd(nn.Module):
         return out
 
     def heads(self, obs):
+        """mu, value of an observation.  Camera networks take the reference's dict {'image','observation'} (:141-145) or the
+        already-encoded trunk input [observation | features] as a tensor (what the agent caches in its rollout buffer)."""
         if self.has_cnn:
-            x = self.trunk_input(obs)
+            x = self.trunk_input(obs) if isinstance(obs, dict) else obs
             if self.normalize_input:
                 with torch.no_grad():
                     xn = self.running_mean_std.running_mean_std["observation"](x.detach())

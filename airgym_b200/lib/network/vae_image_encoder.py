@@ -57,7 +57,12 @@ class VAEImageEncoder(nn.Module):
         self.return_sampled_latent = bool(get("return_sampled_latent", False))
         self.encoder = ImgEncoder(1, self.latent_dim)
         folder, fn = get("model_folder"), get("model_file")
-        if folder and fn and os.path.exists(os.path.join(folder, fn)):
+        if get("allow_random_init", False):  # explicit opt-in (tests, throughput runs without the weight file): frozen random weights
+            if folder and fn and os.path.exists(os.path.join(folder, fn)):
+                self.load_weights(torch.load(os.path.join(folder, fn), map_location="cpu", weights_only=False))
+        else:  # the reference's torch.load raises on a missing file (vae_image_encoder.py:24-27): a mis-set path must not train on garbage latents
+            if not (folder and fn):
+                raise FileNotFoundError("vae network block: model_folder / model_file are not set (allow_random_init: True to run without weights)")
             self.load_weights(torch.load(os.path.join(folder, fn), map_location="cpu", weights_only=False))
         self.eval()
         for p in self.parameters():

@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT)
 
 NUM_ENVS = 65536
 REPLICAS = 8
-GRAPH_PASSES = 8  # the timed loop replays graphs of REPLICAS x GRAPH_PASSES = 64 step launches
+GRAPH_PASSES = 8  # the timed loop replays graphs of REPLICAS x GRAPH_PASSES = 64 step launches (+ ONE graph of steps % 64)
+MIN_TIMED_MS = 50.0  # the K-step block is repeated until this much device time has been measured; the MEDIAN block is reported
 ALGO_BYTES_PER_ENV_STEP = 288  # reads 113 B + writes 174 B (Hovering/CTBR fp32)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of agx_step_kernel<hovering, rate, 128> at 65 536 envs, from the
 # `ncu --set full` capture in profiles/r1_agx_step_hovering_rate_ncu_raw.csv (2 launches: 8.18 MB read, 1.28 / 0 MB written — the
@@ -42,6 +43,10 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="also print an N sweep (2^16..2^22) to stderr")
     ap.add_argument("--opt", action="append", default=[], help="libagx tuning knob key=value (agx_set_option)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning runs only)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO samples/s sub-record")
+    ap.add_argument("--no-extras", action="store_true", help="skip the full-contract and 2^22-env side measurements")
+    ap.add_argument("--ppo-envs", type=int, default=NUM_ENVS, help="envs per GPU of the PPO sub-record")
+    ap.add_argument("--ppo-epochs", type=int, default=6, help="timed PPO epochs (after 3 warm-up / capture epochs)")
     return ap.parse_args()
 
 
@@ -166,6 +171,16 @@ def cpu_oracle_steps_per_s(num_envs, budget_s=12.0, min_steps=3):
                                       f"= fastest of the {avail} available)")
 
 
+def bench_config(num_envs, world, opts=None):
+    """`config` of the JSON line — the same dict for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "num_envs_per_gpu": num_envs, "ctl_mode": "rate", "rng": "in-kernel Philox4x32-10",
+            "l2_policy": f"inputs larger than L2: {REPLICAS} independent env replicas rotated, one launch per step",
+            "launch": f"CUDA graph replay ({REPLICAS * GRAPH_PASSES} step launches per graph + one graph of steps % {REPLICAS * GRAPH_PASSES}), "
+                      "programmatic dependent launch (noise-first, agx.h 'pdl' auto)",
+            "timing": f"the K-step block is repeated until >= {MIN_TIMED_MS:.0f} ms are timed; median block, max over ranks per block",
+            "options": opts or {}, "parallelism": f"env-sharded x{world}, no data-path collective"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -194,8 +209,9 @@ def run_reference(args):
         "impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * el / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD + " — reference step() restated on CPU (oracle/, torch fp32)", "num_envs": N,
-                   "note": "IsaacGym/rlPx4Controller/pytorch3d are absent: the reference cannot run; this is the pinned CPU port"},
+        "config": bench_config(N, args.gpus),
+        "note": "reference step() restated on CPU (oracle/, torch fp32): IsaacGym/rlPx4Controller/pytorch3d are absent, the reference "
+                "itself cannot run; the launch / l2_policy / rng entries of `config` describe the GPU arm's workload it is timed against",
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{K} oracle steps of {N} envs after {W} warm-up; {cores} threads = fastest of {avail} available"},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,7 +221,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def make_envs(num_envs, replicas, rank, world, device):
+def make_envs(num_envs, replicas, rank, world, device, full_contract=False):
     import torch
 
     from airgym_b200.envs.base.hovering import Hovering
@@ -215,9 +231,9 @@ def make_envs(num_envs, replicas, rank, world, device):
     for r in range(replicas):
         cfg = HoveringCfg()
         cfg.env.num_envs, cfg.env.ctl_mode, cfg.seed = num_envs, "rate", 1234 + r
-        cfg.backend.reward_terms = False  # extras["item_reward_info"] is optional logging
-        cfg.backend.export_cmd_thrusts = False  # internal attribute of the reference env, not part of step()'s return
-        cfg.backend.mutate_input_actions = False  # the bench re-feeds one action tensor; Q4's write-back would drift it
+        cfg.backend.reward_terms = full_contract  # extras["item_reward_info"] is optional logging
+        cfg.backend.export_cmd_thrusts = full_contract  # internal attribute of the reference env, not part of step()'s return
+        cfg.backend.mutate_input_actions = full_contract  # the bench re-feeds one action tensor; Q4's write-back would drift it
         env = Hovering(cfg, None, None, device, True)
         env.set_seed(1234 + r, env_offset=rank * num_envs)
         envs.append(env)
@@ -229,63 +245,110 @@ def make_envs(num_envs, replicas, rank, world, device):
     return envs, acts
 
 
-def time_kernel_loop(envs, acts, steps, warmup, dist):
-    """K launches replayed from CUDA graphs (one launch per step, replica i mod R); device-timed, max over ranks."""
+def timed_blocks(block, pre_roll, dist, what):
+    """[pre-roll (untimed, keeps the stream in steady state) | e0 | block | e1] repeated until >= MIN_TIMED_MS of device time
+    (at least 5, at most 400 blocks; the count is agreed across ranks); each block is bracketed by barrier + synchronize, its
+    time is the MAX over ranks; returns the per-block times in ms."""
+    import torch
+
+    def once():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        pre_roll()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        block()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def reduce_max(vals):
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    first = reduce_max([once()])[0]
+    n = int(min(400, max(5, -(-MIN_TIMED_MS // max(first, 1e-3)))))
+    times = reduce_max([once() for _ in range(n)])
+    if not all(t > 0 for t in times):
+        raise RuntimeError(f"bench: non-positive {what} block time")
+    return times
+
+
+def median(v):
+    v = sorted(v)
+    return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
+
+def time_kernel_loop(envs, acts, steps, warmup, dist, fresh=None):
+    """K launches replayed from CUDA graphs (one launch per step, replica i mod R): steps // 64 replays of the 64-launch graph +
+    ONE graph holding the steps % 64 remaining launches; device-timed per block, max over ranks, median block.
+    `fresh` (full-contract variant): pristine copies of the action tensors, copied in before every step because quirk Q4
+    rewrites the caller's tensor in place — as a policy writing new actions every step would."""
     import torch
 
     R = len(envs)
     P = GRAPH_PASSES  # launches per captured graph = R * P (graph-launch gaps amortised; every launch is still one step)
+
+    def step(i):
+        r = i % R
+        if fresh is not None:
+            acts[r].copy_(fresh[r])
+        envs[r].step(acts[r])
+
     for i in range(max(warmup, 3)):
-        envs[i % R].step(acts[i % R])
+        step(i)
     torch.cuda.synchronize()
-    chunk = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(chunk):
-        for _ in range(P):
-            for r in range(R):
-                envs[r].step(acts[r])
-    singles = []
-    for r in range(steps % (R * P)):
+
+    def capture(n_launches):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            envs[r % R].step(acts[r % R])
-        singles.append(g)
-    chunk.replay()  # graph warm-up
+            for i in range(n_launches):
+                step(i)
+        return g
+
+    n_chunks, n_rem = steps // (R * P), steps % (R * P)
+    chunk = capture(R * P) if n_chunks else None
+    rem = capture(n_rem) if n_rem else None
+    pre = capture(R)
+    for g in (chunk, rem, pre):
+        if g is not None:
+            g.replay()  # graph warm-up
     torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps // (R * P)):
-        chunk.replay()
-    for g in singles:
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        ms = float(t.item())
-    return ms
+
+    def block():
+        for _ in range(n_chunks):
+            chunk.replay()
+        if rem is not None:
+            rem.replay()
+
+    times = timed_blocks(block, pre.replay, dist, "kernel")
+    return median(times), times
 
 
-def time_e2e_loop(env, num_envs, steps, warmup, dist):
-    """Public API with HOST buffers: per step H2D(actions) → env.step → D2H(obs, rew, reset); copies in the timed region."""
+def time_e2e_loop(env, num_envs, steps, warmup, dist, device_index):
+    """Public API with HOST buffers: per step H2D(actions) → env.step → ONE D2H of the packed [obs | reward | reset flags] block
+    (env.results_block; reset flags travel as bytes, reset_buf stays int64 on the device); copies in the timed region.  The pinned
+    host buffers are placed on the GPU's NUMA node (agx_host_alloc_pinned)."""
     import torch
 
-    a_host = (torch.rand(num_envs, 4) * 2 - 1).pin_memory()
-    obs_h = torch.empty(num_envs, env.num_obs).pin_memory()
-    rew_h = torch.empty(num_envs).pin_memory()
-    rst_h = torch.empty(num_envs, dtype=torch.long).pin_memory()
+    from airgym_b200 import _capi
+
+    a_bytes = num_envs * 4 * 4
+    a_pin, info_a = _capi.pinned_host_tensor(a_bytes, device_index)
+    a_host = a_pin.view(torch.float32).view(num_envs, 4)
+    a_host.copy_(torch.rand(num_envs, 4) * 2 - 1)
+    blk_h, info_r = _capi.pinned_host_tensor(env.results_block.numel(), device_index)
+    obs_h, rew_h, rst_h = env.unpack_results(blk_h)
     a_dev = [torch.empty(num_envs, 4, device="cuda") for _ in range(2)]  # double-buffered: the H2D of step t+1 rides under the D2H of step t
-    h2d = a_host.numel() * 4
-    d2h = obs_h.numel() * 4 + rew_h.numel() * 4 + rst_h.numel() * 8
+    h2d, d2h = a_bytes, env.results_block.numel()
     main = torch.cuda.current_stream()
     copy_in = torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_step = [torch.cuda.Event() for _ in range(2)]
+    state = {"t": 0}
 
     def stage(t):  # host -> device copy of step t's actions, on the copy stream (PCIe is full duplex)
         with torch.cuda.stream(copy_in):
@@ -293,37 +356,102 @@ def time_e2e_loop(env, num_envs, steps, warmup, dist):
             a_dev[t % 2].copy_(a_host, non_blocking=True)
             ev_in[t % 2].record(copy_in)
 
-    def one(t):
+    def one():
+        t = state["t"]
         main.wait_event(ev_in[t % 2])
-        obs, _, rew, rst, _ = env.step(a_dev[t % 2])
+        env.step(a_dev[t % 2])
         ev_step[t % 2].record(main)
         stage(t + 1)
-        obs_h.copy_(obs, non_blocking=True)
-        rew_h.copy_(rew, non_blocking=True)
-        rst_h.copy_(rst, non_blocking=True)
+        blk_h.copy_(env.results_block, non_blocking=True)
+        state["t"] = t + 1
 
     for e in ev_step:
         e.record(main)
     stage(0)
-    nw = max(3, min(warmup, 20))
-    for t in range(nw):
-        one(t)
+    for _ in range(max(3, min(warmup, 20))):
+        one()
     torch.cuda.synchronize()
+
+    def block():
+        for _ in range(steps):
+            one()
+
+    def pre_roll():
+        for _ in range(3):
+            one()
+
+    times = timed_blocks(block, pre_roll, dist, "e2e")
+    assert float(rew_h.abs().sum()) > 0 and torch.isfinite(obs_h).all() and int(rst_h.max()) <= 1
+    assert torch.equal(rst_h.to(torch.int64), env.reset_buf.cpu()), "the byte flags of the block must equal reset_buf"
+    return median(times), h2d, d2h, {"pinned_numa_node": info_r["numa_node"], "pinned_placed": info_r["placed"] and info_a["placed"]}
+
+
+def ppo_record(args, rank, local, world, dist):
+    """PPO samples/s on the same envs (north_star: "PPO tokens/sec scaling 1->8"): Hovering/CTBR, 65 536 envs per GPU, the reference's
+    ppo_hovering.yaml hyper-parameters with the minibatch scaled to keep its 48 minibatches per mini-epoch; rollout and update replay
+    from CUDA graphs; with more than one rank the gradient all-reduce is fused into the Adam kernel over NVLink peer memory."""
+    import torch
+
+    from airgym_b200.lib.agent.a2c_continuous import A2CAgent
+    from airgym_b200.lib.config import default_ppo_config, scale_minibatch
+    from airgym_b200.lib.utils import tr_helpers
+
+    N = args.ppo_envs
+    cfg = scale_minibatch(default_ppo_config("hovering"), N)
+    c = cfg["params"]["config"]
+    c.update(multi_gpu=world > 1, print_stats=False, write_summaries=False, train_dir="/tmp/agx_bench_ppo", save_frequency=0,
+             save_best_after=10**9, device=f"cuda:{local}")
+    c["env_config"].update(ctl_mode="rate", num_envs=N, seed=1)
+    c["reward_shaper"] = tr_helpers.DefaultRewardsShaper(**c["reward_shaper"])
+    torch.manual_seed(1)
+    agent = A2CAgent("bench", cfg["params"])
+    agent.env_reset()
+    agent.sync_replicas()
+    for _ in range(3):  # eager warm-up, graph capture, first replay
+        agent.train_epoch()
+    E = args.ppo_epochs
     if dist is not None:
         dist.barrier()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(nw, nw + steps):
-        one(t)
+    play = upd = 0.0
+    for _ in range(E):
+        p, u, _ = agent.train_epoch()
+        play, upd = play + p, upd + u
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    t = torch.tensor([e0.elapsed_time(e1), 1e3 * play / E, 1e3 * upd / E], device="cuda", dtype=torch.float64)
     if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    assert float(rew_h.abs().sum()) > 0
-    return ms, h2d, d2h
+    ms, ms_play, ms_upd = t.tolist()
+    allreduce_us = None
+    if agent.comm is not None:  # the stand-alone collective on a gradient-sized message, back to back (eager launches)
+        buf = torch.zeros_like(agent.flat_grads)
+        for _ in range(20):
+            agent.comm.all_reduce(buf)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(200):
+            agent.comm.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        allreduce_us = 1e3 * a0.elapsed_time(a1) / 200
+        agent.comm.check()
+    rec = {"samples_per_s": world * agent.batch_size * E / (ms * 1e-3), "ms_per_epoch": ms / E, "ms_rollout": ms_play, "ms_update": ms_upd,
+           "allreduce_us": allreduce_us, "epochs_timed": E, "num_envs_per_gpu": N, "horizon": agent.horizon_length,
+           "minibatch_per_gpu": agent.minibatch_size, "minibatches_per_epoch": agent.num_minibatches * agent.mini_epochs_num,
+           "collective": ("none (1 rank)" if world == 1 else
+                          ("peer-memory all-reduce fused into the Adam kernel (agx_adam_step_allreduce) + agx_comm_allreduce for the "
+                           "per-epoch moments, all inside the CUDA graphs" if agent.comm is not None else "NCCL all-reduce")),
+           "mean_reward_last": agent.mean_rewards if agent.mean_rewards > -1e8 else None, "kl_last": float(agent.epoch_loss_sums[4]) /
+           (agent.num_minibatches * agent.mini_epochs_num)}
+    if agent.comm is not None:
+        agent.comm.close()
+    return rec
 
 
 def run_ours(args):
@@ -346,7 +474,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
     if rank == 0:
-        graft.build()
+        graft.build_product()  # the checkers (tests/hostsim, oracle/) are not built or loaded by the GPU arm
     if dist is not None:
         dist.barrier()
     N, K, W = args.num_envs, args.steps, max(args.warmup, 3)
@@ -362,25 +490,48 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = time_kernel_loop(envs, acts, K, W, dist)
+    ms, blocks = time_kernel_loop(envs, acts, K, W, dist)
     e2e_steps = max(20, min(K, 300))
     if args.no_e2e:
-        ms_e2e, h2d, d2h = float("nan"), 0, 0
+        ms_e2e, h2d, d2h, e2e_info = float("nan"), 0, 0, {}
     else:
-        ms_e2e, h2d, d2h = time_e2e_loop(envs[0], N, e2e_steps, W, dist)
+        ms_e2e, h2d, d2h, e2e_info = time_e2e_loop(envs[0], N, e2e_steps, W, dist, local)
     clocks = sampler.stop() if rank == 0 else None
 
-    if args.sweep and rank == 0:
+    extras = {}
+    if not args.no_extras:
+        # (1) the full reference contract of step(): extras["item_reward_info"] planes + cmd_thrusts + quirk Q4's in-place remap
+        fenvs, facts = make_envs(N, REPLICAS, rank, world, device, full_contract=True)
+        fresh = [a.clone() for a in facts]
+        fms, _ = time_kernel_loop(fenvs, facts, K, W, dist, fresh=fresh)
+        extras["full_contract"] = {"us_per_step": 1e3 * fms / K, "includes": "reward_terms [12,N] + cmd_thrusts [N,4] outputs and the in-place "
+                                   "action remap (Q4); a fresh 1 MB action tensor is copied in before every step (a second launch inside the timed "
+                                   "region), as a policy writing new actions would — Q4 would otherwise drift the re-fed tensor"}
+        del fenvs, facts, fresh
+        # (2) the bandwidth-bound regime of the same kernel: 2^22 envs per launch
+        n_big = 1 << 22
+        benvs, bacts = make_envs(n_big, 2, rank, world, device)
+        bms, _ = time_kernel_loop(benvs, bacts, 128, 16, dist)
+        extras["n_2pow22"] = {"us_per_step": 1e3 * bms / 128, "algo_GBps": ALGO_BYTES_PER_ENV_STEP * n_big / ((bms / 128) * 1e-3) / 1e9,
+                              "env_steps_per_s_per_gpu": n_big * 128 / (bms * 1e-3)}
+        del benvs, bacts
+        torch.cuda.empty_cache()
+    if args.sweep and rank == 0 and world == 1:
         for logn in (16, 18, 20, 22):
             n = 1 << logn
             reps = max(2, (REPLICAS << 16) // n)
             ev, ac = make_envs(n, reps, 0, 1, device)
-            m = time_kernel_loop(ev, ac, 400, 50, None)
-            gbs = ALGO_BYTES_PER_ENV_STEP * n * 400 / (m * 1e-3) / 1e9
-            print(f"[sweep] N=2^{logn} replicas={reps} us/step={1e3 * m / 400:.2f} env-steps/s={n * 400 / (m * 1e-3):.3e} algo GB/s={gbs:.0f}",
+            m, _ = time_kernel_loop(ev, ac, 384, 50, None)
+            gbs = ALGO_BYTES_PER_ENV_STEP * n * 384 / (m * 1e-3) / 1e9
+            print(f"[sweep] N=2^{logn} replicas={reps} us/step={1e3 * m / 384:.2f} env-steps/s={n * 384 / (m * 1e-3):.3e} algo GB/s={gbs:.0f}",
                   file=sys.stderr, flush=True)
             del ev, ac
             torch.cuda.empty_cache()
+    ppo = None
+    if not args.no_ppo:
+        del envs, acts
+        torch.cuda.empty_cache()
+        ppo = ppo_record(args, rank, local, world, dist)
 
     if rank != 0:
         if dist is not None:
@@ -394,21 +545,23 @@ def run_ours(args):
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "num_envs_per_gpu": N, "ctl_mode": "rate", "rng": "in-kernel Philox4x32-10",
-                   "l2_policy": f"inputs larger than L2: {REPLICAS} independent env replicas rotated, one launch per step",
-                   "launch": f"CUDA graph replay ({REPLICAS * GRAPH_PASSES} step launches per graph), programmatic dependent launch "
-                             "(noise-first, agx.h 'pdl' auto)", "options": opts, "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "config": bench_config(N, world, opts),
+        "blocks": {"n": len(blocks), "ms_median": ms, "ms_min": min(blocks), "ms_max": max(blocks)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if N == NUM_ENVS else None, "traffic_unit": "B/launch (ncu dram read+write; algorithmic: "
                      f"{ALGO_BYTES_PER_ENV_STEP * N} B/launch)", "peak_source": peak_src,
-                     "note": f"{ALGO_BYTES_PER_ENV_STEP} algorithmic B/env-step x {N} envs / (timed region / launches), i.e. launch gaps included"},
+                     "note": f"{ALGO_BYTES_PER_ENV_STEP} algorithmic B/env-step x {N} envs / (median K-step block / K), i.e. launch gaps included"},
         "e2e": {"value": world * N * e2e_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "path": "env.step() via ctypes C ABI; pinned host actions in (copy stream, overlapping the previous step's read-back), "
-                        "obs+reward+reset out to pinned host; every step moves all three"},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                "path": "env.step() via ctypes C ABI; pinned host actions in (copy stream, overlapping the previous step's read-back); "
+                        "obs + reward + reset flags out to pinned host as ONE copy of the env's packed results block (reset flags as "
+                        "bytes; reset_buf stays int64 on the device); host buffers placed on the GPU's NUMA node", **e2e_info},
         "gpu_launches": K,
         "clocks": clocks,
     }
+    line.update(extras)
+    if ppo is not None:
+        line["ppo"] = ppo
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_steps_per_s(N)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}

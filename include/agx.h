@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define AGX_VERSION 120
+#define AGX_VERSION 200
 
 enum AgxError {
     AGX_OK = 0,
@@ -164,6 +164,9 @@ typedef struct AgxStepIO {
     const float* trees;    /* [AGX_NUM_TREES,8] planning only: cylinder table, asset frame: centre xyz, unit axis xyz, radius, half length */
     int32_t  phase;        /* AgxPhase (avoid/planning); must be 0 for the other tasks */
     int32_t  _pad;
+    uint8_t* reset_u8;     /* [N] out, optional (NULL = skip): the new reset flags once more as bytes, so that a caller shipping
+                              results to the HOST can place them behind obs and reward in one block and read all three back
+                              with a single copy (reset_buf itself stays int64 as the reference API has it, base_task.py:75) */
 } AgxStepIO;
 
 /* Depth camera + post-processing of one render step (replaces IsaacGym's camera sensor and Customized.dump_images,
@@ -272,6 +275,54 @@ int agx_ppo_loss(const AgxPpoHyper* hp, int64_t b, int a, const float* mu, const
 int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const float* grads, float* exp_avg,
                   float* exp_avg_sq, float* lr_dev, int64_t* step_dev, const float* kl_dev, float grad_scale,
                   float* grad_norm_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the env path has no collective; the PPO update has one small all-reduce per minibatch
+ * ([flat gradients ‖ loss statistics incl. the KL], reference lib/agent/a2c_base.py:293-309 + a2c_continuous.py:112-123) and a
+ * few per epoch (advantage / RunningMeanStd moments).  These entry points run them as ONE device kernel per rank over NVLink
+ * peer memory instead of a library collective: each rank owns a region in its HBM, mapped into every process of the node with
+ * CUDA IPC; a collective pushes the message into every peer's region, raises a flag there, waits for the peers' flags in its
+ * own region and adds the slots in rank order (bitwise identical results on every rank).  Stream-ordered, graph-capturable
+ * (the call counter lives in the region), no host sync.  All ranks must issue the same sequence of collectives.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define AGX_IPC_HANDLE_BYTES 64
+#define AGX_COMM_MAX_RANKS 8
+enum AgxDtype { AGX_F32 = 0, AGX_F64 = 1 };
+
+typedef struct AgxComm {
+    int32_t rank, world;
+    int64_t slot_bytes;                  /* capacity of one message; a multiple of 256 */
+    void*   region[AGX_COMM_MAX_RANKS];  /* region[rank]: this process's own allocation; the others: IPC mappings of the peers' */
+} AgxComm;
+
+/* bytes of one rank's region for messages of up to slot_bytes (rounded up to a multiple of 256): header + 2 x world slots */
+int64_t agx_comm_region_bytes(int world, int64_t slot_bytes);
+/* cudaMalloc + zero-fill a region on the current device; handle (AGX_IPC_HANDLE_BYTES, may be NULL) = its cudaIpcMemHandle_t */
+int agx_comm_alloc(int64_t bytes, void** ptr, unsigned char* handle);
+/* map a peer's region from its handle (cudaIpcOpenMemHandle, enables peer access) / unmap it / free an own region */
+int agx_comm_open(const unsigned char* handle, void** ptr);
+int agx_comm_close(void* ptr);
+int agx_comm_free(void* ptr);
+/* in-place SUM over the ranks of buf[n] (dtype AGX_F32 | AGX_F64), n * sizeof <= slot_bytes */
+int agx_comm_allreduce(const AgxComm* c, void* buf, int64_t n, int dtype, void* stream);
+/* synchronous read of the own region's header: number of collectives completed, and the error word (0 = none; else
+ * (peer + 1) << 56 | call number of the first collective that timed out waiting for `peer`) */
+int agx_comm_status(const AgxComm* c, uint64_t* seq, uint64_t* err, void* stream);
+
+/* agx_adam_step with the all-reduce fused in front: grads [n_params + n_extra] is summed over the ranks in place (the extra
+ * floats — the loss statistics, kl_dev pointing into them — ride in the same message), then scaled by grad_scale (1/world),
+ * clipped, Adam-stepped; the learning rate follows the all-reduced KL.  One launch per minibatch. */
+int agx_adam_step_allreduce(const AgxPpoHyper* hp, const AgxComm* comm, int64_t n_params, int64_t n_extra, float* params,
+                            float* grads, float* exp_avg, float* exp_avg_sq, float* lr_dev, int64_t* step_dev,
+                            const float* kl_dev, float grad_scale, float* grad_norm_out, void* stream);
+
+/* ---- host staging buffers for the end-to-end path (actions in / results out through host memory every step) --------------
+ * NUMA node of the GPU's PCIe root (sysfs), or -1 when unknown. */
+int agx_device_numa_node(int device);
+/* page-locked host buffer preferring `numa_node` (mmap + mbind + cudaHostRegister); *placed = 1 when the policy call succeeded.
+ * numa_node < 0: plain pinned memory. */
+int agx_host_alloc_pinned(int64_t bytes, int numa_node, void** ptr, int* placed);
+int agx_host_free_pinned(void* ptr, int64_t bytes);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused actor-critic MLP on tensor cores (TF32 operands, fp32 accumulate).  Reference: lib/network/mlp.py:4-39 (three

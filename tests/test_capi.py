@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(names) == set(_capi.EXPORTS), (names, _capi.EXPORTS)
     for n in names:
         assert hasattr(lib, n), f"libagx.so does not export {n}"
-    assert lib.agx_version() == 120
+    assert lib.agx_version() == 200
 
 
 def test_struct_mirrors_match_library(built):

@@ -62,8 +62,8 @@ def test_pretrained_mlp_checkpoint_initialises_cnn_policy(tmp_path):
                           ck["model"]["running_mean_std.running_mean_std.observation.running_mean"])
 
 
-@pytest.mark.parametrize("task", ["avoid", "planning"])
-def test_ppo_trains_on_image_tasks(task):
+@pytest.mark.parametrize("task,fused", [("avoid", True), ("planning", True), ("planning", False)])
+def test_ppo_trains_on_image_tasks(task, fused):
     """ppo_avoid / ppo_planning.yaml shape (CNN 30 + MLP, dict observations) through Runner.run: a few epochs run, statistics stay
     finite, the trunk weights move, the CNN's do not (the reference's no_grad normalisation gives the encoder no gradient)."""
     from airgym_b200.lib.config import default_ppo_config, scale_minibatch
@@ -71,7 +71,8 @@ def test_ppo_trains_on_image_tasks(task):
 
     cfg = scale_minibatch(default_ppo_config(task), 256)
     c = cfg["params"]["config"]
-    c.update(max_epochs=3, print_stats=False, save_frequency=0, save_best_after=10**9, train_dir="/tmp/agx_runs", horizon_length=8)
+    c.update(max_epochs=3, print_stats=False, save_frequency=0, save_best_after=10**9, train_dir="/tmp/agx_runs", horizon_length=8,
+             fused_mlp=fused)  # fused_mlp False: torch fp32 MLP + autograd on the cached trunk input (model.heads takes the tensor)
     c["minibatch_size"] = 256 * 8 // 4
     c["env_config"].update(ctl_mode="rate", num_envs=256, seed=1)
     cfg["params"]["seed"] = 1

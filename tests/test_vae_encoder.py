@@ -22,8 +22,16 @@ def test_key_layout_matches_reference_checkpoint():
     assert have == want
 
 
+def test_missing_weight_file_raises_unless_random_init_is_opted_into():
+    with pytest.raises(FileNotFoundError):
+        VAEImageEncoder(CFG)  # no model_folder / model_file
+    with pytest.raises(FileNotFoundError):
+        VAEImageEncoder(dict(CFG, model_folder="/nonexistent", model_file="vae_model.pth"))  # torch.load raises, as the reference's does
+    assert VAEImageEncoder(dict(CFG, allow_random_init=True)).latent_dim == 64
+
+
 def test_procedural_weights_match_reference_latents():
-    enc = VAEImageEncoder(CFG)
+    enc = VAEImageEncoder(dict(CFG, allow_random_init=True))
     shapes = {"encoder." + k: tuple(v.shape) for k, v in enc.encoder.state_dict().items()}
     # the golden generator drew weights for the whole VAE (encoder + decoder), sorted by name: rebuild with the same indices
     full = {str(r).split(":")[0]: tuple(int(x) for x in str(r).split(":")[1].split(",")) for r in G["encoder_shapes"]}
