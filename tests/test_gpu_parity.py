@@ -88,7 +88,9 @@ def test_per_step_parity_vs_oracle(task, mode, variant):
         obs, _, rew, reset, extras = env.step(a_dev, rand_reset=d["reset"].cuda(), rand_noise=d["noise"].cuda())
         tag = f"{task}/{mode}/{variant} t={t}"
         ok = well_conditioned(orc, pre_q, mode)
-        assert ok.float().mean() > 0.75
+        # measured on the oracle with these seeds: every env qualifies in pos / vel / rate / prop; with uniformly random quaternion
+        # set-points (atti) 83-86 % do (P(ez.ezd < -0.75) alone is 12.5 %) — a regression cannot hide behind a shrinking mask
+        assert ok.float().mean() >= (0.82 if mode == "atti" else 1.0), float(ok.float().mean())
         assert_close(env.root_states.cpu()[ok], orc.root_states[ok], tag + " state")
         assert_close(obs.cpu()[ok], orc.obs_buf[ok], tag + " obs")
         rr, ra = task_tols(task)
@@ -99,6 +101,7 @@ def test_per_step_parity_vs_oracle(task, mode, variant):
             assert_close(env.aux.cpu()[ok], orc.aux_matrix()[ok], tag + " aux")
         # ill-conditioned attitude set-points (see well_conditioned) still agree, just not to 1e-4
         assert_close(env.cmd_thrusts.cpu(), orc.cmd_thrusts, tag + " cmd (all)", rtol=5e-2, atol=5e-3)
+        assert_close(env.root_states.cpu(), orc.root_states, tag + " state (all)", rtol=5e-2, atol=5e-3)
         assert_close(env.actions.cpu(), orc.actions, tag + " actions", rtol=0, atol=0)
         assert_close(env.pre_actions.cpu(), orc.pre_actions, tag + " pre_actions", rtol=0, atol=0)
         assert_close(a_dev.cpu(), a, tag + " in-place remap (Q4)", rtol=0, atol=0)
@@ -334,6 +337,39 @@ def test_full_size_properties_65536():
     assert s[:, 7:10].abs().max() <= 0.5 and s[:, 10:13].abs().max() <= 0.2
     assert abs(float(s[:, 7:10].std()) - 0.5 / 3**0.5) < 0.005 and abs(float(s[:, 10:13].std()) - 0.2 / 3**0.5) < 0.002
     assert (s[:, 6] > 0.99).all()
+
+
+@pytest.mark.parametrize("task,mode", [("hovering", "rate"), ("tracking", "vel")])
+def test_oracle_parity_at_full_size_65536(task, mode):
+    """BASELINE configs 2 / 3 at their stated size against the ORACLE (not just properties): 3 explicit-randomness steps over
+    65 536 envs, the second with a forced time-out wave so both reset passes run; same bar as the N = 1000 test."""
+    N = 65536
+    torch.manual_seed(21)
+    spec = QuadSpec(task=task, ctl_mode=mode)
+    orc = make_oracle(spec, N, rng="torch")
+    env = make_env(task, mode, N)
+    K = spec.ctrl_state_dim
+    for t in range(3):
+        a = torch.rand(N, spec.num_actions) * 2 - 1
+        if t == 1:
+            orc.progress_buf[::17] = spec.max_episode_length - 2
+        sync_from_oracle(env, orc, K)
+        a_dev = a.cuda()
+        orc.step(a)
+        d = orc.last_draws
+        obs, _, rew, reset, extras = env.step(a_dev, rand_reset=d["reset"].cuda(), rand_noise=d["noise"].cuda())
+        tag = f"{task}/{mode} N=65536 t={t}"
+        assert_close(env.root_states.cpu(), orc.root_states, tag + " state")
+        assert_close(obs.cpu(), orc.obs_buf, tag + " obs")
+        rr, ra = task_tols(task)
+        assert_close(rew.cpu(), orc.rew_buf, tag + " rew", rtol=rr, atol=ra)
+        assert_close(env.cmd_thrusts.cpu(), orc.cmd_thrusts, tag + " cmd")
+        assert_close(env.actions.cpu(), orc.actions, tag + " actions", rtol=0, atol=0)
+        assert_close(env.ctrl_state[:K].T.cpu(), orc.controller.state[:, :K], tag + " ctrl")
+        assert torch.equal(reset.cpu(), orc.reset_buf) and torch.equal(env.progress_buf.cpu(), orc.progress_buf), tag
+        assert torch.equal(extras["time_outs"].cpu(), orc.time_out_buf), tag
+        assert torch.equal(env.reset_u8.cpu().long(), orc.reset_buf), tag  # the byte copy of the flags in the packed results block
+    assert int(orc.reset_buf.sum()) > 0  # resets were in flight
 
 
 def test_reset_idx_standalone_and_reset_api():
