@@ -134,6 +134,9 @@ def bind(lib):
     lib.agx_mlp_workspace_floats.argtypes = [C.POINTER(AgxMlpParams)]
     lib.agx_mlp_workspace_floats.restype = C.c_int64
     lib.agx_mlp_backward.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
+    lib.agx_mlp_train_supported.argtypes = [C.POINTER(AgxMlpParams)]
+    lib.agx_mlp_forward_train.argtypes = [C.POINTER(AgxMlpParams), C.c_int64] + [C.c_void_p] * 8
+    lib.agx_mlp_backward_train.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
     lib.agx_sizeof_cnn_params.restype = C.c_int
     lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]
@@ -158,6 +161,7 @@ EXPORTS = (
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
+    "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
     "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",
     "agx_comm_status", "agx_adam_step_allreduce", "agx_device_numa_node", "agx_host_alloc_pinned", "agx_host_free_pinned",
 )

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "agx.h"
+#include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
 
@@ -307,56 +308,12 @@ agx_mlp_forward_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const 
 // training, to HBM for the backward.  TMEM columns: layer 1 → [0,64), layer 2 → [64,192), layer 3 → [192,256), heads → [0,16).
 // The mma.sync kernel above spends 44 us on a 32 768-row minibatch (legacy-MMA issue bound); SASS of this one shows UTCMMA / LDTM.
 namespace tc {
-constexpr int kM = 128, kH1 = 64, kH2 = 128, kH3 = 64;
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__host__ __device__ inline int canon(int r, int k, int rows) { return ((k >> 2) * rows + r) * 4 + (k & 3); }  // rows % 8 == 0
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
-           ((uint64_t)1 << 46);  // version 1 (Blackwell), no swizzle
-}
-// D[128, N] (+)= A[128, K] * B[N, K]^T, issued by ONE thread
-__device__ __forceinline__ void gemm(uint32_t a_base, uint32_t b_base, int N, int K, uint32_t tmem_d, bool accumulate_first = false) {
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-    const uint32_t lboA = (kM / 8) * 128, lboB = (uint32_t)(N / 8) * 128;
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t da = smem_desc(a_base + ks * 2 * lboA, lboA, 128), db = smem_desc(b_base + ks * 2 * lboB, lboB, 128);
-        const uint32_t acc = (ks > 0 || accumulate_first) ? 1u : 0u;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-                     "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                     : "memory");
-    }
-}
-__device__ __forceinline__ void commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
-    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(s32(bar)),
-                 "r"(parity)
-                 : "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// make this thread's generic-proxy shared-memory writes visible to the tensor core, and order its TMEM reads before the barrier;
-// the barrier is the 128-thread named barrier of this thread's tile group (id 1 or 2), or the whole CTA (id 0)
-__device__ __forceinline__ void publish_and_sync(int bar_id, int nthreads) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 // epilogue of one hidden layer for this thread's row: TMEM cols [col0, col0 + W) → + bias → ELU → next A operand (+ HBM copy)
+// keep_row: this row's slot in a row-major [b, W] keep tensor; keep_col (training path): this row's element of plane 0 of a
+// FEATURE-MAJOR [W, ld_t] keep tensor (consecutive rows = consecutive addresses: coalesced scalar stores) — at most one is non-null
 template <int W>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ bias, float* a_next, int r,
-                                                float* __restrict__ keep_row) {
+                                                float* __restrict__ keep_row, float* __restrict__ keep_col = nullptr, int64_t ld_t = 0) {
 #pragma unroll
     for (int c0 = 0; c0 < W; c0 += 16) {
         float v[16];
@@ -369,6 +326,10 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, con
         if (keep_row) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(keep_row + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (keep_col) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) keep_col[(int64_t)(c0 + i) * ld_t] = v[i];
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
@@ -383,7 +344,8 @@ template <int IN_PAD>
 __global__ void __launch_bounds__(kThreads, 1)
 agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs, float* __restrict__ mu,
                           float* __restrict__ value, float* __restrict__ xn_out, float* __restrict__ h1_out, float* __restrict__ h2_out,
-                          float* __restrict__ h3_out) {
+                          float* __restrict__ h3_out, const int keep_t) {  // keep_t: the four keep tensors are feature-major [width, B] planes,
+                                                                            // and plane in_dim of xn_out is set to 1 (bias-gradient column)
     // shared memory carve (floats); every operand base is 128-byte aligned
     float* w1 = g_smem;                       // [64 x IN_PAD] canonical
     float* w2 = w1 + kH1 * IN_PAD;            // [128 x 64]
@@ -475,26 +437,36 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
                 }
                 v[i] = x;
             }
-            if (xn_out && ok) *reinterpret_cast<float4*>(xn_out + row * IN_PAD + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            if (xn_out && ok) {
+                if (keep_t) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xn_out[(int64_t)(c0 + i) * B + row] = (c0 + i == in_dim) ? 1.0f : v[i];
+                } else {
+                    *reinterpret_cast<float4*>(xn_out + row * IN_PAD + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
             *reinterpret_cast<float4*>(Pbuf + canon(tid, c0, kM)) = make_float4(v[0], v[1], v[2], v[3]);
         }
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Pbuf), s32(w1), kH1, IN_PAD, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && ok) ? h1_out + row * kH1 : nullptr);            // A1 → Qbuf
+        const bool kr = ok && !keep_t, kc = ok && keep_t;  // row-major / feature-major keeps
+        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && kr) ? h1_out + row * kH1 : nullptr, (h1_out && kc) ? h1_out + row : nullptr, B);  // A1 → Qbuf
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Qbuf), s32(w2), kH2, kH1, tmem + 64); commit(bar); }
         wait(bar, phase); phase ^= 1;
         // layer 2's 128 columns leave in two halves so that A2 never needs more than the two 32 KB buffers: the first half goes to
         // Pbuf and layer 3 starts on it (K-steps 0..7) while the epilogue of the second half fills Qbuf (A1 is dead by now)
-        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && ok) ? h2_out + row * kH2 : nullptr);
+        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && kr) ? h2_out + row * kH2 : nullptr, (h2_out && kc) ? h2_out + row : nullptr, B);
         publish_and_sync(gbar, kM);
         if (tid == 0) gemm(s32(Pbuf), s32(w3), kH3, kH1, tmem + 192);
-        hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, (h2_out && ok) ? h2_out + row * kH2 + kH1 : nullptr);
+        hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, (h2_out && kr) ? h2_out + row * kH2 + kH1 : nullptr,
+                             (h2_out && kc) ? h2_out + (int64_t)kH1 * B + row : nullptr, B);
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Qbuf), s32(w3) + 8 * 2 * (kH3 / 8) * 128, kH3, kH1, tmem + 192, true); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, (h3_out && ok) ? h3_out + row * kH3 : nullptr);  // A3 → Pbuf
+        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, (h3_out && kr) ? h3_out + row * kH3 : nullptr,
+                             (h3_out && kc) ? h3_out + row : nullptr, B);  // A3 → Pbuf
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Pbuf), s32(wh), kOutPad, kH3, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
@@ -912,8 +884,8 @@ int agx_internal_mlp_option(const char* key, int value) {
     return 0;
 }
 
-int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
-                    float* h1_out, float* h2_out, float* h3_out, void* stream) {
+static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
+                            float* h1_out, float* h2_out, float* h3_out, void* stream, const int keep_t) {
     if (!valid(p) || b <= 0 || !obs || !mu || !value) return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_forward: bad argument");
     const size_t smem = smem_bytes(p, 4);
     if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
@@ -929,19 +901,44 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
         cudaFuncSetAttribute(tc::agx_mlp_forward_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                      \
         const int64_t pairs = ((b + tc::kM - 1) / tc::kM + 1) / 2;                                                                       \
         tc::agx_mlp_forward_tc_kernel<PAD><<<(unsigned)(pairs < kGridMax ? pairs : kGridMax), tc::kThreads, kSm, st>>>(*p, b, obs, mu, value,  \
-                                                                                                                       xn_out, h1_out, h2_out, h3_out); \
+                                                                                                                       xn_out, h1_out, h2_out, h3_out, keep_t); \
     } while (0)
     const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
     // measured (scripts/mlp_bench.py, B200, 32 768 / 65 536 rows): tcgen05 20.6 / 33.5 us vs mma.sync 32.9 / 58.7 us without the kept
     // activations (rollout), 28.4 / 49.0 vs 33.5 / 63.1 us with them (update)
     const bool w_aligned = (((uintptr_t)p->w2 | (uintptr_t)p->w3) & 15u) == 0;  // the tcgen05 kernel stages W2 / W3 with 16-byte loads
     const bool use_tc = keep_aligned && w_aligned && (g_fwd_tc == 2 || (g_fwd_tc == 1 && !xn_out));
-    if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }
+    if (keep_t) {  // training path: feature-major keeps for the tensor-core backward / weight-gradient kernels (agx_mlp_train.cu)
+        if (!(keep_aligned && w_aligned && xn_out && h1_out && h2_out && h3_out && (b % tc::kM) == 0 && p->in_dim < p->in_pad &&
+              (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64))))
+            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward_train: needs the 64-128-64 network, in_pad in {32,48,64} > in_dim, b % 128 == 0");
+        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else AGX_FWD_TC(64);
+    }
+    else if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }
     else if (is_shipped(p, 48)) { if (use_tc) AGX_FWD_TC(48); else AGX_FWD(S48); }
     else AGX_FWD(Dims);
 #undef AGX_FWD
 #undef AGX_FWD_TC
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_forward: launch failed");
+}
+
+int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
+                    float* h1_out, float* h2_out, float* h3_out, void* stream) {
+    return mlp_forward_impl(p, b, obs, mu, value, xn_out, h1_out, h2_out, h3_out, stream, 0);
+}
+
+int agx_mlp_forward_train(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xt, float* h1t,
+                          float* h2t, float* h3t, void* stream) {
+    return mlp_forward_impl(p, b, obs, mu, value, xt, h1t, h2t, h3t, stream, 1);
+}
+
+// launcher of the partial-sum reduction for agx_mlp_train.cu (same partial layout as the mma.sync weight-gradient kernels)
+int agx_internal_wgrad_reduce(const AgxMlpParams* p, const AgxMlpGrads* g, const float* w_partials, int n_cta_w, const float* b_partials,
+                              int n_cta_b, void* stream) {
+    const int pf = partial_floats(p);
+    const unsigned gr = (unsigned)((pf + kBiasSlots + 31) / 32);
+    agx_mlp_wgrad_reduce_kernel<<<gr, 32 * kRedGroups, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, *g, w_partials, n_cta_w, pf, b_partials, n_cta_b);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "wgrad reduce: launch failed");
 }
 
 int64_t agx_mlp_workspace_floats(const AgxMlpParams* p) {

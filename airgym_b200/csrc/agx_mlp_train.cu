@@ -1,0 +1,348 @@
+// agx_mlp_train.cu — backward pass of the actor-critic MLP on the 5th-generation tensor cores (tcgen05 + TMEM), for the shipped
+// 64-128-64 network (reference lib/network/mlp.py:4-39 + the mu / value heads, a2c_continuous_logstd_model.py:159-168; the
+// gradients torch autograd computes inside calc_gradients, lib/agent/a2c_continuous.py:299-369).
+//
+// Every intermediate lives in HBM FEATURE-MAJOR — planes [width][B], written by agx_mlp_forward_train and by the kernel below —
+// because a tf32 tcgen05 operand has to be K-major (agx_tc.cuh) and the weight gradient contracts over the BATCH axis:
+//   dW_l[out, in] = sum_b dZ_l[b, out] * a_{l-1}[b, in]   →   A = dZ_l^T (M = out, K = batch rows), B = a_{l-1}^T (N = in, K = batch rows),
+// i.e. both operands are rows of those planes, 128 contiguous bytes per feature and 32-row stage.
+//
+// agx_mlp_backward_tc_kernel — activation-gradient chain, one 128-row tile per 128-thread group (two groups per CTA hide each
+//   other's MMA / barrier latency, as in the forward kernel): dout → dH3 = dout·W_head → dZ3 = dH3∘elu'(h3) → dH2 = dZ3·W3 → dZ2 →
+//   dH1 = dZ2·W2 → dZ1.  Each product is one accumulation chain of tcgen05.mma (M = 128 rows, N = layer width) with the transposed
+//   weights staged K-major in shared memory once per CTA; thread r owns row r = TMEM lane r: tcgen05.ld, multiply by elu'(h) (h read
+//   back from its plane, coalesced), store the dZ plane element (coalesced) and the next A operand (16-byte chunks).
+// agx_mlp_wgrad_tc_kernel — all four weight gradients AND bias gradients of a batch slab in one persistent CTA per SM: 32-row stages
+//   stream through a double-buffered cp.async pipeline straight into the canonical operand layout, one thread issues 16 MMAs per
+//   stage (4 layers x 4 K-steps) into four TMEM accumulators that live for the whole slab; the bias gradient is the extra output
+//   column produced by a constant ones row appended to each B operand (plane `in_dim` of the normalised input is all ones).
+//   Per-CTA partials go through the same deterministic reduction as the mma.sync path (agx_mlp.cu).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "agx.h"
+#include "agx_tc.cuh"
+
+int agx_internal_fail(int code, const char* msg);
+extern "C" int agx_internal_wgrad_reduce(const AgxMlpParams* p, const AgxMlpGrads* g, const float* w_partials, int n_cta_w,
+                                         const float* b_partials, int n_cta_b, void* stream);
+
+namespace {
+
+constexpr int kOutPad = 16, kMaxW = 128, kBiasSlots = 3 * kMaxW + kOutPad;
+extern __shared__ __align__(128) float t_smem[];
+
+__device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.0f ? 1.0f : h + 1.0f; }
+
+// ---- activation-gradient chain ------------------------------------------------------------------------------------------------
+namespace tcb {
+using namespace tc;
+constexpr int kThreads = 2 * kM;
+constexpr int kW3T = kH2 * kH3, kW2T = kH1 * kH2, kWhT = kH3 * kOutPad;        // floats
+constexpr int kGbuf = kM * kH2, kDbuf = kM * kOutPad;                            // per group
+constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kW3T + kW2T + kWhT + 2 * (kGbuf + kDbuf));
+
+// dZ = dH ∘ elu'(h) for this thread's row: TMEM cols [col0, col0 + W) x the h plane → dZ plane (+ next A operand when a_next)
+template <int W>
+__device__ __forceinline__ void grad_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ h_col, float* __restrict__ dz_col,
+                                              int64_t B, float* a_next, int r) {
+#pragma unroll
+    for (int c0 = 0; c0 < W; c0 += 16) {
+        float h[16], v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = __ldg(h_col + (int64_t)(c0 + i) * B);  // issued before the TMEM load completes
+        tmem_ld16(tmem_row + (uint32_t)(col0 + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= elu_grad_from_out(h[i]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dz_col[(int64_t)(c0 + i) * B] = v[i];
+        if (a_next) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(a_next + canon(r, c0 + i, kM)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ grad_mu,
+                           const float* __restrict__ grad_value, const float* __restrict__ h1t, const float* __restrict__ h2t,
+                           const float* __restrict__ h3t, float* __restrict__ dz1t, float* __restrict__ dz2t, float* __restrict__ dz3t,
+                           float* __restrict__ doutt) {
+    float* w3T = t_smem;              // B operand of dH2 = dZ3·W3: [n = 128 (layer-2 feature)][k = 64 (layer-3 feature)] canonical
+    float* w2T = w3T + kW3T;          // dH1 = dZ2·W2: [n = 64][k = 128]
+    float* whT = w2T + kW2T;          // dH3 = dout·W_head: [n = 64][k = 16]
+    float* act = whT + kWhT;
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base;
+    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all >> 7, tid = tid_all & (kM - 1), A = P.actions_num;
+    float* Gbuf = act + group * (kGbuf + kDbuf);   // dZ3 [128 x 64], then dZ2 [128 x 128]
+    float* Dbuf = Gbuf + kGbuf;                    // dout [128 x 16]
+    uint64_t* bar = &bars[group];
+    // transposed weights, TF32-rounded, K-major canonical.  Global reads are coalesced (torch rows), the strided shared-memory
+    // stores are a one-off per CTA.
+    for (int i = tid_all; i < kH3 * kH2; i += kThreads) { const int k = i / kH2, n = i - k * kH2; w3T[canon(n, k, kH2)] = tc_tf32r(P.w3[i]); }
+    for (int i = tid_all; i < kH2 * kH1; i += kThreads) { const int k = i / kH1, n = i - k * kH1; w2T[canon(n, k, kH1)] = tc_tf32r(P.w2[i]); }
+    for (int i = tid_all; i < kOutPad * kH3; i += kThreads) {
+        const int k = i / kH3, n = i - k * kH3;
+        const float w = k < A ? P.w_mu[k * kH3 + n] : (k == A ? P.w_value[n] : 0.0f);
+        whT[canon(n, k, kH3)] = tc_tf32r(w);
+    }
+    if (tid_all == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp_all == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync(0, kThreads);
+    const uint32_t tmem = tmem_base + (uint32_t)(group * 256);
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp_all & 3) * 32) << 16);
+    const int gbar = 1 + group;
+    uint32_t phase = 0;
+    const int64_t n_tiles = B / kM;  // B % 128 == 0 (checked on the host)
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + group; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+        const int64_t row = tile * kM + tid;
+        {   // dout row = [d loss / d mu (A) | d loss / d value | 0 ...] → its plane and the first A operand (K = 16)
+            float d[kOutPad];
+#pragma unroll
+            for (int c = 0; c < kOutPad; ++c) d[c] = 0.0f;
+            const float gv = grad_value[row];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) d[c] = c < A ? grad_mu[row * A + c] : (c == A ? gv : 0.0f);
+#pragma unroll
+            for (int c = 0; c < kOutPad; ++c) doutt[(int64_t)c * B + row] = d[c];
+#pragma unroll
+            for (int c = 0; c < kOutPad; c += 4) *reinterpret_cast<float4*>(Dbuf + canon(tid, c, kM)) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+        }
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Dbuf), s32(whT), kH3, kOutPad, tmem + 0); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        grad_epilogue<kH3>(tmem_row, 0, h3t + row, dz3t + row, B, Gbuf, tid);
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Gbuf), s32(w3T), kH2, kH3, tmem + 64); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        grad_epilogue<kH2>(tmem_row, 64, h2t + row, dz2t + row, B, Gbuf, tid);  // dZ3 is dead: the MMA that read it has completed
+        publish_and_sync(gbar, kM);
+        if (tid == 0) { gemm(s32(Gbuf), s32(w2T), kH1, kH2, tmem + 192); commit(bar); }
+        wait(bar, phase); phase ^= 1;
+        grad_epilogue<kH1>(tmem_row, 192, h1t + row, dz1t + row, B, nullptr, tid);
+        // the next tile's first MMA writes TMEM columns [0, 64): every thread of the group has finished reading them long ago
+        // (two barriers back); its Dbuf / Gbuf stores are ordered behind this tile's last MMA by the wait above
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp_all == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+}  // namespace tcb
+
+// ---- weight + bias gradients --------------------------------------------------------------------------------------------------
+namespace tcw {
+using namespace tc;
+constexpr int kThreads = 256;
+constexpr int kStage = 32;            // batch rows (= K) per pipeline stage
+constexpr int kKc = kStage / 4;       // 16-byte K-chunks per operand row and stage
+constexpr int kN2 = kH1 + 16, kN3 = kH2 + 16;   // B operands of layers 2 / 3 carry a 16-row block whose first row is all ones (bias column)
+// TMEM columns of the four accumulators (M = 128 lanes each; only the first `out` lanes are meaningful)
+constexpr int kC1 = 0, kC2 = 64, kC3 = kC2 + kN2, kCh = kC3 + kN3;   // 0 | 64 | 144 | 288 (+16) <= 512
+
+template <int IN_PAD>
+struct Layout {  // float offsets inside one stage buffer; every tile is [kKc][rows][4]
+    static constexpr int a1 = 0, a2 = a1 + kKc * kM * 4, a3 = a2 + kKc * kM * 4, ah = a3 + kKc * kM * 4;
+    static constexpr int b1 = ah + kKc * kM * 4, b2 = b1 + kKc * IN_PAD * 4, b3 = b2 + kKc * kN2 * 4, bh = b3 + kKc * kN3 * 4;
+    static constexpr int floats = bh + kKc * kOutPad * 4;
+};
+__device__ __forceinline__ void cp16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(dst)), "l"(src) : "memory");
+}
+// one operand tile of a stage: R feature rows x 32 batch rows from a feature-major plane into [kc][RA][16 B].  A warp covers
+// 16 features x 2 K-chunks: 32-byte global sectors fully used, shared-memory stores at most 2-way conflicted.
+template <int R, int RA>
+__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ plane, int64_t B, int64_t r0) {
+    for (int j = threadIdx.x; j < R * kKc; j += kThreads) {
+        const int kc = ((j >> 5) & 3) * 2 + (j & 1), m = (j >> 7) * 16 + ((j >> 1) & 15);
+        cp16(dst + (kc * RA + m) * 4, plane + (int64_t)m * B + r0 + kc * 4);
+    }
+}
+
+template <int IN_PAD>
+__global__ void __launch_bounds__(kThreads, 1)
+agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ xt, const float* __restrict__ h1t,
+                        const float* __restrict__ h2t, const float* __restrict__ h3t, const float* __restrict__ dz1t,
+                        const float* __restrict__ dz2t, const float* __restrict__ dz3t, const float* __restrict__ doutt,
+                        float* __restrict__ w_partials, float* __restrict__ b_partials, int partial_floats) {
+    using L = Layout<IN_PAD>;
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // constant parts of both stage buffers: zero rows that pad M to 128, and the ones rows behind the bias columns
+    for (int i = tid; i < 2 * L::floats; i += kThreads) t_smem[i] = 0.0f;
+    __syncthreads();
+    for (int i = tid; i < 2 * kStage; i += kThreads) {
+        float* buf = t_smem + (i / kStage) * L::floats;
+        const int k = i % kStage;
+        buf[L::ah + canon(kH3, k, kM)] = 1.0f;    // A of the heads: row 64 = ones → lane 64 of its accumulator = sum_b dout[b, :]
+        buf[L::b2 + canon(kH1, k, kN2)] = 1.0f;   // B of layer 2: row 64 = ones → column 64 = sum_b dZ2[b, :]
+        buf[L::b3 + canon(kH2, k, kN3)] = 1.0f;   // B of layer 3: row 128 = ones
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync(0, kThreads);
+    const uint32_t tmem = tmem_base;
+    const int64_t n_stages_total = B / kStage;  // B % 128 == 0
+    const int64_t s_begin = (int64_t)blockIdx.x * n_stages_total / gridDim.x, s_end = (int64_t)(blockIdx.x + 1) * n_stages_total / gridDim.x;
+    const int S = (int)(s_end - s_begin);
+
+    auto issue = [&](int s) {
+        float* buf = t_smem + (s & 1) * L::floats;
+        const int64_t r0 = (s_begin + s) * kStage;
+        load_tile<kH1, kM>(buf + L::a1, dz1t, B, r0);
+        load_tile<kH2, kM>(buf + L::a2, dz2t, B, r0);
+        load_tile<kH3, kM>(buf + L::a3, dz3t, B, r0);
+        load_tile<kH3, kM>(buf + L::ah, h3t, B, r0);
+        load_tile<IN_PAD, IN_PAD>(buf + L::b1, xt, B, r0);
+        load_tile<kH1, kN2>(buf + L::b2, h1t, B, r0);
+        load_tile<kH2, kN3>(buf + L::b3, h2t, B, r0);
+        load_tile<kOutPad, kOutPad>(buf + L::bh, doutt, B, r0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (S > 0) issue(0);
+    if (S > 1) issue(1);
+    uint32_t phase[2] = {0u, 0u};
+    for (int s = 0; s < S; ++s) {
+        if (s + 1 < S) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        publish_and_sync(0, kThreads);  // every thread's copies of stage s have landed and are visible to the tensor core
+        const int b = s & 1;
+        if (tid == 0) {
+            const uint32_t base = s32(t_smem + b * L::floats);
+            const bool acc = s > 0;
+            gemm(base + 4 * L::a1, base + 4 * L::b1, IN_PAD, kStage, tmem + kC1, acc);
+            gemm(base + 4 * L::a2, base + 4 * L::b2, kN2, kStage, tmem + kC2, acc);
+            gemm(base + 4 * L::a3, base + 4 * L::b3, kN3, kStage, tmem + kC3, acc);
+            gemm(base + 4 * L::ah, base + 4 * L::bh, kOutPad, kStage, tmem + kCh, acc);
+            commit(&bars[b]);
+        }
+        if (s + 2 < S) {  // the MMAs of stage s must have read buffer b before stage s + 2 is copied over it
+            wait(&bars[b], phase[b]); phase[b] ^= 1u;
+            issue(s + 2);
+        }
+    }
+    if (S > 0) {  // the last commit covers every earlier MMA of the issuing thread
+        const int b = (S - 1) & 1;
+        wait(&bars[b], phase[b]);
+    }
+    // ---- epilogue: accumulators → this CTA's partials (layout of agx_mlp.cu: dense [out x in_pad] blocks back to back; bias slots b1|b2|b3|heads)
+    float* wp = w_partials + (int64_t)blockIdx.x * partial_floats;
+    float* bp = b_partials + (int64_t)blockIdx.x * kBiasSlots;
+    const int q = warp & 3, half = warp >> 2, m = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const int in_dim = P.in_dim;
+    constexpr int base2 = kH1 * IN_PAD, base3 = base2 + kH2 * kH1, baseh = base3 + kH3 * kH2;
+    constexpr int n1 = IN_PAD / 16, n2 = kN2 / 16, n3 = kN3 / 16;
+    for (int ci = half; ci < n1 + n2 + n3 + 1; ci += 2) {
+        float v[16];
+        if (S == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        if (ci < n1) {
+            const int c0 = ci * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC1 + c0), v);
+            if (m < kH1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + m * IN_PAD + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (c0 + i == in_dim) bp[0 * kMaxW + m] = v[i];
+            }
+        } else if (ci < n1 + n2) {
+            const int c0 = (ci - n1) * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC2 + c0), v);
+            if (c0 < kH1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + base2 + m * kH1 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                bp[1 * kMaxW + m] = v[0];
+            }
+        } else if (ci < n1 + n2 + n3) {
+            const int c0 = (ci - n1 - n2) * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC3 + c0), v);
+            if (m < kH3) {
+                if (c0 < kH2) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + base3 + m * kH2 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+                    bp[2 * kMaxW + m] = v[0];
+                }
+            }
+        } else {
+            if (S > 0) tmem_ld16(trow + (uint32_t)kCh, v);
+            if (m < kH3) {  // accumulator = dW_head^T: lane = layer-3 feature, column = head output
+#pragma unroll
+                for (int o = 0; o < kOutPad; ++o) wp[baseh + o * kH3 + m] = v[o];
+            } else if (m == kH3) {
+#pragma unroll
+                for (int o = 0; o < kOutPad; ++o) bp[3 * kMaxW + o] = v[o];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+}  // namespace tcw
+
+bool train_ok(const AgxMlpParams* p) {
+    return p && p->h1 == tc::kH1 && p->h2 == tc::kH2 && p->h3 == tc::kH3 && (p->in_pad == 32 || p->in_pad == 48 || p->in_pad == 64) &&
+           p->in_dim > 0 && p->in_dim < p->in_pad && (p->actions_num == 4 || p->actions_num == 5) && p->w1 && p->w2 && p->w3 && p->w_mu && p->w_value;
+}
+
+}  // namespace
+
+extern "C" {
+
+int agx_mlp_train_supported(const AgxMlpParams* p) { return train_ok(p) ? 1 : 0; }
+
+int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
+                           const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t, float* dz3t,
+                           float* doutt, float* workspace, void* stream) {
+    if (!train_ok(p) || !g || b <= 0 || (b % tc::kM) != 0 || !grad_mu || !grad_value || !xt || !h1t || !h2t || !h3t || !dz1t || !dz2t || !dz3t ||
+        !doutt || !workspace || !g->gw1 || !g->gb1 || !g->gw2 || !g->gb2 || !g->gw3 || !g->gb3 || !g->gw_mu || !g->gb_mu || !g->gw_value || !g->gb_value)
+        return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_backward_train: bad argument (64-128-64 network, in_pad in {32,48,64} > in_dim, batch % 128 == 0)");
+    const uintptr_t al = (uintptr_t)xt | (uintptr_t)h1t | (uintptr_t)h2t | (uintptr_t)h3t | (uintptr_t)dz1t | (uintptr_t)dz2t | (uintptr_t)dz3t |
+                         (uintptr_t)doutt | (uintptr_t)workspace;
+    if (al & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_mlp_backward_train: buffers must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    constexpr int kGrid = 148;
+    const int64_t tiles = b / tc::kM, pairs = (tiles + 1) / 2;
+    cudaFuncSetAttribute(tcb::agx_mlp_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmemBytes);
+    tcb::agx_mlp_backward_tc_kernel<<<(unsigned)(pairs < kGrid ? pairs : kGrid), tcb::kThreads, tcb::kSmemBytes, st>>>(
+        *p, b, grad_mu, grad_value, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt);
+    const int pf = p->h1 * p->in_pad + p->h2 * p->h1 + p->h3 * p->h2 + kOutPad * p->h3;
+    const int64_t stages = b / tcw::kStage;
+    const unsigned gw = (unsigned)(stages < kGrid ? stages : kGrid);
+    float* w_partials = workspace;
+    float* b_partials = workspace + (int64_t)kGrid * pf;
+#define AGX_WGRAD_TC(PAD)                                                                                                         \
+    do {                                                                                                                          \
+        constexpr int kSm = 2 * tcw::Layout<PAD>::floats * (int)sizeof(float);                                                    \
+        cudaFuncSetAttribute(tcw::agx_mlp_wgrad_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                \
+        tcw::agx_mlp_wgrad_tc_kernel<PAD><<<gw, tcw::kThreads, kSm, st>>>(*p, b, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, w_partials, \
+                                                                          b_partials, pf);                                        \
+    } while (0)
+    if (p->in_pad == 32) AGX_WGRAD_TC(32); else if (p->in_pad == 48) AGX_WGRAD_TC(48); else AGX_WGRAD_TC(64);
+#undef AGX_WGRAD_TC
+    if (cudaGetLastError() != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward_train: launch failed");
+    return agx_internal_wgrad_reduce(p, g, w_partials, (int)gw, b_partials, (int)gw, stream);
+}
+
+}  // extern "C"

@@ -192,10 +192,16 @@ class A2CAgent:
         self.norm_values, self.norm_returns, self.advantages = f(N * H, 1), f(N * H, 1), f(N * H)
         if self.fused_mlp:
             mb, dims = self.minibatch_size, self.model.fused_keep_dims()
-            self.keep = tuple(f(mb, d) for d in dims)           # normalised (padded) input + post-ELU activations
             self.mlp_ws = self.model.fused_workspace(dev)
-            self.dz = tuple(f(mb, d) for d in dims[1:])         # pre-activation gradients
-            self.dout = f(mb, 16)                                # [dmu | dvalue | 0] padded head gradient
+            # "tcgen05" (default where it applies: 64-128-64 network, minibatch % 128 == 0): forward, activation-gradient chain and
+            # weight gradients on tcgen05.mma with feature-major intermediates; "mma_sync": the warp-level TF32 kernels
+            self.mlp_train_tc = self.config.get("mlp_backward", "tcgen05") == "tcgen05" and self.model.train_supported(mb)
+            if self.mlp_train_tc:
+                self.keep, self.dz, self.dout = self.model.train_buffers(mb, dev)
+            else:
+                self.keep = tuple(f(mb, d) for d in dims)           # normalised (padded) input + post-ELU activations
+                self.dz = tuple(f(mb, d) for d in dims[1:])         # pre-activation gradients
+                self.dout = f(mb, 16)                                # [dmu | dvalue | 0] padded head gradient
             self.mb_mu, self.mb_value = f(mb, A), f(mb)
             self.ro_mu, self.ro_value = f(N, A), f(N)
         self.epoch_loss_sums = torch.zeros(_capi.AGX_PPO_STATS, device=dev)
@@ -399,7 +405,10 @@ class A2CAgent:
                 self._rms_update(self._trunk_rms(), obs)
         self.model.eval()  # statistics are updated explicitly above; forward only normalises
         if self.fused_mlp:
-            self.model.fused_heads(obs, self.mb_mu, self.mb_value, keep=self.keep)
+            if self.mlp_train_tc:
+                self.model.fused_heads_train(obs, self.mb_mu, self.mb_value, self.keep)
+            else:
+                self.model.fused_heads(obs, self.mb_mu, self.mb_value, keep=self.keep)
             mu, value = self.mb_mu, self.mb_value
         else:
             mu, value = self.model.heads(obs)
@@ -436,7 +445,10 @@ class A2CAgent:
     def _manual_backward(self):
         """Backward of the MLP without autograd: activation-gradient chain, split-K weight gradients and their deterministic
         reduction (three launches) write straight into the flat gradient buffer (every parameter's .grad is a view of it)."""
-        self.model.fused_backward(self.grad_mu, self.grad_value, self.keep, self.dz, self.dout, self.mlp_ws)
+        if self.mlp_train_tc:
+            self.model.fused_backward_train(self.grad_mu, self.grad_value, self.keep, self.dz, self.dout, self.mlp_ws)
+        else:
+            self.model.fused_backward(self.grad_mu, self.grad_value, self.keep, self.dz, self.dout, self.mlp_ws)
         self.model.logstd.grad.copy_(self.grad_logstd)
 
     def _update_pass(self, update_rms):

@@ -105,14 +105,15 @@ class ModelA2CContinuousLogStd(nn.Module):
         return flat, grads
 
     # ---- fused tensor-core path (libagx agx_mlp_forward / agx_mlp_backward) -------------------------------------------
-    def fused_params(self):
-        """AgxMlpParams pointing at this module's parameter storage (valid as long as the tensors are not re-allocated)."""
+    def fused_params(self, train=False):
+        """AgxMlpParams pointing at this module's parameter storage (valid as long as the tensors are not re-allocated).
+        train: the tcgen05 training path keeps one spare input plane (index in_dim, all ones: the bias-gradient column)."""
         layers = self.actor_mlp.layers
         if len(layers) != 3 or self.actor_mlp.activation is not F.elu:
             raise NotImplementedError("fused MLP kernels cover the shipped [h1,h2,h3]+ELU network")
         P = _capi.AgxMlpParams()
         P.in_dim = layers[0].in_features
-        P.in_pad = (P.in_dim + 15) // 16 * 16
+        P.in_pad = (P.in_dim + (16 if train else 15)) // 16 * 16
         P.h1, P.h2, P.h3 = layers[0].out_features, layers[1].out_features, layers[2].out_features
         P.actions_num = self.actions_num
         for i, l in enumerate(layers, 1):
@@ -133,6 +134,41 @@ class ModelA2CContinuousLogStd(nn.Module):
         k = keep if keep is not None else (None, None, None, None)
         _capi.check(_capi.load().agx_mlp_forward(C.byref(self._fused), obs.shape[0], p(obs), p(mu_out), p(value_out), p(k[0]), p(k[1]),
                                                  p(k[2]), p(k[3]), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_forward")
+
+    # ---- tcgen05 training path: feature-major intermediates (agx_mlp_forward_train / agx_mlp_backward_train) ----------
+    def train_params(self):
+        if getattr(self, "_fused_t", None) is None:
+            self._fused_t = self.fused_params(train=True)
+        return self._fused_t
+
+    def train_supported(self, batch):
+        """The tensor-core backward covers the shipped 64-128-64 network with batches that are multiples of 128."""
+        try:
+            P = self.train_params()
+        except NotImplementedError:
+            return False
+        return batch % 128 == 0 and bool(_capi.load().agx_mlp_train_supported(C.byref(P)))
+
+    def train_buffers(self, batch, device):
+        """(keep_t, dz_t, dout_t): [width, batch] planes — xt/h1t/h2t/h3t kept by the forward, dz1t/dz2t/dz3t + doutt scratch."""
+        P = self.train_params()
+        f = lambda w: torch.zeros(w, batch, device=device, dtype=torch.float32)
+        return (f(P.in_pad), f(P.h1), f(P.h2), f(P.h3)), (f(P.h1), f(P.h2), f(P.h3)), f(16)
+
+    def fused_heads_train(self, obs, mu_out, value_out, keep_t):
+        p = lambda t: t.data_ptr()
+        _capi.check(_capi.load().agx_mlp_forward_train(C.byref(self.train_params()), obs.shape[0], p(obs), p(mu_out), p(value_out),
+                                                       p(keep_t[0]), p(keep_t[1]), p(keep_t[2]), p(keep_t[3]),
+                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_forward_train")
+
+    def fused_backward_train(self, grad_mu, grad_value, keep_t, dz_t, dout_t, workspace):
+        if getattr(self, "_fused_g", None) is None:
+            self._fused_g = self.fused_grads()
+        p = lambda t: t.data_ptr()
+        _capi.check(_capi.load().agx_mlp_backward_train(
+            C.byref(self.train_params()), C.byref(self._fused_g), grad_mu.shape[0], p(grad_mu), p(grad_value), p(keep_t[0]), p(keep_t[1]),
+            p(keep_t[2]), p(keep_t[3]), p(dz_t[0]), p(dz_t[1]), p(dz_t[2]), p(dout_t), p(workspace),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_backward_train")
 
     def fused_grads(self):
         """AgxMlpGrads pointing at the parameters' .grad tensors (views of the flat gradient buffer)."""
@@ -162,7 +198,12 @@ class ModelA2CContinuousLogStd(nn.Module):
     def fused_workspace(self, device):
         if getattr(self, "_fused", None) is None:
             self._fused = self.fused_params()
-        return torch.zeros(int(_capi.load().agx_mlp_workspace_floats(C.byref(self._fused))), device=device)
+        n = int(_capi.load().agx_mlp_workspace_floats(C.byref(self._fused)))
+        try:  # the training path pads the input wider: size for the larger of the two
+            n = max(n, int(_capi.load().agx_mlp_workspace_floats(C.byref(self.train_params()))))
+        except NotImplementedError:
+            pass
+        return torch.zeros(n, device=device)
 
     # ---- forward ----------------------------------------------------------------------------------------------------
     def norm_obs(self, obs):

@@ -362,6 +362,19 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
                      const float* xn, const float* h1, const float* h2, const float* h3, float* dz1, float* dz2, float* dz3,
                      float* dout, float* workspace, void* stream);
 
+/* Training path on the 5th-generation tensor cores (tcgen05 + TMEM) for the shipped 64-128-64 network: forward, activation-gradient
+ * chain and weight / bias gradients all run on tcgen05.mma.  Intermediates are FEATURE-MAJOR planes ([width][b], b % 128 == 0), which
+ * is what makes both operands of the weight gradient (it contracts over the batch axis) K-major:
+ *   xt [in_pad, b] (plane in_dim = 1: the bias-gradient column; in_pad in {32,48,64} must exceed in_dim), h1t [64, b], h2t [128, b],
+ *   h3t [64, b] written by agx_mlp_forward_train;  dz1t [64, b], dz2t [128, b], dz3t [64, b], doutt [16, b] scratch of the backward.
+ * agx_mlp_backward_train overwrites the gradients in `g` (deterministic); workspace as agx_mlp_workspace_floats. */
+int agx_mlp_train_supported(const AgxMlpParams* p);
+int agx_mlp_forward_train(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xt, float* h1t,
+                          float* h2t, float* h3t, void* stream);
+int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
+                           const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t,
+                           float* dz3t, float* doutt, float* workspace, void* stream);
+
 /* ---- depth-image encoder (row f3) ------------------------------------------------------------------------------------
  * Replaces the forward of lib/network/cnn.py:3-33 (CNNFeatureExtractor: three stride-2 convolutions, each followed by
  * ReLU then BatchNorm2d, global average pool, Linear 64 -> feature_dim) in EVAL mode, with the per-pixel input

@@ -272,3 +272,79 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
     torch.cuda.synchronize()
     for n, p in model.named_parameters():
         assert torch.equal(p.grad, first[n]), n
+
+
+@pytest.mark.parametrize("OBS,B", [(18, 2048), (18, 65536), (48, 1024), (46, 256), (18, 128)])
+def test_tcgen05_train_path_vs_autograd(built, OBS, B):
+    """agx_mlp_forward_train / agx_mlp_backward_train — forward, activation-gradient chain, weight AND bias gradients all on
+    tcgen05.mma (feature-major intermediates) — against the fp32 torch model + autograd, at the TF32 bound of the mma.sync path:
+    outputs 5e-3 rel + 2e-3 abs, parameter gradients 2e-2 of their scale; bitwise reproducible."""
+    from airgym_b200.lib.config import default_ppo_config
+    from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+
+    torch.manual_seed(5)
+    A = 4
+    model = ModelA2CContinuousLogStd(default_ppo_config("hovering")["params"], {"actions_num": A, "input_shape": (OBS,)}).cuda()
+    with torch.no_grad():
+        model.running_mean_std.running_mean.copy_(torch.randn(OBS, dtype=torch.float64) * 0.3)
+        model.running_mean_std.running_var.copy_(torch.rand(OBS, dtype=torch.float64) + 0.5)
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    model.flatten_parameters()
+    model.eval()
+    assert model.train_supported(B) and not model.train_supported(B + 8)
+    P = model.train_params()
+    assert P.in_pad == {18: 32, 48: 64, 46: 48}[OBS]
+    obs = torch.randn(B, OBS, device="cuda") * 2.0
+    mu_ref, v_ref = model.heads(obs)
+    keep, dz, dout = model.train_buffers(B, "cuda")
+    mu, value = torch.zeros(B, A, device="cuda"), torch.zeros(B, device="cuda")
+    model.fused_heads_train(obs, mu, value, keep)
+    assert_close(mu.cpu(), mu_ref.detach().cpu(), "mu", rtol=5e-3, atol=2e-3)
+    assert_close(value.cpu(), v_ref.detach().squeeze(-1).cpu(), "value", rtol=5e-3, atol=2e-3)
+    xn = model.norm_obs(obs)
+    assert_close(keep[0][:OBS].t().cpu(), xn.cpu(), "normalised input planes", rtol=1e-6, atol=1e-6)
+    assert bool((keep[0][OBS] == 1.0).all()) and float(keep[0][OBS + 1:].abs().max() if P.in_pad > OBS + 1 else 0.0) == 0.0
+    with torch.no_grad():
+        h1_ref = torch.nn.functional.elu(model.actor_mlp.layers[0](xn))
+        h2_ref = torch.nn.functional.elu(model.actor_mlp.layers[1](h1_ref))
+    assert_close(keep[1].t().cpu(), h1_ref.cpu(), "h1 planes", rtol=5e-3, atol=3e-3)
+    assert_close(keep[2].t().cpu(), h2_ref.cpu(), "h2 planes", rtol=5e-3, atol=5e-3)
+    g_mu, g_v = torch.randn(B, A, device="cuda") / B, torch.randn(B, device="cuda") / B
+    for p in model.parameters():
+        p.grad.zero_()
+    torch.autograd.backward((mu_ref, v_ref), (g_mu, g_v.view(-1, 1)))
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad.fill_(7.0)  # the kernels overwrite (do not accumulate)
+    ws = model.fused_workspace("cuda")
+    model.fused_backward_train(g_mu, g_v, keep, dz, dout, ws)
+    torch.cuda.synchronize()
+    assert_close(dout[:A].t().cpu(), g_mu.cpu(), "dout planes (mu)", rtol=0, atol=0)
+    assert_close(dout[A].cpu(), g_v.cpu(), "dout plane (value)", rtol=0, atol=0)
+    for n, p in model.named_parameters():
+        if n == "logstd":
+            continue
+        scale = float(ref_grads[n].abs().max()) + 1e-12
+        assert_close((p.grad / scale).cpu(), (ref_grads[n] / scale).cpu(), f"grad {n}", rtol=2e-2, atol=1e-2)
+    first = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.fused_backward_train(g_mu, g_v, keep, dz, dout, ws)
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        assert torch.equal(p.grad, first[n]), n
+    # and against the mma.sync backward on the same kept activations (row-major copies): same TF32 products, different summation order
+    keep_r = tuple(k.t().contiguous() for k in keep)
+    keep_r = (torch.nn.functional.pad(xn, (0, (OBS + 15) // 16 * 16 - OBS)),) + keep_r[1:]
+    dims = model.fused_keep_dims()
+    dz_r, dout_r = tuple(torch.zeros(B, d, device="cuda") for d in dims[1:]), torch.zeros(B, 16, device="cuda")
+    model.fused_heads(obs, mu, value, keep=tuple(torch.zeros(B, d, device="cuda") for d in dims))  # builds model._fused
+    model.fused_backward(g_mu, g_v, keep_r, dz_r, dout_r, ws)
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        if n == "logstd":
+            continue
+        scale = float(first[n].abs().max()) + 1e-12
+        assert_close((p.grad / scale).cpu(), (first[n] / scale).cpu(), f"tcgen05 vs mma.sync grad {n}", rtol=5e-3, atol=3e-3)
+    assert_close(dz_r[2].t().cpu(), dz[2].cpu(), "dz3", rtol=5e-3, atol=1e-7 + 5e-3 * float(dz_r[2].abs().max()))
+    assert_close(dz_r[0].t().cpu(), dz[0].cpu(), "dz1", rtol=5e-3, atol=1e-7 + 1e-2 * float(dz_r[0].abs().max()))
