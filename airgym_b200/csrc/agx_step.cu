@@ -29,6 +29,15 @@ int g_use_bulk = 1;
 int g_pdl = -1;  // -1 auto: noise-first PDL (mode 3) for grids of at most ~one wave, where the kernel boundary dominates
                  // (65 536 envs: 10.3 -> 7.9 us/step); off for multi-wave grids, where early CTAs only steal slots (4 M envs: 357 -> 402 us)
 int g_sm_count = 0;
+int g_balanced = 0;  // equal tiles on a multiple of the SM count for single-wave grids (agx_set_option("balanced", 0|1)): measured 7.28 vs 7.19 us/step at 65 536 envs, i.e. no gain — per-SM load balance is not the limiter — so off by default
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) g_sm_count = sms;
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
 
 int fail(int code, const char* fmt, const char* detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -88,6 +97,7 @@ int agx_set_option(const char* key, int value) {
         return AGX_OK;
     }
     if (!strcmp(key, "use_bulk")) { g_use_bulk = value ? 1 : 0; return AGX_OK; }
+    if (!strcmp(key, "balanced")) { g_balanced = value ? 1 : 0; return AGX_OK; }
     if (!strcmp(key, "pdl")) {
         if (value < -1 || value > 3) return fail(AGX_ERR_ARG, "agx_set_option: pdl must be -1 (auto) or 0..3%s");
         g_pdl = value;

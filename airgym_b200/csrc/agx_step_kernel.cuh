@@ -261,9 +261,19 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     __shared__ unsigned long long s_step;
 
     const int tid = threadIdx.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * BLOCK;
-    const int tile_n = (int)((n - tile0) < (int64_t)BLOCK ? (n - tile0) : (int64_t)BLOCK);
-    const bool bulk = (kflags & 1) && (tile_n == BLOCK);  // CTA-uniform
+    // Tiles: BLOCK consecutive envs per CTA, or — single-wave grids (kflags bit 3) — the env axis cut into gridDim.x nearly equal
+    // tiles whose boundaries are multiples of 4 envs (16-byte aligned spans), with gridDim.x a multiple of the SM count: every SM
+    // then carries the same number of envs (65 536 envs: 592 tiles of 108-112 instead of 512 of 128 spread 4/3 over the SMs).
+    int64_t tile0, tile_end;
+    if (kflags & 8) {
+        tile0 = (((int64_t)blockIdx.x * n) / gridDim.x) & ~(int64_t)3;
+        tile_end = (blockIdx.x + 1 == gridDim.x) ? n : ((((int64_t)(blockIdx.x + 1) * n) / gridDim.x) & ~(int64_t)3);
+    } else {
+        tile0 = (int64_t)blockIdx.x * BLOCK;
+        tile_end = (n - tile0) < (int64_t)BLOCK ? n : tile0 + BLOCK;
+    }
+    const int tile_n = (int)(tile_end - tile0);
+    const bool bulk = (kflags & 1) && tile_n > 0 && (tile_n & 3) == 0;  // CTA-uniform: spans are 16-byte multiples
     const int pdl_mode = (kflags >> 1) & 3;
     const int64_t env = tile0 + tid;
     const bool active = tid < tile_n;
@@ -279,8 +289,8 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         if (bulk) {
             if (tid == 0) {
                 mbar_init(&s_bar, 1);
-                mbar_expect_tx(&s_bar, BLOCK * 13 * 4);
-                bulk_g2s(s_state, io.state + tile0 * 13, BLOCK * 13 * 4, &s_bar);
+                mbar_expect_tx(&s_bar, tile_n * 13 * 4);
+                bulk_g2s(s_state, io.state + tile0 * 13, tile_n * 13 * 4, &s_bar);
             }
         } else {
             const float* src = io.state + tile0 * 13;
@@ -356,13 +366,13 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         // L2 is the GPU's point of coherence, so prefetching this tile's inputs into it is a pure hint whatever the
         // running predecessor still writes: the DRAM reads of step t+1 overlap the compute phase of step t, and the
         // loads after the wait hit L2.
-        if (tile_n == BLOCK && tid < 5 + K) {
-            if (tid == 0) prefetch_l2(io.state + tile0 * 13, BLOCK * 13 * 4);
-            else if (tid == 1) prefetch_l2(io.action + tile0 * A, BLOCK * A * 4);
-            else if (tid == 2) prefetch_l2(io.prev_action + tile0 * A, BLOCK * A * 4);
-            else if (tid == 3) prefetch_l2(io.progress + tile0, BLOCK * 8);
-            else if (tid == 4) prefetch_l2(io.reset + tile0, BLOCK * 8);
-            else if ((n & 3) == 0) prefetch_l2(io.ctrl_state + (int64_t)(tid - 5) * n + tile0, BLOCK * 4);  // plane rows 16-B aligned
+        if (tile_n > 0 && (tile_n & 3) == 0 && tid < 5 + K) {
+            if (tid == 0) prefetch_l2(io.state + tile0 * 13, tile_n * 13 * 4);
+            else if (tid == 1) prefetch_l2(io.action + tile0 * A, tile_n * A * 4);
+            else if (tid == 2) prefetch_l2(io.prev_action + tile0 * A, tile_n * A * 4);
+            else if (tid == 3) prefetch_l2(io.progress + tile0, tile_n * 8);
+            else if (tid == 4) prefetch_l2(io.reset + tile0, tile_n * 8);
+            else if ((n & 3) == 0) prefetch_l2(io.ctrl_state + (int64_t)(tid - 5) * n + tile0, tile_n * 4);  // plane rows 16-B aligned
         }
         take_step();
         if (!io.rand_noise) make_noise();
@@ -476,8 +486,8 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         fence_async_smem();  // generic-proxy smem writes → visible to the async (TMA) proxy
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(io.state + tile0 * 13, s_state, BLOCK * 13 * 4);
-            if (OL::kDense && kTask) bulk_s2g(io.obs + tile0 * NOBS, s_obs, BLOCK * NOBS * 4);
+            bulk_s2g(io.state + tile0 * 13, s_state, tile_n * 13 * 4);
+            if (OL::kDense && kTask) bulk_s2g(io.obs + tile0 * NOBS, s_obs, tile_n * NOBS * 4);
             bulk_commit();
         }
     } else {
@@ -489,8 +499,8 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         float* dst = io.obs + tile0 * NOBS;
         if (OL::kDense) {
             for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i];
-        } else if (tile_n == BLOCK) {  // padded rows → dense float4 stores (BLOCK*NOBS % 4 == 0)
-            for (int i4 = tid; i4 < BLOCK * NOBS / 4; i4 += BLOCK) {
+        } else if ((tile_n * NOBS) % 4 == 0) {  // padded rows → dense float4 stores
+            for (int i4 = tid; i4 < tile_n * NOBS / 4; i4 += BLOCK) {
                 float4 v;
                 const int i = i4 * 4;
                 v.x = s_obs[i + i / NOBS];
@@ -566,7 +576,8 @@ __global__ void agx_reset_idx_kernel(const __grid_constant__ AgxParams P, int64_
 }
 
 // process-wide tuning knobs (agx_set_option), defined in agx_step.cu
-extern int g_block, g_use_bulk, g_pdl, g_sm_count;
+extern int g_block, g_use_bulk, g_pdl, g_sm_count, g_balanced;
+int sm_count();
 int fail(int code, const char* fmt, const char* detail = "");
 
 template <typename Kernel>
@@ -578,18 +589,20 @@ cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, 
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     int pdl = g_pdl;
-    if (pdl < 0) {
-        if (g_sm_count == 0) {
-            int dev = 0, sms = 0;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) g_sm_count = sms;
-            if (g_sm_count <= 0) g_sm_count = 148;
-        }
-        pdl = ((uint64_t)grid * block <= (uint64_t)g_sm_count * 512u) ? 3 : 0;
+    const int sms = sm_count();
+    // balanced tiles for grids that fit one wave (5 CTAs of 128 threads per SM are resident at once): the smallest multiple of the SM
+    // count that keeps every tile within the block (n / G + 4 <= 128)
+    int balanced = 0;
+    if (g_balanced && block == 128 && n >= (int64_t)sms * 64) {
+        const int64_t need = (n + 123) / 124, g = (need + sms - 1) / sms * sms;
+        if (g <= (int64_t)sms * 5) { grid = (unsigned)g; balanced = 1; }
     }
+    cfg.gridDim = dim3(grid);
+    if (pdl < 0) pdl = ((uint64_t)grid * block <= (uint64_t)sms * 512u) ? 3 : 0;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1);
+    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1) | (balanced ? 8 : 0);
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, P, io, n, kflags);

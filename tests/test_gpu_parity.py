@@ -349,6 +349,7 @@ def test_oracle_parity_at_full_size_65536(task, mode):
     orc = make_oracle(spec, N, rng="torch")
     env = make_env(task, mode, N)
     K = spec.ctrl_state_dim
+    resets_seen = 0
     for t in range(3):
         a = torch.rand(N, spec.num_actions) * 2 - 1
         if t == 1:
@@ -369,7 +370,8 @@ def test_oracle_parity_at_full_size_65536(task, mode):
         assert torch.equal(reset.cpu(), orc.reset_buf) and torch.equal(env.progress_buf.cpu(), orc.progress_buf), tag
         assert torch.equal(extras["time_outs"].cpu(), orc.time_out_buf), tag
         assert torch.equal(env.reset_u8.cpu().long(), orc.reset_buf), tag  # the byte copy of the flags in the packed results block
-    assert int(orc.reset_buf.sum()) > 0  # resets were in flight
+        resets_seen += int(orc.reset_buf.sum())
+    assert resets_seen >= N // 17  # the time-out wave (and its re-reset the step after, quirk Q1) went through both reset passes
 
 
 def test_reset_idx_standalone_and_reset_api():
