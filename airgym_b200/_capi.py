@@ -106,6 +106,24 @@ class AgxComm(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slot_bytes", C.c_int64), ("region", C.c_void_p * AGX_COMM_MAX_RANKS)]
 
 
+class AgxPolicyIO(C.Structure):
+    _fields_ = [("logstd", C.c_void_p), ("value_mean", C.c_void_p), ("value_var", C.c_void_p),
+                ("actions", C.c_void_p), ("ld_actions", C.c_int64), ("mus", C.c_void_p), ("ld_mus", C.c_int64),
+                ("sigmas", C.c_void_p), ("ld_sigmas", C.c_int64), ("neglogp", C.c_void_p), ("ld_neglogp", C.c_int64),
+                ("values", C.c_void_p), ("ld_values", C.c_int64), ("obs_out", C.c_void_p), ("ld_obs", C.c_int64),
+                ("dones_out", C.c_void_p), ("ld_dones", C.c_int64), ("dones_in", C.c_void_p), ("env_actions", C.c_void_p),
+                ("act_lo", C.c_void_p), ("act_hi", C.c_void_p), ("noise", C.c_void_p), ("seed", C.c_uint64),
+                ("step_dev", C.c_void_p), ("env_offset", C.c_int64)]
+
+
+class AgxPostIO(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("reset_u8", C.c_void_p), ("timeout", C.c_void_p), ("values", C.c_void_p), ("ld_values", C.c_int64),
+                ("rewards_out", C.c_void_p), ("ld_rewards", C.c_int64), ("cur_reward", C.c_void_p), ("cur_shaped", C.c_void_p),
+                ("cur_length", C.c_void_p), ("dones_state", C.c_void_p), ("ep_stats", C.c_void_p),
+                ("scale", C.c_float), ("shift", C.c_float), ("min_val", C.c_float), ("max_val", C.c_float), ("gamma", C.c_float),
+                ("bootstrap", C.c_int32)]
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -137,6 +155,10 @@ def bind(lib):
     lib.agx_mlp_train_supported.argtypes = [C.POINTER(AgxMlpParams)]
     lib.agx_mlp_forward_train.argtypes = [C.POINTER(AgxMlpParams), C.c_int64] + [C.c_void_p] * 8
     lib.agx_mlp_backward_train.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
+    lib.agx_sizeof_policy_io.restype = C.c_int
+    lib.agx_sizeof_post_io.restype = C.c_int
+    lib.agx_policy_step.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxPolicyIO), C.c_int64, C.c_void_p, C.c_void_p]
+    lib.agx_rollout_post.argtypes = [C.POINTER(AgxPostIO), C.c_int64, C.c_void_p]
     lib.agx_sizeof_cnn_params.restype = C.c_int
     lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]
@@ -161,7 +183,7 @@ EXPORTS = (
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
-    "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
+    "agx_sizeof_policy_io", "agx_policy_step", "agx_sizeof_post_io", "agx_rollout_post", "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
     "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",
     "agx_comm_status", "agx_adam_step_allreduce", "agx_device_numa_node", "agx_host_alloc_pinned", "agx_host_free_pinned",
 )
@@ -181,7 +203,8 @@ def load():
         )
     lib = bind(C.CDLL(LIB_PATH))
     if (lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO)
-            or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO) or lib.agx_sizeof_cnn_params() != C.sizeof(AgxCnnParams)):
+            or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO) or lib.agx_sizeof_cnn_params() != C.sizeof(AgxCnnParams)
+            or lib.agx_sizeof_policy_io() != C.sizeof(AgxPolicyIO) or lib.agx_sizeof_post_io() != C.sizeof(AgxPostIO)):
         raise ImportError("libagx.so struct layout differs from airgym_b200/_capi.py (rebuild the library)")
     _lib = lib
     return lib

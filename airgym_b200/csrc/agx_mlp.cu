@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "agx.h"
+#include "agx_math.cuh"
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
@@ -339,13 +340,70 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, con
     }
 }
 
+// The policy head of one env row (agx.h AgxPolicyIO): heads accumulators v (+ bias) → mu, value; sample, neglogp, record.
+__device__ __forceinline__ void policy_head(const AgxPolicyIO& pol, const float (&v)[16], const float* bh, int A, int64_t row) {
+    float mu[5], z[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) mu[a] = a < A ? v[a] + bh[a] : 0.0f;
+    float val = A == 5 ? v[5] + bh[5] : v[4] + bh[4];
+    if (pol.value_mean) {  // RunningMeanStd(denorm=True), running_mean_std.py:76-80
+        const float m = (float)pol.value_mean[0], sd = sqrtf((float)pol.value_var[0] + 1e-5f);
+        val = sd * fminf(fmaxf(val, -5.0f), 5.0f) + m;
+    }
+    if (pol.noise) {
+#pragma unroll
+        for (int a = 0; a < 5; ++a) z[a] = a < A ? pol.noise[row * A + a] : 0.0f;
+    } else {  // Philox stream 6, two blocks = 8 words = up to 4 Box-Muller pairs (32-bit uniforms)
+        agx::PhiloxCtx ph;
+        const uint64_t genv = (uint64_t)(pol.env_offset + row), step = pol.step_dev ? *pol.step_dev : 0ull;
+        ph.k0 = (uint32_t)pol.seed; ph.k1 = (uint32_t)(pol.seed >> 32);
+        ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
+        ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
+        const agx::U4 r0 = agx::philox_block(ph, 6u, 0u), r1 = agx::philox_block(ph, 6u, 1u);
+        const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float u1 = ((float)(w[2 * k] >> 8) + 1.0f) * 5.9604644775390625e-8f;  // (0, 1]
+            const float u2 = (float)(w[2 * k + 1] >> 8) * 5.9604644775390625e-8f;         // [0, 1)
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincosf(6.283185307179586f * u2, &sn, &cs);
+            z[2 * k] = rad * cs;
+            if (2 * k + 1 < 5) z[2 * k + 1] = rad * sn;
+        }
+    }
+    float nlp = 0.0f, lsum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        if (a < A) {
+            const float ls = pol.logstd[a], sg = expf(ls), act = mu[a] + sg * z[a];
+            const float t = (act - mu[a]) / sg;  // as the model's neglogp evaluates it on the sampled action (:195-198)
+            nlp += t * t;
+            lsum += ls;
+            pol.actions[row * pol.ld_actions + a] = act;
+            pol.mus[row * pol.ld_mus + a] = mu[a];
+            pol.sigmas[row * pol.ld_sigmas + a] = sg;
+            float e = act;
+            if (pol.act_lo) {  // preprocess_actions: clamp to [-1, 1], rescale to the action space (a2c_continuous.py:61-71)
+                const float lo = pol.act_lo[a], hi = pol.act_hi[a];
+                e = fminf(fmaxf(act, -1.0f), 1.0f) * ((hi - lo) * 0.5f) + (hi + lo) * 0.5f;
+            }
+            pol.env_actions[row * A + a] = e;
+        }
+    }
+    pol.neglogp[row * pol.ld_neglogp] = 0.5f * nlp + 0.9189385332046727f * (float)A + lsum;
+    pol.values[row * pol.ld_values] = val;
+    if (pol.dones_out) pol.dones_out[row * pol.ld_dones] = pol.dones_in[row];
+}
+
 constexpr int kThreads = 2 * kM;  // two 128-thread tile groups per CTA: the MMA / barrier latency of one hides under the epilogue of the other
 template <int IN_PAD>
 __global__ void __launch_bounds__(kThreads, 1)
 agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs, float* __restrict__ mu,
                           float* __restrict__ value, float* __restrict__ xn_out, float* __restrict__ h1_out, float* __restrict__ h2_out,
-                          float* __restrict__ h3_out, const int keep_t) {  // keep_t: the four keep tensors are feature-major [width, B] planes,
-                                                                            // and plane in_dim of xn_out is set to 1 (bias-gradient column)
+                          float* __restrict__ h3_out, const int keep_t,  // keep_t: the four keep tensors are feature-major [width, B] planes,
+                                                                         // and plane in_dim of xn_out is set to 1 (bias-gradient column)
+                          const __grid_constant__ AgxPolicyIO pol) {     // pol.actions != NULL: the policy head of a rollout step (agx.h)
     // shared memory carve (floats); every operand base is 128-byte aligned
     float* w1 = g_smem;                       // [64 x IN_PAD] canonical
     float* w2 = w1 + kH1 * IN_PAD;            // [128 x 64]
@@ -430,6 +488,7 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
                 float x = 0.0f;
                 if (ok && c < in_dim) {
                     x = obs[row * in_dim + c];
+                    if (pol.obs_out) pol.obs_out[row * pol.ld_obs + c] = x;
                     if (P.in_mean) {
                         x = (x - nrm[c]) / nrm[IN_PAD + c];
                         x = x < -5.0f ? -5.0f : (x > 5.0f ? 5.0f : x);
@@ -473,7 +532,9 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
         {
             float v[16];
             tmem_ld16(tmem_row + 0u, v);
-            if (ok) {
+            if (ok && pol.actions) {
+                policy_head(pol, v, bia + kH1 + kH2 + kH3, A, row);
+            } else if (ok) {
                 const float* bh = bia + kH1 + kH2 + kH3;
                 for (int a = 0; a < A; ++a) mu[row * A + a] = v[a] + bh[a];
                 float val = v[4] + bh[4];
@@ -885,8 +946,11 @@ int agx_internal_mlp_option(const char* key, int value) {
 }
 
 static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xn_out,
-                            float* h1_out, float* h2_out, float* h3_out, void* stream, const int keep_t) {
-    if (!valid(p) || b <= 0 || !obs || !mu || !value) return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_forward: bad argument");
+                            float* h1_out, float* h2_out, float* h3_out, void* stream, const int keep_t, const AgxPolicyIO* pol_in = nullptr) {
+    if (!valid(p) || b <= 0 || !obs || (!pol_in && (!mu || !value))) return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_forward: bad argument");
+    AgxPolicyIO pol_none;
+    memset(&pol_none, 0, sizeof(pol_none));
+    const AgxPolicyIO* pol = pol_in ? pol_in : &pol_none;
     const size_t smem = smem_bytes(p, 4);
     if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -901,14 +965,19 @@ static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, 
         cudaFuncSetAttribute(tc::agx_mlp_forward_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                      \
         const int64_t pairs = ((b + tc::kM - 1) / tc::kM + 1) / 2;                                                                       \
         tc::agx_mlp_forward_tc_kernel<PAD><<<(unsigned)(pairs < kGridMax ? pairs : kGridMax), tc::kThreads, kSm, st>>>(*p, b, obs, mu, value,  \
-                                                                                                                       xn_out, h1_out, h2_out, h3_out, keep_t); \
+                                                                                                                       xn_out, h1_out, h2_out, h3_out, keep_t, *pol); \
     } while (0)
     const bool keep_aligned = !xn_out || (((uintptr_t)xn_out | (uintptr_t)h1_out | (uintptr_t)h2_out | (uintptr_t)h3_out) & 15u) == 0;
     // measured (scripts/mlp_bench.py, B200, 32 768 / 65 536 rows): tcgen05 20.6 / 33.5 us vs mma.sync 32.9 / 58.7 us without the kept
     // activations (rollout), 28.4 / 49.0 vs 33.5 / 63.1 us with them (update)
     const bool w_aligned = (((uintptr_t)p->w2 | (uintptr_t)p->w3) & 15u) == 0;  // the tcgen05 kernel stages W2 / W3 with 16-byte loads
     const bool use_tc = keep_aligned && w_aligned && (g_fwd_tc == 2 || (g_fwd_tc == 1 && !xn_out));
-    if (keep_t) {  // training path: feature-major keeps for the tensor-core backward / weight-gradient kernels (agx_mlp_train.cu)
+    if (pol_in) {  // rollout step: the policy head lives in the tcgen05 kernel's epilogue only
+        if (!(w_aligned && (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64))))
+            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_policy_step: needs the 64-128-64 network with in_pad in {32,48,64}");
+        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else AGX_FWD_TC(64);
+    }
+    else if (keep_t) {  // training path: feature-major keeps for the tensor-core backward / weight-gradient kernels (agx_mlp_train.cu)
         if (!(keep_aligned && w_aligned && xn_out && h1_out && h2_out && h3_out && (b % tc::kM) == 0 && p->in_dim < p->in_pad &&
               (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64))))
             return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward_train: needs the 64-128-64 network, in_pad in {32,48,64} > in_dim, b % 128 == 0");
@@ -930,6 +999,15 @@ int agx_mlp_forward(const AgxMlpParams* p, int64_t b, const float* obs, float* m
 int agx_mlp_forward_train(const AgxMlpParams* p, int64_t b, const float* obs, float* mu, float* value, float* xt, float* h1t,
                           float* h2t, float* h3t, void* stream) {
     return mlp_forward_impl(p, b, obs, mu, value, xt, h1t, h2t, h3t, stream, 1);
+}
+
+int agx_sizeof_policy_io(void) { return (int)sizeof(AgxPolicyIO); }
+
+int agx_policy_step(const AgxMlpParams* p, const AgxPolicyIO* io, int64_t n, const float* obs, void* stream) {
+    if (!io || !io->logstd || !io->actions || !io->mus || !io->sigmas || !io->neglogp || !io->values || !io->env_actions ||
+        (io->dones_out && !io->dones_in) || ((io->act_lo == nullptr) != (io->act_hi == nullptr)) || ((io->value_mean == nullptr) != (io->value_var == nullptr)))
+        return agx_internal_fail(AGX_ERR_ARG, "agx_policy_step: bad argument");
+    return mlp_forward_impl(p, n, obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream, 0, io);
 }
 
 // launcher of the partial-sum reduction for agx_mlp_train.cu (same partial layout as the mma.sync weight-gradient kernels)

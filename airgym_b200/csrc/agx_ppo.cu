@@ -224,9 +224,54 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, const __grid_constant__ 
     }
 }
 
+// ---- after env.step of a rollout (agx.h AgxPostIO) ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agx_rollout_post_kernel(const __grid_constant__ AgxPostIO io, int64_t n) {
+    __shared__ double s_part[8][4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        const float r = io.reward[e];
+        float sh = (r + io.shift) * io.scale;                       // DefaultRewardsShaper (tr_helpers.py:16-42)
+        sh = fminf(fmaxf(sh, io.min_val), io.max_val);
+        if (io.bootstrap && io.timeout[e]) sh += io.gamma * io.values[e * io.ld_values];  // a2c_base.py:675-676
+        io.rewards_out[e * io.ld_rewards] = sh;
+        const float cr = io.cur_reward[e] + r, cs = io.cur_shaped[e] + sh, cl = io.cur_length[e] + 1.0f;
+        const bool d = io.reset_u8[e] != 0;
+        if (d) { acc[0] += cr; acc[1] += cs; acc[2] += cl; acc[3] += 1.0; }
+        io.cur_reward[e] = d ? 0.0f : cr;
+        io.cur_shaped[e] = d ? 0.0f : cs;
+        io.cur_length[e] = d ? 0.0f : cl;
+        io.dones_state[e] = d ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        if (t != 0.0) atomicAdd(io.ep_stats + threadIdx.x, t);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int agx_sizeof_post_io(void) { return (int)sizeof(AgxPostIO); }
+
+int agx_rollout_post(const AgxPostIO* io, int64_t n, void* stream) {
+    if (!io || n <= 0 || !io->reward || !io->reset_u8 || !io->rewards_out || !io->cur_reward || !io->cur_shaped || !io->cur_length ||
+        !io->dones_state || !io->ep_stats || (io->bootstrap && (!io->timeout || !io->values)))
+        return fail_ppo(AGX_ERR_ARG, "agx_rollout_post: bad argument");
+    int64_t grid = (n + 255) / 256;
+    if (grid > 592) grid = 592;
+    agx_rollout_post_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*io, n);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_rollout_post: launch failed");
+}
+
 
 int agx_gae(int64_t n, int h, float gamma, float tau, const float* rewards, const float* values, const uint8_t* dones,
             const float* last_values, const uint8_t* last_dones, float* adv, float* returns, void* stream) {

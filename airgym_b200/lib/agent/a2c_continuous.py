@@ -22,7 +22,7 @@ from ... import _capi
 from ...comm import PeerComm
 from ..core.moments import batch_sums, moments_from_sums, sums_from_moments
 from ..model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
-from ..utils import vecenv
+from ..utils import tr_helpers, vecenv
 
 
 def rescale_actions(low, high, action):
@@ -169,6 +169,13 @@ class A2CAgent:
             self.value_mean_std = self.model.value_mean_std
         self._graphs = {}
         self.init_tensors()
+        # Fused rollout step (agx_policy_step + env.step + agx_rollout_post: 3 launches instead of ~25) where the policy-head
+        # epilogue exists (tcgen05 forward of the shipped 64-128-64 network) and the shaper is the plain affine/clamp one.
+        sh = self.rewards_shaper
+        self.fused_rollout = bool(config.get("fused_rollout", True)) and self.fused_mlp and self.model.policy_step_supported() and (
+            isinstance(sh, tr_helpers.DefaultRewardsShaper) and not sh.log_val)
+        if self.fused_rollout:
+            self._setup_fused_rollout()
         if self.algo_observer is not None:  # a2c_base.py:147-148,255
             self.algo_observer.before_init(base_name, config, self.experiment_name)
             self.algo_observer.after_init(self)
@@ -243,10 +250,66 @@ class A2CAgent:
             return torch.cat((obs["observation"], feat), dim=-1)
 
     def env_reset(self):
-        self.obs.copy_(self._ingest(self.vec_env.reset(), update_image_rms=False))
+        first = self._ingest(self.vec_env.reset(), update_image_rms=False)
+        if self.fused_rollout and not self.has_cnn:
+            self.obs = first  # the env's own obs_buf (returned by reference, overwritten in place each step): no per-step copy
+        else:
+            self.obs.copy_(first)
         return self.obs
 
+    def _setup_fused_rollout(self):
+        """Argument blocks of the two rollout kernels: one AgxPolicyIO per horizon slot (the rollout-buffer slices differ), one AgxPostIO per slot."""
+        b, A, H = self.buf, self.actions_num, self.horizon_length
+        p = lambda t: t.data_ptr()
+        sh, env = self.rewards_shaper, self.env
+        self._pol, self._post = [], []
+        for n in range(H):
+            io = _capi.AgxPolicyIO()
+            io.logstd = p(self.model.logstd)
+            if self.normalize_value:
+                io.value_mean, io.value_var = p(self.value_mean_std.running_mean), p(self.value_mean_std.running_var)
+            io.actions, io.ld_actions = p(b["actions"][:, n]), H * A
+            io.mus, io.ld_mus = p(b["mus"][:, n]), H * A
+            io.sigmas, io.ld_sigmas = p(b["sigmas"][:, n]), H * A
+            io.neglogp, io.ld_neglogp = p(b["neglogpacs"][:, n]), H
+            io.values, io.ld_values = p(b["values"][:, n]), H
+            io.obs_out, io.ld_obs = p(b["obses"][:, n]), H * self.obs_shape[0]
+            io.dones_out, io.ld_dones, io.dones_in = p(b["dones"][:, n]), H, p(self.dones)
+            io.env_actions = p(self.env_actions)
+            if self.clip_actions:
+                io.act_lo, io.act_hi = p(self.actions_low), p(self.actions_high)
+            io.seed, io.step_dev, io.env_offset = env.rng_seed, p(env._step_dev), env.env_offset
+            self._pol.append(io)
+            po = _capi.AgxPostIO()
+            po.reward, po.reset_u8, po.timeout = p(env.rew_buf), p(env.reset_u8), p(env.time_out_buf)
+            po.values, po.ld_values = p(b["values"][:, n]), H
+            po.rewards_out, po.ld_rewards = p(b["rewards"][:, n]), H
+            po.cur_reward, po.cur_shaped, po.cur_length = p(self.current_rewards), p(self.current_shaped_rewards), p(self.current_lengths)
+            po.dones_state, po.ep_stats = p(self.dones), p(self.ep_stats)
+            po.scale, po.shift, po.gamma = float(sh.scale_value), float(sh.shift_value), float(self.gamma)
+            po.min_val, po.max_val = max(float(sh.min_val), -3.0e38), min(float(sh.max_val), 3.0e38)
+            po.bootstrap = 1 if self.value_bootstrap else 0
+            self._post.append(po)
+
+    def _rollout_step_fused(self, n):
+        """One env step of play_steps (a2c_base.py:657-695) in three launches: policy (network + sampling + buffer writes), env, post."""
+        io = self._pol[n]
+        io.noise = self.noise_table[n].data_ptr() if self.noise_table is not None else None
+        io.seed, io.env_offset = self.env.rng_seed, self.env.env_offset
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _capi.check(self._lib.agx_policy_step(C.byref(self.model.policy_params()), C.byref(io), self.num_actors, self.obs.data_ptr(), st),
+                    "agx_policy_step")
+        obs, _rewards, _dones, infos = self.vec_env.step(self.env_actions)
+        _capi.check(self._lib.agx_rollout_post(C.byref(self._post[n]), self.num_actors, st), "agx_rollout_post")
+        new_obs = self._ingest(obs)
+        if new_obs.data_ptr() != self.obs.data_ptr():
+            self.obs.copy_(new_obs)
+        if self.writer is not None:
+            self._observe_reward_terms(infos)
+
     def _rollout_step(self, n):
+        if self.fused_rollout:
+            return self._rollout_step_fused(n)
         b = self.buf
         self.model.eval()
         self._ro_step = n

@@ -170,6 +170,17 @@ class ModelA2CContinuousLogStd(nn.Module):
             p(keep_t[2]), p(keep_t[3]), p(dz_t[0]), p(dz_t[1]), p(dz_t[2]), p(dout_t), p(workspace),
             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_backward_train")
 
+    def policy_params(self):
+        """Parameters of the fused rollout step: the training-path padding is always one of the widths the tcgen05 kernel is built for."""
+        return self.train_params()
+
+    def policy_step_supported(self):
+        try:
+            P = self.train_params()
+        except NotImplementedError:
+            return False
+        return bool(_capi.load().agx_mlp_train_supported(C.byref(P)))
+
     def fused_grads(self):
         """AgxMlpGrads pointing at the parameters' .grad tensors (views of the flat gradient buffer)."""
         G = _capi.AgxMlpGrads()

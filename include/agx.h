@@ -375,6 +375,52 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
                            const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t,
                            float* dz3t, float* doutt, float* workspace, void* stream);
 
+/* ---- fused rollout step (reference lib/agent/a2c_base.py:651-711 play_steps; get_action_values :357-369; the model's sampling
+ * branch a2c_continuous_logstd_model.py:181-193; preprocess_actions a2c_continuous.py:61-71) -------------------------------------
+ * agx_policy_step = the tcgen05 MLP forward with the whole policy head fused into its epilogue: per env row
+ *   mu, value_n  ← network;  sigma = exp(logstd);  action = mu + sigma * z  (z: explicit draws or Philox stream 6 keyed by
+ *   (seed, env_offset + row, step_dev[0]) → 32-bit Box-Muller);  neglogp;  value = denormalised value_n;
+ * and writes the rollout-buffer slices of this step (row strides in elements: the buffers are env-major [n, horizon, ...]),
+ * the observation row, the done flag before the step, and env_actions = clamp(action, -1, 1) rescaled to [act_lo, act_hi].
+ * One launch replaces ~12 torch kernels per step. */
+typedef struct AgxPolicyIO {
+    const float*  logstd;                 /* [A] */
+    const double *value_mean, *value_var; /* value RunningMeanStd buffers (float64), or NULL: values stay normalised */
+    float* actions;   int64_t ld_actions;
+    float* mus;       int64_t ld_mus;
+    float* sigmas;    int64_t ld_sigmas;
+    float* neglogp;   int64_t ld_neglogp;
+    float* values;    int64_t ld_values;
+    float* obs_out;   int64_t ld_obs;     /* [n, in_dim] slice: copy of the observation the policy saw */
+    uint8_t* dones_out; int64_t ld_dones; /* [n] slice <- dones_in */
+    const uint8_t* dones_in;              /* [n] done flags after the previous step */
+    float* env_actions;                   /* [n, A] dense: what env.step receives */
+    const float *act_lo, *act_hi;         /* [A] action-space bounds, or NULL: env_actions = action (clip_actions: False) */
+    const float* noise;                   /* [n, A] N(0,1) draws, or NULL → Philox */
+    uint64_t seed;
+    const uint64_t* step_dev;             /* device step counter (the env's): read, not advanced */
+    int64_t env_offset;
+} AgxPolicyIO;
+int agx_sizeof_policy_io(void);
+int agx_policy_step(const AgxMlpParams* p, const AgxPolicyIO* io, int64_t n, const float* obs, void* stream);
+
+/* agx_rollout_post = everything play_steps does after env.step (a2c_base.py:667-695): shaped reward
+ * r' = clamp((r + shift) * scale, lo, hi) [+ gamma * value * time_out when bootstrap], stored in the rollout slice; running
+ * episode return / shaped return / length per env; on a done flag their values are added to ep_stats {sum return, sum shaped,
+ * sum length, episodes} (float64 atomics — logging only) and reset; dones_state <- done flags. */
+typedef struct AgxPostIO {
+    const float* reward;  const uint8_t* reset_u8;  const uint8_t* timeout;  /* env outputs [n] */
+    const float* values;  int64_t ld_values;                                  /* this step's denormalised values (rollout slice) */
+    float* rewards_out;   int64_t ld_rewards;                                 /* rollout slice */
+    float *cur_reward, *cur_shaped, *cur_length;                              /* [n] running episode accumulators */
+    uint8_t* dones_state;                                                     /* [n] */
+    double* ep_stats;                                                         /* [4] */
+    float scale, shift, min_val, max_val, gamma;
+    int32_t bootstrap;
+} AgxPostIO;
+int agx_sizeof_post_io(void);
+int agx_rollout_post(const AgxPostIO* io, int64_t n, void* stream);
+
 /* ---- depth-image encoder (row f3) ------------------------------------------------------------------------------------
  * Replaces the forward of lib/network/cnn.py:3-33 (CNNFeatureExtractor: three stride-2 convolutions, each followed by
  * ReLU then BatchNorm2d, global average pool, Linear 64 -> feature_dim) in EVAL mode, with the per-pixel input

@@ -348,3 +348,84 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
         assert_close((p.grad / scale).cpu(), (first[n] / scale).cpu(), f"tcgen05 vs mma.sync grad {n}", rtol=5e-3, atol=3e-3)
     assert_close(dz_r[2].t().cpu(), dz[2].cpu(), "dz3", rtol=5e-3, atol=1e-7 + 5e-3 * float(dz_r[2].abs().max()))
     assert_close(dz_r[0].t().cpu(), dz[0].cpu(), "dz1", rtol=5e-3, atol=1e-7 + 1e-2 * float(dz_r[0].abs().max()))
+
+
+def _rollout_agent(fused_rollout, N=4096, H=8, seed=4):
+    from airgym_b200.lib.agent.a2c_continuous import A2CAgent
+    from airgym_b200.lib.config import default_ppo_config, scale_minibatch
+    from airgym_b200.lib.utils import tr_helpers
+
+    cfg = scale_minibatch(default_ppo_config("hovering"), N)
+    c = cfg["params"]["config"]
+    c.update(horizon_length=H, minibatch_size=N * H // 4, print_stats=False, write_summaries=False, train_dir="/tmp/agx_ro",
+             save_frequency=0, save_best_after=10**9, fused_rollout=fused_rollout, use_cuda_graph=False)
+    c["env_config"].update(ctl_mode="rate", num_envs=N, seed=seed)
+    c["reward_shaper"] = tr_helpers.DefaultRewardsShaper(**c["reward_shaper"])
+    torch.manual_seed(seed)
+    return A2CAgent("ro", cfg["params"])
+
+
+def test_fused_rollout_matches_the_torch_rollout_and_the_oracle(built):
+    """agx_policy_step + agx_rollout_post (3 launches per step) against the per-op torch rollout on identical explicit noise, and
+    the sampling / neglogp / value de-normalisation against oracle/ppo.py (the reference's model code) on the recorded inputs."""
+    N, H, A = 4096, 8, 4
+    gen = torch.Generator().manual_seed(9)
+    noise = torch.randn(H, N, A, generator=gen).cuda()
+    agents = [_rollout_agent(False), _rollout_agent(True)]
+    assert not agents[0].fused_rollout and agents[1].fused_rollout
+    agents[1].flat_params.copy_(agents[0].flat_params)
+    for ag in agents:
+        with torch.no_grad():  # non-trivial normalisation statistics, identical in both
+            ag.model.running_mean_std.running_mean.copy_(torch.linspace(-0.2, 0.2, 18, dtype=torch.float64))
+            ag.model.running_mean_std.running_var.copy_(torch.linspace(0.5, 1.5, 18, dtype=torch.float64))
+            ag.value_mean_std.running_mean.fill_(0.3)
+            ag.value_mean_std.running_var.fill_(2.0)
+        ag.noise_table = noise
+        ag.env.progress_buf[::7] = ag.env.max_episode_length - 4  # time-outs inside the horizon → dones, bootstrap, episode statistics
+        ag.env_reset()
+        ag.ep_stats.zero_()
+        ag.play_steps()
+    torch.cuda.synchronize()
+    a, b = agents
+    for k in ("obses", "actions", "mus", "sigmas", "neglogpacs", "values", "rewards"):
+        assert_close(b.buf[k].cpu(), a.buf[k].cpu(), "rollout buffer " + k, rtol=1e-5, atol=1e-5)
+    assert torch.equal(a.buf["dones"], b.buf["dones"]) and torch.equal(a.dones, b.dones)
+    assert int(a.buf["dones"].sum()) > 0
+    assert_close(b.advs.cpu(), a.advs.cpu(), "advantages", rtol=1e-4, atol=1e-5)
+    assert_close(b.ep_stats.cpu(), a.ep_stats.cpu(), "episode statistics", rtol=1e-6, atol=1e-6)
+    assert float(a.ep_stats[3]) > 0
+    assert_close(b.current_lengths.cpu(), a.current_lengths.cpu(), "running episode lengths", rtol=0, atol=0)
+    # oracle: the reference's sampling / neglogp / denormalisation on what the fused path recorded
+    from oracle import ppo as O
+    mu, sigma = b.buf["mus"].cpu(), b.buf["sigmas"].cpu()
+    z = noise.permute(1, 0, 2).cpu()
+    act = mu + sigma * z
+    assert_close(b.buf["actions"].cpu(), act, "sampled action", rtol=1e-6, atol=1e-6)
+    nlp = O.neglogp(act, mu, sigma, torch.log(sigma))
+    assert_close(b.buf["neglogpacs"].cpu(), nlp, "neglogp vs oracle", rtol=1e-5, atol=1e-5)
+    sd = {k: v.cpu() for k, v in b.model.state_dict().items()}
+    obs_flat = b.buf["obses"].reshape(-1, 18).cpu()
+    mu_o, _ls, _sg, v_o = O.model_forward(sd, obs_flat, normalize_input=True)
+    assert_close(mu.reshape(-1, A), mu_o, "mu vs oracle (TF32 bound)", rtol=5e-3, atol=2e-3)
+    v_den = O.rms_denorm(v_o, sd["value_mean_std.running_mean"], sd["value_mean_std.running_var"])
+    assert_close(b.buf["values"].reshape(-1, 1).cpu(), v_den, "value vs oracle (TF32 bound)", rtol=5e-3, atol=5e-3)
+
+
+def test_fused_rollout_philox_sampling_is_standard_normal_and_partition_invariant(built):
+    ag = _rollout_agent(True, N=8192, H=8)
+    ag.env_reset()
+    ag.play_steps()
+    torch.cuda.synchronize()
+    z = ((ag.buf["actions"] - ag.buf["mus"]) / ag.buf["sigmas"]).flatten()
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01 and float(z.abs().max()) < 6.5
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.1  # kurtosis of a normal
+    # two shards of the env axis (env_offset) draw the same numbers as one env of twice the size
+    half = [_rollout_agent(True, N=4096, H=8) for _ in range(2)]
+    half[1].env.set_seed(half[1].env.rng_seed, env_offset=4096)
+    for h in half:
+        h.flat_params.copy_(ag.flat_params)
+        h.env_reset()
+        h.play_steps()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat((half[0].buf["actions"], half[1].buf["actions"])), ag.buf["actions"])
+    assert torch.equal(torch.cat((half[0].buf["rewards"], half[1].buf["rewards"])), ag.buf["rewards"])
