@@ -69,7 +69,7 @@ class AgxRenderIO(C.Structure):
     _fields_ = [
         ("state", C.c_void_p), ("aux", C.c_void_p), ("assets", C.c_void_p), ("trees", C.c_void_p), ("image", C.c_void_p),
         ("rand_add", C.c_void_p), ("rand_mul", C.c_void_p), ("rand_kern", C.c_void_p),
-        ("seed", C.c_uint64), ("step", C.c_uint64), ("env_offset", C.c_int64),
+        ("seed", C.c_uint64), ("step", C.c_uint64), ("env_offset", C.c_int64), ("step_dev", C.c_void_p),
     ]
 
 

@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(kThreads, 2) agx_render_kernel(const __grid_co
         const uint64_t genv = (uint64_t)(io.env_offset + env);
         ph.k0 = (uint32_t)io.seed; ph.k1 = (uint32_t)(io.seed >> 32);
         ph.env_lo = (uint32_t)genv; ph.env_hi = (uint32_t)(genv >> 32);
-        ph.step_lo = (uint32_t)io.step; ph.step_hi = (uint32_t)(io.step >> 32);
+        const uint64_t step = io.step_dev ? *io.step_dev : io.step;
+        ph.step_lo = (uint32_t)step; ph.step_hi = (uint32_t)(step >> 32);
     }
 
     if (tid == 0) s_ncaps = 0;

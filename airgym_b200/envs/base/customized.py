@@ -61,6 +61,7 @@ class Customized(Hovering):
         rio.rand_mul = rand_image["mul"].data_ptr() if rand_image is not None else None
         rio.rand_kern = rand_image["kern"].data_ptr() if rand_image is not None else None
         rio.seed, rio.step, rio.env_offset = self.rng_seed, self.counter, self.env_offset
+        rio.step_dev = self._step_dev.data_ptr()  # Philox counter word from the device (fresh noise on every CUDA-graph replay)
         stream = torch.cuda.current_stream(self._dev).cuda_stream
         _capi.check(self._lib.agx_render_depth(C.byref(self.params), self.num_envs, C.byref(rio), C.c_void_p(stream)),
                     "agx_render_depth")

@@ -115,8 +115,10 @@ class A2CAgent:
                 from torch.utils.tensorboard import SummaryWriter
                 os.makedirs(self.summaries_dir, exist_ok=True)
                 self.writer = SummaryWriter(self.summaries_dir)
-        # camera tasks run eagerly: the render cadence (every cam_every-th step) and the encoder-feature cache are host-side decisions
-        self.use_cuda_graph = config.get("use_cuda_graph", True) and not self.has_cnn
+        # camera tasks: the render cadence (every cam_every-th step) is a host-side decision baked into the captured rollout, which is
+        # valid as long as every rollout starts at the same phase of it: horizon % cam_every == 0 (24 / 64 vs 4 in the shipped yamls)
+        self.use_cuda_graph = config.get("use_cuda_graph", True) and (
+            not self.has_cnn or self.horizon_length % max(int(getattr(self.env, "cam_every", 1)), 1) == 0)
         self.fused_mlp = config.get("fused_mlp", True)  # tensor-core MLP kernels (TF32) instead of torch fp32 + autograd
         # Collectives of the sharded update.  "peer" (default): libagx kernels over NVLink peer memory — the
         # per-minibatch all-reduce is fused into the Adam launch (agx_adam_step_allreduce), the per-epoch moments go through
@@ -140,7 +142,11 @@ class A2CAgent:
             # 46-wide trunk input [obs16 | cnn(norm(image))] instead of 101 KB images per sample.  (Deviation, DESIGN.md §9: the
             # reference re-encodes the minibatch images in train mode — BatchNorm batch statistics — during the update.)
             self.image_shape = self.obs_shape["image"]
-            self._img_cache = None
+            # static buffers (a captured CUDA graph must find the last render's features / image moments at fixed addresses)
+            self._feat = torch.zeros(self.num_actors, self.model.feature_dim, device=dev)
+            self._img_mean = torch.zeros(self.image_shape, device=dev, dtype=torch.float64)
+            self._img_var = torch.zeros(self.image_shape, device=dev, dtype=torch.float64)
+            self._img_valid = False
             self.obs_shape = (self.obs_shape["observation"][0] + self.model.feature_dim,)
         self.flat_params, self.flat_grads = self.model.flatten_parameters(extra_grad_slots=_capi.AGX_PPO_STATS)
         self.n_params = self.model.num_flat
@@ -232,13 +238,15 @@ class A2CAgent:
             # the camera refreshes every cam_every-th step (customized.py:318-321): between renders the image tensor — and with a
             # frozen encoder its features — do not change, so the CNN runs once per render and the image statistics are merged
             # from the cached batch moments on the steps in between (same counts as the reference's per-sample update)
-            fresh = self._img_cache is None or self.env.counter % self.env.cam_every == 0
+            fresh = not self._img_valid or self.env.counter % self.env.cam_every == 0
             if fresh:
                 img = obs["image"]
                 var, mean = torch.var_mean(img.reshape(img.shape[0], -1), dim=0)
-                feat = self.model.encode_image(img)
-                self._img_cache = (feat, mean.double().reshape(self.image_shape), var.double().reshape(self.image_shape), img.shape[0])
-            feat, mean, var, n = self._img_cache
+                self._feat.copy_(self.model.encode_image(img))
+                self._img_mean.copy_(mean.reshape(self.image_shape))
+                self._img_var.copy_(var.reshape(self.image_shape))
+                self._img_valid = True
+            feat, mean, var, n = self._feat, self._img_mean, self._img_var, obs["image"].shape[0]
             if self.normalize_input and update_image_rms:
                 if self.multi_gpu and self.world_size > 1:  # merge the per-rank moments through their sums
                     s = self._allreduce(sums_from_moments(mean, var, n).contiguous())
@@ -399,7 +407,9 @@ class A2CAgent:
     def play_steps(self):
         """a2c_base.py:651-711: H policy+env steps, bootstrap value, GAE — one CUDA-graph replay."""
         with torch.no_grad():
-            self._run_graphed("rollout", self._rollout)
+            replayed = self._run_graphed("rollout", self._rollout)
+        if replayed == "replayed":  # the env's host-side step counter (render cadence, logging) did not run during the replay
+            self.env.counter += self.horizon_length
 
     # ---- dataset ----------------------------------------------------------------------------------------------------------
     def _allreduce(self, t):
@@ -542,7 +552,7 @@ class A2CAgent:
             graph.replay()
             return None
         g.replay()
-        return None
+        return "replayed"
 
     def train_epoch(self):
         """a2c_continuous.py:78-138"""

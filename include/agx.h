@@ -184,6 +184,8 @@ typedef struct AgxRenderIO {
     const float* rand_kern;/* [N,25]  the blur kernel, or NULL → Philox stream 5 */
     uint64_t seed, step;
     int64_t  env_offset;
+    const uint64_t* step_dev; /* optional DEVICE step counter (AgxStepIO.step_dev): when non-NULL its value replaces `step` as the Philox
+                                 counter word, so a captured CUDA graph draws fresh image noise on every replay */
 } AgxRenderIO;
 
 /* library info */

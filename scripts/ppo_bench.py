@@ -22,6 +22,9 @@ if __name__ == "__main__":
     ap.add_argument("--graph_collectives", action="store_true", help="multi-GPU: replay the update from graphs with NCCL inside")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--skip", type=int, default=3, help="epochs excluded from the timing (graph capture / warm-up)")
+    ap.add_argument("--vae", action="store_true", help="planning: the frozen depth-VAE encoder (latent 64) instead of the CNN (ppo_planning.yaml:33-39); "
+                    "random frozen weights — trained/vae_model.pth does not travel to the GPU box")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = scale_minibatch(default_ppo_config(a.task), a.num_envs)
@@ -30,6 +33,11 @@ if __name__ == "__main__":
              train_dir="/tmp/agx_runs", multi_gpu=world > 1, write_summaries=False,
              graph_collectives=a.graph_collectives)
     c["env_config"].update(ctl_mode=a.ctl_mode, num_envs=a.num_envs, seed=a.seed)
+    c["multi_gpu_comm"] = a.comm
+    if a.vae:
+        cfg["params"]["network"].pop("cnn", None)
+        cfg["params"]["network"]["vae"] = {"latent_dims": 64, "image_res": [120, 212], "interpolation_mode": "bilinear",
+                                           "return_sampled_latent": False, "allow_random_init": True}
     cfg["params"]["seed"] = a.seed
     import contextlib
     r = Runner()
@@ -41,7 +49,8 @@ if __name__ == "__main__":
         frames = sum(x["frame"] - (r.agent.history[i + a.skip - 1]["frame"] if i + a.skip > 0 else 0) for i, x in enumerate(h))
         play, upd = sum(x["play_time"] for x in h), sum(x["update_time"] for x in h)
         print(json.dumps({
-            "task": a.task, "ctl_mode": a.ctl_mode, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "epochs_timed": len(h),
+            "task": a.task, "ctl_mode": a.ctl_mode, "encoder": ("vae" if a.vae else ("cnn" if r.agent.has_cnn else None)),
+            "env_steps_per_s_rollout": frames / play, "fused_rollout": r.agent.fused_rollout, "mlp_backward_tcgen05": getattr(r.agent, "mlp_train_tc", False), "num_envs_per_gpu": a.num_envs, "n_gpus": world, "epochs_timed": len(h),
             "minibatch": c["minibatch_size"], "cuda_graph": not a.no_graph,
             "samples_per_s_rollout": frames / play, "samples_per_s_update": frames / upd, "samples_per_s_total": frames / (play + upd),
             "ms_per_epoch_rollout": 1e3 * play / len(h), "ms_per_epoch_update": 1e3 * upd / len(h),

@@ -381,8 +381,8 @@ def test_fused_rollout_matches_the_torch_rollout_and_the_oracle(built):
             ag.value_mean_std.running_mean.fill_(0.3)
             ag.value_mean_std.running_var.fill_(2.0)
         ag.noise_table = noise
-        ag.env.progress_buf[::7] = ag.env.max_episode_length - 4  # time-outs inside the horizon → dones, bootstrap, episode statistics
         ag.env_reset()
+        ag.env.progress_buf[::7] = ag.env.max_episode_length - 4  # time-outs inside the horizon → dones, bootstrap, episode statistics
         ag.ep_stats.zero_()
         ag.play_steps()
     torch.cuda.synchronize()
