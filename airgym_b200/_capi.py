@@ -124,6 +124,26 @@ class AgxPostIO(C.Structure):
                 ("bootstrap", C.c_int32)]
 
 
+class AgxConvParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+                ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("res", C.c_void_p), ("rH", C.c_int32), ("rW", C.c_int32), ("ry0", C.c_int32), ("rx0", C.c_int32), ("rsy", C.c_int32),
+                ("rsx", C.c_int32), ("y", C.c_void_p), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("sy", C.c_int32), ("sx", C.c_int32), ("py", C.c_int32), ("px", C.c_int32),
+                ("act", C.c_int32), ("_pad", C.c_int32)]
+
+
+class AgxConvFirstParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("_p0", C.c_int32),
+                ("w", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("px_mean", C.c_void_p),
+                ("px_rstd", C.c_void_p), ("y", C.c_void_p), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("sy", C.c_int32), ("sx", C.c_int32), ("py", C.c_int32), ("px", C.c_int32),
+                ("act", C.c_int32)]
+
+
+ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
+
+
 class AgxError(RuntimeError):
     pass
 
@@ -159,6 +179,12 @@ def bind(lib):
     lib.agx_sizeof_post_io.restype = C.c_int
     lib.agx_policy_step.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxPolicyIO), C.c_int64, C.c_void_p, C.c_void_p]
     lib.agx_rollout_post.argtypes = [C.POINTER(AgxPostIO), C.c_int64, C.c_void_p]
+    lib.agx_sizeof_conv_params.restype = C.c_int
+    lib.agx_sizeof_conv_first_params.restype = C.c_int
+    lib.agx_conv2d_nhwc.argtypes = [C.POINTER(AgxConvParams), C.c_void_p]
+    lib.agx_conv2d_first.argtypes = [C.POINTER(AgxConvFirstParams), C.c_void_p]
+    lib.agx_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.agx_pool_fc.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.agx_sizeof_cnn_params.restype = C.c_int
     lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]
@@ -183,6 +209,7 @@ EXPORTS = (
     "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
+    "agx_sizeof_conv_params", "agx_conv2d_nhwc", "agx_sizeof_conv_first_params", "agx_conv2d_first", "agx_resize_bilinear", "agx_pool_fc",
     "agx_sizeof_policy_io", "agx_policy_step", "agx_sizeof_post_io", "agx_rollout_post", "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
     "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",
     "agx_comm_status", "agx_adam_step_allreduce", "agx_device_numa_node", "agx_host_alloc_pinned", "agx_host_free_pinned",
@@ -204,7 +231,8 @@ def load():
     lib = bind(C.CDLL(LIB_PATH))
     if (lib.agx_sizeof_params() != C.sizeof(AgxParams) or lib.agx_sizeof_step_io() != C.sizeof(AgxStepIO)
             or lib.agx_sizeof_render_io() != C.sizeof(AgxRenderIO) or lib.agx_sizeof_cnn_params() != C.sizeof(AgxCnnParams)
-            or lib.agx_sizeof_policy_io() != C.sizeof(AgxPolicyIO) or lib.agx_sizeof_post_io() != C.sizeof(AgxPostIO)):
+            or lib.agx_sizeof_policy_io() != C.sizeof(AgxPolicyIO) or lib.agx_sizeof_post_io() != C.sizeof(AgxPostIO)
+            or lib.agx_sizeof_conv_params() != C.sizeof(AgxConvParams) or lib.agx_sizeof_conv_first_params() != C.sizeof(AgxConvFirstParams)):
         raise ImportError("libagx.so struct layout differs from airgym_b200/_capi.py (rebuild the library)")
     _lib = lib
     return lib

@@ -973,15 +973,15 @@ static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, 
     const bool w_aligned = (((uintptr_t)p->w2 | (uintptr_t)p->w3) & 15u) == 0;  // the tcgen05 kernel stages W2 / W3 with 16-byte loads
     const bool use_tc = keep_aligned && w_aligned && (g_fwd_tc == 2 || (g_fwd_tc == 1 && !xn_out));
     if (pol_in) {  // rollout step: the policy head lives in the tcgen05 kernel's epilogue only
-        if (!(w_aligned && (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64))))
-            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_policy_step: needs the 64-128-64 network with in_pad in {32,48,64}");
-        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else AGX_FWD_TC(64);
+        if (!(w_aligned && (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64) || is_shipped(p, 96))))
+            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_policy_step: needs the 64-128-64 network with in_pad in {32,48,64,96}");
+        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else if (p->in_pad == 64) AGX_FWD_TC(64); else AGX_FWD_TC(96);
     }
     else if (keep_t) {  // training path: feature-major keeps for the tensor-core backward / weight-gradient kernels (agx_mlp_train.cu)
         if (!(keep_aligned && w_aligned && xn_out && h1_out && h2_out && h3_out && (b % tc::kM) == 0 && p->in_dim < p->in_pad &&
-              (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64))))
-            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward_train: needs the 64-128-64 network, in_pad in {32,48,64} > in_dim, b % 128 == 0");
-        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else AGX_FWD_TC(64);
+              (is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64) || is_shipped(p, 96))))
+            return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward_train: needs the 64-128-64 network, in_pad in {32,48,64,96} > in_dim, b % 128 == 0");
+        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else if (p->in_pad == 64) AGX_FWD_TC(64); else AGX_FWD_TC(96);
     }
     else if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }
     else if (is_shipped(p, 48)) { if (use_tc) AGX_FWD_TC(48); else AGX_FWD(S48); }

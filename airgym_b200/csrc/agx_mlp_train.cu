@@ -146,7 +146,7 @@ constexpr int kStage = 32;            // batch rows (= K) per pipeline stage
 constexpr int kKc = kStage / 4;       // 16-byte K-chunks per operand row and stage
 constexpr int kN2 = kH1 + 16, kN3 = kH2 + 16;   // B operands of layers 2 / 3 carry a 16-row block whose first row is all ones (bias column)
 // TMEM columns of the four accumulators (M = 128 lanes each; only the first `out` lanes are meaningful)
-constexpr int kC1 = 0, kC2 = 64, kC3 = kC2 + kN2, kCh = kC3 + kN3;   // 0 | 64 | 144 | 288 (+16) <= 512
+constexpr int kC1 = 0, kC2 = 96, kC3 = kC2 + kN2, kCh = kC3 + kN3;   // 0 (up to 96 input columns) | 96 | 176 | 320 (+16) <= 512
 
 template <int IN_PAD>
 struct Layout {  // float offsets inside one stage buffer; every tile is [kKc][rows][4]
@@ -302,7 +302,7 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
 }  // namespace tcw
 
 bool train_ok(const AgxMlpParams* p) {
-    return p && p->h1 == tc::kH1 && p->h2 == tc::kH2 && p->h3 == tc::kH3 && (p->in_pad == 32 || p->in_pad == 48 || p->in_pad == 64) &&
+    return p && p->h1 == tc::kH1 && p->h2 == tc::kH2 && p->h3 == tc::kH3 && (p->in_pad == 32 || p->in_pad == 48 || p->in_pad == 64 || p->in_pad == 96) &&
            p->in_dim > 0 && p->in_dim < p->in_pad && (p->actions_num == 4 || p->actions_num == 5) && p->w1 && p->w2 && p->w3 && p->w_mu && p->w_value;
 }
 
@@ -317,7 +317,7 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
                            float* doutt, float* workspace, void* stream) {
     if (!train_ok(p) || !g || b <= 0 || (b % tc::kM) != 0 || !grad_mu || !grad_value || !xt || !h1t || !h2t || !h3t || !dz1t || !dz2t || !dz3t ||
         !doutt || !workspace || !g->gw1 || !g->gb1 || !g->gw2 || !g->gb2 || !g->gw3 || !g->gb3 || !g->gw_mu || !g->gb_mu || !g->gw_value || !g->gb_value)
-        return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_backward_train: bad argument (64-128-64 network, in_pad in {32,48,64} > in_dim, batch % 128 == 0)");
+        return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_backward_train: bad argument (64-128-64 network, in_pad in {32,48,64,96} > in_dim, batch % 128 == 0)");
     const uintptr_t al = (uintptr_t)xt | (uintptr_t)h1t | (uintptr_t)h2t | (uintptr_t)h3t | (uintptr_t)dz1t | (uintptr_t)dz2t | (uintptr_t)dz3t |
                          (uintptr_t)doutt | (uintptr_t)workspace;
     if (al & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_mlp_backward_train: buffers must be 16-byte aligned");
@@ -339,7 +339,7 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
         tcw::agx_mlp_wgrad_tc_kernel<PAD><<<gw, tcw::kThreads, kSm, st>>>(*p, b, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, w_partials, \
                                                                           b_partials, pf);                                        \
     } while (0)
-    if (p->in_pad == 32) AGX_WGRAD_TC(32); else if (p->in_pad == 48) AGX_WGRAD_TC(48); else AGX_WGRAD_TC(64);
+    if (p->in_pad == 32) AGX_WGRAD_TC(32); else if (p->in_pad == 48) AGX_WGRAD_TC(48); else if (p->in_pad == 64) AGX_WGRAD_TC(64); else AGX_WGRAD_TC(96);
 #undef AGX_WGRAD_TC
     if (cudaGetLastError() != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward_train: launch failed");
     return agx_internal_wgrad_reduce(p, g, w_partials, (int)gw, b_partials, (int)gw, stream);

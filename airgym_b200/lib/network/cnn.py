@@ -33,7 +33,12 @@ def encoder_params(net):
     return p, keep
 
 
-def native_encode(net, x, px_mean=None, px_rstd=None, out=None, lib=None):
+# which libagx implementation native_encode uses: "tc" = layer by layer, conv2 / conv3 as implicit GEMMs on tcgen05 with a 3xTF32
+# split (tc_encoders.cnn_encode); "fused" = the single persistent fp32-FMA kernel agx_cnn_encode (whole network per env in shared memory)
+ENCODER_IMPL = "tc"
+
+
+def native_encode(net, x, px_mean=None, px_rstd=None, out=None, lib=None, impl=None):
     """features [N, feature_dim] of images x [N,1,212,120] through agx_cnn_encode; px_mean / px_rstd [212*120] fuse the
     RunningMeanStd normalisation clamp((x - mean) * rstd, +-5) into the image load.  `out` may be a column slice of a wider
     row-major buffer (the trunk-input rows); `lib` substitutes another build of libagx (tuning variants, scripts/enc_bench.py)."""
@@ -43,6 +48,9 @@ def native_encode(net, x, px_mean=None, px_rstd=None, out=None, lib=None):
     if out is None:
         out = torch.empty(n, net.fc.out_features, device=x.device, dtype=torch.float32)
     assert out.dtype == torch.float32 and out.shape == (n, net.fc.out_features) and out.stride(1) == 1
+    if (impl or ENCODER_IMPL) == "tc" and lib is None and n > 0:
+        from .tc_encoders import cnn_encode
+        return cnn_encode(net, x, px_mean, px_rstd, out)
     p, keep = encoder_params(net)
     if px_mean is not None:
         px_mean, px_rstd = px_mean.float().contiguous(), px_rstd.float().contiguous()

@@ -55,6 +55,7 @@ class VAEImageEncoder(nn.Module):
         self.image_res = tuple(get("image_res", (120, 212)))
         self.interpolation_mode = get("interpolation_mode", "bilinear")
         self.return_sampled_latent = bool(get("return_sampled_latent", False))
+        self.native = bool(get("native", True))  # False: torch / cuDNN modules (the CPU mirror the goldens are checked against)
         self.encoder = ImgEncoder(1, self.latent_dim)
         folder, fn = get("model_folder"), get("model_file")
         if get("allow_random_init", False):  # explicit opt-in (tests, throughput runs without the weight file): frozen random weights
@@ -78,9 +79,15 @@ class VAEImageEncoder(nn.Module):
 
     @torch.no_grad()
     def encode(self, image_tensors):
-        if tuple(image_tensors.shape[-2:]) != self.image_res:
-            image_tensors = F.interpolate(image_tensors, self.image_res, mode=self.interpolation_mode)
-        out = self.encoder(image_tensors)
+        if (image_tensors.is_cuda and image_tensors.dtype == torch.float32 and image_tensors.shape[1] == 1
+                and self.interpolation_mode == "bilinear" and self.native):
+            # libagx: resize + the nine convolutions + two dense layers on the tensor cores (tc_encoders.vae_encode), no cuDNN
+            from .tc_encoders import vae_encode
+            out = vae_encode(self.encoder, self.image_res, image_tensors)
+        else:
+            if tuple(image_tensors.shape[-2:]) != self.image_res:
+                image_tensors = F.interpolate(image_tensors, self.image_res, mode=self.interpolation_mode)
+            out = self.encoder(image_tensors)
         means, logvar = out[:, :self.latent_dim], out[:, self.latent_dim:]
         if self.return_sampled_latent:
             return means + torch.exp(0.5 * logvar) * torch.randn_like(means)

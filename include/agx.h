@@ -367,7 +367,7 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
 /* Training path on the 5th-generation tensor cores (tcgen05 + TMEM) for the shipped 64-128-64 network: forward, activation-gradient
  * chain and weight / bias gradients all run on tcgen05.mma.  Intermediates are FEATURE-MAJOR planes ([width][b], b % 128 == 0), which
  * is what makes both operands of the weight gradient (it contracts over the batch axis) K-major:
- *   xt [in_pad, b] (plane in_dim = 1: the bias-gradient column; in_pad in {32,48,64} must exceed in_dim), h1t [64, b], h2t [128, b],
+ *   xt [in_pad, b] (plane in_dim = 1: the bias-gradient column; in_pad in {32,48,64,96} must exceed in_dim), h1t [64, b], h2t [128, b],
  *   h3t [64, b] written by agx_mlp_forward_train;  dz1t [64, b], dz2t [128, b], dz3t [64, b], doutt [16, b] scratch of the backward.
  * agx_mlp_backward_train overwrites the gradients in `g` (deterministic); workspace as agx_mlp_workspace_floats. */
 int agx_mlp_train_supported(const AgxMlpParams* p);
@@ -445,6 +445,43 @@ int agx_sizeof_cnn_params(void);
  * arithmetic throughout (no TF32), no activation leaves the SM. */
 int agx_cnn_encode(const AgxCnnParams* p, int64_t n, const float* image, const float* px_mean, const float* px_rstd,
                    float* features, int64_t ld_features, void* stream);
+
+/* ---- encoder layers on the tensor cores (row f3; csrc/agx_conv.cu) ----------------------------------------------------------------
+ * Channels-last (NHWC) fp32 activations.  agx_conv2d_nhwc: one convolution layer as an implicit GEMM on tcgen05.mma — the im2col
+ * operand is gathered from the input by cp.async straight into the tensor core's operand layout; 3xTF32 operand split (w_lo given)
+ * for fp32-level results, or single-pass TF32 (w_lo NULL: what torch/cuDNN run by default).  Epilogue order:
+ * + bias, + residual, activation, per-channel affine.  Replaces the cuDNN calls behind nn.Conv2d / nn.Linear of
+ * lib/network/cnn.py:3-33 and lib/network/VAE.py:52-148. */
+enum AgxAct { AGX_ACT_NONE = 0, AGX_ACT_RELU = 1, AGX_ACT_ELU = 2 };
+typedef struct AgxConvParams {
+    const float* x;  int32_t N, H, W, Cin;     /* input [N,H,W,Cin], Cin % 4 == 0 */
+    const float *w_hi, *w_lo;                   /* weights [Cout][kh][kw][Cin] split as w = w_hi + w_lo with w_hi exactly tf32; w_lo may be NULL */
+    const float* bias;                          /* [Cout] or NULL */
+    const float *scale, *shift;                 /* [Cout] affine applied after the activation (eval-mode BatchNorm), or both NULL */
+    const float* res; int32_t rH, rW, ry0, rx0, rsy, rsx; /* residual [N,rH,rW,Cout] read at (oy*rsy + ry0, ox*rsx + rx0), or NULL */
+    float* y;        int32_t Ho, Wo, Cout;      /* output [N,Ho,Wo,Cout], Cout % 32 == 0 (and % 128 == 0 above 128) */
+    int32_t kh, kw, sy, sx, py, px, act;        /* kernel, stride, zero padding, AgxAct; kh*kw*Cin % 8 == 0 */
+    int32_t _pad;
+} AgxConvParams;
+int agx_sizeof_conv_params(void);
+int agx_conv2d_nhwc(const AgxConvParams* p, void* stream);
+
+/* first layer (one input channel): direct fp32 convolution, output NHWC with Cout = 16 | 32; optional fused input normalisation
+ * clamp((x - px_mean) * px_rstd, +-5) per pixel (lib/core/running_mean_std.py:76-80); bias, activation, affine as above */
+typedef struct AgxConvFirstParams {
+    const float* x;  int32_t N, H, W, _p0;     /* input [N,H,W] */
+    const float *w, *bias, *scale, *shift;      /* w [Cout][kh][kw] (torch OIHW with I = 1) */
+    const float *px_mean, *px_rstd;             /* [H*W] each, or both NULL */
+    float* y;        int32_t Ho, Wo, Cout;
+    int32_t kh, kw, sy, sx, py, px, act;
+} AgxConvFirstParams;
+int agx_sizeof_conv_first_params(void);
+int agx_conv2d_first(const AgxConvFirstParams* p, void* stream);
+/* F.interpolate(x[n,1,H,W], (Ho,Wo), mode='bilinear', align_corners=False) */
+int agx_resize_bilinear(const float* x, float* y, int64_t n, int H, int W, int Ho, int Wo, void* stream);
+/* out[n, :F] = Linear(mean over `pixels` of x[n, pixels, C]) — AdaptiveAvgPool2d((1,1)) + fc of the CNN (cnn.py:27-33) */
+int agx_pool_fc(const float* x, int64_t n, int pixels, int C, const float* wfc, const float* bfc, int F, float* out, int64_t ld_out,
+                void* stream);
 
 #ifdef __cplusplus
 }

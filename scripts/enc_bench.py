@@ -39,11 +39,39 @@ if __name__ == "__main__":
         torch.backends.cudnn.allow_tf32 = False
         from airgym_b200.lib.network.cnn import native_encode
         ref = net.forward_torch(x[:256])
-        got = native_encode(net, x[:256])
-        out["native_max_abs_err_vs_cudnn_fp32"] = float((got - ref).abs().max())
-        out["native_ms"] = timed(lambda: native_encode(net, x))
         mean, rstd = torch.rand(212 * 120, device="cuda"), torch.rand(212 * 120, device="cuda") + 0.5
-        out["native_fused_norm_ms"] = timed(lambda: native_encode(net, x, mean, rstd))
+        for impl in ("fused", "tc"):  # fused: one persistent fp32-FMA kernel; tc: layer by layer, conv2 / conv3 on tcgen05 (3xTF32)
+            got = native_encode(net, x[:256], impl=impl)
+            out[impl + "_max_abs_err_vs_cudnn_fp32"] = float((got - ref).abs().max())
+            out[impl + "_ms"] = timed(lambda: native_encode(net, x, impl=impl))
+            out[impl + "_fused_norm_ms"] = timed(lambda: native_encode(net, x, mean, rstd, impl=impl))
+        from airgym_b200.lib.network import tc_encoders as T
+        out["tc_single_pass_tf32_ms"] = timed(lambda: T.cnn_encode(net, x, precise=False))
+        # per layer (2048-image chunk)
+        xc = x[:2048].reshape(-1, 212, 120)
+        from airgym_b200 import _capi as K
+        W_ = T._prep_cnn(net, True)
+        a1 = T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"])
+        a2 = T.conv2d_nhwc(a1, W_["c2"], K.ACT_RELU, scale=W_["s2"], shift=W_["t2"])
+        out["tc_layers_ms_per_2048"] = {
+            "conv1_direct": timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"])),
+            "conv2_tcgen05": timed(lambda: T.conv2d_nhwc(a1, W_["c2"], K.ACT_RELU, scale=W_["s2"], shift=W_["t2"])),
+            "conv3_tcgen05": timed(lambda: T.conv2d_nhwc(a2, W_["c3"], K.ACT_RELU, scale=W_["s3"], shift=W_["t3"]))}
+        # the VAE ImgEncoder: libagx layers vs torch / cuDNN
+        from airgym_b200.lib.network.vae_image_encoder import VAEImageEncoder
+        vae = VAEImageEncoder({"latent_dims": 64, "image_res": [120, 212], "interpolation_mode": "bilinear", "allow_random_init": True}).cuda()
+        nv = min(a.n, 8192)
+        out["vae_n"] = nv
+        zn = vae.encode(x[:64])
+        vae.native = False
+        zt = vae.encode(x[:64])
+        out["vae_native_max_abs_err_vs_cudnn_fp32"] = float((zn - zt).abs().max())
+        out["vae_cudnn_fp32_ms"] = timed(lambda: vae.encode(x[:nv]), iters=3)
+        torch.backends.cudnn.allow_tf32 = True
+        out["vae_cudnn_tf32_ms"] = timed(lambda: vae.encode(x[:nv]), iters=3)
+        torch.backends.cudnn.allow_tf32 = False
+        vae.native = True
+        out["vae_native_ms"] = timed(lambda: vae.encode(x[:nv]), iters=3)
         if a.libs:
             import ctypes as C
             from airgym_b200 import _capi

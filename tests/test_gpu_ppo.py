@@ -274,7 +274,7 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
         assert torch.equal(p.grad, first[n]), n
 
 
-@pytest.mark.parametrize("OBS,B", [(18, 2048), (18, 65536), (48, 1024), (46, 256), (18, 128)])
+@pytest.mark.parametrize("OBS,B", [(18, 2048), (18, 65536), (48, 1024), (46, 256), (18, 128), (80, 512)])
 def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     """agx_mlp_forward_train / agx_mlp_backward_train — forward, activation-gradient chain, weight AND bias gradients all on
     tcgen05.mma (feature-major intermediates) — against the fp32 torch model + autograd, at the TF32 bound of the mma.sync path:
@@ -295,7 +295,7 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     model.eval()
     assert model.train_supported(B) and not model.train_supported(B + 8)
     P = model.train_params()
-    assert P.in_pad == {18: 32, 48: 64, 46: 48}[OBS]
+    assert P.in_pad == {18: 32, 48: 64, 46: 48, 80: 96}[OBS]  # 80 = 16 + the VAE's 64 latents
     obs = torch.randn(B, OBS, device="cuda") * 2.0
     mu_ref, v_ref = model.heads(obs)
     keep, dz, dout = model.train_buffers(B, "cuda")
