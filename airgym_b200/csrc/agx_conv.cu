@@ -55,9 +55,10 @@ __device__ __forceinline__ void mma_slab(uint32_t a_base, uint32_t b_base, int N
 }
 
 __global__ void __launch_bounds__(kConvThreads)
-agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, const int stage_floats) {
+agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, const int stage_floats, const int log2cin) {
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base;
+    __shared__ int s_tap[32];  // filter tap → ky << 16 | kx (the gather's index arithmetic is shifts, masks and one table look-up per chunk)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool split = P.w_lo != nullptr;
     const int K = P.kh * P.kw * P.Cin, nslabs = (K + kSlab - 1) / kSlab;
@@ -70,7 +71,12 @@ agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, co
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const uint32_t tmem_cols = Nt <= 32 ? 32u : (Nt <= 64 ? 64u : 128u);
+    if (tid < 32) s_tap[tid] = tid < P.kh * P.kw ? ((tid / P.kw) << 16) | (tid % P.kw) : 0;
+    // The tensor core adds into its fp32 accumulator with truncation, so a long accumulation chain drifts by ~(chain length) x 2^-24
+    // of the accumulator's magnitude (measured: 8e-6 relative at K = 800 with one chain).  G accumulators take the K-slabs round
+    // robin and are added in fp32 in the epilogue: chains G times shorter over sums G times smaller.
+    const int G = K <= 512 ? 1 : (K <= 1024 || Nt > 64 ? 2 : 4);  // K = 144 / 288: chains of 60-110 accumulations stay below 4e-6
+    const uint32_t tmem_cols = (uint32_t)(G * Nt) <= 32u ? 32u : ((uint32_t)(G * Nt) <= 64u ? 64u : ((uint32_t)(G * Nt) <= 128u ? 128u : 256u));
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -89,7 +95,8 @@ agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, co
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u, k = s * kSlab + j * 4;
-            const int tap = k / P.Cin, c = k - tap * P.Cin, ky = tap / P.kw, kx = tap - ky * P.kw;
+            const int tap = log2cin >= 0 ? (k >> log2cin) : 0, c = log2cin >= 0 ? (k & (P.Cin - 1)) : k;  // 1x1 layers: tap 0, c = k
+            const int t = s_tap[tap & 31], ky = t >> 16, kx = t & 0xFFFF;
             const int iy = iy0 + ky, ix = ix0 + kx;
             const bool ok = pix_ok && k < K && iy >= 0 && iy < P.H && ix >= 0 && ix < P.W;
             cp16z(buf + (j * kM + r) * 4, ok ? x_img + ((int64_t)iy * P.W + ix) * P.Cin + c : P.x, ok);
@@ -130,10 +137,11 @@ agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, co
         if (tid == 0) {
             const int kk = K - s * kSlab, ksteps = (kk < kSlab ? kk : kSlab) / 8;
             const uint32_t base = s32(buf);
-            mma_slab(base, base + 4 * offBhi, Nt, ksteps, tmem, s > 0);
+            const uint32_t d = tmem + (uint32_t)((s % G) * Nt);
+            mma_slab(base, base + 4 * offBhi, Nt, ksteps, d, s >= G);
             if (split) {
-                mma_slab(base + 4 * offAlo, base + 4 * offBhi, Nt, ksteps, tmem, true);
-                mma_slab(base, base + 4 * offBlo, Nt, ksteps, tmem, true);
+                mma_slab(base + 4 * offAlo, base + 4 * offBhi, Nt, ksteps, d, true);
+                mma_slab(base, base + 4 * offBlo, Nt, ksteps, d, true);
             }
             commit(&bars[b]);
         }
@@ -161,6 +169,12 @@ agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, co
         for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 16) {
             float v[16];
             tmem_ld16(trow + (uint32_t)c0, v);
+            for (int g = 1; g < G && g < nslabs; ++g) {
+                float u[16];
+                tmem_ld16(trow + (uint32_t)(g * Nt + c0), u);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += u[i];
+            }
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -186,47 +200,74 @@ agx_conv2d_nhwc_kernel(const __grid_constant__ AgxConvParams P, const int Nt, co
 template <int COUT>
 __global__ void __launch_bounds__(128)
 agx_conv2d_first_kernel(const __grid_constant__ AgxConvFirstParams P) {
-    __shared__ float s_w[COUT * 32];  // [tap][COUT]
+    // one thread = a strip of 4 horizontally adjacent output pixels x COUT channels: the input window of the strip is loaded once
+    // (kh x (3 sx + kw) values instead of 4 kh kw) and every broadcast LDS.128 of the weights feeds 16 FMAs
+    __shared__ __align__(16) float s_w[COUT * 32];  // [tap][COUT]
     __shared__ float s_b[COUT], s_s[COUT], s_t[COUT];
     const int taps = P.kh * P.kw;
     for (int i = threadIdx.x; i < taps * COUT; i += 128) { const int t = i / COUT, c = i - t * COUT; s_w[i] = P.w[c * taps + t]; }
     for (int i = threadIdx.x; i < COUT; i += 128) { s_b[i] = P.bias ? P.bias[i] : 0.0f; s_s[i] = P.scale ? P.scale[i] : 1.0f; s_t[i] = P.shift ? P.shift[i] : 0.0f; }
     __syncthreads();
-    const int64_t M_total = (int64_t)P.N * P.Ho * P.Wo;
-    for (int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x; p < M_total; p += (int64_t)gridDim.x * 128) {
-        const int n = (int)(p / ((int64_t)P.Ho * P.Wo)), rem = (int)(p - (int64_t)n * P.Ho * P.Wo), oy = rem / P.Wo, ox = rem - oy * P.Wo;
+    const int strips_x = (P.Wo + 3) / 4;
+    const int64_t S_total = (int64_t)P.N * P.Ho * strips_x;
+    for (int64_t sidx = (int64_t)blockIdx.x * 128 + threadIdx.x; sidx < S_total; sidx += (int64_t)gridDim.x * 128) {
+        const int n = (int)(sidx / ((int64_t)P.Ho * strips_x)), rem = (int)(sidx - (int64_t)n * P.Ho * strips_x), oy = rem / strips_x, ox0 = (rem - oy * strips_x) * 4;
         const float* img = P.x + (int64_t)n * P.H * P.W;
-        float acc[COUT];
+        float acc[4][COUT];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[c] = s_b[c];
-        for (int ky = 0; ky < P.kh; ++ky) {
-            const int iy = oy * P.sy - P.py + ky;
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[q][c] = s_b[c];
+        constexpr int KW = 5, SX = 2, SPAN = 3 * SX + KW;  // the two first layers (cnn.py:14, VAE.py:58) are 5x5, stride 2 — checked on the host
+#pragma unroll
+        for (int ky = 0; ky < KW; ++ky) {
+            const int iy = oy * SX - P.py + ky;
             if (iy < 0 || iy >= P.H) continue;
-            for (int kx = 0; kx < P.kw; ++kx) {
-                const int ix = ox * P.sx - P.px + kx;
-                if (ix < 0 || ix >= P.W) continue;
-                float v = __ldg(img + iy * P.W + ix);
-                if (P.px_mean) {  // RunningMeanStd forward: clamp((x - mean) / sqrt(var + eps), +-5), rstd prepared by the caller
-                    v = (v - __ldg(P.px_mean + iy * P.W + ix)) * __ldg(P.px_rstd + iy * P.W + ix);
-                    v = fminf(fmaxf(v, -5.0f), 5.0f);
-                }
-                const float* wt = s_w + (ky * P.kw + kx) * COUT;
+            float row[SPAN];
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wt[c], acc[c]);
+            for (int u = 0; u < SPAN; ++u) {
+                const int ix = ox0 * SX - P.px + u;
+                float v = 0.0f;
+                if (ix >= 0 && ix < P.W) {
+                    v = __ldg(img + iy * P.W + ix);
+                    if (P.px_mean) {  // RunningMeanStd forward: clamp((x - mean) / sqrt(var + eps), +-5), rstd prepared by the caller
+                        v = (v - __ldg(P.px_mean + iy * P.W + ix)) * __ldg(P.px_rstd + iy * P.W + ix);
+                        v = fminf(fmaxf(v, -5.0f), 5.0f);
+                    }
+                }
+                row[u] = v;
+            }
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                const float4* wt = reinterpret_cast<const float4*>(s_w + (ky * KW + kx) * COUT);  // broadcast LDS.128
+#pragma unroll
+                for (int c = 0; c < COUT; c += 4) {
+                    const float4 w4 = wt[c >> 2];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float v = row[q * SX + kx];
+                        acc[q][c] = fmaf(v, w4.x, acc[q][c]); acc[q][c + 1] = fmaf(v, w4.y, acc[q][c + 1]);
+                        acc[q][c + 2] = fmaf(v, w4.z, acc[q][c + 2]); acc[q][c + 3] = fmaf(v, w4.w, acc[q][c + 3]);
+                    }
+                }
             }
         }
-        float* y = P.y + p * COUT;
 #pragma unroll
-        for (int c = 0; c < COUT; c += 4) {
-            float o[4];
+        for (int q = 0; q < 4; ++q) {
+            if (ox0 + q >= P.Wo) continue;
+            float* y = P.y + (((int64_t)n * P.Ho + oy) * P.Wo + ox0 + q) * COUT;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float a = acc[c + i];
-                if (P.act == 1) a = fmaxf(a, 0.0f);
-                else if (P.act == 2) a = a > 0.0f ? a : expm1f(a);
-                o[i] = a * s_s[c + i] + s_t[c + i];
+            for (int c = 0; c < COUT; c += 4) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a = acc[q][c + i];
+                    if (P.act == 1) a = fmaxf(a, 0.0f);
+                    else if (P.act == 2) a = a > 0.0f ? a : expm1f(a);
+                    o[i] = a * s_s[c + i] + s_t[c + i];
+                }
+                *reinterpret_cast<float4*>(y + c) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<float4*>(y + c) = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -299,17 +340,23 @@ int agx_conv2d_nhwc(const AgxConvParams* p, void* stream) {
     if (!attr_set) { cudaFuncSetAttribute(agx_conv2d_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * (8 * 128 * 4 + 8 * 128 * 4) * 4); attr_set = true; }
     const int64_t M_total = (int64_t)p->N * p->Ho * p->Wo;
     const dim3 grid((unsigned)((M_total + kM - 1) / kM), (unsigned)(p->Cout / Nt));
-    agx_conv2d_nhwc_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p, Nt, stage_floats);
+    int log2cin = -1;
+    if (p->kh * p->kw > 1) {
+        if (p->kh * p->kw > 32 || (p->Cin & (p->Cin - 1))) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_conv2d_nhwc: spatial kernels need Cin a power of two and at most 32 taps");
+        for (log2cin = 0; (1 << log2cin) < p->Cin; ++log2cin) {}
+    }
+    agx_conv2d_nhwc_kernel<<<grid, kConvThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*p, Nt, stage_floats, log2cin);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_nhwc: launch failed");
 }
 
 int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
-    if (!p || !p->x || !p->w || !p->y || p->N <= 0 || p->kh * p->kw > 32 || p->kh <= 0 || p->kw <= 0 || ((p->px_mean == nullptr) != (p->px_rstd == nullptr)) ||
-        p->act < 0 || p->act > 2 || p->sy <= 0 || p->sx <= 0)
+    if (!p || !p->x || !p->w || !p->y || p->N <= 0 || ((p->px_mean == nullptr) != (p->px_rstd == nullptr)) || p->act < 0 || p->act > 2)
         return agx_internal_fail(AGX_ERR_ARG, "agx_conv2d_first: bad argument");
+    if (p->kh != 5 || p->kw != 5 || p->sy != 2 || p->sx != 2)
+        return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_conv2d_first: built for the 5x5 stride-2 first layers of the two encoders");
     if ((uintptr_t)p->y & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_conv2d_first: output must be 16-byte aligned");
-    const int64_t M_total = (int64_t)p->N * p->Ho * p->Wo;
-    int64_t grid = (M_total + 127) / 128;
+    const int64_t S_total = (int64_t)p->N * p->Ho * ((p->Wo + 3) / 4);
+    int64_t grid = (S_total + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p->Cout == 16) agx_conv2d_first_kernel<16><<<(unsigned)grid, 128, 0, st>>>(*p);

@@ -56,9 +56,12 @@ def test_conv_layer_vs_float64(built, g, precise):
         y_ref = y_ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
     y = T.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), L, ACT[act][0], res=res, scale=scale, shift=shift)
     torch.cuda.synchronize()
+    y_ref = y_ref.detach()
     err = float((y.permute(0, 3, 1, 2).double() - y_ref).abs().max())
     ref_scale = float(y_ref.abs().max())
-    assert err <= (3e-6 if precise else 4e-3) * max(1.0, ref_scale), (err, ref_scale)
+    # 3xTF32 products are fp32-exact to ~2^-22; what remains is the tensor core's truncating accumulator (split over 2-4 chains by the kernel)
+    K = Cin * (k * k if isinstance(k, int) else k[0] * k[1])
+    assert err <= ((1e-5 if K <= 2048 else 3e-5) if precise else 4e-3) * max(1.0, ref_scale), (err, ref_scale, K)
 
 
 @pytest.mark.parametrize("Cout,k,s,p,H,W", [(16, 5, 2, 2, 212, 120), (32, 5, 2, 2, 120, 212)])
@@ -74,7 +77,7 @@ def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W):
     out = torch.empty(9, W, H, device="cuda")
     _capi.check(_capi.load().agx_resize_bilinear(img.data_ptr(), out.data_ptr(), 9, H, W, W, H, None))
     ref = F.interpolate(img.unsqueeze(1), (W, H), mode="bilinear", align_corners=False).squeeze(1)
-    assert float((out - ref).abs().max()) < 1e-4
+    assert float((out - ref).abs().max()) < 5e-5 * float(ref.abs().max())  # torch's GPU kernel interpolates with a different association
 
 
 def test_cnn_encoder_tc_vs_float64_and_the_fused_kernel(built):
