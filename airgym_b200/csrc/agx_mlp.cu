@@ -951,8 +951,9 @@ static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, 
     AgxPolicyIO pol_none;
     memset(&pol_none, 0, sizeof(pol_none));
     const AgxPolicyIO* pol = pol_in ? pol_in : &pol_none;
-    const size_t smem = smem_bytes(p, 4);
-    if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
+    const size_t smem = smem_bytes(p, 4);  // of the mma.sync kernels; the tcgen05 kernels carve their own
+    const bool tc_only = pol_in != nullptr || keep_t;
+    if (!tc_only && smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define AGX_FWD(D)                                                                                                      \
     do {                                                                                                                \

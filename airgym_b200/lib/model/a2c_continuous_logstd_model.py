@@ -132,7 +132,9 @@ class ModelA2CContinuousLogStd(nn.Module):
             self._fused = self.fused_params()
         p = lambda t: t.data_ptr() if t is not None else None
         k = keep if keep is not None else (None, None, None, None)
-        _capi.check(_capi.load().agx_mlp_forward(C.byref(self._fused), obs.shape[0], p(obs), p(mu_out), p(value_out), p(k[0]), p(k[1]),
+        # inference calls take the padding of the tcgen05 kernels when the network has one (e.g. the 80-wide VAE trunk input → 96)
+        P = self.train_params() if (keep is None and self.policy_step_supported()) else self._fused
+        _capi.check(_capi.load().agx_mlp_forward(C.byref(P), obs.shape[0], p(obs), p(mu_out), p(value_out), p(k[0]), p(k[1]),
                                                  p(k[2]), p(k[3]), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_forward")
 
     # ---- tcgen05 training path: feature-major intermediates (agx_mlp_forward_train / agx_mlp_backward_train) ----------
