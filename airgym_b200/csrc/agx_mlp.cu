@@ -952,8 +952,7 @@ static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, 
     memset(&pol_none, 0, sizeof(pol_none));
     const AgxPolicyIO* pol = pol_in ? pol_in : &pol_none;
     const size_t smem = smem_bytes(p, 4);  // of the mma.sync kernels; the tcgen05 kernels carve their own
-    const bool tc_only = pol_in != nullptr || keep_t;
-    if (!tc_only && smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
+    const bool tc_shape = is_shipped(p, 32) || is_shipped(p, 48) || is_shipped(p, 64) || is_shipped(p, 96);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define AGX_FWD(D)                                                                                                      \
     do {                                                                                                                \
@@ -984,8 +983,12 @@ static int mlp_forward_impl(const AgxMlpParams* p, int64_t b, const float* obs, 
             return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward_train: needs the 64-128-64 network, in_pad in {32,48,64,96} > in_dim, b % 128 == 0");
         if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else if (p->in_pad == 64) AGX_FWD_TC(64); else AGX_FWD_TC(96);
     }
-    else if (is_shipped(p, 32)) { if (use_tc) AGX_FWD_TC(32); else AGX_FWD(S32); }
-    else if (is_shipped(p, 48)) { if (use_tc) AGX_FWD_TC(48); else AGX_FWD(S48); }
+    else if (use_tc && tc_shape) {
+        if (p->in_pad == 32) AGX_FWD_TC(32); else if (p->in_pad == 48) AGX_FWD_TC(48); else if (p->in_pad == 64) AGX_FWD_TC(64); else AGX_FWD_TC(96);
+    }
+    else if (smem > 227 * 1024) return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_mlp_forward: network too large for shared memory");
+    else if (is_shipped(p, 32)) AGX_FWD(S32);
+    else if (is_shipped(p, 48)) AGX_FWD(S48);
     else AGX_FWD(Dims);
 #undef AGX_FWD
 #undef AGX_FWD_TC
