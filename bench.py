@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the full-contract and 2^22-env side measurements")
     ap.add_argument("--ppo-envs", type=int, default=NUM_ENVS, help="envs per GPU of the PPO sub-record")
     ap.add_argument("--ppo-epochs", type=int, default=6, help="timed PPO epochs (after 3 warm-up / capture epochs)")
+    ap.add_argument("--no-camera", action="store_true", help="skip the Avoid / Planning (configs 4-5) side records")
+    ap.add_argument("--camera-envs", type=int, default=32768, help="envs per GPU of the Avoid / Planning side records")
     return ap.parse_args()
 
 
@@ -386,47 +388,49 @@ def time_e2e_loop(env, num_envs, steps, warmup, dist, device_index):
     return median(times), h2d, d2h, {"pinned_numa_node": info_r["numa_node"], "pinned_placed": info_r["placed"] and info_a["placed"]}
 
 
-def ppo_record(args, rank, local, world, dist):
-    """PPO samples/s on the same envs (north_star: "PPO tokens/sec scaling 1->8"): Hovering/CTBR, 65 536 envs per GPU, the reference's
-    ppo_hovering.yaml hyper-parameters with the minibatch scaled to keep its 48 minibatches per mini-epoch; rollout and update replay
-    from CUDA graphs; with more than one rank the gradient all-reduce is fused into the Adam kernel over NVLink peer memory."""
+def ppo_run(task, num_envs, epochs, rank, local, world, dist, vae=False, warm=3):
+    """`epochs` timed PPO epochs (after `warm` eager / capture epochs) of `task` at `num_envs` envs per GPU through the trainer's public
+    classes; rollout and update replay from CUDA graphs; with more than one rank the gradient all-reduce is fused into the Adam kernel
+    over NVLink peer memory.  Device-timed, max over ranks."""
     import torch
 
     from airgym_b200.lib.agent.a2c_continuous import A2CAgent
     from airgym_b200.lib.config import default_ppo_config, scale_minibatch
     from airgym_b200.lib.utils import tr_helpers
 
-    N = args.ppo_envs
-    cfg = scale_minibatch(default_ppo_config("hovering"), N)
+    cfg = scale_minibatch(default_ppo_config(task), num_envs)
     c = cfg["params"]["config"]
     c.update(multi_gpu=world > 1, print_stats=False, write_summaries=False, train_dir="/tmp/agx_bench_ppo", save_frequency=0,
              save_best_after=10**9, device=f"cuda:{local}")
-    c["env_config"].update(ctl_mode="rate", num_envs=N, seed=1)
+    c["env_config"].update(ctl_mode="rate", num_envs=num_envs, seed=1)
     c["reward_shaper"] = tr_helpers.DefaultRewardsShaper(**c["reward_shaper"])
+    if vae:  # ppo_planning.yaml:33-39 — frozen VAE encoder (latent 64); trained/vae_model.pth does not travel: random frozen weights
+        cfg["params"]["network"].pop("cnn", None)
+        cfg["params"]["network"]["vae"] = {"latent_dims": 64, "image_res": [120, 212], "interpolation_mode": "bilinear",
+                                           "return_sampled_latent": False, "allow_random_init": True}
     torch.manual_seed(1)
     agent = A2CAgent("bench", cfg["params"])
     agent.env_reset()
     agent.sync_replicas()
-    for _ in range(3):  # eager warm-up, graph capture, first replay
+    for _ in range(warm):  # eager warm-up, graph capture, first replay
         agent.train_epoch()
-    E = args.ppo_epochs
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     play = upd = 0.0
-    for _ in range(E):
+    for _ in range(epochs):
         p, u, _ = agent.train_epoch()
         play, upd = play + p, upd + u
     e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1), 1e3 * play / E, 1e3 * upd / E], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e0.elapsed_time(e1), 1e3 * play / epochs, 1e3 * upd / epochs], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_play, ms_upd = t.tolist()
     allreduce_us = None
-    if agent.comm is not None:  # the stand-alone collective on a gradient-sized message, back to back (eager launches)
+    if agent.comm is not None and task == "hovering":  # the stand-alone collective on a gradient-sized message, back to back (eager launches)
         buf = torch.zeros_like(agent.flat_grads)
         for _ in range(20):
             agent.comm.all_reduce(buf)
@@ -441,17 +445,44 @@ def ppo_record(args, rank, local, world, dist):
         torch.cuda.synchronize()
         allreduce_us = 1e3 * a0.elapsed_time(a1) / 200
         agent.comm.check()
-    rec = {"samples_per_s": world * agent.batch_size * E / (ms * 1e-3), "ms_per_epoch": ms / E, "ms_rollout": ms_play, "ms_update": ms_upd,
-           "allreduce_us": allreduce_us, "epochs_timed": E, "num_envs_per_gpu": N, "horizon": agent.horizon_length,
-           "minibatch_per_gpu": agent.minibatch_size, "minibatches_per_epoch": agent.num_minibatches * agent.mini_epochs_num,
+    n_mb = agent.num_minibatches * agent.mini_epochs_num
+    rec = {"samples_per_s": world * agent.batch_size * epochs / (ms * 1e-3), "env_steps_per_s_rollout": world * agent.batch_size / (ms_play * 1e-3),
+           "ms_per_epoch": ms / epochs, "ms_rollout": ms_play, "ms_update": ms_upd,
+           "allreduce_us": allreduce_us, "epochs_timed": epochs, "num_envs_per_gpu": num_envs, "horizon": agent.horizon_length,
+           "minibatch_per_gpu": agent.minibatch_size, "minibatches_per_epoch": n_mb,
+           "rollout": "fused: policy step (tcgen05 MLP + sampling + buffer writes) + env step + post kernel" if agent.fused_rollout else "per-op",
+           "mlp_backward": "tcgen05" if getattr(agent, "mlp_train_tc", False) else "mma.sync",
            "collective": ("none (1 rank)" if world == 1 else
                           ("peer-memory all-reduce fused into the Adam kernel (agx_adam_step_allreduce) + agx_comm_allreduce for the "
                            "per-epoch moments, all inside the CUDA graphs" if agent.comm is not None else "NCCL all-reduce")),
-           "mean_reward_last": agent.mean_rewards if agent.mean_rewards > -1e8 else None, "kl_last": float(agent.epoch_loss_sums[4]) /
-           (agent.num_minibatches * agent.mini_epochs_num)}
+           "kl_last": float(agent.epoch_loss_sums[4]) / n_mb}
+    if agent.has_cnn:
+        rec["encoder"] = "frozen VAE ImgEncoder (random weights), libagx tcgen05 layers" if vae else "CNNFeatureExtractor, libagx"
+        rec["render_every"] = agent.env.cam_every
     if agent.comm is not None:
         agent.comm.close()
+    del agent
+    torch.cuda.empty_cache()
     return rec
+
+
+def ppo_record(args, rank, local, world, dist):
+    """PPO samples/s on the same envs (north_star: "PPO tokens/sec scaling 1->8"): Hovering/CTBR, 65 536 envs per GPU, the reference's
+    ppo_hovering.yaml hyper-parameters with the minibatch scaled to keep its 48 minibatches per mini-epoch."""
+    return ppo_run("hovering", args.ppo_envs, args.ppo_epochs, rank, local, world, dist)
+
+
+def camera_records(args, rank, local, world, dist):
+    """BASELINE configs 4 / 5 at their per-GPU share (32 768 envs per GPU; 4 GPUs = 131 072 Avoid envs, 8 GPUs = 262 144 Planning
+    envs): depth camera every 4th step, CNN(30) policy (ppo_avoid.yaml / ppo_planning.yaml) and, for Planning, the VAE variant.
+    Avoid runs in rate mode: the reference itself cannot run Avoid in atti (CTA) mode (avoid.py:226 writes [N,5] into obs[12:16])."""
+    out = {}
+    for key, task, vae, epochs in (("avoid_cnn", "avoid", False, 2), ("planning_cnn", "planning", False, 3), ("planning_vae", "planning", True, 3)):
+        try:
+            out[key] = ppo_run(task, args.camera_envs, epochs, rank, local, world, dist, vae=vae, warm=3)
+        except Exception as exc:  # noqa: BLE001 — side records must never cost the bench line
+            out[key] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+    return out
 
 
 def run_ours(args):
@@ -532,6 +563,9 @@ def run_ours(args):
         del envs, acts
         torch.cuda.empty_cache()
         ppo = ppo_record(args, rank, local, world, dist)
+    camera = None
+    if not args.no_camera:
+        camera = camera_records(args, rank, local, world, dist)
 
     if rank != 0:
         if dist is not None:
@@ -562,6 +596,8 @@ def run_ours(args):
     line.update(extras)
     if ppo is not None:
         line["ppo"] = ppo
+    if camera is not None:
+        line["camera_tasks"] = camera
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_oracle_steps_per_s(N)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
