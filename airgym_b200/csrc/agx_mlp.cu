@@ -315,7 +315,9 @@ namespace tc {
 template <int W>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ bias, float* a_next, int r,
                                                 float* __restrict__ keep_row, float* __restrict__ keep_col = nullptr, int64_t ld_t = 0) {
-#pragma unroll
+    // not unrolled over the column chunks: four call sites x up to 8 chunks of ~250 instructions each overflowed the instruction
+    // cache (ncu: stall_no_instruction 6.2 of 11 cycles per issue with the two tile groups in different code regions)
+#pragma unroll 1
     for (int c0 = 0; c0 < W; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_row + (uint32_t)(col0 + c0), v);

@@ -12,9 +12,9 @@
 //   dH1 = dZ2·W2 → dZ1.  Each product is one accumulation chain of tcgen05.mma (M = 128 rows, N = layer width) with the transposed
 //   weights staged K-major in shared memory once per CTA; thread r owns row r = TMEM lane r: tcgen05.ld, multiply by elu'(h) (h read
 //   back from its plane, coalesced), store the dZ plane element (coalesced) and the next A operand (16-byte chunks).
-// agx_mlp_wgrad_tc_kernel — all four weight gradients AND bias gradients of a batch slab in one persistent CTA per SM: 32-row stages
-//   stream through a double-buffered cp.async pipeline straight into the canonical operand layout, one thread issues 16 MMAs per
-//   stage (4 layers x 4 K-steps) into four TMEM accumulators that live for the whole slab; the bias gradient is the extra output
+// agx_mlp_wgrad_tc_kernel — all four weight gradients AND bias gradients of a batch slab in one persistent CTA per SM: 16-row stages
+//   stream through a four-buffer cp.async pipeline straight into the canonical operand layout, one thread issues 8 MMAs per
+//   stage (4 layers x 2 K-steps) into four TMEM accumulators that live for the whole slab; the bias gradient is the extra output
 //   column produced by a constant ones row appended to each B operand (plane `in_dim` of the normalised input is all ones).
 //   Per-CTA partials go through the same deterministic reduction as the mma.sync path (agx_mlp.cu).
 #include <cuda_runtime.h>
@@ -47,7 +47,7 @@ constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kW3T + kW2T + kWhT + 2 * 
 template <int W>
 __device__ __forceinline__ void grad_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ h_col, float* __restrict__ dz_col,
                                               int64_t B, float* a_next, int r) {
-#pragma unroll
+#pragma unroll 1
     for (int c0 = 0; c0 < W; c0 += 16) {
         float h[16], v[16];
 #pragma unroll
@@ -142,7 +142,9 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
 namespace tcw {
 using namespace tc;
 constexpr int kThreads = 256;
-constexpr int kStage = 32;            // batch rows (= K) per pipeline stage
+constexpr int kStage = 16;            // batch rows (= K) per pipeline stage
+constexpr int kBufs = 4;              // stage buffers: three stages of copies in flight under the MMAs of the fourth (with two 32-row
+                                      // buffers every stage paid a full DRAM round trip: 34.7 us per 32 768-row minibatch, ncu)
 constexpr int kKc = kStage / 4;       // 16-byte K-chunks per operand row and stage
 constexpr int kN2 = kH1 + 16, kN3 = kH2 + 16;   // B operands of layers 2 / 3 carry a 16-row block whose first row is all ones (bias column)
 // TMEM columns of the four accumulators (M = 128 lanes each; only the first `out` lanes are meaningful)
@@ -162,7 +164,7 @@ __device__ __forceinline__ void cp16(float* dst, const float* src) {
 template <int R, int RA>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ plane, int64_t B, int64_t r0) {
     for (int j = threadIdx.x; j < R * kKc; j += kThreads) {
-        const int kc = ((j >> 5) & 3) * 2 + (j & 1), m = (j >> 7) * 16 + ((j >> 1) & 15);
+        const int kc = ((j >> 5) & (kKc / 2 - 1)) * 2 + (j & 1), m = (j / (16 * kKc)) * 16 + ((j >> 1) & 15);
         cp16(dst + (kc * RA + m) * 4, plane + (int64_t)m * B + r0 + kc * 4);
     }
 }
@@ -174,13 +176,13 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
                         const float* __restrict__ dz2t, const float* __restrict__ dz3t, const float* __restrict__ doutt,
                         float* __restrict__ w_partials, float* __restrict__ b_partials, int partial_floats) {
     using L = Layout<IN_PAD>;
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[kBufs];
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // constant parts of both stage buffers: zero rows that pad M to 128, and the ones rows behind the bias columns
-    for (int i = tid; i < 2 * L::floats; i += kThreads) t_smem[i] = 0.0f;
+    // constant parts of the stage buffers: zero rows that pad M to 128, and the ones rows behind the bias columns
+    for (int i = tid; i < kBufs * L::floats / 4; i += kThreads) reinterpret_cast<float4*>(t_smem)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();
-    for (int i = tid; i < 2 * kStage; i += kThreads) {
+    for (int i = tid; i < kBufs * kStage; i += kThreads) {
         float* buf = t_smem + (i / kStage) * L::floats;
         const int k = i % kStage;
         buf[L::ah + canon(kH3, k, kM)] = 1.0f;    // A of the heads: row 64 = ones → lane 64 of its accumulator = sum_b dout[b, :]
@@ -188,8 +190,7 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
         buf[L::b3 + canon(kH2, k, kN3)] = 1.0f;   // B of layer 3: row 128 = ones
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
+        for (int b = 0; b < kBufs; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[b])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -203,7 +204,7 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
     const int S = (int)(s_end - s_begin);
 
     auto issue = [&](int s) {
-        float* buf = t_smem + (s & 1) * L::floats;
+        float* buf = t_smem + (s % kBufs) * L::floats;
         const int64_t r0 = (s_begin + s) * kStage;
         load_tile<kH1, kM>(buf + L::a1, dz1t, B, r0);
         load_tile<kH2, kM>(buf + L::a2, dz2t, B, r0);
@@ -215,14 +216,17 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
         load_tile<kOutPad, kOutPad>(buf + L::bh, doutt, B, r0);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (S > 0) issue(0);
-    if (S > 1) issue(1);
-    uint32_t phase[2] = {0u, 0u};
+    for (int s = 0; s < kBufs - 1 && s < S; ++s) issue(s);
+    uint32_t phase[kBufs];
+#pragma unroll
+    for (int b = 0; b < kBufs; ++b) phase[b] = 0u;
     for (int s = 0; s < S; ++s) {
-        if (s + 1 < S) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        const int pending = (S - s - 1) < (kBufs - 2) ? (S - s - 1) : (kBufs - 2);  // younger copy groups that may still be in flight
+        if (pending >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         publish_and_sync(0, kThreads);  // every thread's copies of stage s have landed and are visible to the tensor core
-        const int b = s & 1;
+        const int b = s % kBufs;
         if (tid == 0) {
             const uint32_t base = s32(t_smem + b * L::floats);
             const bool acc = s > 0;
@@ -232,14 +236,22 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
             gemm(base + 4 * L::ah, base + 4 * L::bh, kOutPad, kStage, tmem + kCh, acc);
             commit(&bars[b]);
         }
-        if (s + 2 < S) {  // the MMAs of stage s must have read buffer b before stage s + 2 is copied over it
-            wait(&bars[b], phase[b]); phase[b] ^= 1u;
-            issue(s + 2);
+        if (s + kBufs - 1 < S) {  // stage s + kBufs - 1 goes into the buffer of stage s - 1: its MMAs (committed one iteration ago) must be done
+            if (s > 0) {
+                const int pb = (s - 1) % kBufs;
+#pragma unroll
+                for (int q = 0; q < kBufs; ++q)
+                    if (q == pb) { wait(&bars[q], phase[q]); phase[q] ^= 1u; }
+            }
+            issue(s + kBufs - 1);
         }
     }
-    if (S > 0) {  // the last commit covers every earlier MMA of the issuing thread
-        const int b = (S - 1) & 1;
-        wait(&bars[b], phase[b]);
+    if (S > 0) {  // the last commit covers every earlier MMA of the issuing thread; earlier unwaited commits only advance their barriers
+        // Stages S-4 .. S-1 were never waited for and sit on four different barriers; every earlier commit of barrier lb was, so the
+        // barrier is at most one completion behind and the parity of its last commit is (number of its commits - 1) & 1.
+        const int lb = (S - 1) % kBufs;
+        const int commits = (S - 1 - lb) / kBufs + 1;
+        wait(&bars[lb], (uint32_t)((commits - 1) & 1));
     }
     // ---- epilogue: accumulators → this CTA's partials (layout of agx_mlp.cu: dense [out x in_pad] blocks back to back; bias slots b1|b2|b3|heads)
     float* wp = w_partials + (int64_t)blockIdx.x * partial_floats;
@@ -334,7 +346,7 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
     float* b_partials = workspace + (int64_t)kGrid * pf;
 #define AGX_WGRAD_TC(PAD)                                                                                                         \
     do {                                                                                                                          \
-        constexpr int kSm = 2 * tcw::Layout<PAD>::floats * (int)sizeof(float);                                                    \
+        constexpr int kSm = tcw::kBufs * tcw::Layout<PAD>::floats * (int)sizeof(float);                                                    \
         cudaFuncSetAttribute(tcw::agx_mlp_wgrad_tc_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);                \
         tcw::agx_mlp_wgrad_tc_kernel<PAD><<<gw, tcw::kThreads, kSm, st>>>(*p, b, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, w_partials, \
                                                                           b_partials, pf);                                        \

@@ -224,6 +224,55 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, const __grid_constant__ 
     }
 }
 
+// ---- RunningMeanStd update in two launches (lib/core/running_mean_std.py:45-60) ------------------------------------------------------
+// (1) float64 column sums / sums of squares of x [n, k]: per-CTA partials, the CTA drawing the last ticket adds them in CTA order
+// (deterministic); (2) after an optional all-reduce of those sums: batch mean, UNBIASED batch variance, parallel-variance merge.
+constexpr int kSumsBlock = 256, kSumsGridMax = 296, kSumsMaxK = 128;
+__global__ void __launch_bounds__(kSumsBlock)
+agx_col_sums_kernel(const float* __restrict__ x, int64_t n, int k, int64_t ld, int cpr, double* __restrict__ sums, double* __restrict__ ws) {
+    __shared__ double s_a[kSumsBlock], s_b[kSumsBlock];
+    __shared__ bool s_last;
+    const int c = threadIdx.x % cpr, rg = threadIdx.x / cpr, rgs = kSumsBlock / cpr;
+    double a = 0.0, b = 0.0;
+    if (c < k)
+        for (int64_t r = (int64_t)blockIdx.x * rgs + rg; r < n; r += (int64_t)gridDim.x * rgs) { const double v = (double)x[r * ld + c]; a += v; b += v * v; }
+    s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+    __syncthreads();
+    double* part = ws + 8 + (int64_t)blockIdx.x * 2 * kSumsMaxK;
+    if (threadIdx.x < cpr && threadIdx.x < k) {
+        double ta = 0.0, tb = 0.0;
+        for (int g = 0; g < rgs; ++g) { ta += s_a[g * cpr + threadIdx.x]; tb += s_b[g * cpr + threadIdx.x]; }
+        part[threadIdx.x] = ta; part[kSumsMaxK + threadIdx.x] = tb;
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x < k) {
+            double ta = 0.0, tb = 0.0;
+            for (unsigned int g = 0; g < gridDim.x; ++g) { ta += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + threadIdx.x); tb += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + kSumsMaxK + threadIdx.x); }
+            sums[threadIdx.x] = ta; sums[k + threadIdx.x] = tb;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+__global__ void agx_rms_merge_kernel(const double* __restrict__ sums, int k, double n_total, double* mean, double* var, double* count) {
+    const int c = threadIdx.x;
+    const double cnt = count[0];
+    __syncthreads();  // every thread has read the count before thread 0 rewrites it
+    if (c < k) {
+        const double bm = sums[c] / n_total, bv = (sums[k + c] - n_total * bm * bm) / (n_total - 1.0);
+        const double delta = bm - mean[c], tot = cnt + n_total;
+        const double m2 = var[c] * cnt + bv * n_total + delta * delta * cnt * n_total / tot;
+        mean[c] = mean[c] + delta * n_total / tot;
+        var[c] = m2 / tot;
+    }
+    if (c == 0) count[0] = cnt + n_total;
+}
+
 // ---- after env.step of a rollout (agx.h AgxPostIO) ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) agx_rollout_post_kernel(const __grid_constant__ AgxPostIO io, int64_t n) {
     __shared__ double s_part[8][4];
@@ -259,6 +308,23 @@ __global__ void __launch_bounds__(256) agx_rollout_post_kernel(const __grid_cons
 }  // namespace
 
 extern "C" {
+
+int64_t agx_col_sums_workspace_doubles(void) { return 8 + (int64_t)kSumsGridMax * 2 * kSumsMaxK; }
+
+int agx_col_sums(const float* x, int64_t n, int k, int64_t ld, double* sums, double* workspace, void* stream) {
+    if (!x || !sums || !workspace || n <= 0 || k <= 0 || k > kSumsMaxK || ld < k) return fail_ppo(AGX_ERR_ARG, "agx_col_sums: bad argument (k <= 128)");
+    const int cpr = k <= 32 ? 32 : (k <= 64 ? 64 : 128), rgs = kSumsBlock / cpr;
+    int64_t grid = (n + rgs * 16 - 1) / (rgs * 16);
+    if (grid > kSumsGridMax) grid = kSumsGridMax;
+    agx_col_sums_kernel<<<(unsigned)grid, kSumsBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, k, ld, cpr, sums, workspace);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_col_sums: launch failed");
+}
+
+int agx_rms_merge(const double* sums, int k, double n_total, double* mean, double* var, double* count, void* stream) {
+    if (!sums || !mean || !var || !count || k <= 0 || k > kSumsMaxK || n_total < 2.0) return fail_ppo(AGX_ERR_ARG, "agx_rms_merge: bad argument");
+    agx_rms_merge_kernel<<<1, kSumsMaxK, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums, k, n_total, mean, var, count);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_rms_merge: launch failed");
+}
 
 int agx_sizeof_post_io(void) { return (int)sizeof(AgxPostIO); }
 

@@ -425,6 +425,21 @@ class A2CAgent:
         """RunningMeanStd train-mode update; with >1 rank the batch moments are merged across ranks first so that
         replicas keep identical statistics (the reference keeps per-rank statistics)."""
         n = x.shape[0]
+        if (x.dim() == 2 and x.shape[1] <= 128 and x.dtype == torch.float32 and x.stride(1) == 1 and rms.running_mean.dim() == 1
+                and self.config.get("fused_rms", True)):
+            # two libagx launches (column sums → [all-reduce] → merge) instead of ~12 torch kernels per update
+            k, st = x.shape[1], C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if not hasattr(self, "_sums_ws"):
+                self._sums_ws = torch.zeros(int(self._lib.agx_col_sums_workspace_doubles()), device=x.device, dtype=torch.float64)
+                self._sums = torch.zeros(2 * 128, device=x.device, dtype=torch.float64)
+            sums = self._sums[: 2 * k]
+            _capi.check(self._lib.agx_col_sums(x.data_ptr(), n, k, x.stride(0), sums.data_ptr(), self._sums_ws.data_ptr(), st), "agx_col_sums")
+            if self.multi_gpu and self.world_size > 1:
+                self._allreduce(sums)
+                n = n * self.world_size
+            _capi.check(self._lib.agx_rms_merge(sums.data_ptr(), k, float(n), rms.running_mean.data_ptr(), rms.running_var.data_ptr(),
+                                                rms.count.data_ptr(), st), "agx_rms_merge")
+            return
         if self.multi_gpu and self.world_size > 1:
             n = n * self.world_size
             mean, var = moments_from_sums(self._allreduce(batch_sums(x)), n)

@@ -423,6 +423,14 @@ typedef struct AgxPostIO {
 int agx_sizeof_post_io(void);
 int agx_rollout_post(const AgxPostIO* io, int64_t n, void* stream);
 
+/* RunningMeanStd.update in two launches (lib/core/running_mean_std.py:45-60; the reference runs ~12 torch kernels per update):
+ * agx_col_sums: sums [2, k] float64 = column sums and sums of squares of x [n, k] (row stride ld), deterministic; workspace of
+ * agx_col_sums_workspace_doubles() float64, zero-filled once.  Between the two a multi-GPU run all-reduces `sums`.
+ * agx_rms_merge: batch mean / UNBIASED variance over n_total rows from the sums, merged into mean / var / count (float64, in place). */
+int64_t agx_col_sums_workspace_doubles(void);
+int agx_col_sums(const float* x, int64_t n, int k, int64_t ld, double* sums, double* workspace, void* stream);
+int agx_rms_merge(const double* sums, int k, double n_total, double* mean, double* var, double* count, void* stream);
+
 /* ---- depth-image encoder (row f3) ------------------------------------------------------------------------------------
  * Replaces the forward of lib/network/cnn.py:3-33 (CNNFeatureExtractor: three stride-2 convolutions, each followed by
  * ReLU then BatchNorm2d, global average pool, Linear 64 -> feature_dim) in EVAL mode, with the per-pixel input

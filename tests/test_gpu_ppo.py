@@ -429,3 +429,29 @@ def test_fused_rollout_philox_sampling_is_standard_normal_and_partition_invarian
     torch.cuda.synchronize()
     assert torch.equal(torch.cat((half[0].buf["actions"], half[1].buf["actions"])), ag.buf["actions"])
     assert torch.equal(torch.cat((half[0].buf["rewards"], half[1].buf["rewards"])), ag.buf["rewards"])
+
+
+@pytest.mark.parametrize("n,k", [(32768, 18), (1000, 1), (4096, 48), (777, 80), (300000, 46)])
+def test_fused_rms_update_matches_the_reference_update(built, n, k):
+    """agx_col_sums + agx_rms_merge against oracle/ppo.py rms_update (lib/core/running_mean_std.py:45-60) on float64 inputs, twice in
+    a row so the merge with non-trivial running statistics is covered; deterministic."""
+    import ctypes as C
+    lib = _capi.load()
+    torch.manual_seed(n + k)
+    ws = torch.zeros(int(lib.agx_col_sums_workspace_doubles()), device="cuda", dtype=torch.float64)
+    sums = torch.zeros(2 * k, device="cuda", dtype=torch.float64)
+    mean, var, count = (torch.zeros(k, device="cuda", dtype=torch.float64), torch.ones(k, device="cuda", dtype=torch.float64),
+                        torch.ones((), device="cuda", dtype=torch.float64))
+    m, v, c = torch.zeros(k, dtype=torch.float64), torch.ones(k, dtype=torch.float64), torch.ones((), dtype=torch.float64)
+    wide = torch.randn(n, k + 5, device="cuda") * 3.0 + 1.5
+    for it in range(2):
+        x = (wide[:, :k] * (1.0 + it)).contiguous() if it else wide[:, :k]  # first pass: a strided view (row stride k + 5)
+        _capi.check(lib.agx_col_sums(x.data_ptr(), n, k, x.stride(0), sums.data_ptr(), ws.data_ptr(), None))
+        first = sums.clone()
+        _capi.check(lib.agx_col_sums(x.data_ptr(), n, k, x.stride(0), sums.data_ptr(), ws.data_ptr(), None))
+        assert torch.equal(first, sums)
+        _capi.check(lib.agx_rms_merge(sums.data_ptr(), k, float(n), mean.data_ptr(), var.data_ptr(), count.data_ptr(), None))
+        m, v, c = O.rms_update(m, v, c, x.double().cpu())
+        torch.cuda.synchronize()
+        assert float(count) == float(c)
+        assert float((mean.cpu() - m).abs().max()) < 1e-10 and float((var.cpu() - v).abs().max()) < 1e-9
