@@ -501,7 +501,7 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
             if (xn_out && ok) {
                 if (keep_t) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) xn_out[(int64_t)(c0 + i) * B + row] = (c0 + i == in_dim) ? 1.0f : v[i];
+                    for (int i = 0; i < 4; ++i) xn_out[((row >> 7) * IN_PAD + c0 + i) * kM + (row & (kM - 1))] = (c0 + i == in_dim) ? 1.0f : v[i];
                 } else {
                     *reinterpret_cast<float4*>(xn_out + row * IN_PAD + c0) = make_float4(v[0], v[1], v[2], v[3]);
                 }
@@ -512,22 +512,27 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
         if (tid == 0) { gemm(s32(Pbuf), s32(w1), kH1, IN_PAD, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
         const bool kr = ok && !keep_t, kc = ok && keep_t;  // row-major / feature-major keeps
-        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && kr) ? h1_out + row * kH1 : nullptr, (h1_out && kc) ? h1_out + row : nullptr, B);  // A1 → Qbuf
+        // feature-major keeps are blocked by 128-row tile: element (row, c) of a W-wide tensor at ((row / 128) * W + c) * 128 + row % 128,
+        // i.e. one tile's planes are one contiguous W x 512-byte region (DRAM-page friendly for this kernel's stores and the weight-gradient kernel's loads)
+        const int64_t tile_row = row >> 7, in_tile = row & (kM - 1);
+        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && kr) ? h1_out + row * kH1 : nullptr,
+                             (h1_out && kc) ? h1_out + tile_row * kH1 * kM + in_tile : nullptr, kM);  // A1 → Qbuf
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Qbuf), s32(w2), kH2, kH1, tmem + 64); commit(bar); }
         wait(bar, phase); phase ^= 1;
         // layer 2's 128 columns leave in two halves so that A2 never needs more than the two 32 KB buffers: the first half goes to
         // Pbuf and layer 3 starts on it (K-steps 0..7) while the epilogue of the second half fills Qbuf (A1 is dead by now)
-        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && kr) ? h2_out + row * kH2 : nullptr, (h2_out && kc) ? h2_out + row : nullptr, B);
+        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && kr) ? h2_out + row * kH2 : nullptr,
+                             (h2_out && kc) ? h2_out + tile_row * kH2 * kM + in_tile : nullptr, kM);
         publish_and_sync(gbar, kM);
         if (tid == 0) gemm(s32(Pbuf), s32(w3), kH3, kH1, tmem + 192);
         hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, (h2_out && kr) ? h2_out + row * kH2 + kH1 : nullptr,
-                             (h2_out && kc) ? h2_out + (int64_t)kH1 * B + row : nullptr, B);
+                             (h2_out && kc) ? h2_out + (tile_row * kH2 + kH1) * kM + in_tile : nullptr, kM);
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Qbuf), s32(w3) + 8 * 2 * (kH3 / 8) * 128, kH3, kH1, tmem + 192, true); commit(bar); }
         wait(bar, phase); phase ^= 1;
         hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, (h3_out && kr) ? h3_out + row * kH3 : nullptr,
-                             (h3_out && kc) ? h3_out + row : nullptr, B);  // A3 → Pbuf
+                             (h3_out && kc) ? h3_out + tile_row * kH3 * kM + in_tile : nullptr, kM);  // A3 → Pbuf
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Pbuf), s32(wh), kOutPad, kH3, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;

@@ -2,7 +2,9 @@
 // 64-128-64 network (reference lib/network/mlp.py:4-39 + the mu / value heads, a2c_continuous_logstd_model.py:159-168; the
 // gradients torch autograd computes inside calc_gradients, lib/agent/a2c_continuous.py:299-369).
 //
-// Every intermediate lives in HBM FEATURE-MAJOR — planes [width][B], written by agx_mlp_forward_train and by the kernel below —
+// Every intermediate lives in HBM FEATURE-MAJOR, blocked by 128-row tile — [B/128][width][128], written by agx_mlp_forward_train and by
+// the kernel below (a tile's planes are one contiguous region: with plain [width][B] planes every 16-row stage of the weight-gradient
+// kernel touched 544 different DRAM pages for 64 bytes each and it ran at 2.1 TB/s) —
 // because a tf32 tcgen05 operand has to be K-major (agx_tc.cuh) and the weight gradient contracts over the BATCH axis:
 //   dW_l[out, in] = sum_b dZ_l[b, out] * a_{l-1}[b, in]   →   A = dZ_l^T (M = out, K = batch rows), B = a_{l-1}^T (N = in, K = batch rows),
 // i.e. both operands are rows of those planes, 128 contiguous bytes per feature and 32-row stage.
@@ -105,6 +107,13 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
     const int64_t n_tiles = B / kM;  // B % 128 == 0 (checked on the host)
     for (int64_t tile = (int64_t)blockIdx.x * 2 + group; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
         const int64_t row = tile * kM + tid;
+        // planes are blocked by 128-row tile (agx_mlp.cu): element (row, c) of a W-wide tensor at (tile * W + c) * 128 + row % 128
+        const float* h3p = h3t + tile * kH3 * kM + tid;
+        const float* h2p = h2t + tile * kH2 * kM + tid;
+        const float* h1p = h1t + tile * kH1 * kM + tid;
+        float* dz3p = dz3t + tile * kH3 * kM + tid;
+        float* dz2p = dz2t + tile * kH2 * kM + tid;
+        float* dz1p = dz1t + tile * kH1 * kM + tid;
         {   // dout row = [d loss / d mu (A) | d loss / d value | 0 ...] → its plane and the first A operand (K = 16)
             float d[kOutPad];
 #pragma unroll
@@ -113,22 +122,22 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
 #pragma unroll
             for (int c = 0; c < 6; ++c) d[c] = c < A ? grad_mu[row * A + c] : (c == A ? gv : 0.0f);
 #pragma unroll
-            for (int c = 0; c < kOutPad; ++c) doutt[(int64_t)c * B + row] = d[c];
+            for (int c = 0; c < kOutPad; ++c) doutt[(tile * kOutPad + c) * kM + tid] = d[c];
 #pragma unroll
             for (int c = 0; c < kOutPad; c += 4) *reinterpret_cast<float4*>(Dbuf + canon(tid, c, kM)) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
         }
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Dbuf), s32(whT), kH3, kOutPad, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH3>(tmem_row, 0, h3t + row, dz3t + row, B, Gbuf, tid);
+        grad_epilogue<kH3>(tmem_row, 0, h3p, dz3p, kM, Gbuf, tid);
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Gbuf), s32(w3T), kH2, kH3, tmem + 64); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH2>(tmem_row, 64, h2t + row, dz2t + row, B, Gbuf, tid);  // dZ3 is dead: the MMA that read it has completed
+        grad_epilogue<kH2>(tmem_row, 64, h2p, dz2p, kM, Gbuf, tid);  // dZ3 is dead: the MMA that read it has completed
         publish_and_sync(gbar, kM);
         if (tid == 0) { gemm(s32(Gbuf), s32(w2T), kH1, kH2, tmem + 192); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH1>(tmem_row, 192, h1t + row, dz1t + row, B, nullptr, tid);
+        grad_epilogue<kH1>(tmem_row, 192, h1p, dz1p, kM, nullptr, tid);
         // the next tile's first MMA writes TMEM columns [0, 64): every thread of the group has finished reading them long ago
         // (two barriers back); its Dbuf / Gbuf stores are ordered behind this tile's last MMA by the wait above
     }
@@ -163,9 +172,10 @@ __device__ __forceinline__ void cp16(float* dst, const float* src) {
 // 16 features x 2 K-chunks: 32-byte global sectors fully used, shared-memory stores at most 2-way conflicted.
 template <int R, int RA>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ plane, int64_t B, int64_t r0) {
+    const float* src = plane + (r0 >> 7) * (R * kM) + (r0 & (kM - 1));  // the 128-row tile's contiguous [R][128] block (R = width of the tensor)
     for (int j = threadIdx.x; j < R * kKc; j += kThreads) {
         const int kc = ((j >> 5) & (kKc / 2 - 1)) * 2 + (j & 1), m = (j / (16 * kKc)) * 16 + ((j >> 1) & 15);
-        cp16(dst + (kc * RA + m) * 4, plane + (int64_t)m * B + r0 + kc * 4);
+        cp16(dst + (kc * RA + m) * 4, src + m * kM + kc * 4);
     }
 }
 

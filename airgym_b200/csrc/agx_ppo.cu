@@ -249,12 +249,18 @@ agx_col_sums_kernel(const float* __restrict__ x, int64_t n, int k, int64_t ld, i
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
     if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (s_last) {
+    if (s_last) {  // partials of all CTAs: row group rg adds CTAs rg, rg + rgs, ... (independent loads), then the groups in order → deterministic
         __threadfence();
-        if (threadIdx.x < k) {
-            double ta = 0.0, tb = 0.0;
-            for (unsigned int g = 0; g < gridDim.x; ++g) { ta += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + threadIdx.x); tb += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + kSumsMaxK + threadIdx.x); }
-            sums[threadIdx.x] = ta; sums[k + threadIdx.x] = tb;
+        double ta = 0.0, tb = 0.0;
+        if (c < k)
+            for (unsigned int g = rg; g < gridDim.x; g += rgs) { ta += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + c); tb += __ldcg(ws + 8 + (int64_t)g * 2 * kSumsMaxK + kSumsMaxK + c); }
+        __syncthreads();
+        s_a[threadIdx.x] = ta; s_b[threadIdx.x] = tb;
+        __syncthreads();
+        if (threadIdx.x < cpr && threadIdx.x < k) {
+            double fa = 0.0, fb = 0.0;
+            for (int g = 0; g < rgs; ++g) { fa += s_a[g * cpr + threadIdx.x]; fb += s_b[g * cpr + threadIdx.x]; }
+            sums[threadIdx.x] = fa; sums[k + threadIdx.x] = fb;
         }
         if (threadIdx.x == 0) *ticket = 0;
     }
@@ -314,8 +320,8 @@ int64_t agx_col_sums_workspace_doubles(void) { return 8 + (int64_t)kSumsGridMax 
 int agx_col_sums(const float* x, int64_t n, int k, int64_t ld, double* sums, double* workspace, void* stream) {
     if (!x || !sums || !workspace || n <= 0 || k <= 0 || k > kSumsMaxK || ld < k) return fail_ppo(AGX_ERR_ARG, "agx_col_sums: bad argument (k <= 128)");
     const int cpr = k <= 32 ? 32 : (k <= 64 ? 64 : 128), rgs = kSumsBlock / cpr;
-    int64_t grid = (n + rgs * 16 - 1) / (rgs * 16);
-    if (grid > kSumsGridMax) grid = kSumsGridMax;
+    int64_t grid = (n + rgs * 32 - 1) / (rgs * 32);
+    if (grid > 148) grid = 148;
     agx_col_sums_kernel<<<(unsigned)grid, kSumsBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, k, ld, cpr, sums, workspace);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : fail_ppo(AGX_ERR_CUDA, "agx_col_sums: launch failed");
 }

@@ -365,7 +365,7 @@ int agx_mlp_backward(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, con
                      float* dout, float* workspace, void* stream);
 
 /* Training path on the 5th-generation tensor cores (tcgen05 + TMEM) for the shipped 64-128-64 network: forward, activation-gradient
- * chain and weight / bias gradients all run on tcgen05.mma.  Intermediates are FEATURE-MAJOR planes ([width][b], b % 128 == 0), which
+ * chain and weight / bias gradients all run on tcgen05.mma.  Intermediates are FEATURE-MAJOR planes ([b/128][width][128] (feature-major, blocked by 128-row tile), b % 128 == 0), which
  * is what makes both operands of the weight gradient (it contracts over the batch axis) K-major:
  *   xt [in_pad, b] (plane in_dim = 1: the bias-gradient column; in_pad in {32,48,64,96} must exceed in_dim), h1t [64, b], h2t [128, b],
  *   h3t [64, b] written by agx_mlp_forward_train;  dz1t [64, b], dz2t [128, b], dz3t [64, b], doutt [16, b] scratch of the backward.

@@ -274,6 +274,12 @@ def test_fused_mlp_forward_backward_vs_autograd(built, task, B):
         assert torch.equal(p.grad, first[n]), n
 
 
+def _rows(planes):
+    """feature-major keep tensor, blocked by 128-row tile ([B/128][W][128], stored as a [W, B] allocation) → row-major [B, W]"""
+    W, B = planes.shape
+    return planes.reshape(B // 128, W, 128).permute(0, 2, 1).reshape(B, W)
+
+
 @pytest.mark.parametrize("OBS,B", [(18, 2048), (18, 65536), (48, 1024), (46, 256), (18, 128), (80, 512)])
 def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     """agx_mlp_forward_train / agx_mlp_backward_train — forward, activation-gradient chain, weight AND bias gradients all on
@@ -304,13 +310,14 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     assert_close(mu.cpu(), mu_ref.detach().cpu(), "mu", rtol=5e-3, atol=2e-3)
     assert_close(value.cpu(), v_ref.detach().squeeze(-1).cpu(), "value", rtol=5e-3, atol=2e-3)
     xn = model.norm_obs(obs)
-    assert_close(keep[0][:OBS].t().cpu(), xn.cpu(), "normalised input planes", rtol=1e-6, atol=1e-6)
-    assert bool((keep[0][OBS] == 1.0).all()) and float(keep[0][OBS + 1:].abs().max() if P.in_pad > OBS + 1 else 0.0) == 0.0
+    x_rows = _rows(keep[0])
+    assert_close(x_rows[:, :OBS].cpu(), xn.cpu(), "normalised input planes", rtol=1e-6, atol=1e-6)
+    assert bool((x_rows[:, OBS] == 1.0).all()) and float(x_rows[:, OBS + 1:].abs().max() if P.in_pad > OBS + 1 else 0.0) == 0.0
     with torch.no_grad():
         h1_ref = torch.nn.functional.elu(model.actor_mlp.layers[0](xn))
         h2_ref = torch.nn.functional.elu(model.actor_mlp.layers[1](h1_ref))
-    assert_close(keep[1].t().cpu(), h1_ref.cpu(), "h1 planes", rtol=5e-3, atol=3e-3)
-    assert_close(keep[2].t().cpu(), h2_ref.cpu(), "h2 planes", rtol=5e-3, atol=5e-3)
+    assert_close(_rows(keep[1]).cpu(), h1_ref.cpu(), "h1 planes", rtol=5e-3, atol=3e-3)
+    assert_close(_rows(keep[2]).cpu(), h2_ref.cpu(), "h2 planes", rtol=5e-3, atol=5e-3)
     g_mu, g_v = torch.randn(B, A, device="cuda") / B, torch.randn(B, device="cuda") / B
     for p in model.parameters():
         p.grad.zero_()
@@ -321,8 +328,8 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     ws = model.fused_workspace("cuda")
     model.fused_backward_train(g_mu, g_v, keep, dz, dout, ws)
     torch.cuda.synchronize()
-    assert_close(dout[:A].t().cpu(), g_mu.cpu(), "dout planes (mu)", rtol=0, atol=0)
-    assert_close(dout[A].cpu(), g_v.cpu(), "dout plane (value)", rtol=0, atol=0)
+    assert_close(_rows(dout)[:, :A].cpu(), g_mu.cpu(), "dout planes (mu)", rtol=0, atol=0)
+    assert_close(_rows(dout)[:, A].cpu(), g_v.cpu(), "dout plane (value)", rtol=0, atol=0)
     for n, p in model.named_parameters():
         if n == "logstd":
             continue
@@ -333,8 +340,10 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
     torch.cuda.synchronize()
     for n, p in model.named_parameters():
         assert torch.equal(p.grad, first[n]), n
+    if OBS == 80:
+        return  # the warp-level mma.sync kernels do not cover this width (shared memory): nothing to cross-check against
     # and against the mma.sync backward on the same kept activations (row-major copies): same TF32 products, different summation order
-    keep_r = tuple(k.t().contiguous() for k in keep)
+    keep_r = tuple(_rows(k).contiguous() for k in keep)
     keep_r = (torch.nn.functional.pad(xn, (0, (OBS + 15) // 16 * 16 - OBS)),) + keep_r[1:]
     dims = model.fused_keep_dims()
     dz_r, dout_r = tuple(torch.zeros(B, d, device="cuda") for d in dims[1:]), torch.zeros(B, 16, device="cuda")
@@ -346,8 +355,8 @@ def test_tcgen05_train_path_vs_autograd(built, OBS, B):
             continue
         scale = float(first[n].abs().max()) + 1e-12
         assert_close((p.grad / scale).cpu(), (first[n] / scale).cpu(), f"tcgen05 vs mma.sync grad {n}", rtol=5e-3, atol=3e-3)
-    assert_close(dz_r[2].t().cpu(), dz[2].cpu(), "dz3", rtol=5e-3, atol=1e-7 + 5e-3 * float(dz_r[2].abs().max()))
-    assert_close(dz_r[0].t().cpu(), dz[0].cpu(), "dz1", rtol=5e-3, atol=1e-7 + 1e-2 * float(dz_r[0].abs().max()))
+    assert_close(dz_r[2].cpu(), _rows(dz[2]).cpu(), "dz3", rtol=5e-3, atol=1e-7 + 5e-3 * float(dz_r[2].abs().max()))
+    assert_close(dz_r[0].cpu(), _rows(dz[0]).cpu(), "dz1", rtol=5e-3, atol=1e-7 + 1e-2 * float(dz_r[0].abs().max()))
 
 
 def _rollout_agent(fused_rollout, N=4096, H=8, seed=4):
