@@ -464,3 +464,63 @@ def test_fused_rms_update_matches_the_reference_update(built, n, k):
         torch.cuda.synchronize()
         assert float(count) == float(c)
         assert float((mean.cpu() - m).abs().max()) < 1e-10 and float((var.cpu() - v).abs().max()) < 1e-9
+
+
+def test_reference_golden_minibatch_through_the_fused_trainer_path(built):
+    """The same recorded reference minibatch through the kernels the TRAINER actually runs by default — agx_mlp_forward_train (tcgen05,
+    TF32 operands), agx_ppo_loss, agx_mlp_backward_train (tcgen05), agx_adam_step — with the TF32 bound stated: network outputs
+    5e-3 rel + 2e-3 abs, loss statistics 2e-2 rel, gradients 2e-2 of each tensor's scale, gradient norm 1e-2; after the Adam step
+    (first step: update = lr * g / |g| per element) parameters within 1e-5 for all but near-zero-gradient entries, which may move
+    by at most 2 lr."""
+    from airgym_b200.lib.config import default_ppo_config
+    from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "ppo_hovering.npz")))
+    lib = _capi.load()
+    N, Hn, A, OBS = int(g["N"]), int(g["H"]), int(g["A"]), int(g["OBS"])
+    model = ModelA2CContinuousLogStd(default_ppo_config("hovering")["params"], {"actions_num": A, "input_shape": (OBS,)}).cuda()
+    model.load_state_dict({k[len("step0/sd_before/"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("step0/sd_before/")})
+    flat, grads = model.flatten_parameters(extra_grad_slots=8)
+    fl, t = O.swap_and_flatten01, (lambda k: torch.from_numpy(g[k]))
+    mb = N * Hn // 2
+    sl = slice(0, mb)
+    assert model.train_supported(mb)
+    obs = fl(t("obs"))[sl].cuda().contiguous()
+    model.running_mean_std.train()
+    model.running_mean_std(obs)
+    model.eval()
+    keep, dz, dout = model.train_buffers(mb, "cuda")
+    mu, value = torch.zeros(mb, A, device="cuda"), torch.zeros(mb, device="cuda")
+    model.fused_heads_train(obs, mu, value, keep)
+    assert_close(mu.cpu(), g["step0/mu"], "mu (TF32)", rtol=5e-3, atol=2e-3)
+    assert_close(value.cpu(), g["step0/value"].reshape(-1), "value (TF32)", rtol=5e-3, atol=2e-3)
+    d = lambda x: x.cuda().contiguous()
+    om, os_ = d(fl(t("mus"))[sl]), d(fl(t("sigmas"))[sl])
+    g_mu, g_val, g_ls = torch.zeros(mb, A, device="cuda"), torch.zeros(mb, device="cuda"), torch.zeros(A, device="cuda")
+    stats = grads[model.num_flat:]
+    ws = torch.zeros(int(lib.agx_ppo_workspace_floats()), device="cuda")
+    Hh = _hyper()
+    ins = [mu, model.logstd, value, d(fl(t("actions"))[sl]), d(fl(t("neglogpacs"))[sl]), d(t("advantages")[sl]), d(t("n_ret")[sl].reshape(-1))]
+    _capi.check(lib.agx_ppo_loss(C.byref(Hh), mb, A, *[x.data_ptr() for x in ins], om.data_ptr(), os_.data_ptr(), g_mu.data_ptr(),
+                                 g_val.data_ptr(), g_ls.data_ptr(), stats.data_ptr(), ws.data_ptr(), None))
+    for j, k in enumerate(("a_loss", "c_loss", "entropy", "b_loss", "kl")):
+        assert_close(stats[j].cpu(), g[f"step0/{k}"], k + " (TF32)", rtol=2e-2, atol=1e-5)
+    model.fused_backward_train(g_mu, g_val, keep, dz, dout, model.fused_workspace("cuda"))
+    model.logstd.grad.copy_(g_ls)
+    for n, p in model.named_parameters():
+        ref = torch.from_numpy(g[f"step0/grads/{n}"])
+        scale = float(ref.abs().max()) + 1e-12
+        assert_close((p.grad.cpu() / scale), ref / scale, f"grad {n} (TF32)", rtol=2e-2, atol=1e-2)
+    m, v = torch.zeros(model.num_flat, device="cuda"), torch.zeros(model.num_flat, device="cuda")
+    lr_in = float(g["step0/lr_in"])
+    lr_dev, step, norm = torch.tensor([lr_in], device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, device="cuda")
+    _capi.check(lib.agx_adam_step(C.byref(Hh), model.num_flat, flat.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), lr_dev.data_ptr(),
+                                  step.data_ptr(), stats[4:5].data_ptr(), 1.0, norm.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert_close(norm.cpu()[0], g["step0/total_norm"], "grad norm (TF32)", rtol=1e-2, atol=0)
+    worst, loose, total = 0.0, 0, 0
+    for n, p in model.named_parameters():
+        diff = (p.detach().cpu() - torch.from_numpy(g[f"step0/sd_after/{n}"])).abs()
+        worst, loose, total = max(worst, float(diff.max())), loose + int((diff > 1e-5).sum()), total + diff.numel()
+    assert worst <= 2.1 * lr_in and loose <= 0.01 * total, (worst, loose, total)
+    assert float(lr_dev) == pytest.approx(float(g["step0/lr_out"]), rel=1e-6)
