@@ -157,6 +157,7 @@ def bind(lib):
     lib.agx_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.agx_params_default.argtypes = [C.POINTER(AgxParams), C.c_int, C.c_int]
     lib.agx_step.argtypes = [C.POINTER(AgxParams), C.c_int64, C.POINTER(AgxStepIO), C.c_void_p]
+    lib.agx_observe.argtypes = [C.POINTER(AgxParams), C.c_int64, C.POINTER(AgxStepIO), C.c_int, C.c_void_p]
     lib.agx_reset_idx.argtypes = [
         C.POINTER(AgxParams), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
@@ -209,7 +210,7 @@ def bind(lib):
 
 EXPORTS = (
     "agx_version", "agx_error_string", "agx_sizeof_params", "agx_sizeof_step_io", "agx_sizeof_render_io", "agx_render_depth", "agx_set_option",
-    "agx_params_default", "agx_step", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
+    "agx_params_default", "agx_step", "agx_observe", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
     "agx_sizeof_conv_params", "agx_conv2d_nhwc", "agx_sizeof_conv_first_params", "agx_conv2d_first", "agx_resize_bilinear", "agx_pool_fc",

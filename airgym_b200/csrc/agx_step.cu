@@ -50,6 +50,11 @@ extern template int agx_dispatch_task<AGX_TASK_TRACKING>(const AgxParams&, int64
 extern template int agx_dispatch_task<AGX_TASK_BALLOON>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
 extern template int agx_dispatch_task<AGX_TASK_AVOID>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
 extern template int agx_dispatch_task<AGX_TASK_PLANNING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+extern template int agx_observe_task<AGX_TASK_HOVERING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
+extern template int agx_observe_task<AGX_TASK_TRACKING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
+extern template int agx_observe_task<AGX_TASK_BALLOON>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
+extern template int agx_observe_task<AGX_TASK_AVOID>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
+extern template int agx_observe_task<AGX_TASK_PLANNING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
 }  // namespace agxk
 
 using namespace agxk;
@@ -225,6 +230,28 @@ int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream) {
             if (!io->assets || misaligned(io->assets) || !io->trees) return fail(AGX_ERR_ARG, "agx_step: planning needs the assets and trees buffers%s");
             return agx_dispatch_task<AGX_TASK_PLANNING>(*p, n, *io, st);
         default: return fail(AGX_ERR_UNSUPPORTED, "agx_step: unknown task%s");
+    }
+}
+
+int agx_observe(const AgxParams* p, int64_t n, const AgxStepIO* io, int what, void* stream) {
+    if (!p || !io || n < 0 || what < 1 || what > 3) return fail(AGX_ERR_ARG, "agx_observe: bad argument (what = 1 observations | 2 reward | 3 both)%s");
+    if (!io->state || !io->actions_out || !io->prev_action || !io->progress || !io->reset || !io->obs || !io->reward)
+        return fail(AGX_ERR_ARG, "agx_observe: a required buffer is null%s");
+    const void* ptrs[] = {io->state, io->actions_out, io->prev_action, io->progress, io->reset, io->obs, io->reward, io->cmd, io->reward_terms, io->rand_noise, io->aux};
+    for (const void* q : ptrs)
+        if (misaligned(q)) return fail(AGX_ERR_ALIGN, "agx_observe: buffer not 16-byte aligned%s");
+    const bool needs_aux = (p->task == AGX_TASK_BALLOON || p->task == AGX_TASK_AVOID || p->task == AGX_TASK_PLANNING);
+    if (needs_aux && !io->aux) return fail(AGX_ERR_ARG, "agx_observe: this task needs the aux buffer%s");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (p->task) {
+        case AGX_TASK_HOVERING: return agx_observe_task<AGX_TASK_HOVERING>(*p, n, *io, st, what);
+        case AGX_TASK_TRACKING: return agx_observe_task<AGX_TASK_TRACKING>(*p, n, *io, st, what);
+        case AGX_TASK_BALLOON: return agx_observe_task<AGX_TASK_BALLOON>(*p, n, *io, st, what);
+        case AGX_TASK_AVOID: return agx_observe_task<AGX_TASK_AVOID>(*p, n, *io, st, what);
+        case AGX_TASK_PLANNING:
+            if (!io->assets || !io->trees) return fail(AGX_ERR_ARG, "agx_observe: planning needs the assets and trees buffers%s");
+            return agx_observe_task<AGX_TASK_PLANNING>(*p, n, *io, st, what);
+        default: return fail(AGX_ERR_UNSUPPORTED, "agx_observe: unknown task%s");
     }
 }
 

@@ -3,6 +3,7 @@
 
 namespace agxk {
 template int agx_dispatch_task<AGX_TASK_HOVERING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+template int agx_observe_task<AGX_TASK_HOVERING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
 }  // namespace agxk
 
 #ifdef AGX_TIMELINE

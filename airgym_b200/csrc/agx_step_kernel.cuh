@@ -275,6 +275,9 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     const int tile_n = (int)(tile_end - tile0);
     const bool bulk = (kflags & 1) && tile_n > 0 && (tile_n & 3) == 0;  // CTA-uniform: spans are 16-byte multiples
     const int pdl_mode = (kflags >> 1) & 3;
+    // TASK phase only — "observe" calls (agx_observe): recompute observations and / or reward from the CURRENT buffers without
+    // stepping: no end-of-step reset, no progress / time-out / state / task-state writes, the step counter is not advanced
+    const bool observe = kTask && !kPhys && (kflags & 16), obs_on = !observe || (kflags & 32), rew_on = !observe || (kflags & 64);
     const int64_t env = tile0 + tid;
     const bool active = tid < tile_n;
 
@@ -310,6 +313,10 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
 #pragma unroll
             for (int k = 0; k < AGX_CTRL_STATE_MAX; ++k) e.cs[k] = (kPhys && k < K) ? io.ctrl_state[(int64_t)k * n + env] : 0.0f;
             e.progress = io.progress[env];
+            if (!kPhys && io.cmd) {  // TASK phase: the effort term reads the rotor commands the physics phase (or the last step) exported
+                const float4 c4 = reinterpret_cast<const float4*>(io.cmd)[env];
+                e.cmd[0] = c4.x; e.cmd[1] = c4.y; e.cmd[2] = c4.z; e.cmd[3] = c4.w;
+            }
             e.pending = kPhys ? (io.reset[env] != 0) : 0;
             e.reset = 0;
             if (kHasAux) {
@@ -328,9 +335,11 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
             if (tid == 0) {
                 unsigned long long s0;
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(s0) : "l"(io.step_dev) : "memory");
-                unsigned int zero;
-                asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)s0));
-                ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
+                if (!observe) {
+                    unsigned int zero;
+                    asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((unsigned int)s0));
+                    ticket = atomicAdd(reinterpret_cast<unsigned long long*>(io.step_dev + 1), 1ULL + zero);
+                }
                 s_step = s0;
             }
             __syncthreads();
@@ -338,7 +347,7 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         }
     };
     auto bump_step = [&]() {
-        if (io.step_dev && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
+        if (io.step_dev && !observe && tid == 0 && ticket == (unsigned long long)gridDim.x - 1ULL) {
             io.step_dev[1] = 0;
             asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(io.step_dev), "l"((unsigned long long)(step + 1)) : "memory");
             __threadfence();
@@ -436,9 +445,25 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
     }
     __syncwarp();
     // ---- end-of-step reset_idx (hovering.py:300-302): fresh rows overwrite the tile, reset_buf stays 1, progress 0
-    if (kTask) warp_reset<TASK>(io, active && e.reset, 1, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
+    if (kTask && !observe) warp_reset<TASK>(io, active && e.reset, 1, step, warp_env0, s_state + warp * 32 * 13, s_ws[warp], e.aux);
 
-    if (active) {
+    if (active && observe) {  // compute_observations() / compute_reward() as stand-alone calls (hovering.py:337-459)
+        if (rew_on) {  // rew_buf, reset_buf overwritten, item_reward_info, pre_actions = actions.clone()
+            if (A == 4) reinterpret_cast<float4*>(io.prev_action)[env] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
+            else {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) io.prev_action[env * 5 + i] = e.pa[i];
+            }
+            io.reset[env] = (int64_t)e.reset;
+            if (io.reset_u8) io.reset_u8[env] = (uint8_t)e.reset;
+            io.reward[env] = e.rew;
+            if (io.reward_terms) {
+                constexpr int NT = (TASK == AGX_TASK_PLANNING) ? 11 : 9;
+#pragma unroll
+                for (int k = 0; k < NT; ++k) io.reward_terms[(int64_t)k * n + env] = e.terms[k];
+            }
+        }
+    } else if (active) {
         if (kTask) {
             if (e.reset) reset_apply(P, e);
             env_finish(P, e);
@@ -486,16 +511,17 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
         fence_async_smem();  // generic-proxy smem writes → visible to the async (TMA) proxy
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(io.state + tile0 * 13, s_state, tile_n * 13 * 4);
-            if (OL::kDense && kTask) bulk_s2g(io.obs + tile0 * NOBS, s_obs, tile_n * NOBS * 4);
+            if (!observe) bulk_s2g(io.state + tile0 * 13, s_state, tile_n * 13 * 4);
+            if (OL::kDense && kTask && obs_on) bulk_s2g(io.obs + tile0 * NOBS, s_obs, tile_n * NOBS * 4);
             bulk_commit();
         }
     } else {
         __syncthreads();
         float* dst = io.state + tile0 * 13;
-        for (int i = tid; i < tile_n * 13; i += BLOCK) dst[i] = s_state[i];
+        if (!observe)
+            for (int i = tid; i < tile_n * 13; i += BLOCK) dst[i] = s_state[i];
     }
-    if (kTask && !(bulk && OL::kDense)) {
+    if (kTask && obs_on && !(bulk && OL::kDense)) {
         float* dst = io.obs + tile0 * NOBS;
         if (OL::kDense) {
             for (int i = tid; i < tile_n * NOBS; i += BLOCK) dst[i] = s_obs[i];
@@ -582,7 +608,7 @@ int fail(int code, const char* fmt, const char* detail = "");
 
 template <typename Kernel>
 cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, const AgxParams& P,
-                      const AgxStepIO& io, int64_t n) {
+                      const AgxStepIO& io, int64_t n, int extra_flags = 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
@@ -602,7 +628,9 @@ cudaError_t launch_ex(Kernel k, unsigned grid, unsigned block, cudaStream_t st, 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1) | (balanced ? 8 : 0);
+    if (extra_flags) pdl = 0;  // observe calls are plain launches
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    const int kflags = (g_use_bulk ? 1 : 0) | ((pdl & 3) << 1) | (balanced ? 8 : 0) | extra_flags;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, P, io, n, kflags);
@@ -626,6 +654,33 @@ int launch_step(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t
     if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_step launch: %s", cudaGetErrorString(err));
     return AGX_OK;
 }
+
+// agx_observe: the TASK phase of the step kernel in "observe" mode (what: 1 observations, 2 reward side, 3 both)
+template <int TASK, int MODE>
+int launch_observe(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st, int what) {
+    if (n == 0) return AGX_OK;
+    cudaError_t err = launch_ex(agx_step_kernel<TASK, MODE, 128, AGX_PHASE_TASK>, (unsigned)((n + 127) / 128), 128, st, P, io, n,
+                                16 | ((what & 1) ? 32 : 0) | ((what & 2) ? 64 : 0));
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(AGX_ERR_CUDA, "agx_observe launch: %s", cudaGetErrorString(err));
+    return AGX_OK;
+}
+template <int TASK>
+int dispatch_observe(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st, int what) {
+    constexpr bool kImageTask = (TASK == AGX_TASK_AVOID || TASK == AGX_TASK_PLANNING);
+    switch (P.ctl_mode) {
+        case AGX_CTL_POS: return launch_observe<TASK, AGX_CTL_POS>(P, n, io, st, what);
+        case AGX_CTL_VEL: return launch_observe<TASK, AGX_CTL_VEL>(P, n, io, st, what);
+        case AGX_CTL_ATTI:
+            if constexpr (kImageTask) return fail(AGX_ERR_UNSUPPORTED, "agx_observe: avoid/planning have no atti mode%s");
+            else return launch_observe<TASK, AGX_CTL_ATTI>(P, n, io, st, what);
+        case AGX_CTL_RATE: return launch_observe<TASK, AGX_CTL_RATE>(P, n, io, st, what);
+        case AGX_CTL_PROP: return launch_observe<TASK, AGX_CTL_PROP>(P, n, io, st, what);
+        default: return fail(AGX_ERR_ARG, "agx_observe: unknown ctl_mode%s");
+    }
+}
+template <int TASK>
+int agx_observe_task(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st, int what) { return dispatch_observe<TASK>(P, n, io, st, what); }
 
 template <int TASK>
 int dispatch_mode(const AgxParams& P, int64_t n, const AgxStepIO& io, cudaStream_t st) {

@@ -3,4 +3,5 @@
 
 namespace agxk {
 template int agx_dispatch_task<AGX_TASK_PLANNING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t);
+template int agx_observe_task<AGX_TASK_PLANNING>(const AgxParams&, int64_t, const AgxStepIO&, cudaStream_t, int);
 }  // namespace agxk

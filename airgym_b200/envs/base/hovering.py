@@ -151,10 +151,23 @@ class Hovering(BaseTask):
     def post_physics_step(self):
         return None
 
-    def compute_observations(self):
-        """obs_buf already holds compute_observations() of the current step (hovering.py:337-358)."""
+    def _observe(self, what, rand_noise=None):
+        io = self._io
+        if (what & 2) and not io.cmd:
+            raise RuntimeError("compute_reward() needs cmd_thrusts (cfg.backend.export_cmd_thrusts = True): the effort term reads them")
+        io.rand_noise = rand_noise.data_ptr() if rand_noise is not None else None
+        io.seed, io.env_offset = self.rng_seed, self.env_offset
+        stream = torch.cuda.current_stream(self._dev).cuda_stream
+        _capi.check(self._lib.agx_observe(C.byref(self.params), self.num_envs, C.byref(io), what, C.c_void_p(stream)), "agx_observe")
+
+    def compute_observations(self, rand_noise=None):
+        """hovering.py:337-358 as a stand-alone call: obs_buf recomputed from the current root states (+ fresh observation noise,
+        or the explicit `rand_noise` [N,18]) by the TASK phase of the step kernel in observe mode (agx_observe)."""
+        self._observe(1, rand_noise)
         return self.obs_buf
 
     def compute_reward(self):
-        """rew_buf/reset_buf/item_reward_info already hold compute_reward() of the current step (:360-459)."""
+        """hovering.py:360-459 as a stand-alone call: rew_buf, reset_buf (overwritten), item_reward_info and
+        pre_actions = actions.clone() recomputed from the current root states, `self.actions` and `cmd_thrusts`."""
+        self._observe(2)
         return self.rew_buf

@@ -214,6 +214,13 @@ int agx_params_default(AgxParams* p, int task, int ctl_mode);
  * for AGX_TASK_TRACKING additionally tracking.py:159-296. */
 int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream);
 
+/* compute_observations() / compute_reward() as stand-alone calls (hovering.py:337-358 / :360-459 and the task overrides): the TASK
+ * phase of the step kernel over the CURRENT buffers without stepping — no reset, no progress / time-out / state / task-state write,
+ * the Philox step counter is read but not advanced.  what = 1: obs (fresh observation noise, or io->rand_noise);
+ * what = 2: reward, reset (overwritten, as compute_reward does), reset_u8, reward_terms, prev_action <- actions_out
+ * (`self.pre_actions = self.actions.clone()`); 3: both.  Reads actions_out (the shaped actions of the last step) and cmd. */
+int agx_observe(const AgxParams* p, int64_t n, const AgxStepIO* io, int what, void* stream);
+
 int agx_render_depth(const AgxParams* p, int64_t n, const AgxRenderIO* io, void* stream);
 int agx_sizeof_render_io(void);
 

@@ -374,6 +374,45 @@ def test_oracle_parity_at_full_size_65536(task, mode):
     assert resets_seen >= N // 17  # the time-out wave (and its re-reset the step after, quirk Q1) went through both reset passes
 
 
+@pytest.mark.parametrize("task,mode", [("hovering", "rate"), ("hovering", "pos"), ("tracking", "vel"), ("balloon", "rate")])
+def test_compute_observations_and_compute_reward_as_standalone_calls(task, mode):
+    """The reference's method names do their work outside step() too (hovering.py:337-459): agx_observe = the TASK phase of the step
+    kernel in observe mode, against the oracle's compute_observations() / compute_reward() on identical buffers."""
+    N = 1000
+    torch.manual_seed(5)
+    spec = QuadSpec(task=task, ctl_mode=mode)
+    orc = make_oracle(spec, N, rng="torch")
+    env = make_env(task, mode, N)
+    K = spec.ctrl_state_dim
+    for t in range(3):  # a few real steps first, so actions / pre_actions / cmd_thrusts / progress are non-trivial
+        a = torch.rand(N, spec.num_actions) * 2 - 1
+        sync_from_oracle(env, orc, K)
+        orc.step(a.clone())
+        d = orc.last_draws
+        env.step(a.cuda(), rand_reset=d["reset"].cuda(), rand_noise=d["noise"].cuda())
+    sync_from_oracle(env, orc, K)
+    env.actions.copy_(orc.actions)
+    env.cmd_thrusts.copy_(orc.cmd_thrusts)
+    before = (env.root_states.clone(), env.progress_buf.clone(), env.time_out_buf.clone(), int(env._step_dev[0]))
+    orc.last_draws = {"reset": torch.zeros(N, 2, orc.RESET_DRAWS), "noise": torch.zeros(N, 18)}
+    orc.compute_observations()
+    obs = env.compute_observations(rand_noise=orc.last_draws["noise"].cuda())
+    assert_close(obs.cpu(), orc.obs_buf, f"{task}/{mode} compute_observations")
+    orc.compute_reward()
+    rew = env.compute_reward()
+    rr, ra = task_tols(task)
+    assert_close(rew.cpu(), orc.rew_buf, f"{task}/{mode} compute_reward", rtol=rr, atol=ra)
+    assert torch.equal(env.reset_buf.cpu(), orc.reset_buf) and torch.equal(env.reset_u8.cpu().long(), orc.reset_buf)
+    assert_close(env.pre_actions.cpu(), orc.pre_actions, "pre_actions = actions.clone()", rtol=0, atol=0)
+    assert_close(env._reward_terms.cpu()[:len(type(orc).REWARD_KEYS)], orc.reward_terms_matrix(), "item_reward_info", rtol=rr, atol=ra)
+    torch.cuda.synchronize()
+    assert torch.equal(env.root_states, before[0]) and torch.equal(env.progress_buf, before[1]) and torch.equal(env.time_out_buf, before[2])
+    assert int(env._step_dev[0]) == before[3] and int(env._step_dev[1]) == 0  # the Philox step counter is read, not advanced
+    # a second compute_reward sees pre_actions == actions (the continuity term changes), like the reference
+    orc.compute_reward()
+    assert_close(env.compute_reward().cpu(), orc.rew_buf, "second compute_reward", rtol=rr, atol=ra)
+
+
 def test_reset_idx_standalone_and_reset_api():
     N = 512
     env = make_env("tracking", "vel", N, seed=2)
