@@ -9,7 +9,7 @@ import torch
 
 from airgym_b200 import _capi
 from oracle import QuadSpec, make_oracle
-from tests.util import assert_close, golden_cases, load_golden, task_tols
+from tests.util import assert_close, golden_cases, load_golden, pokes_at, task_tols
 
 pytestmark = pytest.mark.gpu
 MODES = ["pos", "vel", "atti", "rate", "prop"]
@@ -123,6 +123,8 @@ def test_trajectory_vs_reference_golden(name):
     for t in range(T):
         a = torch.from_numpy(g["action_in"][t].copy()).cuda()
         tag = f"{name} t={t}"
+        for env_i, st in pokes_at(g, t):
+            env.root_states[env_i] = torch.from_numpy(st).cuda()
         if "rendered" in g:  # depth-camera tasks: dict observation; the image noise of a render step is explicit too
             img = None
             if g["rendered"][t]:

@@ -7,7 +7,7 @@ import torch
 from airgym_b200 import _capi
 from oracle import QuadSpec, make_oracle
 from tests.hostsim.driver import HostEnv, build
-from tests.util import assert_close, golden_cases, load_golden, task_tols
+from tests.util import assert_close, golden_cases, load_golden, pokes_at, task_tols
 
 MODES = ["pos", "vel", "atti", "rate", "prop"]
 
@@ -123,6 +123,8 @@ def test_trajectory_vs_reference_golden(built, name):
     for t in range(T):
         a = g["action_in"][t].copy()
         tag = f"{name} t={t}"
+        for env_i, st in pokes_at(g, t):
+            he.state[env_i] = st
         if "rendered" in g and g["rendered"][t]:  # depth-camera task on a render step: PHYSICS half, camera, TASK half
             he.step(a, g["draw_reset"][t].copy(), None, phase=_capi.PHASE_PHYSICS)
             he.render(g["img_add"][r_idx].copy(), g["img_mul"][r_idx].copy(), g["img_kern"][r_idx].copy())

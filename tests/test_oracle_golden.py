@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import QuadSpec, make_oracle
-from tests.util import assert_close, golden_cases, load_golden
+from tests.util import assert_close, golden_cases, load_golden, pokes_at
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -18,6 +18,8 @@ def test_oracle_matches_reference_trajectory(name):
     r_idx = 0
     for t in range(T):
         a = torch.from_numpy(g["action_in"][t].copy())
+        for env_i, st in pokes_at(g, t):
+            orc.root_states[env_i] = torch.from_numpy(st)
         if task in ("avoid", "planning"):  # image tasks: the image noise of a render step is part of the explicit draws
             img = None
             if g["rendered"][t]:
@@ -40,6 +42,21 @@ def test_oracle_matches_reference_trajectory(name):
         assert np.array_equal(orc.reset_buf.numpy(), g["reset"][t])
         assert np.array_equal(orc.progress_buf.numpy(), g["progress"][t])
         assert np.array_equal(orc.time_out_buf.numpy(), g["timeout"][t])
+
+
+def test_event_fixtures_contain_the_events():
+    """The reference-pinned camera-task data holds a goal-reached, a heading < 0.25 and collision terminations (planning.py:263-287,
+    avoid.py:271-284), not just free flight."""
+    from oracle.image_tasks import PlanningOracle
+
+    g, *_ = load_golden("planning_rate_events")
+    k = list(PlanningOracle.REWARD_KEYS)
+    terms = g["terms"]  # [T, K, N]
+    assert (terms[:, k.index("reach_goal_reward")] > 0).sum() >= 2
+    assert (terms[:, k.index("heading_reward")] < 0.25).sum() >= 2
+    assert (g["aux"][:, :, 6] > 0).sum() >= 1 and g["reset"].sum() >= 4 + 5
+    g, *_ = load_golden("avoid_rate_events")
+    assert (g["aux"][:, :, 6] > 0).sum() >= 3 and g["rendered"].sum() == 5
 
 
 def test_golden_covers_resets_and_timeouts():

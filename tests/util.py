@@ -46,3 +46,10 @@ def task_tols(task):
     """(rtol, atol) for reward-like outputs: Balloon's guidance term is 30 x (difference of two norms), i.e. it amplifies
     the last-ulp differences of positions ~30x / |value|; everything else uses the north_star bar."""
     return (1e-4, 3e-3) if task == "balloon" else (RTOL, ATOL)
+
+
+def pokes_at(g, t):
+    """[(env, state row [13])] recorded state edits to apply BEFORE step t (tests/golden/make_golden.py run_case pokes)."""
+    if "poke_t" not in g:
+        return []
+    return [(int(e), st) for pt, e, st in zip(g["poke_t"], g["poke_env"], g["poke_state"]) if int(pt) == t]
