@@ -17,10 +17,12 @@ template <typename T>
 __global__ void __cluster_dims__(agxc::kCluster, 1, 1) __launch_bounds__(agxc::kBlock)
 agx_comm_allreduce_kernel(const __grid_constant__ AgxComm c, T* __restrict__ buf, int64_t n) {
     namespace cg = cooperative_groups;
-    const unsigned long long seq = agxc::push_and_wait<T>(c, buf, n);
-    const int parity = (int)(seq & 1ull);
+    const unsigned long long seq = agxc::push<T>(c, buf, n);
+    if (sizeof(T) == 8) cg::this_cluster().sync();  // 8-byte elements: the two words of an element are pushed by other threads than the one
+                                                    // that overwrites it with the sum (4-byte elements: same thread pushes and overwrites)
     const int64_t first = (int64_t)cg::this_cluster().block_rank() * agxc::kBlock + threadIdx.x, stride = (int64_t)agxc::kCluster * agxc::kBlock;
-    for (int64_t i = first; i < n; i += stride) buf[i] = agxc::reduce_elem<T>(c, parity, i);
+    unsigned long long t0 = 0ull;
+    for (int64_t i = first; i < n; i += stride) buf[i] = agxc::reduce_elem<T>(c, seq, i, t0);
     agxc::finish(c, seq);
 }
 
@@ -38,7 +40,7 @@ extern "C" {
 int64_t agx_comm_region_bytes(int world, int64_t slot_bytes) {
     if (world < 1 || world > AGX_COMM_MAX_RANKS || slot_bytes <= 0) return -1;
     const int64_t sb = (slot_bytes + 255) / 256 * 256;
-    return agxc::kHdrBytes + 2 * (int64_t)world * sb;
+    return agxc::kHdrBytes + 2 * (int64_t)world * (2 * sb);  // 2 parities x world slots of {word, tag} pairs (8 bytes per 32-bit word)
 }
 
 int agx_comm_alloc(int64_t bytes, void** ptr, unsigned char* handle) {

@@ -173,10 +173,11 @@ agx_adam_kernel(const __grid_constant__ AgxPpoHyper hp, const __grid_constant__ 
     float ss = 0.0f;
     unsigned long long seq = 0;
     if (COMM) {
-        seq = agxc::push_and_wait<float>(comm, g, n + n_extra);
-        const int parity = (int)(seq & 1ull);
+        seq = agxc::push<float>(comm, g, n + n_extra);
+        // (element i of g is pushed and later overwritten with the sum by the same thread: no barrier needed in between)
+        unsigned long long t0 = 0ull;
         for (int64_t i = first; i < n + n_extra; i += stride) {
-            const float sum = agxc::reduce_elem<float>(comm, parity, i);
+            const float sum = agxc::reduce_elem<float>(comm, seq, i, t0);
             g[i] = sum;  // re-read below by this same thread
             if (i < n) { const float x = sum * grad_scale; ss += x * x; }
         }

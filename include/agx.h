@@ -290,8 +290,9 @@ int agx_adam_step(const AgxPpoHyper* hp, int64_t n_params, float* params, const 
  * ([flat gradients ‖ loss statistics incl. the KL], reference lib/agent/a2c_base.py:293-309 + a2c_continuous.py:112-123) and a
  * few per epoch (advantage / RunningMeanStd moments).  These entry points run them as ONE device kernel per rank over NVLink
  * peer memory instead of a library collective: each rank owns a region in its HBM, mapped into every process of the node with
- * CUDA IPC; a collective pushes the message into every peer's region, raises a flag there, waits for the peers' flags in its
- * own region and adds the slots in rank order (bitwise identical results on every rank).  Stream-ordered, graph-capturable
+ * CUDA IPC; a collective pushes the message into every peer's region as {word, tag} pairs (one traversal of the fabric: no fence,
+ * no separate flag), polls its own region until every peer's words carry this call's tag and adds the slots in rank order
+ * (bitwise identical results on every rank).  Stream-ordered, graph-capturable
  * (the call counter lives in the region), no host sync.  All ranks must issue the same sequence of collectives.
  * ------------------------------------------------------------------------------------------------------------- */
 #define AGX_IPC_HANDLE_BYTES 64
@@ -304,7 +305,8 @@ typedef struct AgxComm {
     void*   region[AGX_COMM_MAX_RANKS];  /* region[rank]: this process's own allocation; the others: IPC mappings of the peers' */
 } AgxComm;
 
-/* bytes of one rank's region for messages of up to slot_bytes (rounded up to a multiple of 256): header + 2 x world slots */
+/* bytes of one rank's region for messages of up to slot_bytes (rounded up to a multiple of 256): header + 2 x world slots of
+ * {word, tag} pairs (the flag travels with the data: 8 bytes per 32-bit word) */
 int64_t agx_comm_region_bytes(int world, int64_t slot_bytes);
 /* cudaMalloc + zero-fill a region on the current device; handle (AGX_IPC_HANDLE_BYTES, may be NULL) = its cudaIpcMemHandle_t */
 int agx_comm_alloc(int64_t bytes, void** ptr, unsigned char* handle);

@@ -103,4 +103,10 @@ if __name__ == "__main__":
             r = trial(model, tuple(b["signs"]), b["rate_per_unit"], b["thrust_x"], gain, dterm, a.envs, a.steps)
             out.append(r)
             print(json.dumps(r), flush=True)
+    b = sorted(out[1:], key=lambda r: -r["mean_ep_len"])[0]  # refine thrust map and loop gain around the best convention, longer horizon
+    for thrust, gain in itertools.product((0.6, 0.7, 0.8, 0.9), (0.2, 0.3, 0.5, 0.7)):
+        r = trial(model, tuple(b["signs"]), b["rate_per_unit"], thrust, gain, True, a.envs, 2 * a.steps)
+        r["stage"] = "refine (2x steps)"
+        out.append(r)
+        print(json.dumps(r), flush=True)
     print("BEST", json.dumps(sorted(out[1:], key=lambda r: -r["mean_ep_len"])[:10]))

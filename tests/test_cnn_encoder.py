@@ -73,8 +73,18 @@ def test_encoder_schedule_on_cpu_matches_torch(feature_dim, normalise):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("impl", ["fused", "tc"])  # fused: agx_cnn_encode (fp32 FMA, one persistent kernel); tc: tcgen05 layers (3xTF32)
 @pytest.mark.parametrize("n,feature_dim,normalise", [(3, 30, True), (149, 30, False), (300, 12, True), (1, 64, False)])
-def test_encoder_kernel_matches_torch(built, n, feature_dim, normalise):
+def test_encoder_kernel_matches_torch(built, n, feature_dim, normalise, impl):
+    from airgym_b200.lib.network import cnn as cnn_mod
+    cnn_mod.ENCODER_IMPL, saved = impl, cnn_mod.ENCODER_IMPL
+    try:
+        _encoder_kernel_matches_torch(n, feature_dim, normalise, impl)
+    finally:
+        cnn_mod.ENCODER_IMPL = saved
+
+
+def _encoder_kernel_matches_torch(n, feature_dim, normalise, impl):
     net = make_net(feature_dim, seed=feature_dim).cuda()
     x = make_images(n, seed=n).cuda()
     mean = var = m32 = r32 = None
@@ -95,6 +105,8 @@ def test_encoder_kernel_matches_torch(built, n, feature_dim, normalise):
         again = net(x) if not normalise else native_encode(net, x, m32, r32)
     if not normalise:
         assert torch.equal(again, got)
+    if impl != "fused":
+        return
     # the CPU replay of the same phase functions agrees to rounding (fmaf on both sides)
     from tests.hostsim import driver
     lib = driver.build_cnn()

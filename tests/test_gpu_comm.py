@@ -116,5 +116,5 @@ def test_bad_arguments_fail_loudly(built):
     bad = _capi.AgxComm()
     bad.rank, bad.world, bad.slot_bytes = 0, 2, 1024  # regions unmapped
     assert lib.agx_comm_allreduce(C.byref(bad), big.data_ptr(), 16, _capi.AGX_F32, None) == -1
-    assert lib.agx_comm_region_bytes(9, 1024) == -1 and lib.agx_comm_region_bytes(2, 1000) == 256 + 4 * 1024
+    assert lib.agx_comm_region_bytes(9, 1024) == -1 and lib.agx_comm_region_bytes(2, 1000) == 256 + 4 * 2 * 1024
     _free(comms)
