@@ -462,6 +462,10 @@ agx_step_kernel(const __grid_constant__ AgxParams P, const __grid_constant__ Agx
 #pragma unroll
                 for (int k = 0; k < NT; ++k) io.reward_terms[(int64_t)k * n + env] = e.terms[k];
             }
+            if (kHasAux) {  // the Customized family's compute_reward also sets pre_root_positions = root_positions.clone() (balloon.py:153)
+                reinterpret_cast<float4*>(io.aux)[env * 2] = make_float4(e.aux[0], e.aux[1], e.aux[2], e.aux[3]);
+                reinterpret_cast<float4*>(io.aux)[env * 2 + 1] = make_float4(e.aux[4], e.aux[5], e.aux[6], e.aux[7]);
+            }
         }
     } else if (active) {
         if (kTask) {

@@ -218,7 +218,8 @@ int agx_step(const AgxParams* p, int64_t n, const AgxStepIO* io, void* stream);
  * phase of the step kernel over the CURRENT buffers without stepping — no reset, no progress / time-out / state / task-state write,
  * the Philox step counter is read but not advanced.  what = 1: obs (fresh observation noise, or io->rand_noise);
  * what = 2: reward, reset (overwritten, as compute_reward does), reset_u8, reward_terms, prev_action <- actions_out
- * (`self.pre_actions = self.actions.clone()`); 3: both.  Reads actions_out (the shaped actions of the last step) and cmd. */
+ * (`self.pre_actions = self.actions.clone()`) and, for the Customized family, the task state `aux`
+ * (`pre_root_positions = root_positions.clone()`); 3: both.  Reads actions_out (the shaped actions of the last step) and cmd. */
 int agx_observe(const AgxParams* p, int64_t n, const AgxStepIO* io, int what, void* stream);
 
 int agx_render_depth(const AgxParams* p, int64_t n, const AgxRenderIO* io, void* stream);

@@ -407,6 +407,8 @@ def test_compute_observations_and_compute_reward_as_standalone_calls(task, mode)
     assert torch.equal(env.reset_buf.cpu(), orc.reset_buf) and torch.equal(env.reset_u8.cpu().long(), orc.reset_buf)
     assert_close(env.pre_actions.cpu(), orc.pre_actions, "pre_actions = actions.clone()", rtol=0, atol=0)
     assert_close(env._reward_terms.cpu()[:len(type(orc).REWARD_KEYS)], orc.reward_terms_matrix(), "item_reward_info", rtol=rr, atol=ra)
+    if hasattr(orc, "aux_matrix"):
+        assert_close(env.aux.cpu(), orc.aux_matrix(), "task state (pre_root_positions = root_positions.clone())")
     torch.cuda.synchronize()
     assert torch.equal(env.root_states, before[0]) and torch.equal(env.progress_buf, before[1]) and torch.equal(env.time_out_buf, before[2])
     assert int(env._step_dev[0]) == before[3] and int(env._step_dev[1]) == 0  # the Philox step counter is read, not advanced
