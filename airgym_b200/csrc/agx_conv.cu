@@ -27,6 +27,7 @@
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
+extern "C" int agx_internal_conv_tma(const AgxConvParams* p, void* stream);  // agx_conv_tma.cu: 1 launched, 0 not its geometry, < 0 error
 
 namespace {
 
@@ -307,6 +308,10 @@ int agx_conv2d_nhwc(const AgxConvParams* p, void* stream) {
     if (al & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_conv2d_nhwc: buffers must be 16-byte aligned");
     if (p->res && (p->rH <= 0 || p->rW <= 0 || (p->Ho - 1) * p->rsy + p->ry0 >= p->rH || (p->Wo - 1) * p->rsx + p->rx0 >= p->rW || p->ry0 < 0 || p->rx0 < 0))
         return agx_internal_fail(AGX_ERR_ARG, "agx_conv2d_nhwc: residual window outside the residual tensor");
+    {   // spatial layers go to the TMA im2col kernel (agx_conv_tma.cu); the dense layers and odd geometries stay here
+        const int r = agx_internal_conv_tma(p, stream);
+        if (r) return r > 0 ? AGX_OK : r;
+    }
     const bool split = p->w_lo != nullptr;
     const int stage_floats = (split ? 2 : 1) * (kSlabChunks * kM * 4 + kSlabChunks * Nt * 4);
     const size_t smem = 2 * (size_t)stage_floats * sizeof(float);

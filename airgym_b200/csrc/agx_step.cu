@@ -61,6 +61,7 @@ using namespace agxk;
 
 int agx_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 extern "C" int agx_internal_mlp_option(const char* key, int value);  // agx_mlp.cu
+extern "C" int agx_internal_conv_option(const char* key, int value);  // agx_conv_tma.cu
 
 namespace {
 
@@ -108,7 +109,8 @@ int agx_set_option(const char* key, int value) {
         g_pdl = value;
         return AGX_OK;
     }
-    const int r = agx_internal_mlp_option(key, value);
+    int r = agx_internal_mlp_option(key, value);
+    if (r == 0) r = agx_internal_conv_option(key, value);
     if (r == 1) return AGX_OK;
     if (r < 0) return fail(AGX_ERR_ARG, "agx_set_option: bad value for '%s'", key);
     return fail(AGX_ERR_ARG, "agx_set_option: unknown key '%s'", key);

@@ -34,8 +34,14 @@ ACT = {"none": (_capi.ACT_NONE, lambda t: t), "relu": (_capi.ACT_RELU, torch.rel
 
 @pytest.mark.parametrize("g", GEOMS, ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}s{g[3]}_{g[5]}x{g[6]}")
 @pytest.mark.parametrize("precise", [True, False])
-def test_conv_layer_vs_float64(built, g, precise):
+@pytest.mark.parametrize("impl", [1, 0], ids=["tma", "gather"])
+def test_conv_layer_vs_float64(built, g, precise, impl):
+    """impl 1: the TMA im2col kernel (csrc/agx_conv_tma.cu) where the geometry allows — every spatial layer of both encoders; impl 0:
+    the cp.async gather kernel (csrc/agx_conv.cu), which also serves the dense layers under impl 1."""
     Cin, Cout, k, s, p, H, W, act, with_res = g
+    if impl == 0 and H == 1:
+        pytest.skip("dense layers run on the gather kernel under both settings")
+    _capi.check(_capi.load().agx_set_option(b"conv_impl", impl), "conv_impl")
     torch.manual_seed(Cin * 7 + Cout)
     N = 37 if H > 1 else 300  # M = N * Ho * Wo is not a multiple of 128: partial last tile
     conv = nn.Conv2d(Cin, Cout, k, stride=s, padding=p).cuda()
@@ -54,8 +60,11 @@ def test_conv_layer_vs_float64(built, g, precise):
     if act == "relu":
         scale, shift = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
         y_ref = y_ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
-    y = T.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), L, ACT[act][0], res=res, scale=scale, shift=shift)
-    torch.cuda.synchronize()
+    try:
+        y = T.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), L, ACT[act][0], res=res, scale=scale, shift=shift)
+        torch.cuda.synchronize()
+    finally:
+        _capi.load().agx_set_option(b"conv_impl", 1)
     y_ref = y_ref.detach()
     err = float((y.permute(0, 3, 1, 2).double() - y_ref).abs().max())
     ref_scale = float(y_ref.abs().max())
