@@ -8,10 +8,14 @@
 //   K-slab = one filter tap x KS channels (KS = 16 for Cin = 16, else 32): ONE cp.async.bulk.tensor im2col instruction brings the
 //   slab's A operand [128 pixels][KS] (stride, padding and image / batch boundaries resolved by the TMA unit, zero fill outside),
 //   one tiled load each the weight slab's hi and lo parts [Cout][KS]; all land in the 64- / 128-byte-swizzled K-major layout the
-//   tensor core reads.  Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 =
-//   epilogue (TMEM lane quarters 0-3), warps 8-11 = splitter (A_lo = A - tf32(A), element-wise on the stage: the layout does not
-//   matter).  Ring of 3-8 shared-memory stages (full → ready → empty mbarriers) and two TMEM accumulator sets, so the loads of tile
-//   t+1 run under the MMAs of tile t and under the epilogue of tile t-1.
+//   tensor core reads.  Roles (512 threads): warp 0 = TMA producer, warp 1 = MMA issuer (both run converged and issue under
+//   elect.sync: a lone diverged lane makes the compiler wrap every uniform-datapath instruction in an election loop, which made the
+//   first version issue-bound in that one thread at ~290 instructions per slab), warp 2 = TMEM allocator, warps 4-7 = epilogue
+//   (TMEM lane quarters 0-3), warps 8-15 = splitter (A_lo = A - tf32(A), element-wise on the stage: the layout does not matter).
+//   A shared-memory stage holds 1-4 slabs (one full → ready → empty mbarrier round trip per stage, not per slab); ring of 2-8
+//   stages and two TMEM accumulator sets, so the loads of tile t+1 run under the MMAs of tile t and under the epilogue of tile t-1.
+//   Epilogue: TMEM → registers (+ bias, residual, activation, affine) → a 128-byte-swizzled staging tile (bank-conflict-free
+//   row writes) → cp.async.bulk.tensor stores of full 128-byte lines (rows past the end clipped by the TMA unit).
 //   Precision: 3xTF32 as in agx_conv.cu (A_hi·B_hi + A_lo·B_hi + A_hi·B_lo; G accumulator chains for K > 512).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -26,13 +30,13 @@ int agx_internal_fail(int code, const char* msg);
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kMaxStages = 8;
 
 struct ConvGeom {
     int64_t M_total;
-    int32_t num_tiles, Nt, KS, swb, cblocks, nslabs, stages, G, tmem_cols, split;
-    uint32_t a_bytes, b_bytes, stage_bytes, tx_bytes;
+    int32_t num_tiles, Nt, cblocks, nslabs, spp, fills, stages, G, tmem_cols;
+    uint32_t a_bytes, b_bytes, stage_bytes, slab_tx, stg_bytes;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -59,6 +63,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         }
     }
 }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c, int w, int h, int n, uint16_t ow, uint16_t oh) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
@@ -69,10 +78,9 @@ __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* tm,
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
-// K-major operand in the 64- / 128-byte swizzled canonical layout: rows of `swb` bytes, 8-row groups `8 * swb` bytes apart
-__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t swb) {
-    const uint64_t layout = swb == 128 ? 2u : 4u;  // UMMA LayoutType: SWIZZLE_128B = 2, SWIZZLE_64B = 4
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(((8u * swb) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | (layout << 61);
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db),
@@ -82,25 +90,33 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 
 extern __shared__ uint8_t t_smem[];
 
+// KS = K per slab (channels of one filter tap): 16 → 64-byte rows / SWIZZLE_64B, 32 → 128-byte rows / SWIZZLE_128B
+template <int KS, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
-                      const __grid_constant__ AgxConvParams P, const __grid_constant__ ConvGeom Gm) {
+                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ AgxConvParams P, const __grid_constant__ ConvGeom Gm) {
     __shared__ __align__(8) uint64_t full[kMaxStages], ready[kMaxStages], empty[kMaxStages], accfull[2], accempty[2];
     __shared__ uint32_t tmem_base;
     __shared__ __align__(16) float s_bias[128], s_scale[128], s_shift[128];
+    constexpr uint32_t kSwb = KS * 4;
+    // K-major operand in the 64- / 128-byte swizzled canonical layout: rows of kSwb bytes, 8-row groups 8 * kSwb bytes apart.
+    // High word of the shared-memory descriptor: stride byte offset, version 1 (bit 46), UMMA LayoutType SWIZZLE_128B = 2 / SWIZZLE_64B = 4
+    // (bits 61-63); low word: start address >> 4 | leading byte offset 1 << 16 (unused by swizzled K-major layouts).
+    constexpr uint32_t kDescHi = (((8u * kSwb) >> 4) & 0x3FFFu) | (1u << 14) | ((kSwb == 128 ? 2u : 4u) << 29);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (s32(t_smem) + 1023u) & ~1023u;  // swizzle patterns repeat every 1024 bytes of the shared-memory address
-    const int S = Gm.stages, Nt = Gm.Nt, nslabs = Gm.nslabs;
-    const bool split = Gm.split != 0;
-    const uint32_t offAlo = Gm.a_bytes, offBhi = (split ? 2u : 1u) * Gm.a_bytes, offBlo = offBhi + Gm.b_bytes;
+    const uint32_t ring0 = smem0 + Gm.stg_bytes;            // [staging tile of the epilogue | ring of stages]
+    const int S = Gm.stages, Nt = Gm.Nt, nslabs = Gm.nslabs, spp = Gm.spp;
+    const uint32_t offAlo = (uint32_t)spp * Gm.a_bytes, offBhi = (SPLIT ? 2u : 1u) * offAlo, offBlo = offBhi + (uint32_t)spp * Gm.b_bytes;
 
     if (tid == 0) {
-        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 4); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 8); mbar_init(&empty[i], 1); }
         mbar_init(&accfull[0], 1); mbar_init(&accfull[1], 1); mbar_init(&accempty[0], 4); mbar_init(&accempty[1], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBhi)) : "memory");
-        if (split) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
+        if (SPLIT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     }
     if (tid < 128) {
         s_bias[tid] = (P.bias && tid < Nt) ? P.bias[tid] : 0.0f;
@@ -117,94 +133,116 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem = tmem_base;
     const int HoWo = P.Ho * P.Wo;
 
-    if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x) {
-                const int64_t pix0 = (int64_t)tile * kM;
-                const int n0 = (int)(pix0 / HoWo), rem = (int)(pix0 - (int64_t)n0 * HoWo), oy0 = rem / P.Wo, ox0 = rem - oy0 * P.Wo;
-                const int w0 = ox0 * P.sx - P.px, h0 = oy0 * P.sy - P.py;  // base pixel of the tile's first output pixel, input coordinates
-                int tap = 0, cb = 0, ky = 0, kx = 0;
-                for (int s = 0; s < nslabs; ++s) {
-                    mbar_wait(&empty[stage], ph ^ 1u);
-                    mbar_expect_tx(&full[stage], Gm.tx_bytes);
-                    const uint32_t base = smem0 + (uint32_t)stage * Gm.stage_bytes;
-                    tma_im2col_4d(base, &tmA, &full[stage], cb * Gm.KS, w0, h0, n0, (uint16_t)kx, (uint16_t)ky);
-                    tma_tile_2d(base + offBhi, &tmBhi, &full[stage], s * Gm.KS, 0);
-                    if (split) tma_tile_2d(base + offBlo, &tmBlo, &full[stage], s * Gm.KS, 0);
-                    if (++cb == Gm.cblocks) { cb = 0; ++tap; if (++kx == P.kw) { kx = 0; ++ky; } }
-                    if (++stage == S) { stage = 0; ph ^= 1u; }
+    if (warp == 0) {  // ---- TMA producer (whole warp converged; one elected lane issues)
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x) {
+            const int64_t pix0 = (int64_t)tile * kM;
+            const int n0 = (int)(pix0 / HoWo), rem = (int)(pix0 - (int64_t)n0 * HoWo), oy0 = rem / P.Wo, ox0 = rem - oy0 * P.Wo;
+            const int w0 = ox0 * P.sx - P.px, h0 = oy0 * P.sy - P.py;  // base pixel of the tile's first output pixel, input coordinates
+            int cb = 0, ky = 0, kx = 0, s = 0;
+            for (int f = 0; f < Gm.fills; ++f) {
+                const int cnt = nslabs - s < spp ? nslabs - s : spp;
+                mbar_wait(&empty[stage], ph ^ 1u);
+                const bool leader = elect_one();
+                const uint32_t base = ring0 + (uint32_t)stage * Gm.stage_bytes;
+                if (leader) mbar_expect_tx(&full[stage], (uint32_t)cnt * Gm.slab_tx);
+                for (int u = 0; u < cnt; ++u, ++s) {
+                    if (leader) {
+                        tma_im2col_4d(base + (uint32_t)u * Gm.a_bytes, &tmA, &full[stage], cb * KS, w0, h0, n0, (uint16_t)kx, (uint16_t)ky);
+                        tma_tile_2d(base + offBhi + (uint32_t)u * Gm.b_bytes, &tmBhi, &full[stage], s * KS, 0);
+                        if (SPLIT) tma_tile_2d(base + offBlo + (uint32_t)u * Gm.b_bytes, &tmBlo, &full[stage], s * KS, 0);
+                    }
+                    if (++cb == Gm.cblocks) { cb = 0; if (++kx == P.kw) { kx = 0; ++ky; } }
                 }
+                __syncwarp();
+                if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nt >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-            const int ksteps = Gm.KS / 8;
-            int stage = 0;
-            uint32_t ph = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x, ++lt) {
-                const uint32_t buf = lt & 1u;
-                mbar_wait(&accempty[buf], ((lt >> 1) & 1u) ^ 1u);
+    } else if (warp == 1) {  // ---- MMA issuer (whole warp converged; one elected lane issues)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nt >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+        const int gmask = Gm.G - 1;
+        int stage = 0;
+        uint32_t ph = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            mbar_wait(&accempty[buf], ((lt >> 1) & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dbase = tmem + buf * (uint32_t)(Gm.G * Nt);
+            int s = 0;
+            for (int f = 0; f < Gm.fills; ++f) {
+                const int cnt = nslabs - s < spp ? nslabs - s : spp;
+                mbar_wait(&ready[stage], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dbase = tmem + buf * (uint32_t)(Gm.G * Nt);
-                int g = 0;
-                for (int s = 0; s < nslabs; ++s) {
-                    mbar_wait(&ready[stage], ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t base = smem0 + (uint32_t)stage * Gm.stage_bytes;
-                    const uint32_t d = dbase + (uint32_t)(g * Nt);
-                    const bool fresh = s < Gm.G;  // first slab of this accumulator chain overwrites
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        mma_tf32(d, smem_desc_sw(base + ks * 32, Gm.swb), smem_desc_sw(base + offBhi + ks * 32, Gm.swb), idesc, (ks > 0 || !fresh) ? 1u : 0u);
-                    if (split) {
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            mma_tf32(d, smem_desc_sw(base + offAlo + ks * 32, Gm.swb), smem_desc_sw(base + offBhi + ks * 32, Gm.swb), idesc, 1u);
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            mma_tf32(d, smem_desc_sw(base + ks * 32, Gm.swb), smem_desc_sw(base + offBlo + ks * 32, Gm.swb), idesc, 1u);
+                const uint32_t base = ring0 + (uint32_t)stage * Gm.stage_bytes;
+                if (elect_one()) {
+                    for (int u = 0; u < cnt; ++u) {
+                        const int sl = s + u;
+                        const uint32_t d = dbase + (uint32_t)((sl & gmask) * Nt);
+                        const uint32_t acc0 = sl >= Gm.G ? 1u : 0u;  // the first slab of an accumulator chain overwrites
+                        const uint32_t ah = ((base + (uint32_t)u * Gm.a_bytes) >> 4) | 0x10000u, bh = ((base + offBhi + (uint32_t)u * Gm.b_bytes) >> 4) | 0x10000u;
+#pragma unroll
+                        for (int ks = 0; ks < KS / 8; ++ks)  // a K step of 8 tf32 = 32 bytes inside the swizzle atom: start address + 2
+                            mma_tf32(d, ((uint64_t)kDescHi << 32) | (ah + 2u * ks), ((uint64_t)kDescHi << 32) | (bh + 2u * ks), idesc, ks ? 1u : acc0);
+                        if (SPLIT) {
+                            const uint32_t al = ((base + offAlo + (uint32_t)u * Gm.a_bytes) >> 4) | 0x10000u, bl = ((base + offBlo + (uint32_t)u * Gm.b_bytes) >> 4) | 0x10000u;
+#pragma unroll
+                            for (int ks = 0; ks < KS / 8; ++ks) mma_tf32(d, ((uint64_t)kDescHi << 32) | (al + 2u * ks), ((uint64_t)kDescHi << 32) | (bh + 2u * ks), idesc, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < KS / 8; ++ks) mma_tf32(d, ((uint64_t)kDescHi << 32) | (ah + 2u * ks), ((uint64_t)kDescHi << 32) | (bl + 2u * ks), idesc, 1u);
+                        }
                     }
                     commit(&empty[stage]);  // the stage is free once these MMAs have read it
-                    if (++g == Gm.G) g = 0;
-                    if (++stage == S) { stage = 0; ph ^= 1u; }
+                    if (f + 1 == Gm.fills) commit(&accfull[buf]);
                 }
-                commit(&accfull[buf]);
+                __syncwarp();
+                s += cnt;
+                if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
-    } else if (warp >= 8) {  // ---- splitter: A_lo = A - tf32(A) for the 3xTF32 product
+    } else if (warp >= 8) {  // ---- splitter: A_lo = A - tf32(A) for the 3xTF32 product (256 threads)
         const int ts = tid - 256;
         int stage = 0;
         uint32_t ph = 0;
-        const int n4 = (int)(Gm.a_bytes >> 4);
+        constexpr int kPer = (kM * (int)kSwb / 16) / 256;  // 16-byte chunks per thread and slab: 2 (KS = 16) | 4 (KS = 32)
         for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x) {
-            for (int s = 0; s < nslabs; ++s) {
+            int s = 0;
+            for (int f = 0; f < Gm.fills; ++f) {
+                const int cnt = nslabs - s < spp ? nslabs - s : spp;
                 mbar_wait(&full[stage], ph);
-                if (split) {
-                    const uint32_t a = smem0 + (uint32_t)stage * Gm.stage_bytes;
-                    for (int i = ts; i < n4; i += 128) {
-                        float4 v;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a + (uint32_t)i * 16u));
-                        v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                        v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                        v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                        v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + offAlo + (uint32_t)i * 16u), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                if (SPLIT) {
+                    const uint32_t a = ring0 + (uint32_t)stage * Gm.stage_bytes + (uint32_t)ts * 16u;
+                    for (int u = 0; u < cnt; ++u) {
+                        const uint32_t au = a + (uint32_t)u * Gm.a_bytes;
+                        float4 v[kPer];
+#pragma unroll
+                        for (int i = 0; i < kPer; ++i)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(au + (uint32_t)i * 4096u));
+#pragma unroll
+                        for (int i = 0; i < kPer; ++i) {
+                            v[i].x -= __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+                            v[i].y -= __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+                            v[i].z -= __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+                            v[i].w -= __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(au + offAlo + (uint32_t)i * 4096u), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w) : "memory");
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready[stage]);
+                s += cnt;
                 if (++stage == S) { stage = 0; ph ^= 1u; }
             }
         }
-    } else if (warp >= 4) {  // ---- epilogue: thread = pixel = TMEM lane
+    } else if (warp >= 4) {  // ---- epilogue: thread = pixel = TMEM lane; 32-channel blocks through the swizzled staging tile
         const int q = warp - 4, rr = 32 * q + lane;
         const bool affine = P.scale != nullptr;
+        const int chains = Gm.G < nslabs ? Gm.G : nslabs;
+        const uint32_t stg_row = smem0 + (uint32_t)rr * 128u, sw = (uint32_t)(rr & 7);
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1u;
-            mbar_wait(&accfull[buf], (lt >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t p = (int64_t)tile * kM + rr;
             const bool ok = p < Gm.M_total;
             const float* res = nullptr;
@@ -212,9 +250,12 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int pn = (int)(p / HoWo), rem = (int)(p - (int64_t)pn * HoWo), py = rem / P.Wo, px = rem - py * P.Wo;
                 res = P.res + (((int64_t)pn * P.rH + (py * P.rsy + P.ry0)) * P.rW + (px * P.rsx + P.rx0)) * P.Cout;
             }
-            float* y = P.y + p * P.Cout;
+            mbar_wait(&accfull[buf], (lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // the previous tile's stores must have read the staging tile before it is overwritten
+            if (tid == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + buf * (uint32_t)(Gm.G * Nt);
-            const int chains = Gm.G < nslabs ? Gm.G : nslabs;
             for (int c0 = 0; c0 < Nt; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
@@ -224,33 +265,41 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += u[i];
                 }
-                if (ok) {
+                const uint32_t blk = stg_row + (uint32_t)(c0 >> 5) * (uint32_t)(kM * 128);  // staging tile of this 32-channel block
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + i);
-                        float4 a = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
-                        if (res) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(res + c0 + i));
-                            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-                        }
-                        if (P.act == 1) {
-                            a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f);
-                        } else if (P.act == 2) {
-                            a.x = a.x > 0.0f ? a.x : expm1f(a.x); a.y = a.y > 0.0f ? a.y : expm1f(a.y);
-                            a.z = a.z > 0.0f ? a.z : expm1f(a.z); a.w = a.w > 0.0f ? a.w : expm1f(a.w);
-                        }
-                        if (affine) {
-                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + i), sh = *reinterpret_cast<const float4*>(s_shift + c0 + i);
-                            a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
-                        }
-                        *reinterpret_cast<float4*>(y + c0 + i) = a;
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+                    float4 a = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+                    if (res) {
+                        const float4 r = __ldg(reinterpret_cast<const float4*>(res + c0 + i));
+                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
                     }
+                    if (P.act == 1) {
+                        a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f);
+                    } else if (P.act == 2) {
+                        a.x = a.x > 0.0f ? a.x : expm1f(a.x); a.y = a.y > 0.0f ? a.y : expm1f(a.y);
+                        a.z = a.z > 0.0f ? a.z : expm1f(a.z); a.w = a.w > 0.0f ? a.w : expm1f(a.w);
+                    }
+                    if (affine) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + i), sh = *reinterpret_cast<const float4*>(s_shift + c0 + i);
+                        a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+                    }
+                    const uint32_t chunk = (uint32_t)(((c0 & 16) + i) >> 2);  // 16-byte chunk 0..7 of the 128-byte row; SWIZZLE_128B: chunk ^ (row & 7)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(blk + ((chunk ^ sw) << 4)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
                 }
             }
+            // the accumulator set is free as soon as it has been read
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&accempty[buf]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 128) {
+                for (int cbk = 0; cbk < Nt / 32; ++cbk) tma_store_2d(&tmY, smem0 + (uint32_t)cbk * (uint32_t)(kM * 128), cbk * 32, tile * kM);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (tid == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -269,6 +318,7 @@ EncodeIm2colFn g_encode_im2col = nullptr;
 int g_entry_state = 0;  // 0 not looked up, 1 available, -1 unavailable
 int g_sm_count = 0;
 int g_conv_impl = 1;    // agx_set_option("conv_impl", 0 = cp.async gather kernel of agx_conv.cu | 1 = this kernel where the geometry allows)
+int g_conv_spp = 0;     // agx_set_option("conv_spp", 0 = automatic | 1..4 slabs per stage) — A/B knob
 
 bool lookup_entry_points() {
     if (g_entry_state) return g_entry_state > 0;
@@ -287,6 +337,19 @@ bool lookup_entry_points() {
     return ok;
 }
 
+template <int KS, bool SPLIT>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmY, const AgxConvParams* p, const ConvGeom& G, size_t smem,
+           cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(agx_conv2d_tma_kernel<KS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
+        attr_set = true;
+    }
+    const int grid = G.num_tiles < g_sm_count ? G.num_tiles : g_sm_count;
+    agx_conv2d_tma_kernel<KS, SPLIT><<<grid, kThreads, smem, st>>>(tmA, tmBhi, tmBlo, tmY, *p, G);
+    return cudaGetLastError() == cudaSuccess ? 1 : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_nhwc (tma): launch failed");
+}
+
 }  // namespace
 
 extern "C" {
@@ -295,6 +358,11 @@ int agx_internal_conv_option(const char* key, int value) {
     if (!strcmp(key, "conv_impl")) {
         if (value < 0 || value > 1) return -1;
         g_conv_impl = value;
+        return 1;
+    }
+    if (!strcmp(key, "conv_spp")) {
+        if (value < 0 || value > 4) return -1;
+        g_conv_spp = value;
         return 1;
     }
     return 0;
@@ -310,58 +378,68 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
     ConvGeom G;
     memset(&G, 0, sizeof(G));
     G.M_total = (int64_t)p->N * p->Ho * p->Wo;
-    if ((G.M_total + kM - 1) / kM > 0x7FFFFFFF) return 0;
+    if ((G.M_total + kM - 1) / kM > 0x7FFFFF) return 0;
     G.num_tiles = (int)((G.M_total + kM - 1) / kM);
     G.Nt = p->Cout;
-    G.KS = p->Cin == 16 ? 16 : 32;
-    G.swb = G.KS * 4;
-    G.cblocks = p->Cin / G.KS;
+    const int KS = p->Cin == 16 ? 16 : 32, swb = KS * 4;
+    const bool split = p->w_lo != nullptr;
+    G.cblocks = p->Cin / KS;
     G.nslabs = taps * G.cblocks;
-    G.split = p->w_lo != nullptr;
     const int K = taps * p->Cin;
     G.G = K <= 512 ? 1 : ((K <= 1024 || G.Nt > 64) ? 2 : 4);  // accumulator chains, as in agx_conv.cu
     const int cols = 2 * G.G * G.Nt;
-    G.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     if (cols > 512) return 0;
-    G.a_bytes = (uint32_t)kM * G.swb;
-    G.b_bytes = (((uint32_t)G.Nt * G.swb) + 1023u) & ~1023u;
-    G.stage_bytes = (G.split ? 2u : 1u) * (G.a_bytes + G.b_bytes);
-    G.tx_bytes = G.a_bytes + (G.split ? 2u : 1u) * (uint32_t)G.Nt * G.swb;
-    const uint32_t budget = 220u * 1024u;
+    G.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+    G.a_bytes = (uint32_t)kM * swb;
+    G.b_bytes = (uint32_t)G.Nt * swb;  // a multiple of 1024: Nt % 32 == 0, swb >= 64
+    const uint32_t slab_bytes = (split ? 2u : 1u) * (G.a_bytes + G.b_bytes);
+    G.slab_tx = G.a_bytes + (split ? 2u : 1u) * G.b_bytes;
+    G.stg_bytes = (uint32_t)G.Nt * kM * 4;
+    const uint32_t budget = 220u * 1024u - G.stg_bytes;
+    G.spp = g_conv_spp ? g_conv_spp : (int)(65536u / slab_bytes);
+    if (G.spp > 4) G.spp = 4;
+    if (G.spp > G.nslabs) G.spp = G.nslabs;
+    while (G.spp > 1 && budget / (G.spp * slab_bytes) < 2) --G.spp;
+    if (G.spp < 1) G.spp = 1;
+    G.stage_bytes = (uint32_t)G.spp * slab_bytes;
     G.stages = (int)(budget / G.stage_bytes);
     if (G.stages > kMaxStages) G.stages = kMaxStages;
     if (G.stages < 2) return 0;
-    const size_t smem = (size_t)G.stages * G.stage_bytes + 1024;
+    G.fills = (G.nslabs + G.spp - 1) / G.spp;
+    const size_t smem = 1024 + (size_t)G.stg_bytes + (size_t)G.stages * G.stage_bytes;
 
-    const CUtensorMapSwizzle sw = G.swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUtensorMap tmA, tmBhi, tmBlo;
+    const CUtensorMapSwizzle sw = swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap tmA, tmBhi, tmBlo, tmY;
     memset(&tmBlo, 0, sizeof(tmBlo));
     {   // activations as (C, W, H, N); the base-pixel box [-pad, dim + pad - (k - 1)) is traversed with the convolution's stride
         const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
         const cuuint64_t strides[3] = {(cuuint64_t)p->Cin * 4, (cuuint64_t)p->W * p->Cin * 4, (cuuint64_t)p->H * p->W * p->Cin * 4};
         const int lower[2] = {-p->px, -p->py}, upper[2] = {p->px - (p->kw - 1), p->py - (p->kh - 1)};
         const cuuint32_t estr[4] = {1, (cuuint32_t)p->sx, (cuuint32_t)p->sy, 1};
-        const CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p->x), dims, strides, lower, upper, (cuuint32_t)G.KS,
+        const CUresult r = g_encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p->x), dims, strides, lower, upper, (cuuint32_t)KS,
                                            (cuuint32_t)kM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return 0;  // geometry the TMA unit does not take: the gather kernel handles it
     }
-    for (int part = 0; part < (G.split ? 2 : 1); ++part) {
+    for (int part = 0; part < (split ? 2 : 1); ++part) {
         const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
         const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)G.KS, (cuuint32_t)G.Nt}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)G.Nt}, estr[2] = {1, 1};
         const CUresult r = g_encode_tiled(part ? &tmBlo : &tmBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(part ? p->w_lo : p->w_hi), dims, strides,
                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(agx_conv2d_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024 + 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
-        attr_set = true;
+    {   // output as [M_total][Cout]: boxes of 32 channels x 128 pixels, rows past M_total clipped by the TMA unit
+        const cuuint64_t dims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)G.M_total};
+        const cuuint64_t strides[1] = {(cuuint64_t)p->Cout * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)kM}, estr[2] = {1, 1};
+        const CUresult r = g_encode_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
     }
-    const int grid = G.num_tiles < g_sm_count ? G.num_tiles : g_sm_count;
-    agx_conv2d_tma_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmBhi, tmBlo, *p, G);
-    return cudaGetLastError() == cudaSuccess ? 1 : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_nhwc (tma): launch failed");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (KS == 16) return split ? launch<16, true>(tmA, tmBhi, tmBlo, tmY, p, G, smem, st) : launch<16, false>(tmA, tmBhi, tmBhi, tmY, p, G, smem, st);
+    return split ? launch<32, true>(tmA, tmBhi, tmBlo, tmY, p, G, smem, st) : launch<32, false>(tmA, tmBhi, tmBhi, tmY, p, G, smem, st);
 }
 
 }  // extern "C"
