@@ -27,6 +27,7 @@
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
+extern "C" int agx_internal_conv_first_tma(const AgxConvFirstParams* p, void* stream);  // same contract, first layer
 extern "C" int agx_internal_conv_tma(const AgxConvParams* p, void* stream);  // agx_conv_tma.cu: 1 launched, 0 not its geometry, < 0 error
 
 namespace {
@@ -333,6 +334,10 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
         p->act < 0 || p->act > 2 || p->sy <= 0 || p->sx <= 0)
         return agx_internal_fail(AGX_ERR_ARG, "agx_conv2d_first: bad argument");
     if ((uintptr_t)p->y & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_conv2d_first: output must be 16-byte aligned");
+    {   // 5x5 / stride-2 layers go to the tensor-core kernel (agx_conv_tma.cu)
+        const int r = agx_internal_conv_first_tma(p, stream);
+        if (r) return r > 0 ? AGX_OK : r;
+    }
     const int64_t M_total = (int64_t)p->N * p->Ho * p->Wo;
     int64_t grid = (M_total + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;

@@ -307,6 +307,221 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Gm.tmem_cols) : "memory");
 }
 
+// ---- first layer (one input channel, 5x5 / stride 2) on the tensor cores ---------------------------------------------------------
+// GEMM view: M = the pixels of R whole output rows of one image (R * Wo <= 128: 2 x 60 for the CNN, 1 x 106 for the VAE), K = 25 taps
+// padded to 32, N = Cout (16 | 32).  Cin = 1 rules out the TMA im2col mode (its channel run is 4 bytes), so the operand is built by
+// threads: a TMA tile load brings the tile's input strip [(R-1)*2 + 5 rows][from column -4 to (Wo-1)*2 + 4 - pad], image borders zero-filled by the
+// TMA unit (plus the matching strips of the per-pixel mean / rstd planes when the RunningMeanStd normalisation is fused: outside the
+// image all three are 0, so the normalised padding stays 0); 256 builder threads normalise the strip in place, then write each
+// pixel's 25 taps as a 128-byte row of the SWIZZLE_128B K-major layout, hi and lo parts.  ~100 instructions per output pixel
+// instead of the ~700 of the direct kernel (25 x (load + 16 FMA + weight reads)).  Weights [Cout][32] hi / lo stay resident in
+// shared memory.  Roles as above: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, warps 8-15 builders.
+struct FirstGeom {
+    int32_t num_tiles, tiles_per_img, R, rows_px, SR, SW, strip_bytes, norm, sstages, astages;
+    uint32_t stg_bytes;
+};
+
+template <int HALF>
+__device__ __forceinline__ void build_row(const float* sp, int SW, uint32_t row_hi, uint32_t row_lo, uint32_t sw) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        constexpr int kBase = HALF * 16;
+        const int k = kBase + i;
+        v[i] = k < 25 ? sp[(k / 5) * SW + (k % 5)] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t off = (((uint32_t)(HALF * 4 + j)) ^ sw) << 4;
+        float l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l[e] = v[4 * j + e] - __uint_as_float(__float_as_uint(v[4 * j + e]) & 0xFFFFE000u);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row_hi + off), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row_lo + off), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+agx_conv2d_first_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmMean, const __grid_constant__ CUtensorMap tmRstd,
+                            const __grid_constant__ CUtensorMap tmY, const __grid_constant__ AgxConvFirstParams P, const __grid_constant__ FirstGeom Gm) {
+    __shared__ __align__(8) uint64_t sfull[4], sempty[4], aready[4], aempty[4], accfull[2], accempty[2];
+    __shared__ uint32_t tmem_base;
+    __shared__ __align__(16) float s_bias[COUT], s_scale[COUT], s_shift[COUT];
+    constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);  // SWIZZLE_128B K-major, 8-row groups 1024 bytes apart
+    constexpr uint32_t kABytes = kM * 128, kBBytes = COUT * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (s32(t_smem) + 1023u) & ~1023u;
+    // [B_hi | B_lo | staging | A ring (hi, lo per stage) | strip ring (image, mean, rstd per stage)]
+    const uint32_t offB = smem0, offStg = offB + 2 * ((kBBytes + 1023u) & ~1023u), offA = offStg + Gm.stg_bytes, offS = offA + (uint32_t)Gm.astages * 2u * kABytes;
+    const uint32_t strip_stage = (uint32_t)Gm.strip_bytes * (Gm.norm ? 3u : 1u);
+    const int SS = Gm.sstages, AS = Gm.astages;
+
+    if (tid == 0) {
+        for (int i = 0; i < SS; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 8); }
+        for (int i = 0; i < AS; ++i) { mbar_init(&aready[i], 8); mbar_init(&aempty[i], 1); }
+        mbar_init(&accfull[0], 1); mbar_init(&accfull[1], 1); mbar_init(&accempty[0], 4); mbar_init(&accempty[1], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    }
+    if (tid < COUT) {
+        s_bias[tid] = P.bias ? P.bias[tid] : 0.0f;
+        s_scale[tid] = P.scale ? P.scale[tid] : 1.0f;
+        s_shift[tid] = P.shift ? P.shift[tid] : 0.0f;
+    }
+    // resident weights: row o = [w[o][0..24], 0 x 7] as hi (tf32, round to nearest) + lo, SWIZZLE_128B rows
+    for (int i = tid; i < COUT * 32; i += kThreads) {
+        const int o = i >> 5, k = i & 31;
+        const float w = k < 25 ? P.w[o * 25 + k] : 0.0f;
+        const float hi = __uint_as_float((__float_as_uint(w) + 0x1000u) & 0xFFFFE000u);
+        const uint32_t off = (uint32_t)o * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)o & 7u)) << 4) + ((uint32_t)k & 3u) * 4u;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(offB + off), "f"(hi) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(offB + ((kBBytes + 1023u) & ~1023u) + off), "f"(w - hi) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"((uint32_t)(2 * COUT)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+
+    if (warp == 0) {  // ---- TMA producer: the input strip of each tile (+ the mean / rstd strips)
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x) {
+            const int n = tile / Gm.tiles_per_img, oy0 = (tile - n * Gm.tiles_per_img) * Gm.R;
+            mbar_wait(&sempty[stage], ph ^ 1u);
+            if (elect_one()) {
+                const uint32_t dst = offS + (uint32_t)stage * strip_stage;
+                mbar_expect_tx(&sfull[stage], (uint32_t)(Gm.SR * Gm.SW * 4) * (Gm.norm ? 3u : 1u));
+                tma_tile_3d(dst, &tmX, &sfull[stage], -4, oy0 * 2 - P.py, n);
+                if (Gm.norm) {
+                    tma_tile_2d(dst + (uint32_t)Gm.strip_bytes, &tmMean, &sfull[stage], -4, oy0 * 2 - P.py);
+                    tma_tile_2d(dst + 2u * (uint32_t)Gm.strip_bytes, &tmRstd, &sfull[stage], -4, oy0 * 2 - P.py);
+                }
+            }
+            __syncwarp();
+            if (++stage == SS) { stage = 0; ph ^= 1u; }
+        }
+    } else if (warp == 1) {  // ---- MMA issuer
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+        const uint32_t bh = (offB >> 4) | 0x10000u, bl = ((offB + ((kBBytes + 1023u) & ~1023u)) >> 4) | 0x10000u;
+        int stage = 0;
+        uint32_t ph = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            mbar_wait(&accempty[buf], ((lt >> 1) & 1u) ^ 1u);
+            mbar_wait(&aready[stage], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t d = tmem + buf * (uint32_t)COUT;
+                const uint32_t ah = ((offA + (uint32_t)stage * 2u * kABytes) >> 4) | 0x10000u, al = ah + (kABytes >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_tf32(d, ((uint64_t)kDescHi << 32) | (ah + 2u * ks), ((uint64_t)kDescHi << 32) | (bh + 2u * ks), idesc, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_tf32(d, ((uint64_t)kDescHi << 32) | (al + 2u * ks), ((uint64_t)kDescHi << 32) | (bh + 2u * ks), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) mma_tf32(d, ((uint64_t)kDescHi << 32) | (ah + 2u * ks), ((uint64_t)kDescHi << 32) | (bl + 2u * ks), idesc, 1u);
+                commit(&aempty[stage]);
+                commit(&accfull[buf]);
+            }
+            __syncwarp();
+            if (++stage == AS) { stage = 0; ph ^= 1u; }
+        }
+    } else if (warp >= 8) {  // ---- builders: normalise the strip in place, then one 128-byte operand row (hi, lo) per output pixel
+        const int bt = tid - 256, r = bt & 127;
+        const int ry = r / P.Wo, rx = r - ry * P.Wo;
+        const bool rvalid = r < Gm.rows_px;
+        const uint32_t sw = (uint32_t)(r & 7);
+        int sstage = 0, astage = 0;
+        uint32_t sph = 0, aph = 0;
+        const int strip_n = Gm.SR * Gm.SW;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x) {
+            float* strip = reinterpret_cast<float*>(t_smem + (offS - s32(t_smem)) + (size_t)sstage * strip_stage);
+            mbar_wait(&sfull[sstage], sph);
+            if (Gm.norm) {  // RunningMeanStd forward: clamp((x - mean) * rstd, +-5) — the expression of the direct kernel
+                const float* mean = strip + Gm.strip_bytes / 4;
+                const float* rstd = mean + Gm.strip_bytes / 4;
+                for (int i = bt; i < strip_n; i += 256) strip[i] = fminf(fmaxf((strip[i] - mean[i]) * rstd[i], -5.0f), 5.0f);
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+            mbar_wait(&aempty[astage], aph ^ 1u);
+            if (rvalid) {
+                const uint32_t row_hi = offA + (uint32_t)astage * 2u * kABytes + (uint32_t)r * 128u;
+                const float* sp = strip + (ry * 2) * Gm.SW + rx * 2 + (4 - P.px);  // the strip starts at input column -4
+                if (bt < 128) build_row<0>(sp, Gm.SW, row_hi, row_hi + kABytes, sw);
+                else build_row<1>(sp, Gm.SW, row_hi, row_hi + kABytes, sw);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&aready[astage]); mbar_arrive(&sempty[sstage]); }
+            if (++sstage == SS) { sstage = 0; sph ^= 1u; }
+            if (++astage == AS) { astage = 0; aph ^= 1u; }
+        }
+    } else if (warp >= 4) {  // ---- epilogue
+        const int q = warp - 4, rr = 32 * q + lane;
+        const bool affine = P.scale != nullptr;
+        // staging rows of COUT * 4 bytes: SWIZZLE_64B (chunk ^ ((row >> 1) & 3)) for 16 channels, SWIZZLE_128B (chunk ^ (row & 7)) for 32
+        const uint32_t stg_row = offStg + (uint32_t)rr * (uint32_t)(COUT * 4), sw = COUT == 16 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)(rr & 7);
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < Gm.num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            mbar_wait(&accfull[buf], (lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + buf * (uint32_t)COUT;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+                    float4 a = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+                    if (P.act == 1) {
+                        a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f);
+                    } else if (P.act == 2) {
+                        a.x = a.x > 0.0f ? a.x : expm1f(a.x); a.y = a.y > 0.0f ? a.y : expm1f(a.y);
+                        a.z = a.z > 0.0f ? a.z : expm1f(a.z); a.w = a.w > 0.0f ? a.w : expm1f(a.w);
+                    }
+                    if (affine) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + i), sh = *reinterpret_cast<const float4*>(s_shift + c0 + i);
+                        a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+                    }
+                    const uint32_t chunk = (uint32_t)((c0 + i) >> 2);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stg_row + ((chunk ^ sw) << 4)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accempty[buf]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 128) {
+                const int n = tile / Gm.tiles_per_img, oy0 = (tile - n * Gm.tiles_per_img) * Gm.R;
+                tma_store_2d(&tmY, offStg, 0, (n * P.Ho + oy0) * P.Wo);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (tid == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * COUT)) : "memory");
+}
+
 // ---- host side: tensor maps through the driver entry points (no libcuda link dependency) ---------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -440,6 +655,75 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (KS == 16) return split ? launch<16, true>(tmA, tmBhi, tmBlo, tmY, p, G, smem, st) : launch<16, false>(tmA, tmBhi, tmBhi, tmY, p, G, smem, st);
     return split ? launch<32, true>(tmA, tmBhi, tmBlo, tmY, p, G, smem, st) : launch<32, false>(tmA, tmBhi, tmBhi, tmY, p, G, smem, st);
+}
+
+// first layer: returns 1 when launched here, 0 when the geometry belongs to the direct kernel of agx_conv.cu, < 0 on error
+int agx_internal_conv_first_tma(const AgxConvFirstParams* p, void* stream) {
+    if (!g_conv_impl) return 0;
+    if (p->kh != 5 || p->kw != 5 || p->sy != 2 || p->sx != 2 || (p->Cout != 16 && p->Cout != 32) || p->Wo > kM || p->Wo <= 0 || (p->W & 3) || p->px > 4 || p->py > 8) return 0;
+    if ((int64_t)p->N * p->Ho * p->Wo > 0x7FFFFFFF) return 0;
+    if (((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 15u) return 0;
+    if (!lookup_entry_points()) return 0;
+    FirstGeom G;
+    memset(&G, 0, sizeof(G));
+    G.R = 1;
+    for (int r = kM / p->Wo; r >= 1; --r)
+        if (p->Ho % r == 0) { G.R = r; break; }  // whole output rows per tile, a divisor of Ho: the stored box never crosses into the next image
+    G.rows_px = G.R * p->Wo;
+    G.tiles_per_img = p->Ho / G.R;
+    if ((int64_t)p->N * G.tiles_per_img > 0x7FFFFFFF) return 0;
+    G.num_tiles = p->N * G.tiles_per_img;
+    G.SR = (G.R - 1) * 2 + 5;
+    G.SW = (((p->Wo - 1) * 2 + 5 + (4 - p->px)) + 3) & ~3;  // from input column -4: the inner start coordinate of a TMA tile load must be 16-byte aligned
+    if (G.SW > 256 || G.SR > 256) return 0;
+    G.strip_bytes = (G.SR * G.SW * 4 + 127) & ~127;
+    G.norm = p->px_mean != nullptr;
+    G.stg_bytes = (uint32_t)kM * p->Cout * 4;
+    G.astages = 3;
+    G.sstages = 4;
+    const size_t smem = 1024 + 2 * (((size_t)p->Cout * 128 + 1023) & ~(size_t)1023) + G.stg_bytes + (size_t)G.astages * 2 * kM * 128 +
+                        (size_t)G.sstages * G.strip_bytes * (G.norm ? 3 : 1);
+    if (smem > 222 * 1024) return 0;
+    CUtensorMap tmX, tmMean, tmRstd, tmY;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
+        const cuuint64_t strides[2] = {(cuuint64_t)p->W * 4, (cuuint64_t)p->H * p->W * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)G.SW, (cuuint32_t)G.SR, 1}, estr[3] = {1, 1, 1};
+        if (g_encode_tiled(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p->x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 0;
+    }
+    tmMean = tmX;
+    tmRstd = tmX;
+    if (G.norm) {
+        const cuuint64_t dims[2] = {(cuuint64_t)p->W, (cuuint64_t)p->H};
+        const cuuint64_t strides[1] = {(cuuint64_t)p->W * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)G.SW, (cuuint32_t)G.SR}, estr[2] = {1, 1};
+        for (int part = 0; part < 2; ++part)
+            if (g_encode_tiled(part ? &tmRstd : &tmMean, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(part ? p->px_rstd : p->px_mean), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return 0;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)p->N * p->Ho * p->Wo};
+        const cuuint64_t strides[1] = {(cuuint64_t)p->Cout * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)p->Cout, (cuuint32_t)G.rows_px}, estr[2] = {1, 1};
+        if (g_encode_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           p->Cout == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return 0;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(agx_conv2d_first_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(agx_conv2d_first_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
+        attr_set = true;
+    }
+    const int grid = G.num_tiles < g_sm_count ? G.num_tiles : g_sm_count;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->Cout == 16) agx_conv2d_first_tma_kernel<16><<<grid, kThreads, smem, st>>>(tmX, tmMean, tmRstd, tmY, *p, G);
+    else agx_conv2d_first_tma_kernel<32><<<grid, kThreads, smem, st>>>(tmX, tmMean, tmRstd, tmY, *p, G);
+    return cudaGetLastError() == cudaSuccess ? 1 : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first (tma): launch failed");
 }
 
 }  // extern "C"

@@ -74,17 +74,29 @@ def test_conv_layer_vs_float64(built, g, precise, impl):
 
 
 @pytest.mark.parametrize("Cout,k,s,p,H,W", [(16, 5, 2, 2, 212, 120), (32, 5, 2, 2, 120, 212)])
-def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W):
+@pytest.mark.parametrize("impl", [1, 0], ids=["tensor-core", "direct"])
+@pytest.mark.parametrize("norm", [True, False])
+def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W, impl, norm):
+    """impl 1: operand rows built from a TMA-loaded strip, tcgen05 3xTF32 (csrc/agx_conv_tma.cu); impl 0: the direct fp32 kernel."""
     torch.manual_seed(1)
+    lib = _capi.load()
     conv = nn.Conv2d(1, Cout, k, stride=s, padding=p).cuda()
     img = torch.rand(9, H, W, device="cuda") * 10
     mean, rstd = torch.rand(H * W, device="cuda") * 5, torch.rand(H * W, device="cuda") + 0.2
-    y = T.conv2d_first(img, conv, _capi.ACT_RELU, mean, rstd)
-    xn = torch.clamp((img - mean.view(H, W)) * rstd.view(H, W), -5, 5)
-    ref = torch.relu(F.conv2d(xn.unsqueeze(1).double(), conv.weight.double(), conv.bias.double(), stride=s, padding=p))
-    assert float((y.permute(0, 3, 1, 2).double() - ref).abs().max()) < 2e-5
+    scale, shift = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
+    _capi.check(lib.agx_set_option(b"conv_impl", impl), "conv_impl")
+    try:
+        y = T.conv2d_first(img, conv, _capi.ACT_RELU, mean if norm else None, rstd if norm else None, scale, shift)
+        torch.cuda.synchronize()
+    finally:
+        lib.agx_set_option(b"conv_impl", 1)
+    xn = torch.clamp((img - mean.view(H, W)) * rstd.view(H, W), -5, 5) if norm else img
+    with torch.no_grad():
+        ref = torch.relu(F.conv2d(xn.unsqueeze(1).double(), conv.weight.double(), conv.bias.double(), stride=s, padding=p))
+        ref = ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    assert float((y.permute(0, 3, 1, 2).double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
     out = torch.empty(9, W, H, device="cuda")
-    _capi.check(_capi.load().agx_resize_bilinear(img.data_ptr(), out.data_ptr(), 9, H, W, W, H, None))
+    _capi.check(lib.agx_resize_bilinear(img.data_ptr(), out.data_ptr(), 9, H, W, W, H, None))
     ref = F.interpolate(img.unsqueeze(1), (W, H), mode="bilinear", align_corners=False).squeeze(1)
     assert float((out - ref).abs().max()) < 5e-5 * float(ref.abs().max())  # torch's GPU kernel interpolates with a different association
 
