@@ -30,6 +30,8 @@ int agx_internal_fail(int code, const char* msg);
 extern "C" int agx_internal_conv_first_tma(const AgxConvFirstParams* p, void* stream);  // same contract, first layer
 extern "C" int agx_internal_conv_tma(const AgxConvParams* p, void* stream);  // agx_conv_tma.cu: 1 launched, 0 not its geometry, < 0 error
 
+int g_first_impl = 1;  // agx_set_option("conv_first", 0 generic direct kernel | 1 unrolled constant-bank kernel for 5x5 / stride 2 (default) | 2 tcgen05)
+
 namespace {
 
 extern __shared__ __align__(128) float c_smem[];
@@ -248,6 +250,73 @@ agx_conv2d_first_kernel(const __grid_constant__ AgxConvFirstParams P) {
     }
 }
 
+// ---- first layer, 5x5 / stride 2 (both encoders): fully unrolled direct convolution with the weights in the constant bank ---------
+// The generic kernel above spends ~700 instructions per output pixel at IPC 1.2: run-time tap loops with bounds branches, one
+// dependent load per tap, four shared-memory weight reads per 16 FMAs.  Here the 25 taps are loaded up front (predicated, zero
+// outside the image: the convolution pads the NORMALISED image), and every FMA takes its weight as a constant-bank operand
+// (c[bank][imm] after unrolling: no load instruction, no register), so a pixel costs 25 loads + 25 * COUT FMAs + the epilogue.
+// Same tap order and fmaf chain as the generic kernel: results are bit-identical to it.  The weights reach the constant bank by a
+// stream-ordered device-to-device copy (cudaMemcpyToSymbolAsync; a memcpy node under graph capture), one slot per Cout.
+__constant__ float c_first[2][32 * 25 + 3 * 32];  // slot 0: Cout = 16, slot 1: Cout = 32 — [tap][Cout] weights | bias | scale | shift
+
+__global__ void agx_first_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                                      float* __restrict__ out, int cout) {
+    for (int i = threadIdx.x; i < 25 * cout; i += blockDim.x) { const int t = i / cout, c = i - t * cout; out[i] = w[c * 25 + t]; }
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+        out[25 * cout + i] = bias ? bias[i] : 0.0f;
+        out[26 * cout + i] = scale ? scale[i] : 1.0f;
+        out[27 * cout + i] = shift ? shift[i] : 0.0f;
+    }
+}
+
+template <int COUT, bool NORM>
+__global__ void __launch_bounds__(128)
+agx_conv2d_first5_kernel(const __grid_constant__ AgxConvFirstParams P) {
+    constexpr int SLOT = COUT == 16 ? 0 : 1;
+    const int64_t M_total = (int64_t)P.N * P.Ho * P.Wo;
+    const int HoWo = P.Ho * P.Wo;
+    for (int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x; p < M_total; p += (int64_t)gridDim.x * 128) {
+        const int n = (int)(p / HoWo), rem = (int)(p - (int64_t)n * HoWo), oy = rem / P.Wo, ox = rem - oy * P.Wo;
+        const float* img = P.x + (int64_t)n * P.H * P.W;
+        const int iy0 = oy * 2 - P.py, ix0 = ox * 2 - P.px;
+        float v[25];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int iy = iy0 + ky;
+            const bool rok = (unsigned)iy < (unsigned)P.H;
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ix = ix0 + kx;
+                const bool ok = rok && (unsigned)ix < (unsigned)P.W;
+                const int off = ok ? iy * P.W + ix : 0;
+                float t = __ldg(img + off);
+                if (NORM) t = fminf(fmaxf((t - __ldg(P.px_mean + off)) * __ldg(P.px_rstd + off), -5.0f), 5.0f);
+                v[ky * 5 + kx] = ok ? t : 0.0f;
+            }
+        }
+        float acc[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = c_first[SLOT][25 * COUT + c];
+#pragma unroll
+        for (int t = 0; t < 25; ++t)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v[t], c_first[SLOT][t * COUT + c], acc[c]);
+        float* y = P.y + p * COUT;
+#pragma unroll
+        for (int c = 0; c < COUT; c += 4) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = acc[c + i];
+                if (P.act == 1) a = fmaxf(a, 0.0f);
+                else if (P.act == 2) a = a > 0.0f ? a : expm1f(a);
+                o[i] = a * c_first[SLOT][26 * COUT + c + i] + c_first[SLOT][27 * COUT + c + i];
+            }
+            *reinterpret_cast<float4*>(y + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 __global__ void agx_resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int H, int W, int Ho, int Wo) {
     const int64_t total = n * Ho * Wo;
     const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
@@ -334,14 +403,27 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
         p->act < 0 || p->act > 2 || p->sy <= 0 || p->sx <= 0)
         return agx_internal_fail(AGX_ERR_ARG, "agx_conv2d_first: bad argument");
     if ((uintptr_t)p->y & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_conv2d_first: output must be 16-byte aligned");
-    {   // 5x5 / stride-2 layers go to the tensor-core kernel (agx_conv_tma.cu)
-        const int r = agx_internal_conv_first_tma(p, stream);
-        if (r) return r > 0 ? AGX_OK : r;
-    }
     const int64_t M_total = (int64_t)p->N * p->Ho * p->Wo;
     int64_t grid = (M_total + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool five = p->kh == 5 && p->kw == 5 && p->sy == 2 && p->sx == 2 && (p->Cout == 16 || p->Cout == 32);
+    if (five && g_first_impl == 2) {  // operand rows built from a TMA strip, tcgen05 (agx_conv_tma.cu): measured no faster than the generic kernel
+        const int r = agx_internal_conv_first_tma(p, stream);
+        if (r) return r > 0 ? AGX_OK : r;
+    }
+    if (five && g_first_impl >= 1) {
+        static float* pack[2] = {nullptr, nullptr};  // staging for the constant-bank image, one per slot (stream order serialises its reuse)
+        const int slot = p->Cout == 16 ? 0 : 1, nfl = 28 * p->Cout;
+        if (!pack[slot] && cudaMalloc(&pack[slot], sizeof(float) * (32 * 25 + 3 * 32)) != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: cudaMalloc failed");
+        agx_first_pack_kernel<<<1, 128, 0, st>>>(p->w, p->bias, p->scale, p->shift, pack[slot], p->Cout);
+        if (cudaMemcpyToSymbolAsync(c_first, pack[slot], sizeof(float) * nfl, sizeof(float) * slot * (32 * 25 + 3 * 32), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: constant-bank copy failed");
+        const unsigned g = (unsigned)grid;
+        if (p->Cout == 16) { if (p->px_mean) agx_conv2d_first5_kernel<16, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5_kernel<16, false><<<g, 128, 0, st>>>(*p); }
+        else { if (p->px_mean) agx_conv2d_first5_kernel<32, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5_kernel<32, false><<<g, 128, 0, st>>>(*p); }
+        return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: launch failed");
+    }
     if (p->Cout == 16) agx_conv2d_first_kernel<16><<<(unsigned)grid, 128, 0, st>>>(*p);
     else if (p->Cout == 32) agx_conv2d_first_kernel<32><<<(unsigned)grid, 128, 0, st>>>(*p);
     else return agx_internal_fail(AGX_ERR_UNSUPPORTED, "agx_conv2d_first: Cout must be 16 or 32");

@@ -26,6 +26,7 @@
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
+extern int g_first_impl;  // agx_conv.cu
 
 namespace {
 using namespace tc;
@@ -575,6 +576,11 @@ int agx_internal_conv_option(const char* key, int value) {
         g_conv_impl = value;
         return 1;
     }
+    if (!strcmp(key, "conv_first")) {
+        if (value < 0 || value > 2) return -1;
+        g_first_impl = value;
+        return 1;
+    }
     if (!strcmp(key, "conv_spp")) {
         if (value < 0 || value > 4) return -1;
         g_conv_spp = value;
@@ -659,7 +665,6 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
 
 // first layer: returns 1 when launched here, 0 when the geometry belongs to the direct kernel of agx_conv.cu, < 0 on error
 int agx_internal_conv_first_tma(const AgxConvFirstParams* p, void* stream) {
-    if (!g_conv_impl) return 0;
     if (p->kh != 5 || p->kw != 5 || p->sy != 2 || p->sx != 2 || (p->Cout != 16 && p->Cout != 32) || p->Wo > kM || p->Wo <= 0 || (p->W & 3) || p->px > 4 || p->py > 8) return 0;
     if ((int64_t)p->N * p->Ho * p->Wo > 0x7FFFFFFF) return 0;
     if (((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 15u) return 0;

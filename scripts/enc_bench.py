@@ -60,13 +60,17 @@ if __name__ == "__main__":
             "conv2_cp_async": timed(lambda: T.conv2d_nhwc(a1, W_["c2"], K.ACT_RELU, scale=W_["s2"], shift=W_["t2"])),
             "conv3_cp_async": timed(lambda: T.conv2d_nhwc(a2, W_["c3"], K.ACT_RELU, scale=W_["s3"], shift=W_["t3"]))}
         lib_.agx_set_option(b"conv_impl", 1)
+        for mode, nm in ((2, "tcgen05"), (1, "const_bank")):
+            lib_.agx_set_option(b"conv_first", mode)
+            out.setdefault("conv1_ms_per_2048", {})[nm] = timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"]))
+            out["conv1_ms_per_2048"][nm + "_fused_norm"] = timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, mean, rstd, W_["s1"], W_["t1"]))
         a3 = T.conv2d_nhwc(a2, W_["c3"], K.ACT_RELU, scale=W_["s3"], shift=W_["t3"])
         fo = torch.empty(a3.shape[0], 30, device="cuda")
         out["pool_fc_ms_per_2048"] = timed(lambda: lib_.agx_pool_fc(a3.data_ptr(), a3.shape[0], a3.shape[1] * a3.shape[2], a3.shape[3], W_["wfc"].data_ptr(),
                                                                      W_["bfc"].data_ptr(), 30, fo.data_ptr(), 30, None))
         out["tc_layers_ms_per_2048"] = {
-            "conv1_tcgen05": timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"])),
-            "conv1_tcgen05_fused_norm": timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, mean, rstd, W_["s1"], W_["t1"])),
+            "conv1": timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"])),
+            "conv1_fused_norm": timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, mean, rstd, W_["s1"], W_["t1"])),
             "conv2_tcgen05": timed(lambda: T.conv2d_nhwc(a1, W_["c2"], K.ACT_RELU, scale=W_["s2"], shift=W_["t2"])),
             "conv3_tcgen05": timed(lambda: T.conv2d_nhwc(a2, W_["c3"], K.ACT_RELU, scale=W_["s3"], shift=W_["t3"]))}
         # the VAE ImgEncoder: libagx layers vs torch / cuDNN

@@ -74,22 +74,27 @@ def test_conv_layer_vs_float64(built, g, precise, impl):
 
 
 @pytest.mark.parametrize("Cout,k,s,p,H,W", [(16, 5, 2, 2, 212, 120), (32, 5, 2, 2, 120, 212)])
-@pytest.mark.parametrize("impl", [1, 0], ids=["tensor-core", "direct"])
+@pytest.mark.parametrize("impl", [1, 2, 0], ids=["const-bank", "tensor-core", "generic"])
 @pytest.mark.parametrize("norm", [True, False])
 def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W, impl, norm):
-    """impl 1: operand rows built from a TMA-loaded strip, tcgen05 3xTF32 (csrc/agx_conv_tma.cu); impl 0: the direct fp32 kernel."""
+    """conv_first 1 (default): unrolled direct kernel with constant-bank weights; 2: operand rows built from a TMA-loaded strip,
+    tcgen05 3xTF32 (csrc/agx_conv_tma.cu); 0: the generic direct fp32 kernel — 1 and 0 must agree bit for bit (same fmaf chain)."""
     torch.manual_seed(1)
     lib = _capi.load()
     conv = nn.Conv2d(1, Cout, k, stride=s, padding=p).cuda()
     img = torch.rand(9, H, W, device="cuda") * 10
     mean, rstd = torch.rand(H * W, device="cuda") * 5, torch.rand(H * W, device="cuda") + 0.2
     scale, shift = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
-    _capi.check(lib.agx_set_option(b"conv_impl", impl), "conv_impl")
+    _capi.check(lib.agx_set_option(b"conv_first", impl), "conv_first")
     try:
         y = T.conv2d_first(img, conv, _capi.ACT_RELU, mean if norm else None, rstd if norm else None, scale, shift)
         torch.cuda.synchronize()
+        if impl == 1:
+            lib.agx_set_option(b"conv_first", 0)
+            y0 = T.conv2d_first(img, conv, _capi.ACT_RELU, mean if norm else None, rstd if norm else None, scale, shift)
+            assert torch.equal(y, y0)
     finally:
-        lib.agx_set_option(b"conv_impl", 1)
+        lib.agx_set_option(b"conv_first", 1)
     xn = torch.clamp((img - mean.view(H, W)) * rstd.view(H, W), -5, 5) if norm else img
     with torch.no_grad():
         ref = torch.relu(F.conv2d(xn.unsqueeze(1).double(), conv.weight.double(), conv.bias.double(), stride=s, padding=p))
