@@ -30,7 +30,7 @@ int agx_internal_fail(int code, const char* msg);
 extern "C" int agx_internal_conv_first_tma(const AgxConvFirstParams* p, void* stream);  // same contract, first layer
 extern "C" int agx_internal_conv_tma(const AgxConvParams* p, void* stream);  // agx_conv_tma.cu: 1 launched, 0 not its geometry, < 0 error
 
-int g_first_impl = 1;  // agx_set_option("conv_first", 0 generic direct kernel | 1 unrolled constant-bank kernel for 5x5 / stride 2 (default) | 2 tcgen05)
+int g_first_impl = 1;  // agx_set_option("conv_first", 0 generic direct kernel | 1 unrolled constant-bank kernel, two pixels per thread, for 5x5 / stride 2 (default) | 2 tcgen05 | 3 constant-bank kernel, one pixel per thread)
 
 namespace {
 
@@ -317,6 +317,76 @@ agx_conv2d_first5_kernel(const __grid_constant__ AgxConvFirstParams P) {
     }
 }
 
+// two horizontally adjacent output pixels per thread: the 5 x 7 input patch is shared (20 8-byte loads instead of 50 scalar ones), every
+// uniform weight load feeds two FMAs, and a thread stores 2 * COUT contiguous floats.  Same per-pixel fmaf chain as above.
+template <int COUT, bool NORM>
+__global__ void __launch_bounds__(128)
+agx_conv2d_first5x2_kernel(const __grid_constant__ AgxConvFirstParams P) {
+    constexpr int SLOT = COUT == 16 ? 0 : 1;
+    const int Wp = P.Wo >> 1;
+    const int64_t pairs = (int64_t)P.N * P.Ho * Wp;
+    for (int64_t q = (int64_t)blockIdx.x * 128 + threadIdx.x; q < pairs; q += (int64_t)gridDim.x * 128) {
+        const int64_t row = q / Wp;  // n * Ho + oy
+        const int j = (int)(q - row * Wp), n = (int)(row / P.Ho), oy = (int)(row - (int64_t)n * P.Ho);
+        const float* img = P.x + (int64_t)n * P.H * P.W;
+        const int iy0 = oy * 2 - P.py, ix0 = j * 4 - P.px;  // even: W and px are even, so a column pair is inside the image or outside as a whole
+        float v[5][7];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int iy = iy0 + ky;
+            const bool rok = (unsigned)iy < (unsigned)P.H;
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                const int ix = ix0 + 2 * c2;
+                const bool ok = rok && (unsigned)ix < (unsigned)P.W;
+                const int off = ok ? iy * P.W + ix : 0;
+                if (c2 < 3) {
+                    float2 t = __ldg(reinterpret_cast<const float2*>(img + off));
+                    if (NORM) {
+                        const float2 m = __ldg(reinterpret_cast<const float2*>(P.px_mean + off)), r = __ldg(reinterpret_cast<const float2*>(P.px_rstd + off));
+                        t.x = fminf(fmaxf((t.x - m.x) * r.x, -5.0f), 5.0f);
+                        t.y = fminf(fmaxf((t.y - m.y) * r.y, -5.0f), 5.0f);
+                    }
+                    v[ky][2 * c2] = ok ? t.x : 0.0f;
+                    v[ky][2 * c2 + 1] = ok ? t.y : 0.0f;
+                } else {
+                    float t = __ldg(img + off);
+                    if (NORM) t = fminf(fmaxf((t - __ldg(P.px_mean + off)) * __ldg(P.px_rstd + off), -5.0f), 5.0f);
+                    v[ky][6] = ok ? t : 0.0f;
+                }
+            }
+        }
+        float a0[COUT], a1[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) a0[c] = a1[c] = c_first[SLOT][25 * COUT + c];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    const float w = c_first[SLOT][(ky * 5 + kx) * COUT + c];
+                    a0[c] = fmaf(v[ky][kx], w, a0[c]);
+                    a1[c] = fmaf(v[ky][kx + 2], w, a1[c]);
+                }
+        float* y = P.y + (row * P.Wo + 2 * j) * COUT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < COUT; c += 4) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a = h ? a1[c + i] : a0[c + i];
+                    if (P.act == 1) a = fmaxf(a, 0.0f);
+                    else if (P.act == 2) a = a > 0.0f ? a : expm1f(a);
+                    o[i] = a * c_first[SLOT][26 * COUT + c + i] + c_first[SLOT][27 * COUT + c + i];
+                }
+                *reinterpret_cast<float4*>(y + h * COUT + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+    }
+}
+
 __global__ void agx_resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int H, int W, int Ho, int Wo) {
     const int64_t total = n * Ho * Wo;
     const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
@@ -419,6 +489,15 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
         agx_first_pack_kernel<<<1, 128, 0, st>>>(p->w, p->bias, p->scale, p->shift, pack[slot], p->Cout);
         if (cudaMemcpyToSymbolAsync(c_first, pack[slot], sizeof(float) * nfl, sizeof(float) * slot * (32 * 25 + 3 * 32), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: constant-bank copy failed");
+        const bool pair_ok = !(p->Wo & 1) && !(p->W & 1) && !(p->px & 1) && !(((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 7u);
+        if (pair_ok && g_first_impl == 1) {
+            int64_t g2 = (M_total / 2 + 127) / 128;
+            if (g2 > 148 * 16) g2 = 148 * 16;
+            const unsigned g = (unsigned)g2;
+            if (p->Cout == 16) { if (p->px_mean) agx_conv2d_first5x2_kernel<16, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5x2_kernel<16, false><<<g, 128, 0, st>>>(*p); }
+            else { if (p->px_mean) agx_conv2d_first5x2_kernel<32, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5x2_kernel<32, false><<<g, 128, 0, st>>>(*p); }
+            return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: launch failed");
+        }
         const unsigned g = (unsigned)grid;
         if (p->Cout == 16) { if (p->px_mean) agx_conv2d_first5_kernel<16, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5_kernel<16, false><<<g, 128, 0, st>>>(*p); }
         else { if (p->px_mean) agx_conv2d_first5_kernel<32, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5_kernel<32, false><<<g, 128, 0, st>>>(*p); }

@@ -79,6 +79,11 @@ __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* tm,
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
@@ -147,13 +152,13 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&empty[stage], ph ^ 1u);
                 const bool leader = elect_one();
                 const uint32_t base = ring0 + (uint32_t)stage * Gm.stage_bytes;
-                if (leader) mbar_expect_tx(&full[stage], (uint32_t)cnt * Gm.slab_tx);
+                if (leader) {  // the weight slabs of a fill arrive as one box [spp][Nt][KS] (slabs past the end zero-filled, bytes counted in full)
+                    mbar_expect_tx(&full[stage], (uint32_t)cnt * Gm.a_bytes + (SPLIT ? 2u : 1u) * (uint32_t)spp * Gm.b_bytes);
+                    tma_tile_3d(base + offBhi, &tmBhi, &full[stage], 0, 0, s);
+                    if (SPLIT) tma_tile_3d(base + offBlo, &tmBlo, &full[stage], 0, 0, s);
+                }
                 for (int u = 0; u < cnt; ++u, ++s) {
-                    if (leader) {
-                        tma_im2col_4d(base + (uint32_t)u * Gm.a_bytes, &tmA, &full[stage], cb * KS, w0, h0, n0, (uint16_t)kx, (uint16_t)ky);
-                        tma_tile_2d(base + offBhi + (uint32_t)u * Gm.b_bytes, &tmBhi, &full[stage], s * KS, 0);
-                        if (SPLIT) tma_tile_2d(base + offBlo + (uint32_t)u * Gm.b_bytes, &tmBlo, &full[stage], s * KS, 0);
-                    }
+                    if (leader) tma_im2col_4d(base + (uint32_t)u * Gm.a_bytes, &tmA, &full[stage], cb * KS, w0, h0, n0, (uint16_t)kx, (uint16_t)ky);
                     if (++cb == Gm.cblocks) { cb = 0; if (++kx == P.kw) { kx = 0; ++ky; } }
                 }
                 __syncwarp();
@@ -213,21 +218,28 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&full[stage], ph);
                 if (SPLIT) {
                     const uint32_t a = ring0 + (uint32_t)stage * Gm.stage_bytes + (uint32_t)ts * 16u;
-                    for (int u = 0; u < cnt; ++u) {
-                        const uint32_t au = a + (uint32_t)u * Gm.a_bytes;
-                        float4 v[kPer];
+                    float4 v[4][kPer];
 #pragma unroll
-                        for (int i = 0; i < kPer; ++i)
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(au + (uint32_t)i * 4096u));
+                    for (int u = 0; u < 4; ++u)
+                        if (u < cnt) {
 #pragma unroll
-                        for (int i = 0; i < kPer; ++i) {
-                            v[i].x -= __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-                            v[i].y -= __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-                            v[i].z -= __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-                            v[i].w -= __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(au + offAlo + (uint32_t)i * 4096u), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w) : "memory");
+                            for (int i = 0; i < kPer; ++i)
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u][i].x), "=f"(v[u][i].y), "=f"(v[u][i].z), "=f"(v[u][i].w)
+                                             : "r"(a + (uint32_t)u * Gm.a_bytes + (uint32_t)i * 4096u));
                         }
-                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u < cnt) {
+#pragma unroll
+                            for (int i = 0; i < kPer; ++i) {
+                                float4 l = v[u][i];
+                                l.x -= __uint_as_float(__float_as_uint(l.x) & 0xFFFFE000u);
+                                l.y -= __uint_as_float(__float_as_uint(l.y) & 0xFFFFE000u);
+                                l.z -= __uint_as_float(__float_as_uint(l.z) & 0xFFFFE000u);
+                                l.w -= __uint_as_float(__float_as_uint(l.w) & 0xFFFFE000u);
+                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + offAlo + (uint32_t)u * Gm.a_bytes + (uint32_t)i * 4096u), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w));
+                            }
+                        }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 }
                 __syncwarp();
@@ -258,6 +270,18 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + buf * (uint32_t)(Gm.G * Nt);
             for (int c0 = 0; c0 < Nt; c0 += 16) {
+                float4 cb[4], cs[4], ch[4];  // bias / scale / shift of this chunk: issued before the TMEM read so their latency hides under it
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cb[i] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);
+                    cs[i] = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * i);
+                    ch[i] = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * i);
+                }
+                float4 rv[4];
+                if (res) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(res + c0 + 4 * i));
+                }
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 for (int g = 1; g < chains; ++g) {
@@ -269,10 +293,10 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint32_t blk = stg_row + (uint32_t)(c0 >> 5) * (uint32_t)(kM * 128);  // staging tile of this 32-channel block
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+                    const float4 b = cb[i >> 2];
                     float4 a = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
                     if (res) {
-                        const float4 r = __ldg(reinterpret_cast<const float4*>(res + c0 + i));
+                        const float4 r = rv[i >> 2];
                         a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
                     }
                     if (P.act == 1) {
@@ -282,11 +306,11 @@ agx_conv2d_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         a.z = a.z > 0.0f ? a.z : expm1f(a.z); a.w = a.w > 0.0f ? a.w : expm1f(a.w);
                     }
                     if (affine) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + i), sh = *reinterpret_cast<const float4*>(s_shift + c0 + i);
+                        const float4 sc = cs[i >> 2], sh = ch[i >> 2];
                         a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
                     }
                     const uint32_t chunk = (uint32_t)(((c0 & 16) + i) >> 2);  // 16-byte chunk 0..7 of the 128-byte row; SWIZZLE_128B: chunk ^ (row & 7)
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(blk + ((chunk ^ sw) << 4)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(blk + ((chunk ^ sw) << 4)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w));
                 }
             }
             // the accumulator set is free as soon as it has been read
@@ -340,12 +364,6 @@ __device__ __forceinline__ void build_row(const float* sp, int SW, uint32_t row_
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row_hi + off), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row_lo + off), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
     }
-}
-
-__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
 }
 
 template <int COUT>
@@ -535,6 +553,7 @@ int g_entry_state = 0;  // 0 not looked up, 1 available, -1 unavailable
 int g_sm_count = 0;
 int g_conv_impl = 1;    // agx_set_option("conv_impl", 0 = cp.async gather kernel of agx_conv.cu | 1 = this kernel where the geometry allows)
 int g_conv_spp = 0;     // agx_set_option("conv_spp", 0 = automatic | 1..4 slabs per stage) — A/B knob
+int g_conv_stages = 0;  // agx_set_option("conv_stages", 0 = as many as fit | 2..8) — A/B knob
 
 bool lookup_entry_points() {
     if (g_entry_state) return g_entry_state > 0;
@@ -577,8 +596,13 @@ int agx_internal_conv_option(const char* key, int value) {
         return 1;
     }
     if (!strcmp(key, "conv_first")) {
-        if (value < 0 || value > 2) return -1;
+        if (value < 0 || value > 3) return -1;
         g_first_impl = value;
+        return 1;
+    }
+    if (!strcmp(key, "conv_stages")) {
+        if (value != 0 && (value < 2 || value > kMaxStages)) return -1;
+        g_conv_stages = value;
         return 1;
     }
     if (!strcmp(key, "conv_spp")) {
@@ -625,6 +649,7 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
     G.stage_bytes = (uint32_t)G.spp * slab_bytes;
     G.stages = (int)(budget / G.stage_bytes);
     if (G.stages > kMaxStages) G.stages = kMaxStages;
+    if (g_conv_stages && G.stages > g_conv_stages) G.stages = g_conv_stages;
     if (G.stages < 2) return 0;
     G.fills = (G.nslabs + G.spp - 1) / G.spp;
     const size_t smem = 1024 + (size_t)G.stg_bytes + (size_t)G.stages * G.stage_bytes;
@@ -642,11 +667,11 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return 0;  // geometry the TMA unit does not take: the gather kernel handles it
     }
-    for (int part = 0; part < (split ? 2 : 1); ++part) {
-        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
-        const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)KS, (cuuint32_t)G.Nt}, estr[2] = {1, 1};
-        const CUresult r = g_encode_tiled(part ? &tmBlo : &tmBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(part ? p->w_lo : p->w_hi), dims, strides,
+    for (int part = 0; part < (split ? 2 : 1); ++part) {  // weights [Cout][K] viewed as (KS, Cout, slab): a box = the slabs of one stage fill
+        const cuuint64_t dims[3] = {(cuuint64_t)KS, (cuuint64_t)p->Cout, (cuuint64_t)G.nslabs};
+        const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)KS * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)KS, (cuuint32_t)G.Nt, (cuuint32_t)G.spp}, estr[3] = {1, 1, 1};
+        const CUresult r = g_encode_tiled(part ? &tmBlo : &tmBhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(part ? p->w_lo : p->w_hi), dims, strides,
                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return 0;
     }

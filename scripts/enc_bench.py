@@ -60,7 +60,7 @@ if __name__ == "__main__":
             "conv2_cp_async": timed(lambda: T.conv2d_nhwc(a1, W_["c2"], K.ACT_RELU, scale=W_["s2"], shift=W_["t2"])),
             "conv3_cp_async": timed(lambda: T.conv2d_nhwc(a2, W_["c3"], K.ACT_RELU, scale=W_["s3"], shift=W_["t3"]))}
         lib_.agx_set_option(b"conv_impl", 1)
-        for mode, nm in ((2, "tcgen05"), (1, "const_bank")):
+        for mode, nm in ((2, "tcgen05"), (3, "const_bank_1px"), (1, "const_bank_2px")):
             lib_.agx_set_option(b"conv_first", mode)
             out.setdefault("conv1_ms_per_2048", {})[nm] = timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, None, None, W_["s1"], W_["t1"]))
             out["conv1_ms_per_2048"][nm + "_fused_norm"] = timed(lambda: T.conv2d_first(xc, net.features[0], K.ACT_RELU, mean, rstd, W_["s1"], W_["t1"]))

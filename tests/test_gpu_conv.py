@@ -74,11 +74,12 @@ def test_conv_layer_vs_float64(built, g, precise, impl):
 
 
 @pytest.mark.parametrize("Cout,k,s,p,H,W", [(16, 5, 2, 2, 212, 120), (32, 5, 2, 2, 120, 212)])
-@pytest.mark.parametrize("impl", [1, 2, 0], ids=["const-bank", "tensor-core", "generic"])
+@pytest.mark.parametrize("impl", [1, 3, 2, 0], ids=["const-bank-x2", "const-bank", "tensor-core", "generic"])
 @pytest.mark.parametrize("norm", [True, False])
 def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W, impl, norm):
-    """conv_first 1 (default): unrolled direct kernel with constant-bank weights; 2: operand rows built from a TMA-loaded strip,
-    tcgen05 3xTF32 (csrc/agx_conv_tma.cu); 0: the generic direct fp32 kernel — 1 and 0 must agree bit for bit (same fmaf chain)."""
+    """conv_first 1 (default): unrolled direct kernel with constant-bank weights, two pixels per thread; 3: one pixel per thread;
+    2: operand rows built from a TMA-loaded strip, tcgen05 3xTF32 (csrc/agx_conv_tma.cu); 0: the generic direct fp32 kernel —
+    1, 3 and 0 must agree bit for bit (same fmaf chain)."""
     torch.manual_seed(1)
     lib = _capi.load()
     conv = nn.Conv2d(1, Cout, k, stride=s, padding=p).cuda()
@@ -89,7 +90,7 @@ def test_first_layer_and_resize_vs_torch(built, Cout, k, s, p, H, W, impl, norm)
     try:
         y = T.conv2d_first(img, conv, _capi.ACT_RELU, mean if norm else None, rstd if norm else None, scale, shift)
         torch.cuda.synchronize()
-        if impl == 1:
+        if impl in (1, 3):
             lib.agx_set_option(b"conv_first", 0)
             y0 = T.conv2d_first(img, conv, _capi.ACT_RELU, mean if norm else None, rstd if norm else None, scale, shift)
             assert torch.equal(y, y0)
