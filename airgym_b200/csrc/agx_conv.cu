@@ -317,45 +317,51 @@ agx_conv2d_first5_kernel(const __grid_constant__ AgxConvFirstParams P) {
     }
 }
 
-// two horizontally adjacent output pixels per thread: the 5 x 7 input patch is shared (20 8-byte loads instead of 50 scalar ones), every
-// uniform weight load feeds two FMAs, and a thread stores 2 * COUT contiguous floats.  Same per-pixel fmaf chain as above.
+// two horizontally adjacent output pixels per thread, one output row (segment of 32 pixel pairs) per warp: each lane loads ONE aligned
+// float4 per input row (a warp reads the row as a single coalesced 512-byte request; ncu of the version with four overlapping 8-byte
+// loads per row: L1 70 % busy at 4 wavefronts per load) and takes the two columns to its left and the one to its right from its
+// neighbours by shuffle (the segment's edge lanes fetch theirs); every uniform weight load feeds two FMAs, and a thread stores
+// 2 * COUT contiguous floats.  Same per-pixel fmaf chain as above.  Needs W % 4 == 0, Wo even, pad 2.
 template <int COUT, bool NORM>
 __global__ void __launch_bounds__(128)
 agx_conv2d_first5x2_kernel(const __grid_constant__ AgxConvFirstParams P) {
     constexpr int SLOT = COUT == 16 ? 0 : 1;
-    const int Wp = P.Wo >> 1;
-    const int64_t pairs = (int64_t)P.N * P.Ho * Wp;
-    for (int64_t q = (int64_t)blockIdx.x * 128 + threadIdx.x; q < pairs; q += (int64_t)gridDim.x * 128) {
-        const int64_t row = q / Wp;  // n * Ho + oy
-        const int j = (int)(q - row * Wp), n = (int)(row / P.Ho), oy = (int)(row - (int64_t)n * P.Ho);
+    const int Wp = P.Wo >> 1, segs = (Wp + 31) >> 5, lane = threadIdx.x & 31;
+    const int64_t items = (int64_t)P.N * P.Ho * segs;
+    auto norm1 = [&](float t, int off) { return NORM ? fminf(fmaxf((t - __ldg(P.px_mean + off)) * __ldg(P.px_rstd + off), -5.0f), 5.0f) : t; };
+    for (int64_t it = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); it < items; it += (int64_t)gridDim.x * 4) {
+        const int64_t row = it / segs;  // n * Ho + oy
+        const int sg = (int)(it - row * segs), j = sg * 32 + lane, n = (int)(row / P.Ho), oy = (int)(row - (int64_t)n * P.Ho);
         const float* img = P.x + (int64_t)n * P.H * P.W;
-        const int iy0 = oy * 2 - P.py, ix0 = j * 4 - P.px;  // even: W and px are even, so a column pair is inside the image or outside as a whole
+        const int iy0 = oy * 2 - P.py, xa = 4 * j;  // this lane's aligned columns xa .. xa+3; its pixel pair reads columns xa-2 .. xa+4
         float v[5][7];
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
             const int iy = iy0 + ky;
-            const bool rok = (unsigned)iy < (unsigned)P.H;
-#pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {
-                const int ix = ix0 + 2 * c2;
-                const bool ok = rok && (unsigned)ix < (unsigned)P.W;
-                const int off = ok ? iy * P.W + ix : 0;
-                if (c2 < 3) {
-                    float2 t = __ldg(reinterpret_cast<const float2*>(img + off));
-                    if (NORM) {
-                        const float2 m = __ldg(reinterpret_cast<const float2*>(P.px_mean + off)), r = __ldg(reinterpret_cast<const float2*>(P.px_rstd + off));
-                        t.x = fminf(fmaxf((t.x - m.x) * r.x, -5.0f), 5.0f);
-                        t.y = fminf(fmaxf((t.y - m.y) * r.y, -5.0f), 5.0f);
-                    }
-                    v[ky][2 * c2] = ok ? t.x : 0.0f;
-                    v[ky][2 * c2 + 1] = ok ? t.y : 0.0f;
-                } else {
-                    float t = __ldg(img + off);
-                    if (NORM) t = fminf(fmaxf((t - __ldg(P.px_mean + off)) * __ldg(P.px_rstd + off), -5.0f), 5.0f);
-                    v[ky][6] = ok ? t : 0.0f;
-                }
+            const bool rok = (unsigned)iy < (unsigned)P.H, ok = rok && xa < P.W;
+            const int off = ok ? iy * P.W + xa : 0;
+            float4 t = __ldg(reinterpret_cast<const float4*>(img + off));
+            if (NORM) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(P.px_mean + off)), r = __ldg(reinterpret_cast<const float4*>(P.px_rstd + off));
+                t.x = fminf(fmaxf((t.x - m.x) * r.x, -5.0f), 5.0f); t.y = fminf(fmaxf((t.y - m.y) * r.y, -5.0f), 5.0f);
+                t.z = fminf(fmaxf((t.z - m.z) * r.z, -5.0f), 5.0f); t.w = fminf(fmaxf((t.w - m.w) * r.w, -5.0f), 5.0f);
             }
+            if (!ok) t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float l0 = __shfl_up_sync(0xFFFFFFFFu, t.z, 1), l1 = __shfl_up_sync(0xFFFFFFFFu, t.w, 1), r0 = __shfl_down_sync(0xFFFFFFFFu, t.x, 1);
+            if (lane == 0) {  // left neighbour lives in the previous segment (or is the zero padding)
+                const bool lok = rok && sg > 0;
+                const int lo = lok ? iy * P.W + xa - 2 : 0;
+                l0 = lok ? norm1(__ldg(img + lo), lo) : 0.0f;
+                l1 = lok ? norm1(__ldg(img + lo + 1), lo + 1) : 0.0f;
+            }
+            if (lane == 31) {
+                const bool rk = rok && xa + 4 < P.W;
+                const int ro = rk ? iy * P.W + xa + 4 : 0;
+                r0 = rk ? norm1(__ldg(img + ro), ro) : 0.0f;
+            }
+            v[ky][0] = l0; v[ky][1] = l1; v[ky][2] = t.x; v[ky][3] = t.y; v[ky][4] = t.z; v[ky][5] = t.w; v[ky][6] = r0;
         }
+        if (j >= Wp) continue;  // idle lanes of the row's last segment took part in the shuffles only
         float a0[COUT], a1[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) a0[c] = a1[c] = c_first[SLOT][25 * COUT + c];
@@ -489,9 +495,9 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
         agx_first_pack_kernel<<<1, 128, 0, st>>>(p->w, p->bias, p->scale, p->shift, pack[slot], p->Cout);
         if (cudaMemcpyToSymbolAsync(c_first, pack[slot], sizeof(float) * nfl, sizeof(float) * slot * (32 * 25 + 3 * 32), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: constant-bank copy failed");
-        const bool pair_ok = !(p->Wo & 1) && !(p->W & 1) && !(p->px & 1) && !(((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 7u);
+        const bool pair_ok = !(p->Wo & 1) && !(p->W & 3) && p->px == 2 && !(((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 15u);
         if (pair_ok && g_first_impl == 1) {
-            int64_t g2 = (M_total / 2 + 127) / 128;
+            int64_t g2 = ((int64_t)p->N * p->Ho * ((p->Wo / 2 + 31) / 32) + 3) / 4;  // one (row, 32-pair segment) per warp, 4 warps per block
             if (g2 > 148 * 16) g2 = 148 * 16;
             const unsigned g = (unsigned)g2;
             if (p->Cout == 16) { if (p->px_mean) agx_conv2d_first5x2_kernel<16, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5x2_kernel<16, false><<<g, 128, 0, st>>>(*p); }
