@@ -188,6 +188,7 @@ def bind(lib):
     lib.agx_conv2d_nhwc.argtypes = [C.POINTER(AgxConvParams), C.c_void_p]
     lib.agx_conv2d_first.argtypes = [C.POINTER(AgxConvFirstParams), C.c_void_p]
     lib.agx_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.agx_bn_train.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.agx_pool_fc.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.agx_sizeof_cnn_params.restype = C.c_int
     lib.agx_cnn_encode.argtypes = [C.POINTER(AgxCnnParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -213,7 +214,7 @@ EXPORTS = (
     "agx_params_default", "agx_step", "agx_observe", "agx_reset_idx", "agx_philox_fill", "agx_gae", "agx_ppo_workspace_floats",
     "agx_ppo_loss", "agx_adam_step", "agx_mlp_forward", "agx_mlp_workspace_floats", "agx_mlp_backward",
     "agx_sizeof_cnn_params", "agx_cnn_encode",
-    "agx_sizeof_conv_params", "agx_conv2d_nhwc", "agx_sizeof_conv_first_params", "agx_conv2d_first", "agx_resize_bilinear", "agx_pool_fc",
+    "agx_sizeof_conv_params", "agx_conv2d_nhwc", "agx_sizeof_conv_first_params", "agx_conv2d_first", "agx_resize_bilinear", "agx_pool_fc", "agx_bn_train",
     "agx_col_sums_workspace_doubles", "agx_col_sums", "agx_rms_merge",
     "agx_sizeof_policy_io", "agx_policy_step", "agx_sizeof_post_io", "agx_rollout_post", "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
     "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",

@@ -393,6 +393,78 @@ agx_conv2d_first5x2_kernel(const __grid_constant__ AgxConvFirstParams P) {
     }
 }
 
+// flattened variant (pixel pairs numbered across rows, no shuffles): keeps every lane busy when a row's pair count is far from a multiple
+// of 32 (the VAE's 53 pairs per row), at four overlapping 8-byte loads per input row — used without the fused normalisation only.
+// Two horizontally adjacent output pixels per thread: the 5 x 7 input patch is shared (20 8-byte loads instead of 50 scalar ones), every
+// uniform weight load feeds two FMAs, and a thread stores 2 * COUT contiguous floats.  Same per-pixel fmaf chain as above.
+template <int COUT, bool NORM>
+__global__ void __launch_bounds__(128)
+agx_conv2d_first5x2_flat_kernel(const __grid_constant__ AgxConvFirstParams P) {
+    constexpr int SLOT = COUT == 16 ? 0 : 1;
+    const int Wp = P.Wo >> 1;
+    const int64_t pairs = (int64_t)P.N * P.Ho * Wp;
+    for (int64_t q = (int64_t)blockIdx.x * 128 + threadIdx.x; q < pairs; q += (int64_t)gridDim.x * 128) {
+        const int64_t row = q / Wp;  // n * Ho + oy
+        const int j = (int)(q - row * Wp), n = (int)(row / P.Ho), oy = (int)(row - (int64_t)n * P.Ho);
+        const float* img = P.x + (int64_t)n * P.H * P.W;
+        const int iy0 = oy * 2 - P.py, ix0 = j * 4 - P.px;  // even: W and px are even, so a column pair is inside the image or outside as a whole
+        float v[5][7];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int iy = iy0 + ky;
+            const bool rok = (unsigned)iy < (unsigned)P.H;
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                const int ix = ix0 + 2 * c2;
+                const bool ok = rok && (unsigned)ix < (unsigned)P.W;
+                const int off = ok ? iy * P.W + ix : 0;
+                if (c2 < 3) {
+                    float2 t = __ldg(reinterpret_cast<const float2*>(img + off));
+                    if (NORM) {
+                        const float2 m = __ldg(reinterpret_cast<const float2*>(P.px_mean + off)), r = __ldg(reinterpret_cast<const float2*>(P.px_rstd + off));
+                        t.x = fminf(fmaxf((t.x - m.x) * r.x, -5.0f), 5.0f);
+                        t.y = fminf(fmaxf((t.y - m.y) * r.y, -5.0f), 5.0f);
+                    }
+                    v[ky][2 * c2] = ok ? t.x : 0.0f;
+                    v[ky][2 * c2 + 1] = ok ? t.y : 0.0f;
+                } else {
+                    float t = __ldg(img + off);
+                    if (NORM) t = fminf(fmaxf((t - __ldg(P.px_mean + off)) * __ldg(P.px_rstd + off), -5.0f), 5.0f);
+                    v[ky][6] = ok ? t : 0.0f;
+                }
+            }
+        }
+        float a0[COUT], a1[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) a0[c] = a1[c] = c_first[SLOT][25 * COUT + c];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    const float w = c_first[SLOT][(ky * 5 + kx) * COUT + c];
+                    a0[c] = fmaf(v[ky][kx], w, a0[c]);
+                    a1[c] = fmaf(v[ky][kx + 2], w, a1[c]);
+                }
+        float* y = P.y + (row * P.Wo + 2 * j) * COUT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < COUT; c += 4) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a = h ? a1[c + i] : a0[c + i];
+                    if (P.act == 1) a = fmaxf(a, 0.0f);
+                    else if (P.act == 2) a = a > 0.0f ? a : expm1f(a);
+                    o[i] = a * c_first[SLOT][26 * COUT + c + i] + c_first[SLOT][27 * COUT + c + i];
+                }
+                *reinterpret_cast<float4*>(y + h * COUT + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+    }
+}
+
 __global__ void agx_resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int H, int W, int Ho, int Wo) {
     const int64_t total = n * Ho * Wo;
     const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
@@ -432,6 +504,40 @@ agx_pool_fc_kernel(const float* __restrict__ x, int pixels, int C, const float* 
         float a = bfc[threadIdx.x];
         for (int k = 0; k < C; ++k) a = fmaf(wfc[threadIdx.x * C + k], s_mean[k], a);
         out[img * ld_out + threadIdx.x] = a;
+    }
+}
+
+
+// ---- train-mode BatchNorm2d over a channels-last activation x [rows, C] (reference lib/network/cnn.py:9-21 in train mode: Conv → ReLU →
+// BatchNorm with BATCH statistics).  `sums` [2, C] float64 = per-channel sums and sums of squares over the rows (agx_col_sums: deterministic,
+// all-reducible across ranks); every CTA derives scale = gamma / sqrt(biased var + eps), shift = beta - mean * scale and rewrites its share of
+// x in place; CTA 0 also moves the running statistics: running = (1 - momentum) * running + momentum * batch (variance UNBIASED, as torch).
+__global__ void __launch_bounds__(256)
+agx_bn_train_kernel(float* __restrict__ x, int64_t rows, int C, const double* __restrict__ sums, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, float momentum, float* running_mean, float* running_var) {
+    __shared__ float s_s[128], s_t[128];
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        const double n = (double)rows, mean = sums[c] / n;
+        double var = sums[C + c] / n - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float sc = (gamma ? gamma[c] : 1.0f) / sqrtf((float)var + eps);
+        s_s[c] = sc;
+        s_t[c] = (beta ? beta[c] : 0.0f) - (float)mean * sc;
+        if (blockIdx.x == 0 && running_mean) {
+            const double unb = rows > 1 ? var * n / (n - 1.0) : var;
+            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    }
+    __syncthreads();
+    const int64_t total4 = rows * C / 4;  // C % 4 == 0
+    float4* x4 = reinterpret_cast<float4*>(x);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)gridDim.x * 256) {
+        const int c = (int)((i * 4) % C);
+        float4 v = x4[i];
+        v.x = v.x * s_s[c] + s_t[c]; v.y = v.y * s_s[c + 1] + s_t[c + 1]; v.z = v.z * s_s[c + 2] + s_t[c + 2]; v.w = v.w * s_s[c + 3] + s_t[c + 3];
+        x4[i] = v;
     }
 }
 
@@ -497,7 +603,15 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
             return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: constant-bank copy failed");
         const bool pair_ok = !(p->Wo & 1) && !(p->W & 3) && p->px == 2 && !(((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 15u);
         if (pair_ok && g_first_impl == 1) {
-            int64_t g2 = ((int64_t)p->N * p->Ho * ((p->Wo / 2 + 31) / 32) + 3) / 4;  // one (row, 32-pair segment) per warp, 4 warps per block
+            const int Wp = p->Wo / 2, segs = (Wp + 31) / 32;
+            if (!p->px_mean && Wp * 10 < segs * 32 * 9) {  // rows fill their 32-lane segments below 90 %: flattened pairs
+                int64_t g2 = (M_total / 2 + 127) / 128;
+                if (g2 > 148 * 16) g2 = 148 * 16;
+                if (p->Cout == 16) agx_conv2d_first5x2_flat_kernel<16, false><<<(unsigned)g2, 128, 0, st>>>(*p);
+                else agx_conv2d_first5x2_flat_kernel<32, false><<<(unsigned)g2, 128, 0, st>>>(*p);
+                return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: launch failed");
+            }
+            int64_t g2 = ((int64_t)p->N * p->Ho * segs + 3) / 4;  // one (row, 32-pair segment) per warp, 4 warps per block
             if (g2 > 148 * 16) g2 = 148 * 16;
             const unsigned g = (unsigned)g2;
             if (p->Cout == 16) { if (p->px_mean) agx_conv2d_first5x2_kernel<16, true><<<g, 128, 0, st>>>(*p); else agx_conv2d_first5x2_kernel<16, false><<<g, 128, 0, st>>>(*p); }
@@ -521,6 +635,16 @@ int agx_resize_bilinear(const float* x, float* y, int64_t n, int H, int W, int H
     if (grid > 148 * 32) grid = 148 * 32;
     agx_resize_bilinear_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n, H, W, Ho, Wo);
     return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_resize_bilinear: launch failed");
+}
+
+int agx_bn_train(float* x, int64_t rows, int C, const double* sums, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, void* stream) {
+    if (!x || !sums || rows <= 0 || C <= 0 || C > 128 || (C & 3) || ((running_mean == nullptr) != (running_var == nullptr)) || ((uintptr_t)x & 15u))
+        return agx_internal_fail(AGX_ERR_ARG, "agx_bn_train: bad argument (C % 4 == 0, C <= 128, x 16-byte aligned)");
+    int64_t grid = (rows * C / 4 + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    agx_bn_train_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, rows, C, sums, gamma, beta, eps, momentum, running_mean, running_var);
+    return cudaGetLastError() == cudaSuccess ? AGX_OK : agx_internal_fail(AGX_ERR_CUDA, "agx_bn_train: launch failed");
 }
 
 int agx_pool_fc(const float* x, int64_t n, int pixels, int C, const float* wfc, const float* bfc, int F, float* out, int64_t ld_out, void* stream) {

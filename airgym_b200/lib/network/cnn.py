@@ -4,8 +4,10 @@ its checkpoints load key for key (lib/network/cnn.py:3-33: `features.{0,3,6}` co
 
 Inference (eval-mode BatchNorm — the only mode the trainer uses: the reference's encoder never receives a gradient, DESIGN.md
 §4.4) runs on the libagx kernel `agx_cnn_encode`: one persistent launch, the whole network per env in
-shared memory, fp32 FMA arithmetic, optional fused per-pixel input normalisation.  Train-mode BatchNorm (batch statistics) is
-not on the product path; calling the module in train mode uses torch's library convolutions."""
+shared memory, fp32 FMA arithmetic, optional fused per-pixel input normalisation.  In train mode without autograd (what the
+reference's update pass amounts to: its encoder output is cut from the graph) the forward runs natively too, with BATCH statistics
+and the running-statistics update (tc_encoders.cnn_encode_train: agx_col_sums + agx_bn_train between the convolution layers);
+with autograd enabled the module falls back to torch's library convolutions."""
 import ctypes as C
 
 import torch
@@ -74,7 +76,7 @@ class CNNFeatureExtractor(nn.Module):
         self.fc = nn.Linear(64, feature_dim)
 
     def native_ok(self, x):
-        return (not self.training and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+        return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
                 and tuple(x.shape[1:]) == (1, _capi.AGX_CAM_W, _capi.AGX_CAM_H) and self.fc.out_features <= 64)
 
     def forward_torch(self, x):
@@ -83,5 +85,8 @@ class CNNFeatureExtractor(nn.Module):
 
     def forward(self, x):
         if self.native_ok(x):
+            if self.training:  # BatchNorm with batch statistics + running-statistics update, no autograd
+                from .tc_encoders import cnn_encode_train
+                return cnn_encode_train(self, x)
             return native_encode(self, x)
         return self.forward_torch(x)

@@ -145,6 +145,52 @@ def cnn_encode(net, x, px_mean=None, px_rstd=None, out=None, precise=True):
     return out
 
 
+def _bn_train_inplace(act, bn, ws):
+    """Train-mode BatchNorm2d on a channels-last activation, in place: batch statistics over all N*H*W rows (agx_col_sums in float64,
+    deterministic), normalisation + affine + running-statistics update in agx_bn_train; num_batches_tracked bumped like torch does."""
+    lib = _capi.load()
+    rows, Cc = act.shape[0] * act.shape[1] * act.shape[2], act.shape[3]
+    st = C.c_void_p(torch.cuda.current_stream(act.device).cuda_stream)
+    sums = torch.empty(2, Cc, device=act.device, dtype=torch.float64)
+    _capi.check(lib.agx_col_sums(act.data_ptr(), rows, Cc, Cc, sums.data_ptr(), ws.data_ptr(), st), "agx_col_sums")
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track:
+        bn.num_batches_tracked += 1
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    else:
+        momentum = 0.0
+    _capi.check(lib.agx_bn_train(act.data_ptr(), rows, Cc, sums.data_ptr(), bn.weight.data_ptr() if bn.affine else None,
+                                 bn.bias.data_ptr() if bn.affine else None, float(bn.eps), float(momentum),
+                                 bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None, st), "agx_bn_train")
+    return act
+
+
+def cnn_encode_train(net, x, px_mean=None, px_rstd=None, out=None):
+    """CNNFeatureExtractor forward in TRAIN mode (BatchNorm with batch statistics over the whole call's batch, running statistics and
+    num_batches_tracked updated) — what the reference's update pass runs on the minibatch images (lib/network/cnn.py:3-33 under
+    model.train()).  Inference only (no autograd: the reference's encoder receives no gradient either, base_model.py:29-31).  The batch
+    is processed in one piece (batch statistics do not chunk): 0.72 MB of activations per image."""
+    lib = _capi.load()
+    n, H, W = x.shape[0], x.shape[2], x.shape[3]
+    if out is None:
+        out = torch.empty(n, net.fc.out_features, device=x.device, dtype=torch.float32)
+    f = net.features
+    if not hasattr(net, "_tc_prep"):
+        net._tc_prep = {True: _Prepared(), False: _Prepared()}
+    W_ = net._tc_prep[True].get(list(net.parameters()) + list(net.buffers()), lambda: _prep_cnn(net, True))
+    if px_mean is not None:
+        px_mean, px_rstd = px_mean.float().contiguous(), px_rstd.float().contiguous()
+    ws = torch.zeros(int(lib.agx_col_sums_workspace_doubles()), device=x.device, dtype=torch.float64)
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    a = conv2d_first(x.contiguous().reshape(-1, H, W), f[0], _capi.ACT_RELU, px_mean, px_rstd)
+    a = _bn_train_inplace(a, f[2], ws)
+    a = _bn_train_inplace(conv2d_nhwc(a, W_["c2"], _capi.ACT_RELU), f[5], ws)
+    a = _bn_train_inplace(conv2d_nhwc(a, W_["c3"], _capi.ACT_RELU), f[8], ws)
+    _capi.check(lib.agx_pool_fc(a.data_ptr(), a.shape[0], a.shape[1] * a.shape[2], a.shape[3], W_["wfc"].data_ptr(), W_["bfc"].data_ptr(),
+                                net.fc.out_features, out.data_ptr(), out.stride(0), st), "agx_pool_fc")
+    return out
+
+
 # ---- VAE ImgEncoder ---------------------------------------------------------------------------------------------------------------
 def _prep_vae(enc, precise):
     names = ("conv0_1", "conv1_0", "conv1_1", "conv2_0", "conv2_1", "conv3_0", "conv0_jump_2", "conv1_jump_3")

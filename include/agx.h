@@ -497,6 +497,12 @@ int agx_sizeof_conv_first_params(void);
 int agx_conv2d_first(const AgxConvFirstParams* p, void* stream);
 /* F.interpolate(x[n,1,H,W], (Ho,Wo), mode='bilinear', align_corners=False) */
 int agx_resize_bilinear(const float* x, float* y, int64_t n, int H, int W, int Ho, int Wo, void* stream);
+/* Train-mode BatchNorm2d over a channels-last activation x [rows, C] in place (lib/network/cnn.py:9-21 called in train mode, as the
+ * reference's update pass does): `sums` [2, C] float64 from agx_col_sums(x, rows, C, C, ...) — between the two calls a multi-GPU run may
+ * all-reduce them; y = (x - batch mean) / sqrt(biased batch var + eps) * gamma + beta; running_mean / running_var (or both NULL) move by
+ * `momentum` towards the batch mean / UNBIASED batch variance.  The caller bumps num_batches_tracked. */
+int agx_bn_train(float* x, int64_t rows, int C, const double* sums, const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var, void* stream);
 /* out[n, :F] = Linear(mean over `pixels` of x[n, pixels, C]) — AdaptiveAvgPool2d((1,1)) + fc of the CNN (cnn.py:27-33) */
 int agx_pool_fc(const float* x, int64_t n, int pixels, int C, const float* wfc, const float* bfc, int F, float* out, int64_t ld_out,
                 void* stream);

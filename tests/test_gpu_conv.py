@@ -132,6 +132,39 @@ def test_cnn_encoder_tc_vs_float64_and_the_fused_kernel(built):
     assert torch.equal(wide[:, 16:], tc) and float(wide[:, :16].abs().max()) == 0.0
 
 
+def test_cnn_encoder_train_mode_batchnorm_vs_torch(built):
+    """model.train() without autograd: conv -> ReLU -> BatchNorm with BATCH statistics (agx_col_sums + agx_bn_train between the layer
+    kernels), running_mean / running_var / num_batches_tracked updated like torch's modules — against the torch module in float64,
+    two consecutive calls (the second starts from the first one's running statistics), then eval mode on the updated statistics."""
+    import copy
+
+    from airgym_b200.lib.network.cnn import CNNFeatureExtractor
+
+    torch.manual_seed(5)
+    net = CNNFeatureExtractor(30).cuda()
+    with torch.no_grad():
+        for bn in (net.features[2], net.features[5], net.features[8]):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    ref = copy.deepcopy(net).double()
+    net.train(); ref.train()
+    for it in range(2):
+        img = torch.rand(41, 1, 212, 120, device="cuda") * (9 + it)
+        with torch.no_grad():
+            got = net(img)
+            want = ref.forward_torch(img.double())
+        sc = max(1.0, float(want.abs().max()))
+        assert float((got.double() - want).abs().max()) <= 3e-5 * sc, it
+        for k in (2, 5, 8):
+            a, b = net.features[k], ref.features[k]
+            assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == it + 1
+            assert float((a.running_mean.double() - b.running_mean).abs().max()) <= 1e-5 * max(1.0, float(b.running_mean.abs().max()))
+            assert float((a.running_var.double() - b.running_var).abs().max()) <= 1e-5 * max(1.0, float(b.running_var.abs().max()))
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        got, want = net(img), ref.forward_torch(img.double())
+    assert float((got.double() - want).abs().max()) <= 3e-5 * max(1.0, float(want.abs().max()))
+
+
 def test_vae_encoder_tc_vs_mirror_and_golden(built):
     from airgym_b200.lib.network.vae_image_encoder import VAEImageEncoder
     from tests.util_vae import procedural_images, procedural_state
