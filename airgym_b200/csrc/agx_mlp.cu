@@ -312,13 +312,14 @@ namespace tc {
 // epilogue of one hidden layer for this thread's row: TMEM cols [col0, col0 + W) → + bias → ELU → next A operand (+ HBM copy)
 // keep_row: this row's slot in a row-major [b, W] keep tensor; keep_col (training path): this row's element of plane 0 of a
 // FEATURE-MAJOR [W, ld_t] keep tensor (consecutive rows = consecutive addresses: coalesced scalar stores) — at most one is non-null
+// half: which half of the W columns this thread handles (two warps share a TMEM lane quarter and split the columns between them)
 template <int W>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ bias, float* a_next, int r,
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ bias, float* a_next, int r, int half,
                                                 float* __restrict__ keep_row, float* __restrict__ keep_col = nullptr, int64_t ld_t = 0) {
     // not unrolled over the column chunks: four call sites x up to 8 chunks of ~250 instructions each overflowed the instruction
     // cache (ncu: stall_no_instruction 6.2 of 11 cycles per issue with the two tile groups in different code regions)
 #pragma unroll 1
-    for (int c0 = 0; c0 < W; c0 += 16) {
+    for (int c0 = half * (W / 2); c0 < (half + 1) * (W / 2); c0 += 16) {
         float v[16];
         tmem_ld16(tmem_row + (uint32_t)(col0 + c0), v);
 #pragma unroll
@@ -398,7 +399,10 @@ __device__ __forceinline__ void policy_head(const AgxPolicyIO& pol, const float 
     if (pol.dones_out) pol.dones_out[row * pol.ld_dones] = pol.dones_in[row];
 }
 
-constexpr int kThreads = 2 * kM;  // two 128-thread tile groups per CTA: the MMA / barrier latency of one hides under the epilogue of the other
+// Two tile groups per CTA (the MMA / barrier latency of one hides under the epilogue of the other), 256 threads per group: thread
+// (row, half) — the two warps of a TMEM lane quarter split every layer's columns, which halves the per-tile epilogue chain (the
+// kernel is bound by that chain: one 32 768-row minibatch is a single pass of 256 tiles over the 296 groups of the grid)
+constexpr int kGroup = 2 * kM, kThreads = 2 * kGroup;
 template <int IN_PAD>
 __global__ void __launch_bounds__(kThreads, 1)
 agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ obs, float* __restrict__ mu,
@@ -416,7 +420,8 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
     float* act = nrm + 2 * IN_PAD;            // per group: Pbuf [128 x 64] (A0, A2[:, :64], A3) | Qbuf [128 x 64] (A1, A2[:, 64:])
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base;
-    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all >> 7, tid = tid_all & (kM - 1), A = P.actions_num, in_dim = P.in_dim;
+    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all / kGroup, tig = tid_all % kGroup, tid = tig & (kM - 1), half = tig >> 7,
+              A = P.actions_num, in_dim = P.in_dim;
     float* Pbuf = act + group * (2 * kM * kH1);
     float* Qbuf = Pbuf + kM * kH1;
     uint64_t* bar = &bars[group];
@@ -483,6 +488,7 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
         // normalised input row (RunningMeanStd eval branch, lib/core/running_mean_std.py:76-80) → A0 in Pbuf
 #pragma unroll
         for (int c0 = 0; c0 < IN_PAD; c0 += 4) {
+            if (((c0 >> 2) & 1) != half) continue;  // the two threads of a row take alternate 16-byte chunks
             float v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -508,35 +514,35 @@ agx_mlp_forward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, con
             }
             *reinterpret_cast<float4*>(Pbuf + canon(tid, c0, kM)) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Pbuf), s32(w1), kH1, IN_PAD, tmem + 0); commit(bar); }
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Pbuf), s32(w1), kH1, IN_PAD, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
         const bool kr = ok && !keep_t, kc = ok && keep_t;  // row-major / feature-major keeps
         // feature-major keeps are blocked by 128-row tile: element (row, c) of a W-wide tensor at ((row / 128) * W + c) * 128 + row % 128,
         // i.e. one tile's planes are one contiguous W x 512-byte region (DRAM-page friendly for this kernel's stores and the weight-gradient kernel's loads)
         const int64_t tile_row = row >> 7, in_tile = row & (kM - 1);
-        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, (h1_out && kr) ? h1_out + row * kH1 : nullptr,
+        hidden_epilogue<kH1>(tmem_row, 0, bia, Qbuf, tid, half, (h1_out && kr) ? h1_out + row * kH1 : nullptr,
                              (h1_out && kc) ? h1_out + tile_row * kH1 * kM + in_tile : nullptr, kM);  // A1 → Qbuf
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Qbuf), s32(w2), kH2, kH1, tmem + 64); commit(bar); }
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Qbuf), s32(w2), kH2, kH1, tmem + 64); commit(bar); }
         wait(bar, phase); phase ^= 1;
         // layer 2's 128 columns leave in two halves so that A2 never needs more than the two 32 KB buffers: the first half goes to
         // Pbuf and layer 3 starts on it (K-steps 0..7) while the epilogue of the second half fills Qbuf (A1 is dead by now)
-        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, (h2_out && kr) ? h2_out + row * kH2 : nullptr,
+        hidden_epilogue<kH1>(tmem_row, 64, bia + kH1, Pbuf, tid, half, (h2_out && kr) ? h2_out + row * kH2 : nullptr,
                              (h2_out && kc) ? h2_out + tile_row * kH2 * kM + in_tile : nullptr, kM);
-        publish_and_sync(gbar, kM);
-        if (tid == 0) gemm(s32(Pbuf), s32(w3), kH3, kH1, tmem + 192);
-        hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, (h2_out && kr) ? h2_out + row * kH2 + kH1 : nullptr,
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) gemm(s32(Pbuf), s32(w3), kH3, kH1, tmem + 192);
+        hidden_epilogue<kH1>(tmem_row, 64 + kH1, bia + kH1 + kH1, Qbuf, tid, half, (h2_out && kr) ? h2_out + row * kH2 + kH1 : nullptr,
                              (h2_out && kc) ? h2_out + (tile_row * kH2 + kH1) * kM + in_tile : nullptr, kM);
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Qbuf), s32(w3) + 8 * 2 * (kH3 / 8) * 128, kH3, kH1, tmem + 192, true); commit(bar); }
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Qbuf), s32(w3) + 8 * 2 * (kH3 / 8) * 128, kH3, kH1, tmem + 192, true); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, (h3_out && kr) ? h3_out + row * kH3 : nullptr,
+        hidden_epilogue<kH3>(tmem_row, 192, bia + kH1 + kH2, Pbuf, tid, half, (h3_out && kr) ? h3_out + row * kH3 : nullptr,
                              (h3_out && kc) ? h3_out + tile_row * kH3 * kM + in_tile : nullptr, kM);  // A3 → Pbuf
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Pbuf), s32(wh), kOutPad, kH3, tmem + 0); commit(bar); }
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Pbuf), s32(wh), kOutPad, kH3, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        {
+        if (half == 0) {  // the 16 head columns: one thread per row
             float v[16];
             tmem_ld16(tmem_row + 0u, v);
             if (ok && pol.actions) {

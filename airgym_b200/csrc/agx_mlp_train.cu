@@ -40,7 +40,9 @@ __device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.0f ? 
 // ---- activation-gradient chain ------------------------------------------------------------------------------------------------
 namespace tcb {
 using namespace tc;
-constexpr int kThreads = 2 * kM;
+// two tile groups per CTA, 256 threads per group: thread (row, half) — the two warps of a TMEM lane quarter split every layer's
+// columns (agx_mlp.cu's forward does the same: both kernels are bound by the per-tile epilogue chain, not by the MMAs)
+constexpr int kGroup = 2 * kM, kThreads = 2 * kGroup;
 constexpr int kW3T = kH2 * kH3, kW2T = kH1 * kH2, kWhT = kH3 * kOutPad;        // floats
 constexpr int kGbuf = kM * kH2, kDbuf = kM * kOutPad;                            // per group
 constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kW3T + kW2T + kWhT + 2 * (kGbuf + kDbuf));
@@ -48,9 +50,9 @@ constexpr size_t kSmemBytes = sizeof(float) * (size_t)(kW3T + kW2T + kWhT + 2 * 
 // dZ = dH ∘ elu'(h) for this thread's row: TMEM cols [col0, col0 + W) x the h plane → dZ plane (+ next A operand when a_next)
 template <int W>
 __device__ __forceinline__ void grad_epilogue(uint32_t tmem_row, int col0, const float* __restrict__ h_col, float* __restrict__ dz_col,
-                                              int64_t B, float* a_next, int r) {
+                                              int64_t B, float* a_next, int r, int half) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < W; c0 += 16) {
+    for (int c0 = half * (W / 2); c0 < (half + 1) * (W / 2); c0 += 16) {
         float h[16], v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) h[i] = __ldg(h_col + (int64_t)(c0 + i) * B);  // issued before the TMEM load completes
@@ -77,18 +79,34 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
     float* act = whT + kWhT;
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_base;
-    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all >> 7, tid = tid_all & (kM - 1), A = P.actions_num;
+    const int tid_all = threadIdx.x, warp_all = tid_all >> 5, group = tid_all / kGroup, tig = tid_all % kGroup, tid = tig & (kM - 1), half = tig >> 7,
+              A = P.actions_num;
     float* Gbuf = act + group * (kGbuf + kDbuf);   // dZ3 [128 x 64], then dZ2 [128 x 128]
     float* Dbuf = Gbuf + kGbuf;                    // dout [128 x 16]
     uint64_t* bar = &bars[group];
     // transposed weights, TF32-rounded, K-major canonical.  Global reads are coalesced (torch rows), the strided shared-memory
     // stores are a one-off per CTA.
-    for (int i = tid_all; i < kH3 * kH2; i += kThreads) { const int k = i / kH2, n = i - k * kH2; w3T[canon(n, k, kH2)] = tc_tf32r(P.w3[i]); }
-    for (int i = tid_all; i < kH2 * kH1; i += kThreads) { const int k = i / kH1, n = i - k * kH1; w2T[canon(n, k, kH1)] = tc_tf32r(P.w2[i]); }
-    for (int i = tid_all; i < kOutPad * kH3; i += kThreads) {
-        const int k = i / kH3, n = i - k * kH3;
-        const float w = k < A ? P.w_mu[k * kH3 + n] : (k == A ? P.w_value[n] : 0.0f);
-        whT[canon(n, k, kH3)] = tc_tf32r(w);
+    // All of a thread's loads are issued before its first store (ncu of the un-batched loops: 45 % of the kernel's stall samples sat on
+    // their 16 + 16 + 2 serialised L2 round trips).
+    {
+        constexpr int k3 = kH3 * kH2 / kThreads, k2 = kH2 * kH1 / kThreads, kh = kOutPad * kH3 / kThreads;
+        static_assert(kH3 * kH2 % kThreads == 0 && kH2 * kH1 % kThreads == 0 && kOutPad * kH3 % kThreads == 0, "staging loops assume exact division");
+        float v3[k3], v2[k2], vh[kh];
+#pragma unroll
+        for (int u = 0; u < k3; ++u) v3[u] = __ldg(P.w3 + tid_all + u * kThreads);
+#pragma unroll
+        for (int u = 0; u < k2; ++u) v2[u] = __ldg(P.w2 + tid_all + u * kThreads);
+#pragma unroll
+        for (int u = 0; u < kh; ++u) {
+            const int i = tid_all + u * kThreads, k = i / kH3, n = i - k * kH3;
+            vh[u] = k < A ? __ldg(P.w_mu + k * kH3 + n) : (k == A ? __ldg(P.w_value + n) : 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < k3; ++u) { const int i = tid_all + u * kThreads, k = i / kH2, n = i - k * kH2; w3T[canon(n, k, kH2)] = tc_tf32r(v3[u]); }
+#pragma unroll
+        for (int u = 0; u < k2; ++u) { const int i = tid_all + u * kThreads, k = i / kH1, n = i - k * kH1; w2T[canon(n, k, kH1)] = tc_tf32r(v2[u]); }
+#pragma unroll
+        for (int u = 0; u < kh; ++u) { const int i = tid_all + u * kThreads, k = i / kH3, n = i - k * kH3; whT[canon(n, k, kH3)] = tc_tf32r(vh[u]); }
     }
     if (tid_all == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
@@ -114,7 +132,7 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
         float* dz3p = dz3t + tile * kH3 * kM + tid;
         float* dz2p = dz2t + tile * kH2 * kM + tid;
         float* dz1p = dz1t + tile * kH1 * kM + tid;
-        {   // dout row = [d loss / d mu (A) | d loss / d value | 0 ...] → its plane and the first A operand (K = 16)
+        if (half == 0) {  // dout row = [d loss / d mu (A) | d loss / d value | 0 ...] → its plane and the first A operand (K = 16)
             float d[kOutPad];
 #pragma unroll
             for (int c = 0; c < kOutPad; ++c) d[c] = 0.0f;
@@ -126,18 +144,18 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
 #pragma unroll
             for (int c = 0; c < kOutPad; c += 4) *reinterpret_cast<float4*>(Dbuf + canon(tid, c, kM)) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
         }
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Dbuf), s32(whT), kH3, kOutPad, tmem + 0); commit(bar); }
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Dbuf), s32(whT), kH3, kOutPad, tmem + 0); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH3>(tmem_row, 0, h3p, dz3p, kM, Gbuf, tid);
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Gbuf), s32(w3T), kH2, kH3, tmem + 64); commit(bar); }
+        grad_epilogue<kH3>(tmem_row, 0, h3p, dz3p, kM, Gbuf, tid, half);
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Gbuf), s32(w3T), kH2, kH3, tmem + 64); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH2>(tmem_row, 64, h2p, dz2p, kM, Gbuf, tid);  // dZ3 is dead: the MMA that read it has completed
-        publish_and_sync(gbar, kM);
-        if (tid == 0) { gemm(s32(Gbuf), s32(w2T), kH1, kH2, tmem + 192); commit(bar); }
+        grad_epilogue<kH2>(tmem_row, 64, h2p, dz2p, kM, Gbuf, tid, half);  // dZ3 is dead: the MMA that read it has completed
+        publish_and_sync(gbar, kGroup);
+        if (tig == 0) { gemm(s32(Gbuf), s32(w2T), kH1, kH2, tmem + 192); commit(bar); }
         wait(bar, phase); phase ^= 1;
-        grad_epilogue<kH1>(tmem_row, 192, h1p, dz1p, kM, nullptr, tid);
+        grad_epilogue<kH1>(tmem_row, 192, h1p, dz1p, kM, nullptr, tid, half);
         // the next tile's first MMA writes TMEM columns [0, 64): every thread of the group has finished reading them long ago
         // (two barriers back); its Dbuf / Gbuf stores are ordered behind this tile's last MMA by the wait above
     }
