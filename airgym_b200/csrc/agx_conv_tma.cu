@@ -613,6 +613,18 @@ int agx_internal_conv_option(const char* key, int value) {
     return 0;
 }
 
+// tiled tensor map for other translation units (agx_mlp_train.cu): rank 2 / 3, fp32, swizzle 0 / 64 / 128 bytes; 1 = encoded, 0 = unavailable
+int agx_internal_tmap_tiled(void* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    if (!lookup_entry_points() || rank < 2 || rank > 3) return 0;
+    cuuint64_t d[3], st[2];
+    cuuint32_t b[3], es[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    return g_encode_tiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 1 : 0;
+}
+
 // returns 1 when the layer was launched here, 0 when the geometry belongs to the gather kernel, < 0 on error (already recorded)
 int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
     if (!g_conv_impl) return 0;

@@ -18,6 +18,7 @@
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
+extern int g_wgrad_tma;  // agx_mlp_train.cu: operands of the weight-gradient kernel by TMA (agx_set_option("mlp_wgrad_tma"))
 
 namespace {
 
@@ -955,6 +956,7 @@ int agx_internal_mlp_option(const char* key, int value) {
         return 1;
     }
     if (!strcmp(key, "mlp_wgrad_staged")) { g_wgrad_staged = value ? 1 : 0; return 1; }
+    if (!strcmp(key, "mlp_wgrad_tma")) { g_wgrad_tma = value ? 1 : 0; return 1; }
     return 0;
 }
 

@@ -19,6 +19,7 @@
 //   stage (4 layers x 2 K-steps) into four TMEM accumulators that live for the whole slab; the bias gradient is the extra output
 //   column produced by a constant ones row appended to each B operand (plane `in_dim` of the normalised input is all ones).
 //   Per-CTA partials go through the same deterministic reduction as the mma.sync path (agx_mlp.cu).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -27,6 +28,9 @@
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
+extern "C" int agx_internal_tmap_tiled(void* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                       int swizzle_bytes);  // agx_conv_tma.cu
+int g_wgrad_tma = 1;  // agx_set_option("mlp_wgrad_tma", 0 | 1)
 extern "C" int agx_internal_wgrad_reduce(const AgxMlpParams* p, const AgxMlpGrads* g, const float* w_partials, int n_cta_w,
                                          const float* b_partials, int n_cta_b, void* stream);
 
@@ -341,6 +345,192 @@ agx_mlp_wgrad_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const
 }
 }  // namespace tcw
 
+// ---- weight + bias gradients, operands by TMA ---------------------------------------------------------------------------------------
+// Same GEMMs, accumulators, ones rows and epilogue as tcw above; what changes is how the operands reach shared memory.  A feature-major
+// plane blocked by 128-row tile, [tile][R][128], IS a K-major operand [R rows][K = batch]: a 3-D tensor map (128, R, tiles) with a box of
+// (32, R, 1) and SWIZZLE_128B drops the stage's [R][32] slice into the layout tcgen05 reads — ONE cp.async.bulk.tensor per operand and
+// stage (8 per 32 batch rows) instead of 71 680 16-byte cp.async per stage pair (the gather kernel was bound by the request rate of those:
+// 31 us per 32 768-row minibatch at 2.1-2.4 TB/s).  Warp 0 = producer, warp 1 = MMA issuer (both converged, elect.sync), two stages of
+// ~100 KB; all eight warps run the epilogue.
+namespace tcw2 {
+using namespace tc;
+constexpr int kThreads = 256, kStageRows = 32, kStages = 2;
+constexpr int kN2 = kH1 + 16, kN3 = kH2 + 16;
+constexpr int kC1 = 0, kC2 = 96, kC3 = kC2 + kN2, kCh = kC3 + kN3;  // TMEM columns, as tcw
+template <int IN_PAD>
+struct Layout {  // byte offsets inside one stage; every operand is [rows][128 B] (SWIZZLE_128B), 1024-byte aligned
+    static constexpr uint32_t a1 = 0, a2 = a1 + kM * 128, a3 = a2 + kM * 128, ah = a3 + kM * 128;
+    static constexpr uint32_t b1 = ah + kM * 128, b2 = b1 + ((IN_PAD * 128 + 1023) & ~1023), b3 = b2 + ((kN2 * 128 + 1023) & ~1023), bh = b3 + ((kN3 * 128 + 1023) & ~1023);
+    static constexpr uint32_t bytes = bh + ((kOutPad * 128 + 1023) & ~1023);
+    static constexpr uint32_t tx = (uint32_t)(kH1 + kH2 + kH3 + kH3 + IN_PAD + kH1 + kH2 + kOutPad) * 128u;  // bytes the eight boxes of a stage bring
+};
+struct Maps { CUtensorMap dz1, dz2, dz3, h3, x, h1, h2, dout; };
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_plain(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma3(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// D[128, N] (+)= A[128, 32] * B[N, 32]^T, both operands [rows][128 B] SWIZZLE_128B: 4 K steps of 8 (start address + 32 bytes each)
+__device__ __forceinline__ void gemm_sw128(uint32_t a, uint32_t b, int N, uint32_t d, bool acc) {
+    constexpr uint32_t kHi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+    const uint32_t al = (a >> 4) | 0x10000u, bl = (b >> 4) | 0x10000u;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t on = (ks > 0 || acc) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+                     "l"(((uint64_t)kHi << 32) | (al + 2u * ks)), "l"(((uint64_t)kHi << 32) | (bl + 2u * ks)), "r"(idesc), "r"(on)
+                     : "memory");
+    }
+}
+
+extern __shared__ uint8_t w_smem[];
+
+template <int IN_PAD>
+__global__ void __launch_bounds__(kThreads, 1)
+agx_mlp_wgrad_tma_kernel(const __grid_constant__ Maps M, const __grid_constant__ AgxMlpParams P, int64_t B, float* __restrict__ w_partials,
+                         float* __restrict__ b_partials, int partial_floats) {
+    using L = Layout<IN_PAD>;
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages], done;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (s32(w_smem) + 1023u) & ~1023u;
+    uint8_t* gen0 = w_smem + (smem0 - s32(w_smem));
+    // constant parts of the stage buffers: zero rows that pad the operands, and the ones rows behind the bias columns
+    for (uint32_t i = tid; i < kStages * L::bytes / 16; i += kThreads) reinterpret_cast<float4*>(gen0)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncthreads();
+    for (int i = tid; i < kStages * 3 * 32; i += kThreads) {
+        const int st = i / 96, which = (i / 32) % 3, k = i & 31;
+        const uint32_t off = which == 0 ? L::ah + kH3 * 128 : (which == 1 ? L::b2 + kH1 * 128 : L::b3 + kH2 * 128);  // row 64 of A_heads / row 64 of B2 / row 128 of B3
+        reinterpret_cast<float*>(gen0 + st * L::bytes + off)[k] = 1.0f;  // a row of 32 ones reads the same under any swizzle
+    }
+    if (tid == 0) {
+        for (int b = 0; b < kStages; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&full[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&empty[b])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&done)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync(0, kThreads);
+    const uint32_t tmem = tmem_base;
+    const int64_t n_stages_total = B / kStageRows;  // B % 128 == 0
+    const int64_t s_begin = (int64_t)blockIdx.x * n_stages_total / gridDim.x, s_end = (int64_t)(blockIdx.x + 1) * n_stages_total / gridDim.x;
+    const int S = (int)(s_end - s_begin);
+    if (warp == 0) {  // ---- producer
+        for (int s = 0; s < S; ++s) {
+            const int b = s % kStages;
+            mbar_wait_plain(&empty[b], (uint32_t)(((s / kStages) & 1) ^ 1));
+            if (elect_one()) {
+                const int64_t r0 = (s_begin + s) * kStageRows;
+                const int tile = (int)(r0 >> 7), k0 = (int)(r0 & (kM - 1));
+                const uint32_t base = smem0 + (uint32_t)b * L::bytes;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&full[b])), "r"(L::tx) : "memory");
+                tma3(base + L::a1, &M.dz1, &full[b], k0, 0, tile);
+                tma3(base + L::a2, &M.dz2, &full[b], k0, 0, tile);
+                tma3(base + L::a3, &M.dz3, &full[b], k0, 0, tile);
+                tma3(base + L::ah, &M.h3, &full[b], k0, 0, tile);
+                tma3(base + L::b1, &M.x, &full[b], k0, 0, tile);
+                tma3(base + L::b2, &M.h1, &full[b], k0, 0, tile);
+                tma3(base + L::b3, &M.h2, &full[b], k0, 0, tile);
+                tma3(base + L::bh, &M.dout, &full[b], k0, 0, tile);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {  // ---- MMA issuer
+        for (int s = 0; s < S; ++s) {
+            const int b = s % kStages;
+            mbar_wait_plain(&full[b], (uint32_t)((s / kStages) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t base = smem0 + (uint32_t)b * L::bytes;
+                const bool acc = s > 0;
+                gemm_sw128(base + L::a1, base + L::b1, IN_PAD, tmem + kC1, acc);
+                gemm_sw128(base + L::a2, base + L::b2, kN2, tmem + kC2, acc);
+                gemm_sw128(base + L::a3, base + L::b3, kN3, tmem + kC3, acc);
+                gemm_sw128(base + L::ah, base + L::bh, kOutPad, tmem + kCh, acc);
+                commit(&empty[b]);
+                if (s + 1 == S) commit(&done);
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (S > 0) { mbar_wait_plain(&done, 0u); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+    // ---- epilogue: accumulators → this CTA's partials (layout of agx_mlp.cu: dense [out x in_pad] blocks back to back; bias slots b1|b2|b3|heads)
+    float* wp = w_partials + (int64_t)blockIdx.x * partial_floats;
+    float* bp = b_partials + (int64_t)blockIdx.x * kBiasSlots;
+    const int q = warp & 3, half = warp >> 2, m = 32 * q + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const int in_dim = P.in_dim;
+    constexpr int base2 = kH1 * IN_PAD, base3 = base2 + kH2 * kH1, baseh = base3 + kH3 * kH2;
+    constexpr int n1 = IN_PAD / 16, n2 = kN2 / 16, n3 = kN3 / 16;
+    for (int ci = half; ci < n1 + n2 + n3 + 1; ci += 2) {
+        float v[16];
+        if (S == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        if (ci < n1) {
+            const int c0 = ci * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC1 + c0), v);
+            if (m < kH1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + m * IN_PAD + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (c0 + i == in_dim) bp[0 * kMaxW + m] = v[i];
+            }
+        } else if (ci < n1 + n2) {
+            const int c0 = (ci - n1) * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC2 + c0), v);
+            if (c0 < kH1) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + base2 + m * kH1 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+                bp[1 * kMaxW + m] = v[0];
+            }
+        } else if (ci < n1 + n2 + n3) {
+            const int c0 = (ci - n1 - n2) * 16;
+            if (S > 0) tmem_ld16(trow + (uint32_t)(kC3 + c0), v);
+            if (m < kH3) {
+                if (c0 < kH2) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(wp + base3 + m * kH2 + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+                    bp[2 * kMaxW + m] = v[0];
+                }
+            }
+        } else {
+            if (S > 0) tmem_ld16(trow + (uint32_t)kCh, v);
+            if (m < kH3) {  // accumulator = dW_head^T: lane = layer-3 feature, column = head output
+#pragma unroll
+                for (int o = 0; o < kOutPad; ++o) wp[baseh + o * kH3 + m] = v[o];
+            } else if (m == kH3) {
+#pragma unroll
+                for (int o = 0; o < kOutPad; ++o) bp[3 * kMaxW + o] = v[o];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+}  // namespace tcw2
+
 bool train_ok(const AgxMlpParams* p) {
     return p && p->h1 == tc::kH1 && p->h2 == tc::kH2 && p->h3 == tc::kH3 && (p->in_pad == 32 || p->in_pad == 48 || p->in_pad == 64 || p->in_pad == 96) &&
            p->in_dim > 0 && p->in_dim < p->in_pad && (p->actions_num == 4 || p->actions_num == 5) && p->w1 && p->w2 && p->w3 && p->w_mu && p->w_value;
@@ -379,10 +569,37 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
         tcw::agx_mlp_wgrad_tc_kernel<PAD><<<gw, tcw::kThreads, kSm, st>>>(*p, b, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, w_partials, \
                                                                           b_partials, pf);                                        \
     } while (0)
-    if (p->in_pad == 32) AGX_WGRAD_TC(32); else if (p->in_pad == 48) AGX_WGRAD_TC(48); else if (p->in_pad == 64) AGX_WGRAD_TC(64); else AGX_WGRAD_TC(96);
+    // operands by TMA (tcw2) when the tensor maps can be built; the cp.async gather kernel (tcw) otherwise or on agx_set_option("mlp_wgrad_tma", 0)
+    tcw2::Maps maps;
+    bool tma = g_wgrad_tma != 0;
+    if (tma) {
+        const uint64_t ntile = (uint64_t)tiles;
+        auto mk = [&](CUtensorMap* m, const float* plane, int R) {
+            const uint64_t dims[3] = {(uint64_t)tc::kM, (uint64_t)R, ntile}, strides[2] = {(uint64_t)tc::kM * 4, (uint64_t)R * tc::kM * 4};
+            const uint32_t box[3] = {(uint32_t)tcw2::kStageRows, (uint32_t)R, 1};
+            return agx_internal_tmap_tiled(m, plane, 3, dims, strides, box, 128) == 1;
+        };
+        tma = mk(&maps.dz1, dz1t, tc::kH1) && mk(&maps.dz2, dz2t, tc::kH2) && mk(&maps.dz3, dz3t, tc::kH3) && mk(&maps.h3, h3t, tc::kH3) &&
+              mk(&maps.x, xt, p->in_pad) && mk(&maps.h1, h1t, tc::kH1) && mk(&maps.h2, h2t, tc::kH2) && mk(&maps.dout, doutt, kOutPad);
+    }
+    unsigned gused = gw;
+    if (tma) {
+        const int64_t st2 = b / tcw2::kStageRows;
+        gused = (unsigned)(st2 < kGrid ? st2 : kGrid);
+#define AGX_WGRAD_TMA(PAD)                                                                                                        \
+    do {                                                                                                                          \
+        constexpr int kSm = tcw2::kStages * (int)tcw2::Layout<PAD>::bytes + 1024;                                                  \
+        cudaFuncSetAttribute(tcw2::agx_mlp_wgrad_tma_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm);               \
+        tcw2::agx_mlp_wgrad_tma_kernel<PAD><<<gused, tcw2::kThreads, kSm, st>>>(maps, *p, b, w_partials, b_partials, pf);          \
+    } while (0)
+        if (p->in_pad == 32) AGX_WGRAD_TMA(32); else if (p->in_pad == 48) AGX_WGRAD_TMA(48); else if (p->in_pad == 64) AGX_WGRAD_TMA(64); else AGX_WGRAD_TMA(96);
+#undef AGX_WGRAD_TMA
+    } else {
+        if (p->in_pad == 32) AGX_WGRAD_TC(32); else if (p->in_pad == 48) AGX_WGRAD_TC(48); else if (p->in_pad == 64) AGX_WGRAD_TC(64); else AGX_WGRAD_TC(96);
+    }
 #undef AGX_WGRAD_TC
     if (cudaGetLastError() != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward_train: launch failed");
-    return agx_internal_wgrad_reduce(p, g, w_partials, (int)gw, b_partials, (int)gw, stream);
+    return agx_internal_wgrad_reduce(p, g, w_partials, (int)gused, b_partials, (int)gused, stream);
 }
 
 }  // extern "C"
