@@ -84,6 +84,11 @@ class AgxPpoHyper(C.Structure):
 AGX_PPO_STATS = 8
 
 
+class AgxLossIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mu", "logstd", "value", "actions", "old_neglogp", "adv", "returns", "old_mu", "old_sigma",
+                                          "grad_logstd", "stats", "workspace")] + [("a", C.c_int32), ("_pad", C.c_int32)]
+
+
 class AgxMlpParams(C.Structure):
     _fields_ = [("in_dim", C.c_int32), ("in_pad", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32),
                 ("actions_num", C.c_int32)] + [(n, C.c_void_p) for n in (
@@ -176,6 +181,8 @@ def bind(lib):
     lib.agx_mlp_train_supported.argtypes = [C.POINTER(AgxMlpParams)]
     lib.agx_mlp_forward_train.argtypes = [C.POINTER(AgxMlpParams), C.c_int64] + [C.c_void_p] * 8
     lib.agx_mlp_backward_train.argtypes = [C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 12
+    lib.agx_sizeof_loss_io.restype = C.c_int
+    lib.agx_ppo_loss_backward_train.argtypes = [C.POINTER(AgxPpoHyper), C.POINTER(AgxLossIO), C.POINTER(AgxMlpParams), C.POINTER(AgxMlpGrads), C.c_int64] + [C.c_void_p] * 10
     lib.agx_col_sums_workspace_doubles.restype = C.c_int64
     lib.agx_col_sums.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.agx_rms_merge.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -216,7 +223,7 @@ EXPORTS = (
     "agx_sizeof_cnn_params", "agx_cnn_encode",
     "agx_sizeof_conv_params", "agx_conv2d_nhwc", "agx_sizeof_conv_first_params", "agx_conv2d_first", "agx_resize_bilinear", "agx_pool_fc", "agx_bn_train",
     "agx_col_sums_workspace_doubles", "agx_col_sums", "agx_rms_merge",
-    "agx_sizeof_policy_io", "agx_policy_step", "agx_sizeof_post_io", "agx_rollout_post", "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train",
+    "agx_sizeof_policy_io", "agx_policy_step", "agx_sizeof_post_io", "agx_rollout_post", "agx_mlp_train_supported", "agx_mlp_forward_train", "agx_mlp_backward_train", "agx_sizeof_loss_io", "agx_ppo_loss_backward_train",
     "agx_comm_region_bytes", "agx_comm_alloc", "agx_comm_open", "agx_comm_close", "agx_comm_free", "agx_comm_allreduce",
     "agx_comm_status", "agx_adam_step_allreduce", "agx_device_numa_node", "agx_host_alloc_pinned", "agx_host_free_pinned",
 )

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "agx.h"
+#include "agx_ppo_math.cuh"
 #include "agx_tc.cuh"
 
 int agx_internal_fail(int code, const char* msg);
@@ -72,11 +73,14 @@ __device__ __forceinline__ void grad_epilogue(uint32_t tmem_row, int col0, const
     }
 }
 
+constexpr int kLossPartial = 16, kLossGridMax = 296;  // workspace layout of agx_ppo.cu: [grid][16] partials, then the ticket
+// LOSS: the PPO loss of this thread's row computed in place of reading grad_mu / grad_value (agx.h AgxLossIO)
+template <bool LOSS>
 __global__ void __launch_bounds__(kThreads, 1)
 agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, const float* __restrict__ grad_mu,
                            const float* __restrict__ grad_value, const float* __restrict__ h1t, const float* __restrict__ h2t,
                            const float* __restrict__ h3t, float* __restrict__ dz1t, float* __restrict__ dz2t, float* __restrict__ dz3t,
-                           float* __restrict__ doutt) {
+                           float* __restrict__ doutt, const __grid_constant__ AgxPpoHyper hp, const __grid_constant__ AgxLossIO lio) {
     float* w3T = t_smem;              // B operand of dH2 = dZ3·W3: [n = 128 (layer-2 feature)][k = 64 (layer-3 feature)] canonical
     float* w2T = w3T + kW3T;          // dH1 = dZ2·W2: [n = 64][k = 128]
     float* whT = w2T + kW2T;          // dH3 = dout·W_head: [n = 64][k = 16]
@@ -127,6 +131,15 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
     const int gbar = 1 + group;
     uint32_t phase = 0;
     const int64_t n_tiles = B / kM;  // B % 128 == 0 (checked on the host)
+    float lacc[kLossPartial];  // LOSS: this thread's sums of a_loss, c_loss, entropy, b_loss, kl, g_logstd[0..a)
+#pragma unroll
+    for (int i = 0; i < kLossPartial; ++i) lacc[i] = 0.0f;
+    float lls[agx::kMaxAct];
+    const float inv_b = 1.0f / (float)B;
+    if (LOSS) {
+#pragma unroll
+        for (int i = 0; i < agx::kMaxAct; ++i) lls[i] = i < A ? lio.logstd[i] : 0.0f;
+    }
     for (int64_t tile = (int64_t)blockIdx.x * 2 + group; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
         const int64_t row = tile * kM + tid;
         // planes are blocked by 128-row tile (agx_mlp.cu): element (row, c) of a W-wide tensor at (tile * W + c) * 128 + row % 128
@@ -140,9 +153,32 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
             float d[kOutPad];
 #pragma unroll
             for (int c = 0; c < kOutPad; ++c) d[c] = 0.0f;
-            const float gv = grad_value[row];
+            if (LOSS) {
+                float m[agx::kMaxAct], ac[agx::kMaxAct], om[agx::kMaxAct], os[agx::kMaxAct];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) d[c] = c < A ? grad_mu[row * A + c] : (c == A ? gv : 0.0f);
+                for (int i = 0; i < agx::kMaxAct; ++i) {
+                    const bool on = i < A;
+                    m[i] = on ? lio.mu[row * A + i] : 0.0f; ac[i] = on ? lio.actions[row * A + i] : 0.0f;
+                    om[i] = on ? lio.old_mu[row * A + i] : 0.0f; os[i] = on ? lio.old_sigma[row * A + i] : 1.0f;
+                }
+                agx::PpoSampleOut o;
+                agx::ppo_sample(hp, A, m, lls, lio.value[row], ac, lio.old_neglogp[row], lio.adv[row], lio.returns[row], om, os, o);
+#pragma unroll
+                for (int i = 0; i < agx::kMaxAct; ++i) {
+                    if (i < A) {
+                        d[i] = o.g_mu[i] * inv_b;
+                        lio.old_mu[row * A + i] = m[i];  // PPODataset.update_mu_sigma
+                        lio.old_sigma[row * A + i] = expf(lls[i]);
+                        lacc[5 + i] += o.g_logstd[i];
+                    }
+                }
+                if (A == 4) d[4] = o.g_value * inv_b; else d[5] = o.g_value * inv_b;
+                lacc[0] += o.a_loss; lacc[1] += o.c_loss; lacc[2] += o.entropy; lacc[3] += o.b_loss; lacc[4] += o.kl;
+            } else {
+                const float gv = grad_value[row];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d[c] = c < A ? grad_mu[row * A + c] : (c == A ? gv : 0.0f);
+            }
 #pragma unroll
             for (int c = 0; c < kOutPad; ++c) doutt[(tile * kOutPad + c) * kM + tid] = d[c];
 #pragma unroll
@@ -166,6 +202,44 @@ agx_mlp_backward_tc_kernel(const __grid_constant__ AgxMlpParams P, int64_t B, co
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp_all == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (LOSS) {  // loss statistics: warp sums → CTA partial → the CTA drawing the last ticket adds the partials in CTA order (deterministic)
+        __shared__ float s_part[kThreads / 32][kLossPartial];
+        __shared__ bool s_last;
+        const int lane = tid_all & 31;
+#pragma unroll
+        for (int i = 0; i < kLossPartial; ++i) {
+            float v = lacc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[warp_all][i] = v;
+        }
+        __syncthreads();
+        float* partials = lio.workspace;
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(lio.workspace + (int64_t)kLossGridMax * kLossPartial);
+        if (tid_all < 5 + A) {
+            float v = 0.0f;
+            for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][tid_all];
+            partials[(int64_t)blockIdx.x * kLossPartial + tid_all] = v;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid_all == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int i = warp_all; i < 5 + A; i += kThreads / 32) {
+                float v = 0.0f;
+                for (unsigned int c = lane; c < gridDim.x; c += 32) v += __ldcg(partials + (int64_t)c * kLossPartial + i);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) {
+                    if (i < 5) lio.stats[i] = v * inv_b;
+                    else lio.grad_logstd[i - 5] = v * inv_b - hp.entropy_coef;  // d(-coef * mean entropy)/d logstd_i = -coef
+                }
+            }
+            if (tid_all == 0) *ticket = 0;
+        }
+    }
 }
 }  // namespace tcb
 
@@ -542,21 +616,34 @@ extern "C" {
 
 int agx_mlp_train_supported(const AgxMlpParams* p) { return train_ok(p) ? 1 : 0; }
 
-int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
-                           const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t, float* dz3t,
-                           float* doutt, float* workspace, void* stream) {
-    if (!train_ok(p) || !g || b <= 0 || (b % tc::kM) != 0 || !grad_mu || !grad_value || !xt || !h1t || !h2t || !h3t || !dz1t || !dz2t || !dz3t ||
+static int backward_train_impl(const AgxPpoHyper* hp, const AgxLossIO* lio, const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu,
+                               const float* grad_value, const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t,
+                               float* dz3t, float* doutt, float* workspace, void* stream) {
+    if (!train_ok(p) || !g || b <= 0 || (b % tc::kM) != 0 || (!lio && (!grad_mu || !grad_value)) || !xt || !h1t || !h2t || !h3t || !dz1t || !dz2t || !dz3t ||
         !doutt || !workspace || !g->gw1 || !g->gb1 || !g->gw2 || !g->gb2 || !g->gw3 || !g->gb3 || !g->gw_mu || !g->gb_mu || !g->gw_value || !g->gb_value)
         return agx_internal_fail(AGX_ERR_ARG, "agx_mlp_backward_train: bad argument (64-128-64 network, in_pad in {32,48,64,96} > in_dim, batch % 128 == 0)");
+    if (lio && (!hp || !lio->mu || !lio->logstd || !lio->value || !lio->actions || !lio->old_neglogp || !lio->adv || !lio->returns || !lio->old_mu ||
+                !lio->old_sigma || !lio->grad_logstd || !lio->stats || !lio->workspace || lio->a != p->actions_num))
+        return agx_internal_fail(AGX_ERR_ARG, "agx_ppo_loss_backward_train: bad loss block (a must equal the network's actions_num)");
     const uintptr_t al = (uintptr_t)xt | (uintptr_t)h1t | (uintptr_t)h2t | (uintptr_t)h3t | (uintptr_t)dz1t | (uintptr_t)dz2t | (uintptr_t)dz3t |
                          (uintptr_t)doutt | (uintptr_t)workspace;
     if (al & 15u) return agx_internal_fail(AGX_ERR_ALIGN, "agx_mlp_backward_train: buffers must be 16-byte aligned");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int kGrid = 148;
     const int64_t tiles = b / tc::kM, pairs = (tiles + 1) / 2;
-    cudaFuncSetAttribute(tcb::agx_mlp_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmemBytes);
-    tcb::agx_mlp_backward_tc_kernel<<<(unsigned)(pairs < kGrid ? pairs : kGrid), tcb::kThreads, tcb::kSmemBytes, st>>>(
-        *p, b, grad_mu, grad_value, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt);
+    AgxPpoHyper hz;
+    AgxLossIO lz;
+    memset(&hz, 0, sizeof(hz));
+    memset(&lz, 0, sizeof(lz));
+    if (lio) {
+        cudaFuncSetAttribute(tcb::agx_mlp_backward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmemBytes);
+        tcb::agx_mlp_backward_tc_kernel<true><<<(unsigned)(pairs < kGrid ? pairs : kGrid), tcb::kThreads, tcb::kSmemBytes, st>>>(
+            *p, b, nullptr, nullptr, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, *hp, *lio);
+    } else {
+        cudaFuncSetAttribute(tcb::agx_mlp_backward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcb::kSmemBytes);
+        tcb::agx_mlp_backward_tc_kernel<false><<<(unsigned)(pairs < kGrid ? pairs : kGrid), tcb::kThreads, tcb::kSmemBytes, st>>>(
+            *p, b, grad_mu, grad_value, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, hz, lz);
+    }
     const int pf = p->h1 * p->in_pad + p->h2 * p->h1 + p->h3 * p->h2 + kOutPad * p->h3;
     const int64_t stages = b / tcw::kStage;
     const unsigned gw = (unsigned)(stages < kGrid ? stages : kGrid);
@@ -600,6 +687,21 @@ int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t 
 #undef AGX_WGRAD_TC
     if (cudaGetLastError() != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_mlp_backward_train: launch failed");
     return agx_internal_wgrad_reduce(p, g, w_partials, (int)gused, b_partials, (int)gused, stream);
+}
+
+int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
+                           const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t, float* dz3t,
+                           float* doutt, float* workspace, void* stream) {
+    return backward_train_impl(nullptr, nullptr, p, g, b, grad_mu, grad_value, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, workspace, stream);
+}
+
+int agx_sizeof_loss_io(void) { return (int)sizeof(AgxLossIO); }
+
+int agx_ppo_loss_backward_train(const AgxPpoHyper* hp, const AgxLossIO* lio, const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b,
+                                const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t, float* dz3t,
+                                float* doutt, float* workspace, void* stream) {
+    if (!lio || !hp) return agx_internal_fail(AGX_ERR_ARG, "agx_ppo_loss_backward_train: null loss block");
+    return backward_train_impl(hp, lio, p, g, b, nullptr, nullptr, xt, h1t, h2t, h3t, dz1t, dz2t, dz3t, doutt, workspace, stream);
 }
 
 }  // extern "C"

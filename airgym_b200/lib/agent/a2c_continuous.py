@@ -209,6 +209,8 @@ class A2CAgent:
             # "tcgen05" (default where it applies: 64-128-64 network, minibatch % 128 == 0): forward, activation-gradient chain and
             # weight gradients on tcgen05.mma with feature-major intermediates; "mma_sync": the warp-level TF32 kernels
             self.mlp_train_tc = self.config.get("mlp_backward", "tcgen05") == "tcgen05" and self.model.train_supported(mb)
+            # the PPO loss inside the backward kernel's first stage (agx_ppo_loss_backward_train); False: the stand-alone agx_ppo_loss launch
+            self.fuse_loss = bool(self.config.get("fuse_loss", True))
             if self.mlp_train_tc:
                 self.keep, self.dz, self.dout = self.model.train_buffers(mb, dev)
             else:
@@ -502,12 +504,25 @@ class A2CAgent:
             mu, value = self.model.heads(obs)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: t.data_ptr()
-        _capi.check(self._lib.agx_ppo_loss(
-            C.byref(self.hyper), mb, A, p(mu), p(self.model.logstd), p(value), p(b["actions"].view(-1, A)[sl]),
-            p(b["neglogpacs"].view(-1)[sl]), p(self.advantages[sl]), p(self.norm_returns[sl]), p(b["mus"].view(-1, A)[sl]),
-            p(b["sigmas"].view(-1, A)[sl]), p(self.grad_mu), p(self.grad_value), p(self.grad_logstd), p(self.stats),
-            p(self.workspace), st), "agx_ppo_loss")
-        if self.fused_mlp:
+        if self.fused_mlp and self.mlp_train_tc and self.fuse_loss:
+            # the loss lives in the first stage of the tcgen05 backward (agx_ppo_loss_backward_train): one launch less per minibatch
+            lio = _capi.AgxLossIO()
+            lio.mu, lio.logstd, lio.value = p(mu), p(self.model.logstd), p(value)
+            lio.actions, lio.old_neglogp = p(b["actions"].view(-1, A)[sl]), p(b["neglogpacs"].view(-1)[sl])
+            lio.adv, lio.returns = p(self.advantages[sl]), p(self.norm_returns[sl])
+            lio.old_mu, lio.old_sigma = p(b["mus"].view(-1, A)[sl]), p(b["sigmas"].view(-1, A)[sl])
+            lio.grad_logstd, lio.stats, lio.workspace, lio.a = p(self.grad_logstd), p(self.stats), p(self.workspace), A
+            self.model.fused_loss_backward_train(self.hyper, lio, self.keep, self.dz, self.dout, self.mlp_ws)
+            self.model.logstd.grad.copy_(self.grad_logstd)
+        else:
+            _capi.check(self._lib.agx_ppo_loss(
+                C.byref(self.hyper), mb, A, p(mu), p(self.model.logstd), p(value), p(b["actions"].view(-1, A)[sl]),
+                p(b["neglogpacs"].view(-1)[sl]), p(self.advantages[sl]), p(self.norm_returns[sl]), p(b["mus"].view(-1, A)[sl]),
+                p(b["sigmas"].view(-1, A)[sl]), p(self.grad_mu), p(self.grad_value), p(self.grad_logstd), p(self.stats),
+                p(self.workspace), st), "agx_ppo_loss")
+        if self.fused_mlp and self.mlp_train_tc and self.fuse_loss:
+            pass
+        elif self.fused_mlp:
             self._manual_backward()
         else:
             self.flat_grads[: self.n_params].zero_()

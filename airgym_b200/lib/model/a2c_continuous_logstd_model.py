@@ -172,6 +172,17 @@ class ModelA2CContinuousLogStd(nn.Module):
             p(keep_t[2]), p(keep_t[3]), p(dz_t[0]), p(dz_t[1]), p(dz_t[2]), p(dout_t), p(workspace),
             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_mlp_backward_train")
 
+    def fused_loss_backward_train(self, hyper, lio, keep_t, dz_t, dout_t, workspace):
+        """agx_ppo_loss_backward_train: the PPO loss of the minibatch (lio: _capi.AgxLossIO) computed inside the first stage of the tcgen05
+        backward — loss statistics, grad_logstd, old_mu / old_sigma and every parameter gradient from ONE call (3 launches)."""
+        if getattr(self, "_fused_g", None) is None:
+            self._fused_g = self.fused_grads()
+        p = lambda t: t.data_ptr()
+        _capi.check(_capi.load().agx_ppo_loss_backward_train(
+            C.byref(hyper), C.byref(lio), C.byref(self.train_params()), C.byref(self._fused_g), keep_t[0].shape[1], p(keep_t[0]), p(keep_t[1]),
+            p(keep_t[2]), p(keep_t[3]), p(dz_t[0]), p(dz_t[1]), p(dz_t[2]), p(dout_t), p(workspace),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "agx_ppo_loss_backward_train")
+
     def policy_params(self):
         """Parameters of the fused rollout step: the training-path padding is always one of the widths the tcgen05 kernel is built for."""
         return self.train_params()

@@ -386,6 +386,24 @@ int agx_mlp_forward_train(const AgxMlpParams* p, int64_t b, const float* obs, fl
 int agx_mlp_backward_train(const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b, const float* grad_mu, const float* grad_value,
                            const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t,
                            float* dz3t, float* doutt, float* workspace, void* stream);
+/* The PPO loss (agx_ppo_loss: a2c_continuous.py:299-369 after the network heads) folded into the first stage of the tcgen05 backward:
+ * the thread that owns a minibatch row computes its clipped-surrogate / value / bound-loss gradients from mu, value and the stored
+ * rollout quantities right where the backward needs d loss / d (mu | value), updates old_mu / old_sigma (PPODataset.update_mu_sigma) and
+ * accumulates the loss statistics; the CTA drawing the last ticket reduces the per-CTA partials in CTA order (deterministic) into
+ * stats [AGX_PPO_STATS] and grad_logstd [a].  One launch less per minibatch and no grad_mu / grad_value round trip; same arithmetic
+ * per row as agx_ppo_loss, statistics identical up to the summation order.  `workspace` as agx_ppo_workspace_floats(). */
+typedef struct AgxLossIO {
+    const float *mu, *logstd, *value;              /* [b,a] / [a] / [b]: network outputs of agx_mlp_forward_train, the model's logstd */
+    const float *actions, *old_neglogp, *adv, *returns; /* [b,a] / [b] / [b] / [b] minibatch slices of the rollout buffers */
+    float *old_mu, *old_sigma;                     /* [b,a] in/out */
+    float *grad_logstd, *stats, *workspace;        /* [a] / [AGX_PPO_STATS] out; scratch */
+    int32_t a, _pad;                               /* actions_num: 4 | 5 */
+} AgxLossIO;
+int agx_sizeof_loss_io(void);
+int agx_ppo_loss_backward_train(const AgxPpoHyper* hp, const AgxLossIO* lio, const AgxMlpParams* p, const AgxMlpGrads* g, int64_t b,
+                                const float* xt, const float* h1t, const float* h2t, const float* h3t, float* dz1t, float* dz2t, float* dz3t,
+                                float* doutt, float* workspace, void* stream);
+
 
 /* ---- fused rollout step (reference lib/agent/a2c_base.py:651-711 play_steps; get_action_values :357-369; the model's sampling
  * branch a2c_continuous_logstd_model.py:181-193; preprocess_actions a2c_continuous.py:61-71) -------------------------------------

@@ -280,11 +280,22 @@ def _rows(planes):
     return planes.reshape(B // 128, W, 128).permute(0, 2, 1).reshape(B, W)
 
 
+@pytest.fixture(params=[1, 0], ids=["wgrad-tma", "wgrad-gather"])
+def wgrad_impl(request):
+    """weight-gradient operands by TMA boxes (default) or by the cp.async gather kernel (agx_set_option("mlp_wgrad_tma"))"""
+    from airgym_b200 import _capi
+
+    lib = _capi.load()
+    _capi.check(lib.agx_set_option(b"mlp_wgrad_tma", request.param), "mlp_wgrad_tma")
+    yield request.param
+    lib.agx_set_option(b"mlp_wgrad_tma", 1)
+
+
 @pytest.mark.parametrize("OBS,B", [(18, 2048), (18, 65536), (48, 1024), (46, 256), (18, 128), (80, 512)])
-def test_tcgen05_train_path_vs_autograd(built, OBS, B):
+def test_tcgen05_train_path_vs_autograd(built, OBS, B, wgrad_impl):
     """agx_mlp_forward_train / agx_mlp_backward_train — forward, activation-gradient chain, weight AND bias gradients all on
     tcgen05.mma (feature-major intermediates) — against the fp32 torch model + autograd, at the TF32 bound of the mma.sync path:
-    outputs 5e-3 rel + 2e-3 abs, parameter gradients 2e-2 of their scale; bitwise reproducible."""
+    outputs 5e-3 rel + 2e-3 abs, parameter gradients 2e-2 of their scale; bitwise reproducible.  Both weight-gradient kernels."""
     from airgym_b200.lib.config import default_ppo_config
     from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
 
@@ -511,6 +522,27 @@ def test_reference_golden_minibatch_through_the_fused_trainer_path(built):
         ref = torch.from_numpy(g[f"step0/grads/{n}"])
         scale = float(ref.abs().max()) + 1e-12
         assert_close((p.grad.cpu() / scale), ref / scale, f"grad {n} (TF32)", rtol=2e-2, atol=1e-2)
+    # the trainer's default: the loss folded into the backward's first stage (agx_ppo_loss_backward_train) — same per-row arithmetic, so
+    # the parameter gradients and the old_mu / old_sigma updates are bit-identical, the statistics equal up to the summation order
+    sep = {n: p.grad.clone() for n, p in model.named_parameters()}
+    sep_stats, sep_gls, sep_om, sep_os = stats[:5].clone(), g_ls.clone(), om.clone(), os_.clone()
+    om2, os2 = d(fl(t("mus"))[sl]), d(fl(t("sigmas"))[sl])
+    g_ls2, stats2 = torch.zeros(A, device="cuda"), torch.zeros(_capi.AGX_PPO_STATS, device="cuda")
+    assert lib.agx_sizeof_loss_io() == C.sizeof(_capi.AgxLossIO)
+    lio = _capi.AgxLossIO()
+    lio.mu, lio.logstd, lio.value, lio.actions, lio.old_neglogp, lio.adv, lio.returns = [x.data_ptr() for x in ins]
+    lio.old_mu, lio.old_sigma, lio.grad_logstd, lio.stats, lio.workspace, lio.a = om2.data_ptr(), os2.data_ptr(), g_ls2.data_ptr(), stats2.data_ptr(), ws.data_ptr(), A
+    for p in model.parameters():
+        p.grad.fill_(3.0)
+    model.fused_loss_backward_train(Hh, lio, keep, dz, dout, model.fused_workspace("cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(om2, sep_om) and torch.equal(os2, sep_os)
+    assert_close(stats2[:5].cpu(), sep_stats.cpu(), "fused loss statistics", rtol=2e-5, atol=1e-7)
+    assert_close(g_ls2.cpu(), sep_gls.cpu(), "fused grad_logstd", rtol=2e-5, atol=1e-8)
+    for n, p in model.named_parameters():
+        if n != "logstd":
+            assert torch.equal(p.grad, sep[n]), f"fused loss + backward: grad {n}"
+    model.logstd.grad.copy_(g_ls)
     m, v = torch.zeros(model.num_flat, device="cuda"), torch.zeros(model.num_flat, device="cuda")
     lr_in = float(g["step0/lr_in"])
     lr_dev, step, norm = torch.tensor([lr_in], device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, device="cuda")
