@@ -37,7 +37,7 @@ constexpr int kMaxStages = 8;
 struct ConvGeom {
     int64_t M_total;
     int32_t num_tiles, Nt, cblocks, nslabs, spp, fills, stages, G, tmem_cols;
-    uint32_t a_bytes, b_bytes, stage_bytes, slab_tx, stg_bytes;
+    uint32_t a_bytes, b_bytes, stage_bytes, stg_bytes;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -650,7 +650,6 @@ int agx_internal_conv_tma(const AgxConvParams* p, void* stream) {
     G.a_bytes = (uint32_t)kM * swb;
     G.b_bytes = (uint32_t)G.Nt * swb;  // a multiple of 1024: Nt % 32 == 0, swb >= 64
     const uint32_t slab_bytes = (split ? 2u : 1u) * (G.a_bytes + G.b_bytes);
-    G.slab_tx = G.a_bytes + (split ? 2u : 1u) * G.b_bytes;
     G.stg_bytes = (uint32_t)G.Nt * kM * 4;
     const uint32_t budget = 220u * 1024u - G.stg_bytes;
     G.spp = g_conv_spp ? g_conv_spp : (int)(65536u / slab_bytes);
