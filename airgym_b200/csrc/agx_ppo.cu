@@ -235,8 +235,18 @@ agx_col_sums_kernel(const float* __restrict__ x, int64_t n, int k, int64_t ld, i
     __shared__ bool s_last;
     const int c = threadIdx.x % cpr, rg = threadIdx.x / cpr, rgs = kSumsBlock / cpr;
     double a = 0.0, b = 0.0;
-    if (c < k)
-        for (int64_t r = (int64_t)blockIdx.x * rgs + rg; r < n; r += (int64_t)gridDim.x * rgs) { const double v = (double)x[r * ld + c]; a += v; b += v * v; }
+    if (c < k) {  // four rows' loads in flight per thread, added in row order (the sums are bit-identical to the one-load-per-iteration loop, whose
+                  // ~14 serialised L2 round trips were most of this kernel's 17 us)
+        const int64_t stride = (int64_t)gridDim.x * rgs;
+        for (int64_t r = (int64_t)blockIdx.x * rgs + rg; r < n; r += 4 * stride) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (r + u * stride < n) ? __ldg(x + (r + u * stride) * ld + c) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r + u * stride < n) { const double w = (double)v[u]; a += w; b += w * w; }
+        }
+    }
     s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
     __syncthreads();
     double* part = ws + 8 + (int64_t)blockIdx.x * 2 * kSumsMaxK;

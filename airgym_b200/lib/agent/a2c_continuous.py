@@ -511,9 +511,9 @@ class A2CAgent:
             lio.actions, lio.old_neglogp = p(b["actions"].view(-1, A)[sl]), p(b["neglogpacs"].view(-1)[sl])
             lio.adv, lio.returns = p(self.advantages[sl]), p(self.norm_returns[sl])
             lio.old_mu, lio.old_sigma = p(b["mus"].view(-1, A)[sl]), p(b["sigmas"].view(-1, A)[sl])
-            lio.grad_logstd, lio.stats, lio.workspace, lio.a = p(self.grad_logstd), p(self.stats), p(self.workspace), A
+            # grad_logstd lands straight in logstd.grad (a view of the flat gradient buffer): no copy kernel per minibatch
+            lio.grad_logstd, lio.stats, lio.workspace, lio.a = p(self.model.logstd.grad), p(self.stats), p(self.workspace), A
             self.model.fused_loss_backward_train(self.hyper, lio, self.keep, self.dz, self.dout, self.mlp_ws)
-            self.model.logstd.grad.copy_(self.grad_logstd)
         else:
             _capi.check(self._lib.agx_ppo_loss(
                 C.byref(self.hyper), mb, A, p(mu), p(self.model.logstd), p(value), p(b["actions"].view(-1, A)[sl]),
