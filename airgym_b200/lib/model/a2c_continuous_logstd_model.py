@@ -59,11 +59,13 @@ class ModelA2CContinuousLogStd(nn.Module):
         if self.has_vae:  # :33-35 — a frozen, pre-trained encoder: a plain attribute in the reference (its weights are not part of
             enc = VAEImageEncoder(net["vae"])   # the policy's state_dict), so it is kept out of the module registry here too
             self.feature_dim = enc.latent_dim
+            enc.encoder_precise = bool(net["vae"].get("encoder_precise", True))  # False: single-pass TF32 (cuDNN's default precision)
             object.__setattr__(self, "actor_enc", enc)
             self.actor_mlp = MLP(input_shape["observation"][0] + self.feature_dim, units, act)
         elif self.has_cnn:  # :30-32
             self.feature_dim = int(net["cnn"]["output_dim"])
             self.actor_cnn = CNNFeatureExtractor(feature_dim=self.feature_dim)
+            self.actor_cnn.encoder_precise = bool(net["cnn"].get("encoder_precise", True))  # False: single-pass TF32 (cuDNN's default precision)
             self.actor_mlp = MLP(input_shape["observation"][0] + self.feature_dim, units, act)
         else:
             self.actor_mlp = MLP(input_shape[0], units, act)

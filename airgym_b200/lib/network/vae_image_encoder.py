@@ -83,7 +83,7 @@ class VAEImageEncoder(nn.Module):
                 and self.interpolation_mode == "bilinear" and self.native):
             # libagx: resize + the nine convolutions + two dense layers on the tensor cores (tc_encoders.vae_encode), no cuDNN
             from .tc_encoders import vae_encode
-            out = vae_encode(self.encoder, self.image_res, image_tensors)
+            out = vae_encode(self.encoder, self.image_res, image_tensors, precise=getattr(self, "encoder_precise", True))
         else:
             if tuple(image_tensors.shape[-2:]) != self.image_res:
                 image_tensors = F.interpolate(image_tensors, self.image_res, mode=self.interpolation_mode)

@@ -25,6 +25,7 @@ if __name__ == "__main__":
     ap.add_argument("--vae", action="store_true", help="planning: the frozen depth-VAE encoder (latent 64) instead of the CNN (ppo_planning.yaml:33-39); "
                     "random frozen weights — trained/vae_model.pth does not travel to the GPU box")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--encoder_tf32", action="store_true", help="camera tasks: single-pass TF32 encoder convolutions (cuDNN's default precision) instead of 3xTF32")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = scale_minibatch(default_ppo_config(a.task), a.num_envs)
@@ -38,6 +39,10 @@ if __name__ == "__main__":
         cfg["params"]["network"].pop("cnn", None)
         cfg["params"]["network"]["vae"] = {"latent_dims": 64, "image_res": [120, 212], "interpolation_mode": "bilinear",
                                            "return_sampled_latent": False, "allow_random_init": True}
+    if a.encoder_tf32:
+        for k in ("cnn", "vae"):
+            if k in cfg["params"]["network"]:
+                cfg["params"]["network"][k]["encoder_precise"] = False
     cfg["params"]["seed"] = a.seed
     import contextlib
     r = Runner()
@@ -49,7 +54,7 @@ if __name__ == "__main__":
         frames = sum(x["frame"] - (r.agent.history[i + a.skip - 1]["frame"] if i + a.skip > 0 else 0) for i, x in enumerate(h))
         play, upd = sum(x["play_time"] for x in h), sum(x["update_time"] for x in h)
         print(json.dumps({
-            "task": a.task, "ctl_mode": a.ctl_mode, "encoder": ("vae" if a.vae else ("cnn" if r.agent.has_cnn else None)),
+            "task": a.task, "ctl_mode": a.ctl_mode, "encoder": ("vae" if a.vae else ("cnn" if r.agent.has_cnn else None)), "encoder_precision": ("tf32" if a.encoder_tf32 else "3xtf32"),
             "env_steps_per_s_rollout": frames / play, "fused_rollout": r.agent.fused_rollout, "mlp_backward_tcgen05": getattr(r.agent, "mlp_train_tc", False), "num_envs_per_gpu": a.num_envs, "n_gpus": world, "epochs_timed": len(h),
             "minibatch": c["minibatch_size"], "cuda_graph": not a.no_graph,
             "samples_per_s_rollout": frames / play, "samples_per_s_update": frames / upd, "samples_per_s_total": frames / (play + upd),
