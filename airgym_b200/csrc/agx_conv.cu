@@ -258,6 +258,7 @@ agx_conv2d_first_kernel(const __grid_constant__ AgxConvFirstParams P) {
 // Same tap order and fmaf chain as the generic kernel: results are bit-identical to it.  The weights reach the constant bank by a
 // stream-ordered device-to-device copy (cudaMemcpyToSymbolAsync; a memcpy node under graph capture), one slot per Cout.
 __constant__ float c_first[2][32 * 25 + 3 * 32];  // slot 0: Cout = 16, slot 1: Cout = 32 — [tap][Cout] weights | bias | scale | shift
+__device__ float g_first_pack[2][32 * 25 + 3 * 32];  // staging of the constant-bank image (a static buffer: no allocation inside a stream capture)
 
 __global__ void agx_first_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                                       float* __restrict__ out, int cout) {
@@ -595,11 +596,13 @@ int agx_conv2d_first(const AgxConvFirstParams* p, void* stream) {
         if (r) return r > 0 ? AGX_OK : r;
     }
     if (five && g_first_impl >= 1) {
-        static float* pack[2] = {nullptr, nullptr};  // staging for the constant-bank image, one per slot (stream order serialises its reuse)
         const int slot = p->Cout == 16 ? 0 : 1, nfl = 28 * p->Cout;
-        if (!pack[slot] && cudaMalloc(&pack[slot], sizeof(float) * (32 * 25 + 3 * 32)) != cudaSuccess) return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: cudaMalloc failed");
-        agx_first_pack_kernel<<<1, 128, 0, st>>>(p->w, p->bias, p->scale, p->shift, pack[slot], p->Cout);
-        if (cudaMemcpyToSymbolAsync(c_first, pack[slot], sizeof(float) * nfl, sizeof(float) * slot * (32 * 25 + 3 * 32), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        static float* pack_base = nullptr;  // device address of g_first_pack (stream order serialises the reuse of a slot)
+        if (!pack_base && cudaGetSymbolAddress(reinterpret_cast<void**>(&pack_base), g_first_pack) != cudaSuccess)
+            return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: cudaGetSymbolAddress failed");
+        float* pack = pack_base + slot * (32 * 25 + 3 * 32);
+        agx_first_pack_kernel<<<1, 128, 0, st>>>(p->w, p->bias, p->scale, p->shift, pack, p->Cout);
+        if (cudaMemcpyToSymbolAsync(c_first, pack, sizeof(float) * nfl, sizeof(float) * slot * (32 * 25 + 3 * 32), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             return agx_internal_fail(AGX_ERR_CUDA, "agx_conv2d_first: constant-bank copy failed");
         const bool pair_ok = !(p->Wo & 1) && !(p->W & 3) && p->px == 2 && !(((uintptr_t)p->x | (uintptr_t)p->px_mean | (uintptr_t)p->px_rstd) & 15u);
         if (pair_ok && g_first_impl == 1) {

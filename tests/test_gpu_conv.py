@@ -165,6 +165,32 @@ def test_cnn_encoder_train_mode_batchnorm_vs_torch(built):
     assert float((got.double() - want).abs().max()) <= 3e-5 * max(1.0, float(want.abs().max()))
 
 
+def test_cnn_encoder_replays_from_a_cuda_graph(built):
+    """The layer sequence is capturable (the first layer's constant-bank image travels as a memcpy node, the tensor maps as kernel
+    arguments): a replay after the weights and the images changed in place reproduces the eager result bit for bit."""
+    from airgym_b200.lib.network.cnn import CNNFeatureExtractor, native_encode
+
+    torch.manual_seed(7)
+    net = CNNFeatureExtractor(30).cuda().eval()
+    img = torch.rand(300, 1, 212, 120, device="cuda") * 9
+    mean, rstd = torch.rand(212 * 120, device="cuda") * 4, torch.rand(212 * 120, device="cuda") * 0.5 + 0.2
+    out = torch.zeros(300, 30, device="cuda")
+    with torch.no_grad():
+        native_encode(net, img, mean, rstd, out=out)  # warm-up: weight preparation cached, attributes set
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            native_encode(net, img, mean, rstd, out=out)
+        img.mul_(0.5).add_(1.0)
+        net.features[0].weight.mul_(1.5)  # first-layer weights are re-read from the parameter on every replay
+        net.features[0].bias.add_(0.1)
+        g.replay()
+        torch.cuda.synchronize()
+        got = out.clone()
+        want = native_encode(net, img, mean, rstd)
+    assert torch.equal(got, want)
+
+
 def test_vae_encoder_tc_vs_mirror_and_golden(built):
     from airgym_b200.lib.network.vae_image_encoder import VAEImageEncoder
     from tests.util_vae import procedural_images, procedural_state
