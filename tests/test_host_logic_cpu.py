@@ -63,6 +63,31 @@ def test_new_struct_mirrors_match_the_library(built):
     p = _capi.AgxMlpParams()
     assert lib.agx_mlp_train_supported(C.byref(p)) == 0
     assert lib.agx_col_sums(None, 4, 4, 4, None, None, None) == -1 and lib.agx_rms_merge(None, 4, 10.0, None, None, None, None) == -1
+    # second half of round 2: loss block of the fused loss + backward, train-mode BatchNorm, the option keys of the TMA kernels
+    assert lib.agx_sizeof_loss_io() == C.sizeof(_capi.AgxLossIO)
+    assert lib.agx_ppo_loss_backward_train(None, None, None, None, 128, *([None] * 10)) == -1
+    assert lib.agx_bn_train(None, 4, 16, None, None, None, 1e-5, 0.1, None, None, None) == -1
+    for key, good, bad in ((b"conv_impl", 1, 2), (b"conv_first", 1, 4), (b"conv_spp", 0, 5), (b"conv_stages", 0, 1), (b"mlp_wgrad_tma", 1, None)):
+        assert lib.agx_set_option(key, good) == 0
+        if bad is not None:
+            assert lib.agx_set_option(key, bad) == -1
+            assert lib.agx_set_option(key, good) == 0
+
+
+def test_encoder_precision_switch_reaches_the_modules():
+    """network.cnn.encoder_precise: False = single-pass TF32 convolutions (cuDNN's default precision); default 3xTF32."""
+    import copy
+
+    from airgym_b200.lib.config import default_ppo_config
+    from airgym_b200.lib.model.a2c_continuous_logstd_model import ModelA2CContinuousLogStd
+
+    params = copy.deepcopy(default_ppo_config("planning")["params"])
+    shape = {"image": (1, 212, 120), "observation": (16,)}
+    m = ModelA2CContinuousLogStd(params, {"actions_num": 4, "input_shape": shape})
+    assert m.actor_cnn.encoder_precise is True
+    params["network"]["cnn"]["encoder_precise"] = False
+    m = ModelA2CContinuousLogStd(params, {"actions_num": 4, "input_shape": shape})
+    assert m.actor_cnn.encoder_precise is False
 
 
 def test_train_padding_keeps_a_spare_input_plane():
